@@ -1,0 +1,158 @@
+"""ctypes binding of ``libeqf_b200.so`` (C ABI declared in ``include/eqf_b200.h``).
+
+The shared library is built in-tree by :func:`build` (``nvcc -gencode arch=compute_100a,code=sm_100a``)
+and loaded lazily.  There is deliberately **no fallback**: if the library is missing or a kernel entry
+point fails, the call raises - the product path never routes through a CPU or eager-torch restatement
+(the only CPU restatement lives in ``oracle/`` and is test infrastructure).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+import threading
+from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_void_p
+from pathlib import Path
+
+PKG_DIR = Path(__file__).resolve().parent
+CSRC_DIR = PKG_DIR / "csrc"
+INCLUDE_DIR = PKG_DIR.parent / "include"
+LIB_PATH = PKG_DIR / "libeqf_b200.so"
+SOURCES = ("eqf_abi.cu", "eqf_dtp.cu", "eqf_attn.cu")
+
+EQF_MAX_BLOCKS = 8
+EQF_MAX_HEADS = 16
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17", "--shared", "-Xcompiler", "-fPIC",
+]
+
+
+class EqfPathDesc(ctypes.Structure):
+    _fields_ = [
+        ("l1", c_int32), ("l2", c_int32), ("l3", c_int32), ("mul", c_int32),
+        ("in1_block", c_int32), ("in2_off", c_int32), ("out_group", c_int32),
+        ("out_chan_off", c_int32), ("w_off", c_int32), ("cg_off", c_int32),
+    ]
+
+
+class EqfEdgeOperands(ctypes.Structure):
+    _fields_ = [
+        ("x", c_void_p * EQF_MAX_BLOCKS),
+        ("x2", c_void_p * EQF_MAX_BLOCKS),
+        ("src", c_void_p),
+        ("dst", c_void_p),
+        ("y", c_void_p),
+        ("w", c_void_p),
+        ("w_shared", c_int32),
+        ("g", c_void_p * EQF_MAX_BLOCKS),
+    ]
+
+
+class EqfHeadLayout(ctypes.Structure):
+    _fields_ = [
+        ("n_groups", c_int32),
+        ("d", c_int32 * EQF_MAX_BLOCKS),
+        ("C", c_int32 * EQF_MAX_BLOCKS),
+        ("n_heads", c_int32),
+    ]
+
+
+PtrArray = c_void_p * EQF_MAX_BLOCKS
+
+# name -> (restype, argtypes); every symbol include/eqf_b200.h declares
+SIGNATURES = {
+    "eqf_version": (c_int32, []),
+    "eqf_last_error": (c_char_p, []),
+    "eqf_device_sm_count": (c_int32, []),
+    "eqf_plan_create": (c_int32, [POINTER(EqfPathDesc), c_int32, POINTER(c_int32), POINTER(c_int32), c_int32,
+                                  POINTER(c_int32), POINTER(c_int32), c_int32, c_int32, c_int32,
+                                  POINTER(c_float), c_int32, POINTER(c_void_p)]),
+    "eqf_plan_destroy": (None, [c_void_p]),
+    "eqf_plan_info": (c_int32, [c_void_p, POINTER(c_int32), c_int32]),
+    "eqf_plan_partial_rows": (c_int32, [c_void_p, c_int64]),
+    "eqf_dtp_forward": (c_int32, [c_void_p, POINTER(EqfEdgeOperands), c_int64, POINTER(c_void_p), c_void_p]),
+    "eqf_dtp_grad_x": (c_int32, [c_void_p, POINTER(EqfEdgeOperands), c_int64, POINTER(c_void_p), c_void_p]),
+    "eqf_dtp_grad_w": (c_int32, [c_void_p, POINTER(EqfEdgeOperands), c_int64, c_void_p, c_void_p]),
+    "eqf_dtp_grad_y": (c_int32, [c_void_p, POINTER(EqfEdgeOperands), c_int64, c_void_p, c_void_p]),
+    "eqf_dtp_grad_xw": (c_int32, [c_void_p, POINTER(EqfEdgeOperands), c_int64, POINTER(c_void_p), c_void_p, c_void_p]),
+    "eqf_seg_softmax": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p]),
+    "eqf_attn_aggregate": (c_int32, [POINTER(EqfHeadLayout), c_void_p, POINTER(c_void_p), c_void_p, c_int64,
+                                     POINTER(c_void_p), c_void_p]),
+    "eqf_attn_edge_dot": (c_int32, [POINTER(EqfHeadLayout), POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_int64,
+                                    c_void_p, c_void_p]),
+    "eqf_attn_edge_scale": (c_int32, [POINTER(EqfHeadLayout), c_void_p, POINTER(c_void_p), c_void_p, c_int64,
+                                      POINTER(c_void_p), c_void_p]),
+}
+
+
+class EqfError(RuntimeError):
+    pass
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def sources():
+    return [CSRC_DIR / s for s in SOURCES if (CSRC_DIR / s).exists()]
+
+
+def needs_build() -> bool:
+    if not LIB_PATH.exists():
+        return True
+    mtime = LIB_PATH.stat().st_mtime
+    deps = sources() + list(CSRC_DIR.glob("*.cuh")) + [INCLUDE_DIR / "eqf_b200.h"]
+    return any(p.stat().st_mtime > mtime for p in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile ``csrc/*.cu`` for sm_100a into ``equiformer_b200/libeqf_b200.so`` (in-tree)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise EqfError("nvcc not found: cannot build libeqf_b200.so")
+    tmp = LIB_PATH.with_suffix(".so.tmp%d" % os.getpid())
+    cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE_DIR), "-o", str(tmp), *[str(s) for s in sources()]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise EqfError("nvcc failed:\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    os.replace(tmp, LIB_PATH)
+    return LIB_PATH
+
+
+def load():
+    """Return the loaded library (raises :class:`EqfError` when it is absent - no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not LIB_PATH.exists():
+            raise EqfError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(the sm_100a kernels are the only implementation of the edge path)")
+        lib = ctypes.CDLL(str(LIB_PATH))
+        for name, (restype, argtypes) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as exc:  # stale build
+                raise EqfError(f"libeqf_b200.so does not export {name}; rebuild it") from exc
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load().eqf_last_error()
+        raise EqfError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")

@@ -1,0 +1,74 @@
+// eqf_common.cuh - shared device/host definitions for libeqf_b200.so (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/eqf_b200.h"
+
+struct EqfPlan;
+
+namespace eqf {
+
+constexpr int kThreads = 256;           // threads per CTA for the edge kernels
+constexpr int kWarps = kThreads / 32;
+constexpr int kMaxD = 7;                // degrees 0..3  (2l+1 <= 7)
+
+// Device-side path record (one Clebsch-Gordan path); mirrors EqfPathDesc + derived fields.
+struct PathDev {
+  int d1, d2, d3;   // 2l+1 of in1, in2, out
+  int mul;          // channels
+  int xb;           // in1 block
+  int y_off;        // offset of the l2 SH in an edge_attr row
+  int og;           // output group
+  int koff;         // channel offset inside the output group
+  int w_off;        // offset in the weight row
+  int cg_off;       // offset in the dense CG table [d1][d2][d3]
+  int m_off;        // offset in the per-edge M scratch [d1][d3]
+  int pad;
+};
+static_assert(sizeof(PathDev) == 48, "PathDev layout");
+
+// Header passed by value to every edge kernel; offsets index the int/float blob in global memory.
+struct PlanHdr {
+  int n_paths, n_in1, n_out, d_y, w_numel, m_size, cg_len;
+  int n_wtasks;     // (path, 32-channel chunk) tasks per edge   [forward / grad_w / grad_y]
+  int n_xtasks;     // (in1 block, 32-channel chunk) tasks per edge [grad_x / grad_xw]
+  int blob_words;
+  int off_paths, off_cg, off_mdesc, off_wtasks, off_xtasks, off_xbstart, off_xbpaths;
+  int te;           // edges per tile
+  int in1_d[EQF_MAX_BLOCKS], in1_mul[EQF_MAX_BLOCKS];
+  int out_d[EQF_MAX_BLOCKS], out_mul[EQF_MAX_BLOCKS];
+};
+
+struct EdgeArgs {
+  const float* x[EQF_MAX_BLOCKS];
+  const float* x2[EQF_MAX_BLOCKS];
+  const long long* src;
+  const long long* dst;
+  const float* y;
+  const float* w;
+  int w_shared;
+  const float* g[EQF_MAX_BLOCKS];
+  float* out[EQF_MAX_BLOCKS];   // forward outputs (per output group)
+  float* gx[EQF_MAX_BLOCKS];    // grad_x outputs (per in1 block)
+  float* gw;                    // [E][W] or [grid][W]
+  float* gy;                    // [E][d_y]
+  long long E;
+};
+
+void set_error(const std::string& msg);
+int check_cuda(cudaError_t err, const char* what);
+int ensure_device(const EqfPlan* plan);  // uploads the table blob on first use
+
+}  // namespace eqf
+
+struct EqfPlan {
+  eqf::PlanHdr hdr;
+  std::vector<uint32_t> blob;   // host copy
+  uint32_t* d_blob = nullptr;   // device copy
+  int device = -1;
+  int sm_count = 148;
+  size_t smem_bytes = 0;        // dynamic shared memory per CTA
+};

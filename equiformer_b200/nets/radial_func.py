@@ -1,0 +1,39 @@
+"""Radial profile MLP producing the per-edge DTP weights (drop-in for ``nets/radial_func.py``).
+
+``Linear -> LayerNorm -> SiLU`` per hidden width, then ``Linear(no bias) + offset`` (``radial_func.py:9-50``);
+``state_dict`` keys ``net.{0,1,3,4,6}.*`` and ``offset`` as in the reference.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+from torch import nn
+
+
+class RadialProfile(nn.Module):
+    def __init__(self, ch_list, use_layer_norm: bool = True, use_offset: bool = True):
+        super().__init__()
+        layers = []
+        last = len(ch_list) - 1
+        for i in range(1, len(ch_list)):
+            is_last = i == last
+            layers.append(nn.Linear(ch_list[i - 1], ch_list[i], bias=not (is_last and use_offset)))
+            if is_last:
+                break
+            if use_layer_norm:
+                layers.append(nn.LayerNorm(ch_list[i]))
+            layers.append(nn.SiLU())
+        self.net = nn.Sequential(*layers)
+        self.offset = None
+        if use_offset:
+            self.offset = nn.Parameter(torch.zeros(ch_list[-1]))
+            fan_in = ch_list[-2]
+            bound = 1.0 / math.sqrt(fan_in) if fan_in > 0 else 0.0
+            nn.init.uniform_(self.offset, -bound, bound)
+
+    def forward(self, f_in):
+        out = self.net(f_in)
+        if self.offset is not None:
+            out = out + self.offset.reshape(1, -1)
+        return out

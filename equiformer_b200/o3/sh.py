@@ -1,0 +1,89 @@
+"""Real spherical harmonics of edge vectors, e3nn convention, twice differentiable.
+
+Replaces ``e3nn.o3.spherical_harmonics(l, x, normalize, normalization)`` at the reference's
+call sites (``nets/graph_attention_transformer.py:869-870``,
+``nets/graph_attention_transformer_md17.py:283-284``).  Convention (e3nn 0.4.4): y is the polar
+axis, ``Y_1 = (x, y, z)``, higher degrees by the coupling recurrence
+``Y_{l+1} = c_l * w3j(l+1, 1, l) . (x (x) Y_l)`` with a positive constant so that
+``|Y_l(unit)| = 1`` ('norm'); 'component' multiplies by ``sqrt(2l+1)``; 'integral' divides
+that by ``sqrt(4 pi)``.
+
+The function is a short chain of plain torch ops (node/edge-level producer, SURVEY.md row a11;
+it is *not* one of the hand-written kernels) so autograd gives the first and second derivatives
+w.r.t. the edge vector that MD17 forces need (``graph_attention_transformer_md17.py:318-325``).
+"""
+from __future__ import annotations
+
+import functools
+import math
+from typing import List, Sequence, Union
+
+import numpy as np
+import torch
+
+from .irreps import Irreps
+from .wigner import wigner_3j_np
+
+
+@functools.lru_cache(maxsize=None)
+def _coupling(l: int) -> np.ndarray:
+    """``A[k, j, i]`` with ``Y_{l+1,k} = sum_ji A[k,j,i] xhat_j Y_{l,i}`` in 'norm' normalisation."""
+    c = wigner_3j_np(l + 1, 1, l)
+    # the constant is direction independent; evaluate it on the polar axis (0, 1, 0)
+    yl = _polar_value(l)
+    pole = np.array([0.0, 1.0, 0.0])
+    raw = np.einsum("kji,j,i->k", c, pole, yl)
+    n = np.linalg.norm(raw)
+    return c / n
+
+
+@functools.lru_cache(maxsize=None)
+def _polar_value(l: int) -> np.ndarray:
+    if l == 0:
+        return np.ones(1)
+    if l == 1:
+        return np.array([0.0, 1.0, 0.0])
+    prev = _polar_value(l - 1)
+    return np.einsum("kji,j,i->k", _coupling(l - 1), np.array([0.0, 1.0, 0.0]), prev)
+
+
+def _ls_from(l: Union[int, Sequence[int], str, Irreps]) -> List[int]:
+    if isinstance(l, int):
+        return [l]
+    if isinstance(l, (str, Irreps)) or hasattr(l, "lmax"):
+        irreps = Irreps(l)
+        out = []
+        for mul, ir in irreps:
+            out.extend([ir.l] * mul)
+        return out
+    return [int(v) for v in l]
+
+
+def spherical_harmonics(l, x: torch.Tensor, normalize: bool, normalization: str = "integral") -> torch.Tensor:
+    """``[..., 3] -> [..., sum(2l+1)]``; same arguments as ``e3nn.o3.spherical_harmonics``."""
+    if normalization not in ("integral", "component", "norm"):
+        raise ValueError("normalization must be 'integral', 'component' or 'norm'")
+    ls = _ls_from(l)
+    if x.shape[-1] != 3:
+        raise ValueError("last dimension of x must be 3")
+    lmax = max(ls)
+    lead = x.shape[:-1]
+    v = x.reshape(-1, 3)
+    if normalize:
+        v = torch.nn.functional.normalize(v, dim=-1)
+    ys = [torch.ones_like(v[:, :1])]
+    if lmax >= 1:
+        ys.append(v)
+    for deg in range(1, lmax):
+        a = torch.as_tensor(_coupling(deg), dtype=v.dtype, device=v.device)
+        t = torch.einsum("kji,ei->ekj", a, ys[deg])
+        ys.append(torch.einsum("ekj,ej->ek", t, v))
+    out = []
+    for deg in ls:
+        y = ys[deg]
+        if normalization == "component":
+            y = y * math.sqrt(2 * deg + 1)
+        elif normalization == "integral":
+            y = y * math.sqrt((2 * deg + 1) / (4 * math.pi))
+        out.append(y)
+    return torch.cat(out, dim=-1).reshape(*lead, -1)

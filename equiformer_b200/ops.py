@@ -1,0 +1,583 @@
+"""Autograd operators over the sm_100a edge kernels (``libeqf_b200.so``).
+
+Two closed families (every derivative of a member is another member, so ``create_graph=True`` -
+the MD17 force path, ``nets/graph_attention_transformer_md17.py:318-325`` - works to any order):
+
+* depth-wise tensor product: ``DtpOut`` / ``DtpGradX`` / ``DtpGradW`` / ``DtpGradY`` are the four
+  partial derivatives of ``S(x, y, w, g)`` (see ``csrc/eqf_dtp.cu``);
+* attention aggregation: ``AttnAggregate`` / ``EdgeDot`` / ``EdgeScale`` are the three partial
+  derivatives of ``T(alpha, V, G)`` (see ``csrc/eqf_attn.cu``); ``SegSoftmax`` has a kernel forward
+  and a backward written with differentiable ops on the small ``[E, H]`` tensors.
+
+All operands are planar blocks ``[rows, 2l+1, mul]`` (see ``plan.py``).  Tensors must be CUDA fp32;
+anything else raises - there is no CPU implementation on the product path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from .plan import DtpPlan
+
+# ----------------------------------------------------------------------------- helpers
+
+
+def _require_cuda(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.EqfError(
+            f"{name} lives on {t.device}: the equiformer_b200 edge kernels are CUDA-only (sm_100a); "
+            "there is no CPU fallback on the product path")
+    if t.dtype != torch.float32:
+        raise _lib.EqfError(f"{name} must be float32 (the reference trains in fp32), got {t.dtype}")
+    return t.contiguous()
+
+
+def _require_index(t: torch.Tensor, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.EqfError(f"{name} lives on {t.device}: CUDA index tensor required")
+    if t.dtype != torch.int64:
+        t = t.to(torch.int64)
+    return t.contiguous()
+
+
+def _stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr_array(ts: Sequence[torch.Tensor]):
+    arr = (ctypes.c_void_p * _lib.EQF_MAX_BLOCKS)()
+    for i, t in enumerate(ts):
+        arr[i] = t.data_ptr()
+    return arr
+
+
+def _operands(plan: DtpPlan, xs, y, w, gs, w_shared: bool) -> _lib.EqfEdgeOperands:
+    op = _lib.EqfEdgeOperands()
+    if xs is not None:
+        for i, t in enumerate(xs):
+            op.x[i] = t.data_ptr()
+    if gs is not None:
+        for i, t in enumerate(gs):
+            op.g[i] = t.data_ptr()
+    op.y = y.data_ptr()
+    op.w = w.data_ptr() if w is not None else None
+    op.w_shared = 1 if w_shared else 0
+    return op
+
+
+def _check_blocks(plan: DtpPlan, xs, E: int, what: str):
+    if len(xs) != len(plan.in1_blocks):
+        raise ValueError(f"{what}: expected {len(plan.in1_blocks)} in1 blocks, got {len(xs)}")
+    out = []
+    for t, (l, mul) in zip(xs, plan.in1_blocks):
+        t = _require_cuda(t, what)
+        if tuple(t.shape) != (E, 2 * l + 1, mul):
+            raise ValueError(f"{what}: block shape {tuple(t.shape)} != {(E, 2 * l + 1, mul)}")
+        out.append(t)
+    return out
+
+
+def _check_groups(plan: DtpPlan, gs, E: int, what: str):
+    if len(gs) != len(plan.out_groups):
+        raise ValueError(f"{what}: expected {len(plan.out_groups)} output groups, got {len(gs)}")
+    out = []
+    for t, (l, _p, mul) in zip(gs, plan.out_groups):
+        t = _require_cuda(t, what)
+        if tuple(t.shape) != (E, 2 * l + 1, mul):
+            raise ValueError(f"{what}: group shape {tuple(t.shape)} != {(E, 2 * l + 1, mul)}")
+        out.append(t)
+    return out
+
+
+def _check_yw(plan: DtpPlan, y, w, E: Optional[int] = None):
+    y = _require_cuda(y, "edge_attr")
+    if y.dim() != 2 or y.shape[1] != plan.d_y:
+        raise ValueError(f"edge_attr must be [E, {plan.d_y}], got {tuple(y.shape)}")
+    E = y.shape[0]
+    shared = None
+    if w is not None:
+        w = _require_cuda(w, "weight")
+        if w.dim() == 1:
+            shared = True
+            if w.shape[0] != plan.weight_numel:
+                raise ValueError(f"shared weight must be [{plan.weight_numel}], got {tuple(w.shape)}")
+        else:
+            shared = False
+            if tuple(w.shape) != (E, plan.weight_numel):
+                raise ValueError(f"per-edge weight must be [{E}, {plan.weight_numel}], got {tuple(w.shape)}")
+    return y, w, E, shared
+
+
+# ----------------------------------------------------------------------------- raw kernel calls
+
+
+def dtp_forward_raw(plan: DtpPlan, xs, y, w) -> List[torch.Tensor]:
+    y, w, E, shared = _check_yw(plan, y, w)
+    xs = _check_blocks(plan, xs, E, "dtp_forward x")
+    outs = [torch.empty((E, 2 * l + 1, mul), device=y.device, dtype=torch.float32) for l, _p, mul in plan.out_groups]
+    op = _operands(plan, xs, y, w, None, shared)
+    with torch.cuda.device(y.device):
+        rc = _lib.load().eqf_dtp_forward(plan.handle, ctypes.byref(op), E, _ptr_array(outs), _stream())
+    _lib.check(rc, "eqf_dtp_forward")
+    return outs
+
+
+def dtp_grad_x_raw(plan: DtpPlan, gs, y, w) -> List[torch.Tensor]:
+    y, w, E, shared = _check_yw(plan, y, w)
+    gs = _check_groups(plan, gs, E, "dtp_grad_x g")
+    gxs = [torch.empty((E, 2 * l + 1, mul), device=y.device, dtype=torch.float32) for l, mul in plan.in1_blocks]
+    op = _operands(plan, None, y, w, gs, shared)
+    with torch.cuda.device(y.device):
+        rc = _lib.load().eqf_dtp_grad_x(plan.handle, ctypes.byref(op), E, _ptr_array(gxs), _stream())
+    _lib.check(rc, "eqf_dtp_grad_x")
+    return gxs
+
+
+def _gw_buffer(plan: DtpPlan, E: int, shared: bool, device) -> torch.Tensor:
+    if shared:
+        rows = _lib.load().eqf_plan_partial_rows(plan.handle, E)
+        return torch.empty((max(rows, 1), plan.weight_numel), device=device, dtype=torch.float32)
+    return torch.empty((E, plan.weight_numel), device=device, dtype=torch.float32)
+
+
+def dtp_grad_w_raw(plan: DtpPlan, xs, y, gs, shared: bool) -> torch.Tensor:
+    y, _, E, _ = _check_yw(plan, y, None)
+    xs = _check_blocks(plan, xs, E, "dtp_grad_w x")
+    gs = _check_groups(plan, gs, E, "dtp_grad_w g")
+    if E == 0:
+        return torch.zeros((plan.weight_numel,) if shared else (0, plan.weight_numel), device=y.device)
+    gw = _gw_buffer(plan, E, shared, y.device)
+    op = _operands(plan, xs, y, None, gs, shared)
+    with torch.cuda.device(y.device):
+        rc = _lib.load().eqf_dtp_grad_w(plan.handle, ctypes.byref(op), E, ctypes.c_void_p(gw.data_ptr()), _stream())
+    _lib.check(rc, "eqf_dtp_grad_w")
+    return gw.sum(dim=0) if shared else gw
+
+
+def dtp_grad_y_raw(plan: DtpPlan, xs, w, gs, y_like) -> torch.Tensor:
+    y, w, E, shared = _check_yw(plan, y_like, w)
+    xs = _check_blocks(plan, xs, E, "dtp_grad_y x")
+    gs = _check_groups(plan, gs, E, "dtp_grad_y g")
+    gy = torch.empty((E, plan.d_y), device=y.device, dtype=torch.float32)
+    op = _operands(plan, xs, y, w, gs, shared)
+    with torch.cuda.device(y.device):
+        rc = _lib.load().eqf_dtp_grad_y(plan.handle, ctypes.byref(op), E, ctypes.c_void_p(gy.data_ptr()), _stream())
+    _lib.check(rc, "eqf_dtp_grad_y")
+    return gy
+
+
+def dtp_grad_xw_raw(plan: DtpPlan, xs, y, w, gs) -> Tuple[List[torch.Tensor], torch.Tensor]:
+    y, w, E, shared = _check_yw(plan, y, w)
+    xs = _check_blocks(plan, xs, E, "dtp_grad_xw x")
+    gs = _check_groups(plan, gs, E, "dtp_grad_xw g")
+    gxs = [torch.empty((E, 2 * l + 1, mul), device=y.device, dtype=torch.float32) for l, mul in plan.in1_blocks]
+    if E == 0:
+        return gxs, torch.zeros_like(w)
+    gw = _gw_buffer(plan, E, shared, y.device)
+    op = _operands(plan, xs, y, w, gs, shared)
+    with torch.cuda.device(y.device):
+        rc = _lib.load().eqf_dtp_grad_xw(plan.handle, ctypes.byref(op), E, _ptr_array(gxs),
+                                         ctypes.c_void_p(gw.data_ptr()), _stream())
+    _lib.check(rc, "eqf_dtp_grad_xw")
+    return gxs, (gw.sum(dim=0) if shared else gw)
+
+
+# ----------------------------------------------------------------------------- DTP autograd family
+
+
+def _fill(gs, likes):
+    return [g if g is not None else torch.zeros_like(t) for g, t in zip(gs, likes)]
+
+
+class DtpOut(torch.autograd.Function):
+    """fs = dS/dg (x, y, w): the tensor product itself.  apply(plan, y, w, *xs) -> tuple(groups)."""
+
+    @staticmethod
+    def forward(ctx, plan: DtpPlan, y, w, *xs):
+        ctx.plan = plan
+        outs = dtp_forward_raw(plan, xs, y, w)
+        ctx.save_for_backward(y, w, *xs)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        plan = ctx.plan
+        y, w, *xs = ctx.saved_tensors
+        nb = len(xs)
+        E = y.shape[0]
+        gs = [g if g is not None else torch.zeros((E, 2 * l + 1, m), device=y.device)
+              for g, (l, _p, m) in zip(gs, plan.out_groups)]
+        need_y, need_w = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        need_x = any(ctx.needs_input_grad[3:3 + nb])
+        gy = gw = None
+        gxs = [None] * nb
+        if torch.is_grad_enabled():  # create_graph=True: stay inside the differentiable family
+            if need_x:
+                gxs = list(DtpGradX.apply(plan, y, w, *gs))
+            if need_w:
+                gw = DtpGradW.apply(plan, y, w.dim() == 1, *xs, *gs)
+            if need_y:
+                gy = DtpGradY.apply(plan, y, w, *xs, *gs)
+        else:
+            gs = [g.contiguous() for g in gs]
+            if need_x and need_w:
+                gxs, gw = dtp_grad_xw_raw(plan, xs, y, w, gs)
+            elif need_x:
+                gxs = dtp_grad_x_raw(plan, gs, y, w)
+            elif need_w:
+                gw = dtp_grad_w_raw(plan, xs, y, gs, w.dim() == 1)
+            if need_y:
+                gy = dtp_grad_y_raw(plan, xs, w, gs, y)
+        return (None, gy, gw, *gxs)
+
+
+class DtpGradX(torch.autograd.Function):
+    """gxs = dS/dx (g, y, w).  apply(plan, y, w, *gs) -> tuple(in1 blocks)."""
+
+    @staticmethod
+    def forward(ctx, plan: DtpPlan, y, w, *gs):
+        ctx.plan = plan
+        outs = dtp_grad_x_raw(plan, gs, y, w)
+        ctx.save_for_backward(y, w, *gs)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *cxs):  # cotangents shaped like xs
+        plan = ctx.plan
+        y, w, *gs = ctx.saved_tensors
+        E = y.shape[0]
+        cxs = [c if c is not None else torch.zeros((E, 2 * l + 1, m), device=y.device)
+               for c, (l, m) in zip(cxs, plan.in1_blocks)]
+        need_y, need_w = ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        need_g = any(ctx.needs_input_grad[3:])
+        gy = gw = None
+        ggs = [None] * len(gs)
+        if need_g:
+            ggs = list(DtpOut.apply(plan, y, w, *cxs))
+        if need_w:
+            gw = DtpGradW.apply(plan, y, w.dim() == 1, *cxs, *gs)
+        if need_y:
+            gy = DtpGradY.apply(plan, y, w, *cxs, *gs)
+        return (None, gy, gw, *ggs)
+
+
+class DtpGradW(torch.autograd.Function):
+    """gw = dS/dw (x, y, g).  apply(plan, y, shared, *xs, *gs) -> [E, W] or [W]."""
+
+    @staticmethod
+    def forward(ctx, plan: DtpPlan, y, shared: bool, *xg):
+        nb = len(plan.in1_blocks)
+        xs, gs = xg[:nb], xg[nb:]
+        ctx.plan, ctx.shared = plan, shared
+        out = dtp_grad_w_raw(plan, xs, y, gs, shared)
+        ctx.save_for_backward(y, *xg)
+        return out
+
+    @staticmethod
+    def backward(ctx, cw):
+        plan = ctx.plan
+        y, *xg = ctx.saved_tensors
+        nb = len(plan.in1_blocks)
+        xs, gs = xg[:nb], xg[nb:]
+        need_y = ctx.needs_input_grad[1]
+        need_x = any(ctx.needs_input_grad[3:3 + nb])
+        need_g = any(ctx.needs_input_grad[3 + nb:])
+        cw = cw.contiguous()
+        gy = None
+        gxs = [None] * nb
+        ggs = [None] * len(gs)
+        if need_x:
+            gxs = list(DtpGradX.apply(plan, y, cw, *gs))
+        if need_g:
+            ggs = list(DtpOut.apply(plan, y, cw, *xs))
+        if need_y:
+            gy = DtpGradY.apply(plan, y, cw, *xs, *gs)
+        return (None, gy, None, *gxs, *ggs)
+
+
+class DtpGradY(torch.autograd.Function):
+    """gy = dS/dy (x, w, g).  apply(plan, y_like, w, *xs, *gs) -> [E, d_y] (y only fixes the shape)."""
+
+    @staticmethod
+    def forward(ctx, plan: DtpPlan, y_like, w, *xg):
+        nb = len(plan.in1_blocks)
+        xs, gs = xg[:nb], xg[nb:]
+        ctx.plan = plan
+        out = dtp_grad_y_raw(plan, xs, w, gs, y_like)
+        ctx.save_for_backward(w, *xg)
+        return out
+
+    @staticmethod
+    def backward(ctx, cy):
+        plan = ctx.plan
+        w, *xg = ctx.saved_tensors
+        nb = len(plan.in1_blocks)
+        xs, gs = xg[:nb], xg[nb:]
+        need_w = ctx.needs_input_grad[2]
+        need_x = any(ctx.needs_input_grad[3:3 + nb])
+        need_g = any(ctx.needs_input_grad[3 + nb:])
+        cy = cy.contiguous()
+        gw = None
+        gxs = [None] * nb
+        ggs = [None] * len(gs)
+        if need_x:
+            gxs = list(DtpGradX.apply(plan, cy, w, *gs))
+        if need_g:
+            ggs = list(DtpOut.apply(plan, cy, w, *xs))
+        if need_w:
+            gw = DtpGradW.apply(plan, cy, w.dim() == 1, *xs, *gs)
+        return (None, None, gw, *gxs, *ggs)
+
+
+def depthwise_tensor_product(plan: DtpPlan, xs: Sequence[torch.Tensor], y: torch.Tensor, w: torch.Tensor):
+    """Planar DTP: ``xs`` per in1 block ``[E, 2l+1, mul]`` -> list per output group ``[E, 2l+1, K]``."""
+    return list(DtpOut.apply(plan, y, w, *xs))
+
+
+# ----------------------------------------------------------------------------- attention family
+
+
+class HeadLayout:
+    """Planar value layout: groups ``[rows, d[g], C[g]]``; head h owns channels ``[h*C/H, (h+1)*C/H)``."""
+
+    def __init__(self, ds: Sequence[int], Cs: Sequence[int], n_heads: int):
+        if len(ds) != len(Cs) or not ds:
+            raise ValueError("bad head layout")
+        if len(ds) > _lib.EQF_MAX_BLOCKS or n_heads > _lib.EQF_MAX_HEADS:
+            raise NotImplementedError("head layout exceeds kernel limits")
+        for c in Cs:
+            if c % n_heads:
+                raise ValueError("channels per group must be divisible by the number of heads")
+        self.ds, self.Cs, self.n_heads = tuple(ds), tuple(Cs), int(n_heads)
+        c = _lib.EqfHeadLayout()
+        c.n_groups = len(ds)
+        c.n_heads = n_heads
+        for i, (d, C) in enumerate(zip(ds, Cs)):
+            c.d[i], c.C[i] = d, C
+        self.c = c
+
+    def check(self, ts, rows: int, what: str):
+        if len(ts) != len(self.ds):
+            raise ValueError(f"{what}: expected {len(self.ds)} groups")
+        out = []
+        for t, d, C in zip(ts, self.ds, self.Cs):
+            t = _require_cuda(t, what)
+            if tuple(t.shape) != (rows, d, C):
+                raise ValueError(f"{what}: group shape {tuple(t.shape)} != {(rows, d, C)}")
+            out.append(t)
+        return out
+
+
+class Graph:
+    """Destination-sorted edge list + CSR ``row_ptr`` (built once per forward, shared by all layers)."""
+
+    def __init__(self, edge_src: torch.Tensor, edge_dst: torch.Tensor, n_nodes: int, check_sorted: bool = True):
+        self.n_nodes = int(n_nodes)
+        self.perm = None
+        edge_src = _require_index(edge_src, "edge_src")
+        edge_dst = _require_index(edge_dst, "edge_dst")
+        if check_sorted and edge_dst.numel() > 1 and bool((edge_dst[1:] < edge_dst[:-1]).any()):
+            self.perm = torch.sort(edge_dst, stable=True).indices
+            edge_src, edge_dst = edge_src[self.perm], edge_dst[self.perm]
+        self.src, self.dst = edge_src, edge_dst
+        self.n_edges = int(edge_dst.numel())
+        counts = torch.bincount(edge_dst, minlength=self.n_nodes)
+        self.row_ptr = torch.zeros(self.n_nodes + 1, dtype=torch.int64, device=edge_dst.device)
+        torch.cumsum(counts, 0, out=self.row_ptr[1:])
+
+    def sort_edges(self, t: torch.Tensor) -> torch.Tensor:
+        return t if self.perm is None else t.index_select(0, self.perm)
+
+
+def seg_softmax_raw(z: torch.Tensor, graph: Graph) -> torch.Tensor:
+    z = _require_cuda(z, "attention logits")
+    if z.dim() != 2 or z.shape[0] != graph.n_edges:
+        raise ValueError("logits must be [E, H]")
+    alpha = torch.empty_like(z)
+    with torch.cuda.device(z.device):
+        rc = _lib.load().eqf_seg_softmax(z.data_ptr(), graph.row_ptr.data_ptr(), graph.n_nodes, z.shape[1],
+                                         alpha.data_ptr(), _stream())
+    _lib.check(rc, "eqf_seg_softmax")
+    return alpha
+
+
+def attn_aggregate_raw(lay: HeadLayout, alpha, Vs, graph: Graph) -> List[torch.Tensor]:
+    Vs = lay.check(Vs, graph.n_edges, "aggregate V")
+    if alpha is not None:
+        alpha = _require_cuda(alpha, "alpha")
+        if tuple(alpha.shape) != (graph.n_edges, lay.n_heads):
+            raise ValueError("alpha must be [E, H]")
+    dev = Vs[0].device
+    outs = [torch.empty((graph.n_nodes, d, C), device=dev, dtype=torch.float32) for d, C in zip(lay.ds, lay.Cs)]
+    with torch.cuda.device(dev):
+        rc = _lib.load().eqf_attn_aggregate(ctypes.byref(lay.c), alpha.data_ptr() if alpha is not None else None,
+                                            _ptr_array(Vs), graph.row_ptr.data_ptr(), graph.n_nodes,
+                                            _ptr_array(outs), _stream())
+    _lib.check(rc, "eqf_attn_aggregate")
+    return outs
+
+
+def attn_edge_dot_raw(lay: HeadLayout, Vs, Gs, graph: Graph) -> torch.Tensor:
+    Vs = lay.check(Vs, graph.n_edges, "edge_dot V")
+    Gs = lay.check(Gs, graph.n_nodes, "edge_dot G")
+    out = torch.empty((graph.n_edges, lay.n_heads), device=Vs[0].device, dtype=torch.float32)
+    with torch.cuda.device(out.device):
+        rc = _lib.load().eqf_attn_edge_dot(ctypes.byref(lay.c), _ptr_array(Vs), _ptr_array(Gs),
+                                           graph.dst.data_ptr(), graph.n_edges, out.data_ptr(), _stream())
+    _lib.check(rc, "eqf_attn_edge_dot")
+    return out
+
+
+def attn_edge_scale_raw(lay: HeadLayout, alpha, Gs, graph: Graph) -> List[torch.Tensor]:
+    Gs = lay.check(Gs, graph.n_nodes, "edge_scale G")
+    if alpha is not None:
+        alpha = _require_cuda(alpha, "alpha")
+    dev = Gs[0].device
+    outs = [torch.empty((graph.n_edges, d, C), device=dev, dtype=torch.float32) for d, C in zip(lay.ds, lay.Cs)]
+    with torch.cuda.device(dev):
+        rc = _lib.load().eqf_attn_edge_scale(ctypes.byref(lay.c), alpha.data_ptr() if alpha is not None else None,
+                                             _ptr_array(Gs), graph.dst.data_ptr(), graph.n_edges,
+                                             _ptr_array(outs), _stream())
+    _lib.check(rc, "eqf_attn_edge_scale")
+    return outs
+
+
+class SegSoftmax(torch.autograd.Function):
+    """alpha = softmax of z over each destination segment (PyG semantics, +1e-16 in the denominator)."""
+
+    @staticmethod
+    def forward(ctx, z, graph: Graph):
+        alpha = seg_softmax_raw(z, graph)
+        ctx.graph = graph
+        ctx.save_for_backward(alpha)
+        return alpha
+
+    @staticmethod
+    def backward(ctx, ga):
+        (alpha,) = ctx.saved_tensors
+        g = ctx.graph
+        # d alpha_e / d z_f = alpha_e (delta_ef - alpha_f) inside a segment (the 1e-16 is below fp32 resolution
+        # of any non-empty segment sum, which is >= 1); small [E, H] tensors -> differentiable torch ops.
+        t = alpha * ga
+        s = torch.zeros((g.n_nodes, alpha.shape[1]), device=alpha.device, dtype=alpha.dtype).index_add(0, g.dst, t)
+        return t - alpha * s.index_select(0, g.dst), None
+
+
+class AttnAggregate(torch.autograd.Function):
+    """outs[g][t] = sum_{e->t} alpha[e, head] V[g][e].  apply(lay, graph, alpha_or_None, *Vs)."""
+
+    @staticmethod
+    def forward(ctx, lay: HeadLayout, graph: Graph, alpha, *Vs):
+        ctx.lay, ctx.graph = lay, graph
+        ctx.has_alpha = alpha is not None
+        outs = attn_aggregate_raw(lay, alpha, Vs, graph)
+        if ctx.has_alpha:
+            ctx.save_for_backward(alpha, *Vs)
+        else:
+            ctx.save_for_backward(*Vs)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *Gs):
+        lay, graph = ctx.lay, ctx.graph
+        saved = ctx.saved_tensors
+        alpha, Vs = (saved[0], saved[1:]) if ctx.has_alpha else (None, saved)
+        Gs = [G.contiguous() if G is not None else torch.zeros((graph.n_nodes, d, C), device=Vs[0].device)
+              for G, d, C in zip(Gs, lay.ds, lay.Cs)]
+        ga = None
+        gVs = [None] * len(Vs)
+        if ctx.has_alpha and ctx.needs_input_grad[2]:
+            ga = EdgeDot.apply(lay, graph, *Vs, *Gs)
+        if any(ctx.needs_input_grad[3:]):
+            gVs = list(EdgeScale.apply(lay, graph, alpha, *Gs))
+        return (None, None, ga, *gVs)
+
+
+class EdgeDot(torch.autograd.Function):
+    """galpha[e,h] = sum_{j in h} V[e,j] G[dst e, j].  apply(lay, graph, *Vs, *Gs)."""
+
+    @staticmethod
+    def forward(ctx, lay: HeadLayout, graph: Graph, *VG):
+        n = len(lay.ds)
+        ctx.lay, ctx.graph = lay, graph
+        out = attn_edge_dot_raw(lay, VG[:n], VG[n:], graph)
+        ctx.save_for_backward(*VG)
+        return out
+
+    @staticmethod
+    def backward(ctx, ca):
+        lay, graph = ctx.lay, ctx.graph
+        n = len(lay.ds)
+        VG = ctx.saved_tensors
+        Vs, Gs = VG[:n], VG[n:]
+        ca = ca.contiguous()
+        gVs = [None] * n
+        gGs = [None] * n
+        if any(ctx.needs_input_grad[2:2 + n]):
+            gVs = list(EdgeScale.apply(lay, graph, ca, *Gs))
+        if any(ctx.needs_input_grad[2 + n:]):
+            gGs = list(AttnAggregate.apply(lay, graph, ca, *Vs))
+        return (None, None, *gVs, *gGs)
+
+
+class EdgeScale(torch.autograd.Function):
+    """outs[g][e] = alpha[e, head] G[g][dst e]  (alpha None: plain gather).  apply(lay, graph, alpha, *Gs)."""
+
+    @staticmethod
+    def forward(ctx, lay: HeadLayout, graph: Graph, alpha, *Gs):
+        ctx.lay, ctx.graph = lay, graph
+        ctx.has_alpha = alpha is not None
+        outs = attn_edge_scale_raw(lay, alpha, Gs, graph)
+        if ctx.has_alpha:
+            ctx.save_for_backward(alpha, *Gs)
+        else:
+            ctx.save_for_backward(*Gs)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *cVs):
+        lay, graph = ctx.lay, ctx.graph
+        saved = ctx.saved_tensors
+        alpha, Gs = (saved[0], saved[1:]) if ctx.has_alpha else (None, saved)
+        cVs = [c.contiguous() if c is not None else torch.zeros((graph.n_edges, d, C), device=Gs[0].device)
+               for c, d, C in zip(cVs, lay.ds, lay.Cs)]
+        ga = None
+        gGs = [None] * len(Gs)
+        if ctx.has_alpha and ctx.needs_input_grad[2]:
+            ga = EdgeDot.apply(lay, graph, *cVs, *Gs)
+        if any(ctx.needs_input_grad[3:]):
+            gGs = list(AttnAggregate.apply(lay, graph, alpha, *cVs))
+        return (None, None, ga, *gGs)
+
+
+def attention_aggregate(lay: HeadLayout, graph: Graph, alpha: Optional[torch.Tensor], Vs: Sequence[torch.Tensor]):
+    return list(AttnAggregate.apply(lay, graph, alpha, *Vs))
+
+
+def segment_softmax(z: torch.Tensor, graph: Graph) -> torch.Tensor:
+    return SegSoftmax.apply(z, graph)
+
+
+# ----------------------------------------------------------------------------- layout conversion
+
+
+def to_planar(x: torch.Tensor, irreps) -> List[torch.Tensor]:
+    """e3nn row layout ``[R, sum mul*(2l+1)]`` -> one ``[R, 2l+1, mul]`` block per irreps entry."""
+    out = []
+    off = 0
+    R = x.shape[0]
+    for mul, ir in irreps:
+        d = ir.dim
+        blk = x.narrow(1, off, mul * d).reshape(R, mul, d)
+        out.append(blk.transpose(1, 2).contiguous() if d > 1 else blk.reshape(R, 1, mul))
+        off += mul * d
+    return out
+
+
+def from_planar(blocks: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Inverse of :func:`to_planar` (entries concatenated in order)."""
+    R = blocks[0].shape[0]
+    return torch.cat([b.transpose(1, 2).reshape(R, -1) for b in blocks], dim=1)

@@ -1,0 +1,135 @@
+/* eqf_b200.h - C ABI of libeqf_b200.so, the sm_100a edge kernels behind the Equiformer hot path.
+ *
+ * The reference (atomicarchitects/equiformer) has no FFI layer of its own: the boundary is the
+ * Python nn.Module surface of nets/tensor_product_rescale.py and nets/graph_attention_transformer.py
+ * (SURVEY.md section 8b).  This library sits *under* the drop-in modules in equiformer_b200/nets and
+ * is bound with ctypes (equiformer_b200/_lib.py).  Each entry point names the reference code whose
+ * GPU work it replaces.  Conventions:
+ *
+ *   - every pointer is a DEVICE pointer unless marked "host"; tensors are fp32, index arrays int64;
+ *   - "planar" layout: an irrep block (mul x degree l) of R rows is stored as [R][2l+1][mul]
+ *     (component-major, channel innermost), one buffer per block; this is the e3nn layout
+ *     [R][mul][2l+1] transposed per row, chosen so that lanes = channels gives coalesced access and
+ *     the per-degree channel-mixing linears that follow are plain row-major GEMMs;
+ *   - `stream` is a cudaStream_t passed as void*; launches are asynchronous on it;
+ *   - return value 0 = ok, negative = error; eqf_last_error() returns a thread-local message;
+ *   - no global state except immutable plans owned by the caller.
+ */
+#ifndef EQF_B200_H_
+#define EQF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EQF_MAX_BLOCKS 8   /* max irrep blocks per operand (in1 blocks / output groups / value groups) */
+#define EQF_MAX_HEADS 16
+
+#define EQF_OK 0
+#define EQF_ERR_INVALID (-1)
+#define EQF_ERR_CUDA (-2)
+#define EQF_ERR_UNSUPPORTED (-3)
+
+typedef struct EqfPlan EqfPlan;
+
+/* One Clebsch-Gordan path of a depth-wise ('uvu', mul(in2)=1) tensor product:
+ * reference instruction (i_in1, i_in2, i_out, 'uvu', True) built at
+ * nets/graph_attention_transformer.py:166-172 and executed by o3.TensorProduct inside
+ * TensorProductRescale (nets/tensor_product_rescale.py:33-37, :126). */
+typedef struct {
+  int32_t l1, l2, l3;      /* degrees of in1 block, in2 (edge SH) irrep, output irrep            */
+  int32_t mul;             /* channels u of the in1 block                                         */
+  int32_t in1_block;       /* index into the in1 block list                                      */
+  int32_t in2_off;         /* float offset of the degree-l2 SH inside one edge_attr row          */
+  int32_t out_group;       /* index of the output group (all paths with equal (l3,p3), sorted)   */
+  int32_t out_chan_off;    /* first channel of this path inside its output group                 */
+  int32_t w_off;           /* float offset of this path's [mul] weights in a weight row          */
+  int32_t cg_off;          /* float offset into `cg`: dense [2l1+1][2l2+1][2l3+1], path weight folded in */
+} EqfPathDesc;
+
+/* Operand bundle shared by the four contraction kernels.  Unused members are NULL. */
+typedef struct {
+  const float* x[EQF_MAX_BLOCKS];    /* in1 blocks, planar [Rx][2l1+1][mul]                        */
+  const float* x2[EQF_MAX_BLOCKS];   /* optional second table added to x (gathered by `dst`)      */
+  const int64_t* src;                /* optional: row of x used by edge e (NULL: row e)           */
+  const int64_t* dst;                /* row of x2 used by edge e (required iff x2[0] != NULL)     */
+  const float* y;                    /* edge_attr (SH), [E][d_y]                                  */
+  const float* w;                    /* per-edge weights [E][W] or shared [W]                     */
+  int32_t w_shared;                  /* 1: w is [W] (internal weights), 0: [E][W]                 */
+  const float* g[EQF_MAX_BLOCKS];    /* output-group tensors (cotangents), planar [E][2l3+1][K]   */
+} EqfEdgeOperands;
+
+int eqf_version(void);
+const char* eqf_last_error(void);
+int eqf_device_sm_count(void);
+
+/* Build the immutable device tables for one depth-wise tensor product
+ * (DepthwiseTensorProduct, nets/graph_attention_transformer.py:157-183).  All arrays are host. */
+int eqf_plan_create(const EqfPathDesc* paths, int32_t n_paths,
+                    const int32_t* in1_l, const int32_t* in1_mul, int32_t n_in1,
+                    const int32_t* out_l, const int32_t* out_mul, int32_t n_out,
+                    int32_t d_y, int32_t weight_numel,
+                    const float* cg, int32_t cg_len, EqfPlan** plan_out);
+void eqf_plan_destroy(EqfPlan* plan);
+/* host-side introspection: out[0..n) = {n_paths, m_size, n_wtasks, n_xtasks, tile_edges, smem_bytes, blob_words, weight_numel} */
+int eqf_plan_info(const EqfPlan* plan, int32_t* out, int32_t n);
+/* number of CTAs eqf_dtp_grad_w launches (rows of the shared-weight partial buffer) */
+int eqf_plan_partial_rows(const EqfPlan* plan, int64_t n_edges);
+
+/* out[g][e,k,koff+u] = w[e,p,u] * sum_ij cg_p[i,j,k] x[e,i,u] y[e,j]
+ * == TensorProductRescale.forward(x, y, weight) for the DTP (tensor_product_rescale.py:139-141),
+ * optionally with the gather+add of graph_attention_transformer.py:487 folded into the x load. */
+int eqf_dtp_forward(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_edges,
+                    float* const* out_groups /* host array[n_out] of device ptrs */, void* stream);
+
+/* d/dx of <g, forward>: gx[b][e,i,u] (what autograd derives for the e3nn TP in the reference). */
+int eqf_dtp_grad_x(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_edges,
+                   float* const* gx_blocks /* host array[n_in1] */, void* stream);
+
+/* d/dw: per-edge gw[E][W], or for shared weights per-CTA partial sums gw[partial_rows][W]
+ * (caller reduces over rows; deterministic). */
+int eqf_dtp_grad_w(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_edges,
+                   float* gw, void* stream);
+
+/* d/dy: gy[E][d_y] (needed for MD17 forces, graph_attention_transformer_md17.py:318-325). */
+int eqf_dtp_grad_y(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_edges,
+                   float* gy, void* stream);
+
+/* gx and gw in one pass over g (first-order training path). gw as in eqf_dtp_grad_w. */
+int eqf_dtp_grad_xw(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_edges,
+                    float* const* gx_blocks, float* gw, void* stream);
+
+/* ---- attention softmax + aggregation over destination-sorted edges ------------------------------
+ * Value tensors are `n_groups` planar buffers [rows][d[g]][C[g]]; head h owns channels
+ * [h*C/H, (h+1)*C/H) of every group (Vec2AttnHeads, graph_attention_transformer.py:252-285).      */
+typedef struct {
+  int32_t n_groups;
+  int32_t d[EQF_MAX_BLOCKS];
+  int32_t C[EQF_MAX_BLOCKS];
+  int32_t n_heads;
+} EqfHeadLayout;
+
+/* alpha[e,h] = exp(z[e,h]-max_seg)/(sum_seg exp + 1e-16): torch_geometric.utils.softmax(alpha, edge_dst)
+ * at graph_attention_transformer.py:508 (PyG 2.0.3 semantics).  row_ptr is the CSR of edge_dst.   */
+int eqf_seg_softmax(const float* z, const int64_t* row_ptr, int64_t n_nodes, int32_t n_heads,
+                    float* alpha, void* stream);
+
+/* out[g][t,j] = sum_{e in seg(t)} alpha[e,head(j)] * V[g][e,j]   (alpha NULL: plain segment sum)
+ * == value*alpha followed by torch_scatter.scatter(..., edge_dst) (:512-513).                     */
+int eqf_attn_aggregate(const EqfHeadLayout* lay, const float* alpha, const float* const* V,
+                       const int64_t* row_ptr, int64_t n_nodes, float* const* out, void* stream);
+
+/* galpha[e,h] = sum_{j in head h} V[g][e,j] * G[g][dst[e],j]       (transpose of aggregate w.r.t. alpha) */
+int eqf_attn_edge_dot(const EqfHeadLayout* lay, const float* const* V, const float* const* G,
+                      const int64_t* dst, int64_t n_edges, float* galpha, void* stream);
+
+/* out[g][e,j] = alpha[e,head(j)] * G[g][dst[e],j]                  (transpose w.r.t. V; alpha NULL: gather) */
+int eqf_attn_edge_scale(const EqfHeadLayout* lay, const float* alpha, const float* const* G,
+                        const int64_t* dst, int64_t n_edges, float* const* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EQF_B200_H_ */

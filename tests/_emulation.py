@@ -1,0 +1,138 @@
+"""TEST-ONLY stand-ins for the raw kernel entry points of ``equiformer_b200.ops``.
+
+The product has no CPU path (CPU tensors raise).  To exercise the *host* logic - planar layouts, weight views, head
+layouts, the autograd families and their closure under differentiation - without a GPU, the CPU test-suite
+monkeypatches the ``*_raw`` functions with these torch restatements that walk the same plan tables the kernels use.
+Nothing outside ``tests/`` imports this module.
+"""
+from __future__ import annotations
+
+import contextlib
+
+import torch
+
+from equiformer_b200 import ops
+
+
+def _cg(plan, p, dtype):
+    d1, d2, d3 = 2 * p.l1 + 1, 2 * p.l2 + 1, 2 * p.l3 + 1
+    c = torch.from_numpy(plan.cg64[p.cg_off:p.cg_off + d1 * d2 * d3].copy()).reshape(d1, d2, d3)
+    return c.to(dtype)
+
+
+def _w(plan, p, w):
+    wv = w[..., p.w_off:p.w_off + p.mul]
+    return wv if wv.dim() == 2 else wv[None, :]
+
+
+def dtp_forward_raw(plan, xs, y, w):
+    E = y.shape[0]
+    outs = [y.new_zeros((E, 2 * l + 1, mul)) for l, _p, mul in plan.out_groups]
+    for p in plan.paths:
+        M = torch.einsum("ijk,ej->eik", _cg(plan, p, y.dtype), y[:, p.in2_off:p.in2_off + 2 * p.l2 + 1])
+        val = torch.einsum("eiu,eik->eku", xs[p.in1_block], M) * _w(plan, p, w)[:, None, :]
+        outs[p.out_group][:, :, p.out_chan_off:p.out_chan_off + p.mul] = val
+    return outs
+
+
+def dtp_grad_x_raw(plan, gs, y, w):
+    E = y.shape[0]
+    gxs = [y.new_zeros((E, 2 * l + 1, mul)) for l, mul in plan.in1_blocks]
+    for p in plan.paths:
+        M = torch.einsum("ijk,ej->eik", _cg(plan, p, y.dtype), y[:, p.in2_off:p.in2_off + 2 * p.l2 + 1])
+        g = gs[p.out_group][:, :, p.out_chan_off:p.out_chan_off + p.mul]
+        gxs[p.in1_block] = gxs[p.in1_block] + torch.einsum("eku,eik->eiu", g, M) * _w(plan, p, w)[:, None, :]
+    return gxs
+
+
+def dtp_grad_w_raw(plan, xs, y, gs, shared):
+    E = y.shape[0]
+    gw = y.new_zeros((E, plan.weight_numel))
+    for p in plan.paths:
+        M = torch.einsum("ijk,ej->eik", _cg(plan, p, y.dtype), y[:, p.in2_off:p.in2_off + 2 * p.l2 + 1])
+        g = gs[p.out_group][:, :, p.out_chan_off:p.out_chan_off + p.mul]
+        gw[:, p.w_off:p.w_off + p.mul] = torch.einsum("eiu,eik,eku->eu", xs[p.in1_block], M, g)
+    return gw.sum(0) if shared else gw
+
+
+def dtp_grad_y_raw(plan, xs, w, gs, y_like):
+    E = y_like.shape[0]
+    gy = y_like.new_zeros((E, plan.d_y))
+    for p in plan.paths:
+        g = gs[p.out_group][:, :, p.out_chan_off:p.out_chan_off + p.mul]
+        N = torch.einsum("eiu,eku,eu->eik", xs[p.in1_block], g, _w(plan, p, w).expand(E, -1))
+        d2 = 2 * p.l2 + 1
+        gy[:, p.in2_off:p.in2_off + d2] = gy[:, p.in2_off:p.in2_off + d2] + torch.einsum(
+            "ijk,eik->ej", _cg(plan, p, y_like.dtype), N)
+    return gy
+
+
+def dtp_grad_xw_raw(plan, xs, y, w, gs):
+    return dtp_grad_x_raw(plan, gs, y, w), dtp_grad_w_raw(plan, xs, y, gs, w.dim() == 1)
+
+
+def _head_of(lay, g):
+    C = lay.Cs[g]
+    return torch.arange(C) // (C // lay.n_heads)
+
+
+def seg_softmax_raw(z, graph):
+    out = torch.empty_like(z)
+    rp = graph.row_ptr.tolist()
+    for t in range(graph.n_nodes):
+        a, b = rp[t], rp[t + 1]
+        if b > a:
+            seg = z[a:b]
+            e = (seg - seg.max(dim=0, keepdim=True).values).exp()
+            out[a:b] = e / (e.sum(dim=0, keepdim=True) + 1e-16)
+    return out
+
+
+def attn_aggregate_raw(lay, alpha, Vs, graph):
+    outs = []
+    for g, V in enumerate(Vs):
+        val = V if alpha is None else V * alpha[:, _head_of(lay, g)][:, None, :]
+        out = V.new_zeros((graph.n_nodes,) + tuple(V.shape[1:]))
+        outs.append(out.index_add(0, graph.dst, val))
+    return outs
+
+
+def attn_edge_dot_raw(lay, Vs, Gs, graph):
+    E = graph.n_edges
+    out = Vs[0].new_zeros((E, lay.n_heads))
+    for g, (V, G) in enumerate(zip(Vs, Gs)):
+        prod = (V * G.index_select(0, graph.dst)).sum(dim=1)  # [E, C]
+        out = out.index_add(1, _head_of(lay, g), prod)
+    return out
+
+
+def attn_edge_scale_raw(lay, alpha, Gs, graph):
+    outs = []
+    for g, G in enumerate(Gs):
+        val = G.index_select(0, graph.dst)
+        if alpha is not None:
+            val = val * alpha[:, _head_of(lay, g)][:, None, :]
+        outs.append(val)
+    return outs
+
+
+_PATCHED = ["dtp_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
+            "seg_softmax_raw", "attn_aggregate_raw", "attn_edge_dot_raw", "attn_edge_scale_raw"]
+
+
+@contextlib.contextmanager
+def emulated_kernels():
+    """Swap the raw kernel calls (and the CUDA-only checks) for the torch stand-ins above."""
+    saved = {name: getattr(ops, name) for name in _PATCHED}
+    saved["_require_cuda"] = ops._require_cuda
+    saved["_require_index"] = ops._require_index
+    g = globals()
+    try:
+        for name in _PATCHED:
+            setattr(ops, name, g[name])
+        ops._require_cuda = lambda t, name: t.contiguous()
+        ops._require_index = lambda t, name: t.to(torch.int64).contiguous()
+        yield
+    finally:
+        for name, fn in saved.items():
+            setattr(ops, name, fn)
