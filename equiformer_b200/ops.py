@@ -14,6 +14,7 @@ anything else raises - there is no CPU implementation on the product path.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 from typing import List, Optional, Sequence, Tuple
 
@@ -111,6 +112,72 @@ def _check_yw(plan: DtpPlan, y, w, E: Optional[int] = None):
     return y, w, E, shared
 
 
+# ----------------------------------------------------------------------------- launch accounting
+
+
+class KernelProfile:
+    """Optional per-launch accounting used by ``bench.py``: launch count and CUDA-event timing per kernel name.
+
+    ``records`` holds ``(name, algorithmic_bytes, start_event, end_event)`` for every launch of one of *our* kernels
+    while the profile is installed (events are recorded on the launching stream, around the launch only).
+    """
+
+    def __init__(self, time_events: bool = True):
+        self.time_events = time_events
+        self.launches = 0
+        self.records = []
+
+    def summary(self):
+        out = {}
+        for name, nbytes, s, e in self.records:
+            ms = s.elapsed_time(e)
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
+            d["launches"] += 1
+            d["ms"] += ms
+            d["bytes"] += nbytes
+        return out
+
+
+PROFILE: Optional[KernelProfile] = None
+
+
+@contextlib.contextmanager
+def _kernel(name: str, nbytes: int):
+    prof = PROFILE
+    if prof is None:
+        yield
+        return
+    prof.launches += 1
+    if not prof.time_events:
+        yield
+        return
+    s = torch.cuda.Event(enable_timing=True)
+    e = torch.cuda.Event(enable_timing=True)
+    s.record()
+    yield
+    e.record()
+    prof.records.append((name, nbytes, s, e))
+
+
+def _dtp_bytes(plan: DtpPlan, E: int, shared: bool, kind: str) -> int:
+    d_in, d_out, w = plan.irreps_in1.dim, plan.irreps_out.dim, (0 if shared else plan.weight_numel)
+    per_edge = {"forward": d_in + plan.d_y + w + d_out,
+                "grad_x": d_out + plan.d_y + w + d_in,
+                "grad_w": d_out + plan.d_y + d_in + w,
+                "grad_y": d_out + d_in + w + 2 * plan.d_y,
+                "grad_xw": d_out + d_in + plan.d_y + w + d_in + w}[kind]
+    return 4 * per_edge * E
+
+
+def _attn_bytes(lay: "HeadLayout", rows_edge: int, rows_node: int, kind: str) -> int:
+    dv = sum(d * c for d, c in zip(lay.ds, lay.Cs))
+    h = lay.n_heads
+    per = {"aggregate": rows_edge * (dv + h) + rows_node * dv,
+           "edge_dot": rows_edge * (2 * dv + h),
+           "edge_scale": rows_edge * (2 * dv + h)}[kind]
+    return 4 * per
+
+
 # ----------------------------------------------------------------------------- raw kernel calls
 
 
@@ -119,7 +186,7 @@ def dtp_forward_raw(plan: DtpPlan, xs, y, w) -> List[torch.Tensor]:
     xs = _check_blocks(plan, xs, E, "dtp_forward x")
     outs = [torch.empty((E, 2 * l + 1, mul), device=y.device, dtype=torch.float32) for l, _p, mul in plan.out_groups]
     op = _operands(plan, xs, y, w, None, shared)
-    with torch.cuda.device(y.device):
+    with torch.cuda.device(y.device), _kernel("dtp_forward", _dtp_bytes(plan, E, shared, "forward")):
         rc = _lib.load().eqf_dtp_forward(plan.handle, ctypes.byref(op), E, _ptr_array(outs), _stream())
     _lib.check(rc, "eqf_dtp_forward")
     return outs
@@ -130,7 +197,7 @@ def dtp_grad_x_raw(plan: DtpPlan, gs, y, w) -> List[torch.Tensor]:
     gs = _check_groups(plan, gs, E, "dtp_grad_x g")
     gxs = [torch.empty((E, 2 * l + 1, mul), device=y.device, dtype=torch.float32) for l, mul in plan.in1_blocks]
     op = _operands(plan, None, y, w, gs, shared)
-    with torch.cuda.device(y.device):
+    with torch.cuda.device(y.device), _kernel("dtp_grad_x", _dtp_bytes(plan, E, shared, "grad_x")):
         rc = _lib.load().eqf_dtp_grad_x(plan.handle, ctypes.byref(op), E, _ptr_array(gxs), _stream())
     _lib.check(rc, "eqf_dtp_grad_x")
     return gxs
@@ -151,7 +218,7 @@ def dtp_grad_w_raw(plan: DtpPlan, xs, y, gs, shared: bool) -> torch.Tensor:
         return torch.zeros((plan.weight_numel,) if shared else (0, plan.weight_numel), device=y.device)
     gw = _gw_buffer(plan, E, shared, y.device)
     op = _operands(plan, xs, y, None, gs, shared)
-    with torch.cuda.device(y.device):
+    with torch.cuda.device(y.device), _kernel("dtp_grad_w", _dtp_bytes(plan, E, shared, "grad_w")):
         rc = _lib.load().eqf_dtp_grad_w(plan.handle, ctypes.byref(op), E, ctypes.c_void_p(gw.data_ptr()), _stream())
     _lib.check(rc, "eqf_dtp_grad_w")
     return gw.sum(dim=0) if shared else gw
@@ -163,7 +230,7 @@ def dtp_grad_y_raw(plan: DtpPlan, xs, w, gs, y_like) -> torch.Tensor:
     gs = _check_groups(plan, gs, E, "dtp_grad_y g")
     gy = torch.empty((E, plan.d_y), device=y.device, dtype=torch.float32)
     op = _operands(plan, xs, y, w, gs, shared)
-    with torch.cuda.device(y.device):
+    with torch.cuda.device(y.device), _kernel("dtp_grad_y", _dtp_bytes(plan, E, shared, "grad_y")):
         rc = _lib.load().eqf_dtp_grad_y(plan.handle, ctypes.byref(op), E, ctypes.c_void_p(gy.data_ptr()), _stream())
     _lib.check(rc, "eqf_dtp_grad_y")
     return gy
@@ -178,7 +245,7 @@ def dtp_grad_xw_raw(plan: DtpPlan, xs, y, w, gs) -> Tuple[List[torch.Tensor], to
         return gxs, torch.zeros_like(w)
     gw = _gw_buffer(plan, E, shared, y.device)
     op = _operands(plan, xs, y, w, gs, shared)
-    with torch.cuda.device(y.device):
+    with torch.cuda.device(y.device), _kernel("dtp_grad_xw", _dtp_bytes(plan, E, shared, "grad_xw")):
         rc = _lib.load().eqf_dtp_grad_xw(plan.handle, ctypes.byref(op), E, _ptr_array(gxs),
                                          ctypes.c_void_p(gw.data_ptr()), _stream())
     _lib.check(rc, "eqf_dtp_grad_xw")
@@ -397,7 +464,7 @@ def seg_softmax_raw(z: torch.Tensor, graph: Graph) -> torch.Tensor:
     if z.dim() != 2 or z.shape[0] != graph.n_edges:
         raise ValueError("logits must be [E, H]")
     alpha = torch.empty_like(z)
-    with torch.cuda.device(z.device):
+    with torch.cuda.device(z.device), _kernel("seg_softmax", 8 * z.numel()):
         rc = _lib.load().eqf_seg_softmax(z.data_ptr(), graph.row_ptr.data_ptr(), graph.n_nodes, z.shape[1],
                                          alpha.data_ptr(), _stream())
     _lib.check(rc, "eqf_seg_softmax")
@@ -412,7 +479,7 @@ def attn_aggregate_raw(lay: HeadLayout, alpha, Vs, graph: Graph) -> List[torch.T
             raise ValueError("alpha must be [E, H]")
     dev = Vs[0].device
     outs = [torch.empty((graph.n_nodes, d, C), device=dev, dtype=torch.float32) for d, C in zip(lay.ds, lay.Cs)]
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _kernel("attn_aggregate", _attn_bytes(lay, graph.n_edges, graph.n_nodes, "aggregate")):
         rc = _lib.load().eqf_attn_aggregate(ctypes.byref(lay.c), alpha.data_ptr() if alpha is not None else None,
                                             _ptr_array(Vs), graph.row_ptr.data_ptr(), graph.n_nodes,
                                             _ptr_array(outs), _stream())
@@ -424,7 +491,7 @@ def attn_edge_dot_raw(lay: HeadLayout, Vs, Gs, graph: Graph) -> torch.Tensor:
     Vs = lay.check(Vs, graph.n_edges, "edge_dot V")
     Gs = lay.check(Gs, graph.n_nodes, "edge_dot G")
     out = torch.empty((graph.n_edges, lay.n_heads), device=Vs[0].device, dtype=torch.float32)
-    with torch.cuda.device(out.device):
+    with torch.cuda.device(out.device), _kernel("attn_edge_dot", _attn_bytes(lay, graph.n_edges, graph.n_nodes, "edge_dot")):
         rc = _lib.load().eqf_attn_edge_dot(ctypes.byref(lay.c), _ptr_array(Vs), _ptr_array(Gs),
                                            graph.dst.data_ptr(), graph.n_edges, out.data_ptr(), _stream())
     _lib.check(rc, "eqf_attn_edge_dot")
@@ -437,7 +504,7 @@ def attn_edge_scale_raw(lay: HeadLayout, alpha, Gs, graph: Graph) -> List[torch.
         alpha = _require_cuda(alpha, "alpha")
     dev = Gs[0].device
     outs = [torch.empty((graph.n_edges, d, C), device=dev, dtype=torch.float32) for d, C in zip(lay.ds, lay.Cs)]
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _kernel("attn_edge_scale", _attn_bytes(lay, graph.n_edges, graph.n_nodes, "edge_scale")):
         rc = _lib.load().eqf_attn_edge_scale(ctypes.byref(lay.c), alpha.data_ptr() if alpha is not None else None,
                                              _ptr_array(Gs), graph.dst.data_ptr(), graph.n_edges,
                                              _ptr_array(outs), _stream())

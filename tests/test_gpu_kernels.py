@@ -1,0 +1,160 @@
+"""-m gpu: every sm_100a kernel against the fp64 oracle (and the table-walking emulation) on seeded inputs.
+
+Tolerance: fp32 kernels vs fp64 oracle, max-abs error relative to the output's max magnitude <= 2e-5 for a single
+kernel (north_star: 1e-4 relative end to end).
+"""
+from __future__ import annotations
+
+import pytest
+import torch
+
+from tests import _emulation as emu
+from tests.helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5
+
+CONFIGS = {
+    "qm9_l2": ("128x0e+64x1e+32x2e", "1x0e+1x1e+1x2e", "128x0e+64x1e+32x2e"),
+    "md17_l3": ("128x0e+64x1e+64x2e+32x3e", "1x0e+1x1e+1x2e+1x3e", "128x0e+64x1e+64x2e+32x3e"),
+    "oc20_l1": ("256x0e+128x1e", "1x0e+1x1e", "256x0e+128x1e"),
+    "odd_mul": ("20x0e+12x1e+4x2e", "1x0e+1x1e+1x2e", "20x0e+12x1e+4x2e"),
+    "e3_parity": ("32x0e+8x0o+8x1e+8x1o+4x2e+4x2o", "1x0e+1x1o+1x2e", "32x0e+8x0o+8x1e+8x1o+4x2e+4x2o"),
+}
+
+
+def _dtp(name):
+    from equiformer_b200.nets.graph_attention_transformer import DepthwiseTensorProduct
+    a, b, c = CONFIGS[name]
+    return DepthwiseTensorProduct(a, b, c, internal_weights=False, bias=False)
+
+
+def _inputs(plan, E, shared, seed=0, dtype=torch.float64):
+    g = torch.Generator().manual_seed(seed)
+    xs = [torch.randn(E, 2 * l + 1, mul, generator=g, dtype=dtype) for l, mul in plan.in1_blocks]
+    y = torch.randn(E, plan.d_y, generator=g, dtype=dtype)
+    w = torch.randn((plan.weight_numel,) if shared else (E, plan.weight_numel), generator=g, dtype=dtype)
+    gs = [torch.randn(E, 2 * l + 1, mul, generator=g, dtype=dtype) for l, _p, mul in plan.out_groups]
+    return xs, y, w, gs
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+@pytest.mark.parametrize("shared", [False, True])
+@pytest.mark.parametrize("E", [1, 37, 1000])
+def test_dtp_family_vs_emulation(cuda_device, name, shared, E):
+    """forward / grad_x / grad_w / grad_y / grad_xw kernels == fp64 table walk (ragged tile: E not a multiple of 8)."""
+    from equiformer_b200 import ops
+    plan = _dtp(name).tp.plan
+    xs, y, w, gs = _inputs(plan, E, shared)
+    f = lambda t: t.float().to(cuda_device)
+    xs_d, y_d, w_d, gs_d = [f(t) for t in xs], f(y), f(w), [f(t) for t in gs]
+    # references are computed from the fp32-rounded inputs, in fp64
+    r = lambda t: t.float().double()
+    xs_r, y_r, w_r, gs_r = [r(t) for t in xs], r(y), r(w), [r(t) for t in gs]
+
+    out = ops.dtp_forward_raw(plan, xs_d, y_d, w_d)
+    ref = emu.dtp_forward_raw(plan, xs_r, y_r, w_r)
+    for a, b in zip(out, ref):
+        assert rel_err(a, b) < TOL
+    gx = ops.dtp_grad_x_raw(plan, gs_d, y_d, w_d)
+    for a, b in zip(gx, emu.dtp_grad_x_raw(plan, gs_r, y_r, w_r)):
+        assert rel_err(a, b) < TOL
+    gw = ops.dtp_grad_w_raw(plan, xs_d, y_d, gs_d, shared)
+    assert rel_err(gw, emu.dtp_grad_w_raw(plan, xs_r, y_r, gs_r, shared)) < TOL
+    gy = ops.dtp_grad_y_raw(plan, xs_d, w_d, gs_d, y_d)
+    assert rel_err(gy, emu.dtp_grad_y_raw(plan, xs_r, w_r, gs_r, y_r)) < TOL
+    gx2, gw2 = ops.dtp_grad_xw_raw(plan, xs_d, y_d, w_d, gs_d)
+    for a, b in zip(gx2, gx):
+        assert rel_err(a, b) < TOL
+    assert rel_err(gw2, gw) < TOL
+
+
+@pytest.mark.parametrize("name", ["qm9_l2", "md17_l3", "oc20_l1"])
+def test_dtp_e3nn_layout_vs_oracle(cuda_device, name):
+    """TensorProductRescale.forward(x, y, weight) in e3nn layout == oracle per-instruction einsum (ref tensor_product_rescale.py:139-141)."""
+    from oracle import e3nn_ref as e3
+    from oracle import equiformer_ref as R
+    dtp = _dtp(name)
+    a, b, c = CONFIGS[name]
+    E = 257
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(E, dtp.irreps_in1.dim, generator=g)
+    y = torch.randn(E, dtp.irreps_in2.dim, generator=g)
+    w = torch.randn(E, dtp.tp.weight_numel, generator=g)
+    out = dtp.to(cuda_device)(x.to(cuda_device), y.to(cuda_device), w.to(cuda_device))
+    irr_out, ins = R.dtp_instructions(e3.parse_irreps(a), e3.parse_irreps(b), e3.parse_irreps(c))
+    ref = e3.tensor_product(x.double(), y.double(), w.double(), e3.parse_irreps(a), e3.parse_irreps(b), irr_out, ins, False)
+    assert str(dtp.irreps_out) == "+".join(f"{m}x{l}{'e' if p == 1 else 'o'}" for m, l, p in irr_out)
+    assert rel_err(out, ref) < TOL
+
+
+def test_dtp_empty_and_errors(cuda_device):
+    from equiformer_b200 import _lib, ops
+    plan = _dtp("qm9_l2").tp.plan
+    xs, y, w, gs = _inputs(plan, 0, False, dtype=torch.float32)
+    out = ops.dtp_forward_raw(plan, [t.to(cuda_device) for t in xs], y.to(cuda_device), w.to(cuda_device))
+    assert [tuple(o.shape) for o in out] == [(0, 1, 224), (0, 3, 384), (0, 5, 352)]
+    xs, y, w, gs = _inputs(plan, 4, False, dtype=torch.float32)
+    with pytest.raises(_lib.EqfError):  # CPU tensors must fail loudly - no fallback
+        ops.dtp_forward_raw(plan, xs, y, w)
+    with pytest.raises(ValueError):
+        ops.dtp_forward_raw(plan, [t.to(cuda_device) for t in xs[:-1]], y.to(cuda_device), w.to(cuda_device))
+
+
+def _graph(n_nodes, E, seed, device, with_empty=True):
+    from equiformer_b200 import ops
+    g = torch.Generator().manual_seed(seed)
+    dst = torch.randint(0, n_nodes, (E,), generator=g)
+    if with_empty and n_nodes > 2:
+        dst[dst == 1] = 0  # node 1 has no incoming edge
+    dst = torch.sort(dst).values
+    src = torch.randint(0, n_nodes, (E,), generator=g)
+    return ops.Graph(src.to(device), dst.to(device), n_nodes), src, dst
+
+
+@pytest.mark.parametrize("H,dims,chans", [(4, (1, 3, 5), (128, 64, 32)), (8, (1, 3), (256, 128)), (1, (1, 3, 5), (20, 12, 4)),
+                                          (4, (1, 3, 5, 7), (128, 64, 64, 32))])
+def test_attention_family(cuda_device, H, dims, chans):
+    """seg_softmax (PyG semantics, :508), aggregate (:512-513), edge_dot, edge_scale vs fp64 torch on ragged segments."""
+    from equiformer_b200 import ops
+    from oracle import equiformer_ref as R
+    n_nodes, E = 61, 700
+    graph, src, dst = _graph(n_nodes, E, 5, cuda_device)
+    g = torch.Generator().manual_seed(7)
+    z = torch.randn(E, H, generator=g) * 3
+    Vs = [torch.randn(E, d, c, generator=g) for d, c in zip(dims, chans)]
+    Gs = [torch.randn(n_nodes, d, c, generator=g) for d, c in zip(dims, chans)]
+    lay = ops.HeadLayout(dims, chans, H)
+    dev = lambda t: t.to(cuda_device)
+
+    alpha = ops.seg_softmax_raw(dev(z), graph)
+    alpha_ref = R.pyg_softmax(z.double(), dst, n_nodes)
+    assert rel_err(alpha, alpha_ref) < TOL
+    sums = torch.zeros(n_nodes, H, dtype=torch.float64).index_add_(0, dst, alpha.double().cpu())
+    has = torch.bincount(dst, minlength=n_nodes) > 0
+    assert torch.allclose(sums[has], torch.ones_like(sums[has]), atol=1e-5) and (sums[~has] == 0).all()
+
+    cpu_graph = type("G", (), {"dst": dst, "n_nodes": n_nodes, "n_edges": E})
+    a64 = alpha_ref
+    out = ops.attn_aggregate_raw(lay, dev(a64.float()), [dev(v) for v in Vs], graph)
+    ref = emu.attn_aggregate_raw(lay, a64.float().double(), [v.double() for v in Vs], cpu_graph)
+    for a, b in zip(out, ref):
+        assert rel_err(a, b) < TOL
+    out = ops.attn_aggregate_raw(lay, None, [dev(v) for v in Vs], graph)       # plain segment sum
+    for a, b in zip(out, emu.attn_aggregate_raw(lay, None, [v.double() for v in Vs], cpu_graph)):
+        assert rel_err(a, b) < TOL
+    ga = ops.attn_edge_dot_raw(lay, [dev(v) for v in Vs], [dev(t) for t in Gs], graph)
+    assert rel_err(ga, emu.attn_edge_dot_raw(lay, [v.double() for v in Vs], [t.double() for t in Gs], cpu_graph)) < TOL
+    sc = ops.attn_edge_scale_raw(lay, dev(a64.float()), [dev(t) for t in Gs], graph)
+    for a, b in zip(sc, emu.attn_edge_scale_raw(lay, a64.float().double(), [t.double() for t in Gs], cpu_graph)):
+        assert rel_err(a, b) < TOL
+
+
+def test_unsorted_edges_are_sorted_once(cuda_device):
+    from equiformer_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    dst = torch.randint(0, 9, (50,), generator=g)
+    src = torch.randint(0, 9, (50,), generator=g)
+    graph = ops.Graph(src.to(cuda_device), dst.to(cuda_device), 9)
+    assert graph.perm is not None and bool((graph.dst[1:] >= graph.dst[:-1]).all())
+    assert graph.row_ptr[-1].item() == 50

@@ -1,0 +1,137 @@
+"""-m gpu: drop-in modules on the B200 (fp32) against the CPU oracle (fp64, same weights, same inputs).
+
+Tolerances follow north_star: energies / node irreps / forces within 1e-4 relative (to the max magnitude of the
+reference quantity); parameter gradients within 1e-3 of the largest gradient entry (they accumulate over all edges).
+"""
+from __future__ import annotations
+
+import pytest
+import torch
+
+from tests.helpers import aspirin_like, molecules, qm9_like_batch, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle import equiformer_ref as R
+    return R
+
+
+def _build(name, dev, **kw):
+    from equiformer_b200.nets import model_entrypoint
+    torch.manual_seed(0)
+    args = dict(irreps_in="5x0e", radius=5.0, num_basis=128)
+    args.update(kw)
+    return model_entrypoint(name)(**args).to(dev).eval()
+
+
+def _perturb(model, seed=1):
+    """Make every parameter non-trivial (biases / affine terms are zero- or one-initialised)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(torch.randn(p.shape, generator=g).to(p.device) * 0.05)
+
+
+@pytest.mark.parametrize("name,nonlinear", [("graph_attention_transformer_nonlinear_l2", True),
+                                            ("graph_attention_transformer_l2", False)])
+def test_qm9_model_energy_and_param_grads(cuda_device, name, nonlinear):
+    R = _oracle()
+    model = _build(name, cuda_device)
+    _perturb(model)
+    pos, batch, z = molecules([9, 14, 5, 11, 7], seed=2)
+    out = model(f_in=None, pos=pos.to(cuda_device), batch=batch.to(cuda_device), node_atom=z.to(cuda_device))
+    out.sum().backward()
+
+    params = {k: v.requires_grad_(v.is_floating_point()) for k, v in R.cast_params(model.state_dict(), torch.float64).items()}
+    cfg = R.Config(nonlinear_message=nonlinear)
+    ref = R.model_forward(params, cfg, pos.double(), batch, z, 5)
+    ref.sum().backward()
+    assert rel_err(out, ref) < 1e-4
+    worst = 0.0
+    for k, p in model.named_parameters():
+        if p.grad is None:
+            continue
+        gref = params[k].grad
+        assert gref is not None, k
+        worst = max(worst, ((p.grad.double().cpu() - gref).abs().max() / gref.abs().max().clamp_min(1e-12)).item())
+    assert worst < 1e-3, worst
+
+
+def test_graph_attention_layer_node_irreps(cuda_device):
+    """One GraphAttention layer: node irreps out (e3nn layout) vs oracle, QM9-shaped batch slice."""
+    R = _oracle()
+    from oracle import e3nn_ref as e3
+    from equiformer_b200 import o3
+    from equiformer_b200.graph import radius_graph
+    from equiformer_b200.nets import GraphAttention
+    torch.manual_seed(0)
+    irreps = "128x0e+64x1e+32x2e"
+    ga = GraphAttention(irreps, "1x0e", "1x0e+1x1e+1x2e", irreps, [128, 64, 64], "32x0e+16x1e+8x2e", 4,
+                        nonlinear_message=True, alpha_drop=0.0, proj_drop=0.0).to(cuda_device).eval()
+    _perturb(ga)
+    pos, batch, _ = qm9_like_batch(8, seed=4)
+    src, dst = radius_graph(pos, 5.0, batch, max_num_neighbors=1000)
+    vec = pos[src] - pos[dst]
+    sh = o3.spherical_harmonics("1x0e+1x1e+1x2e", vec, True, "component")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(pos.shape[0], 480, generator=g)
+    rbf = torch.randn(src.numel(), 128, generator=g)
+    d = lambda t: t.to(cuda_device)
+    out = ga(d(x), None, d(src), d(dst), d(sh), d(rbf), d(batch))
+    params = R.cast_params(ga.state_dict(), torch.float64)
+    ir = e3.parse_irreps(irreps)
+    params = {"ga." + k: v for k, v in params.items()}
+    ref = R.graph_attention(params, "ga", ir, e3.parse_irreps("1x0e+1x1e+1x2e"), e3.parse_irreps("32x0e+16x1e+8x2e"), 4, ir,
+                            True, x.double(), src, dst, sh.double(), rbf.double())
+    assert rel_err(out, ref) < 1e-4
+
+
+@pytest.mark.parametrize("name,basis,lmax", [("graph_attention_transformer_nonlinear_exp_l2_md17", 128, 2),
+                                             ("graph_attention_transformer_nonlinear_exp_l3_md17", 32, 3)])
+def test_md17_energy_forces_and_double_backward(cuda_device, name, basis, lmax):
+    """Energy, autograd forces (first backward inside forward) and the gradient of a force loss (backward of backward)."""
+    R = _oracle()
+    model = _build(name, cuda_device, irreps_in="64x0e", num_basis=basis)
+    _perturb(model)
+    pos, batch, z = aspirin_like(seed=1)
+    energy, forces = model(node_atom=z.to(cuda_device), pos=pos.clone().to(cuda_device), batch=batch.to(cuda_device))
+    loss = energy.sum() + (forces ** 2).sum()
+    loss.backward()
+
+    params = {k: v.requires_grad_(v.is_floating_point()) for k, v in R.cast_params(model.state_dict(), torch.float64).items()}
+    if lmax == 2:
+        cfg = R.Config(basis_type="exp", number_of_basis=basis, max_atom_type=64, qm9_atom_remap=False)
+    else:
+        cfg = R.Config(irreps_node_embedding="128x0e+64x1e+64x2e+32x3e", irreps_sh="1x0e+1x1e+1x2e+1x3e",
+                       irreps_head="32x0e+16x1e+16x2e+8x3e", irreps_mlp_mid="384x0e+192x1e+192x2e+96x3e",
+                       basis_type="exp", number_of_basis=basis, max_atom_type=64, qm9_atom_remap=False)
+    e_ref, f_ref = R.energy_and_forces(params, cfg, pos.double(), batch, z, 1, create_graph=True)
+    (e_ref.sum() + (f_ref ** 2).sum()).backward()
+    assert rel_err(energy, e_ref) < 1e-4
+    assert rel_err(forces, f_ref) < 1e-4
+    worst = 0.0
+    for k, p in model.named_parameters():
+        if p.grad is None or params[k].grad is None:
+            continue
+        gref = params[k].grad
+        worst = max(worst, ((p.grad.double().cpu() - gref).abs().max() / gref.abs().max().clamp_min(1e-12)).item())
+    assert worst < 2e-3, worst
+
+
+def test_qm9_full_batch_invariants(cuda_device):
+    """BASELINE config 2 at full size (128 molecules): rotation/translation invariance and permutation of graphs."""
+    model = _build("graph_attention_transformer_nonlinear_l2", cuda_device)
+    pos, batch, z = qm9_like_batch(128, seed=0)
+    d = lambda t: t.to(cuda_device)
+    with torch.no_grad():
+        e0 = model(f_in=None, pos=d(pos), batch=d(batch), node_atom=d(z))
+        g = torch.Generator().manual_seed(9)
+        q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
+        if torch.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        pos_r = (pos.double() @ q.T + torch.tensor([0.3, -1.2, 2.0], dtype=torch.float64)).float()
+        e1 = model(f_in=None, pos=d(pos_r), batch=d(batch), node_atom=d(z))
+    assert e0.shape == (128, 1)
+    assert rel_err(e1, e0) < 1e-4

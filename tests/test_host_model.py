@@ -1,0 +1,99 @@
+"""CPU: host logic of the drop-in modules (layouts, weight views, autograd families) against the oracle.
+
+The kernels themselves cannot run here; ``tests/_emulation.py`` swaps the raw kernel calls for fp64 torch walks over
+the same plan tables so that everything *around* the kernels is exercised end to end in fp64 (tolerance 1e-9).
+The kernels are compared with the same oracle on the GPU box (tests/test_gpu_*.py).
+"""
+from __future__ import annotations
+
+import pytest
+import torch
+
+from oracle import equiformer_ref as R
+from tests._emulation import emulated_kernels
+from tests.helpers import aspirin_like, molecules, rel_err
+
+
+def _build(name, **kw):
+    from equiformer_b200.nets import model_entrypoint
+    torch.manual_seed(0)
+    args = dict(irreps_in="5x0e", radius=5.0, num_basis=128)
+    args.update(kw)
+    model = model_entrypoint(name)(**args).double().eval()
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(torch.randn(p.shape, generator=g, dtype=torch.float64) * 0.05)
+    return model
+
+
+def _grads_match(model, params, tol):
+    worst = 0.0
+    for k, p in model.named_parameters():
+        if p.grad is None and params[k].grad is None:
+            continue
+        assert p.grad is not None and params[k].grad is not None, k
+        worst = max(worst, ((p.grad - params[k].grad).abs().max() / params[k].grad.abs().max().clamp_min(1e-12)).item())
+    assert worst < tol, worst
+
+
+@pytest.mark.parametrize("name,nonlinear", [("graph_attention_transformer_nonlinear_l2", True),
+                                            ("graph_attention_transformer_l2", False)])
+def test_qm9_model_matches_oracle(name, nonlinear):
+    model = _build(name)
+    pos, batch, z = molecules([6, 9, 4], seed=2, dtype=torch.float64)
+    with emulated_kernels():
+        out = model(f_in=None, pos=pos, batch=batch, node_atom=z)
+        out.sum().backward()
+    params = {k: v.requires_grad_(v.is_floating_point()) for k, v in R.cast_params(model.state_dict(), torch.float64).items()}
+    ref = R.model_forward(params, R.Config(nonlinear_message=nonlinear), pos, batch, z, 3)
+    ref.sum().backward()
+    assert rel_err(out, ref) < 1e-10
+    _grads_match(model, params, 1e-8)
+
+
+def test_md17_forces_and_double_backward_match_oracle():
+    """BASELINE config 1 geometry (aspirin-like, 21 atoms): energy, forces, and d(force loss)/d(params)."""
+    model = _build("graph_attention_transformer_nonlinear_exp_l2_md17", irreps_in="64x0e", num_basis=32)
+    pos, batch, z = aspirin_like(seed=1, dtype=torch.float64)
+    with emulated_kernels():
+        energy, forces = model(node_atom=z, pos=pos.clone(), batch=batch)
+        (energy.sum() + (forces ** 2).sum()).backward()
+    params = {k: v.requires_grad_(v.is_floating_point()) for k, v in R.cast_params(model.state_dict(), torch.float64).items()}
+    cfg = R.Config(basis_type="exp", number_of_basis=32, max_atom_type=64, qm9_atom_remap=False)
+    e_ref, f_ref = R.energy_and_forces(params, cfg, pos, batch, z, 1, create_graph=True)
+    (e_ref.sum() + (f_ref ** 2).sum()).backward()
+    assert rel_err(energy, e_ref) < 1e-10
+    assert rel_err(forces, f_ref) < 1e-9
+    _grads_match(model, params, 1e-7)
+
+
+def test_state_dict_keys_follow_reference_names():
+    from equiformer_b200.nets import model_entrypoint
+    model = model_entrypoint("graph_attention_transformer_nonlinear_l2")(irreps_in="5x0e", radius=5.0)
+    keys = set(model.state_dict())
+    for k in ["blocks.0.ga.merge_src.tp.weight", "blocks.0.ga.merge_src.bias.0", "blocks.0.ga.sep_act.dtp_rad.net.0.weight",
+              "blocks.0.ga.sep_act.dtp_rad.net.6.weight", "blocks.0.ga.sep_act.dtp_rad.offset",
+              "blocks.0.ga.sep_act.lin.tp.weight", "blocks.0.ga.sep_act.lin.bias.0", "blocks.0.ga.sep_alpha.tp.weight",
+              "blocks.0.ga.sep_value.dtp.tp.weight", "blocks.0.ga.sep_value.lin.tp.weight", "blocks.0.ga.alpha_dot",
+              "blocks.0.ga.proj.tp.weight", "blocks.0.norm_1.affine_weight", "blocks.0.norm_2.affine_bias",
+              "blocks.0.ffn.fctp_1.tp.weight", "blocks.0.ffn.fctp_2.tp.weight", "blocks.5.ffn_shortcut.tp.weight",
+              "edge_deg_embed.exp.tp.weight", "edge_deg_embed.rad.net.6.weight", "edge_deg_embed.proj.tp.weight",
+              "atom_embed.atom_type_lin.tp.weight", "rbf.mean", "rbf.std", "norm.affine_weight", "head.0.tp.weight",
+              "head.2.tp.weight"]:
+        assert k in keys, k
+    ga = model.blocks[0].ga
+    assert ga.sep_act.dtp.tp.weight_numel == 960 and str(ga.sep_act.dtp.irreps_out.simplify()) == "224x0e+384x1e+352x2e"
+    assert ga.sep_act.lin.tp.weight.numel() == 86016 and ga.sep_alpha.tp.weight.numel() == 28672
+    assert ga.sep_value.lin.tp.weight.numel() == 64512
+    assert sum(p.numel() for p in model.parameters()) == 3531715
+
+
+def test_product_refuses_cpu_tensors():
+    """No CPU fallback: the edge path raises on CPU inputs instead of silently computing somewhere else."""
+    from equiformer_b200 import _lib
+    from equiformer_b200.nets.graph_attention_transformer import DepthwiseTensorProduct
+    dtp = DepthwiseTensorProduct("8x0e+4x1e", "1x0e+1x1e", "8x0e+4x1e", internal_weights=False, bias=False)
+    x, y, w = torch.randn(5, 20), torch.randn(5, 4), torch.randn(5, dtp.tp.weight_numel)
+    with pytest.raises(_lib.EqfError):
+        dtp(x, y, w)
