@@ -1,0 +1,63 @@
+"""CPU: the N>1 plumbing (flat gradient bucket + one all-reduce per step) with world_size-2 gloo processes."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from equiformer_b200.parallel import FlatGradAllReduce, broadcast_parameters, init_distributed
+    r, _l, w = init_distributed("gloo")
+    assert (r, w) == (rank, world)
+    torch.manual_seed(100 + rank)                     # different init per rank -> broadcast must equalise
+    model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.SiLU(), torch.nn.Linear(5, 1)).double()
+    broadcast_parameters(model)
+    bucket = FlatGradAllReduce(model.parameters())
+    g = torch.Generator().manual_seed(7)
+    data = torch.randn(8, 6, generator=g, dtype=torch.float64)   # same full batch on every rank
+    shard = data[rank::world]                                     # each rank owns its molecules
+    bucket.zero_grad()
+    (model(shard).sum() / data.shape[0] * world).backward()       # so that the rank-average equals the full-batch grad
+    bucket.reduce()
+    flat = bucket.flat.clone()
+    # single-process reference on the full batch
+    ref_model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.SiLU(), torch.nn.Linear(5, 1)).double()
+    ref_model.load_state_dict(model.state_dict())
+    (ref_model(data).sum() / data.shape[0]).backward()
+    ref = torch.cat([p.grad.reshape(-1) for p in ref_model.parameters()])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    ok = all(torch.allclose(t, ref, atol=1e-12) for t in gathered)
+    views_ok = all(p.grad.untyped_storage().data_ptr() == bucket.flat.untyped_storage().data_ptr() for p in model.parameters())
+    if rank == 0:
+        ret["ok"] = bool(ok and views_ok)
+    dist.destroy_process_group()
+
+
+def test_flat_bucket_allreduce_matches_single_process():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert ret.get("ok") is True
+
+
+def test_bench_reference_arm_ranks_other_than_zero_exit_quietly(monkeypatch, capsys):
+    import bench
+    monkeypatch.setenv("RANK", "1")
+
+    class A:
+        gpus, steps, warmup, ref_graphs = 2, 1, 0, 1
+    bench.run_reference(A())
+    assert capsys.readouterr().out == ""
