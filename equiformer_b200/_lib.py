@@ -19,7 +19,9 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC_DIR = PKG_DIR / "csrc"
 INCLUDE_DIR = PKG_DIR.parent / "include"
 LIB_PATH = PKG_DIR / "libeqf_b200.so"
-SOURCES = ("eqf_abi.cu", "eqf_dtp.cu", "eqf_attn.cu")
+SOURCES = ("eqf_abi.cu", "eqf_dtp.cu", "eqf_dtp_vec.cu", "eqf_attn.cu")
+GEMM_LIB_PATH = PKG_DIR / "libeqf_gemm.so"
+GEMM_SOURCES = ("eqf_gemm.cu",)
 
 EQF_MAX_BLOCKS = 8
 EQF_MAX_HEADS = 16
@@ -88,6 +90,14 @@ SIGNATURES = {
 }
 
 
+GEMM_SIGNATURES = {
+    "eqf_gemm_f32": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                c_int64, c_float, c_void_p, c_int64, c_void_p]),
+    "eqf_gemm_workspace_bytes": (c_int64, []),
+    "eqf_gemm_last_error": (c_char_p, []),
+}
+
+
 class EqfError(RuntimeError):
     pass
 
@@ -126,6 +136,75 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         print(proc.stderr)
     os.replace(tmp, LIB_PATH)
     return LIB_PATH
+
+
+def cutlass_include_dirs():
+    """CUTLASS/CuTe header trees vendored in site-packages (Environment section of the task statement)."""
+    import importlib.util
+    for pkg, rel in (("flashinfer", "data/cutlass"), ("tilelang", "3rdparty/cutlass")):
+        spec = importlib.util.find_spec(pkg)
+        if spec is None or not spec.submodule_search_locations:
+            continue
+        root = Path(list(spec.submodule_search_locations)[0]) / rel
+        if (root / "include" / "cutlass" / "cutlass.h").exists():
+            dirs = [root / "include"]
+            if (root / "tools" / "util" / "include").exists():
+                dirs.append(root / "tools" / "util" / "include")
+            return dirs
+    raise EqfError("CUTLASS headers not found (expected under site-packages/flashinfer/data/cutlass)")
+
+
+def gemm_needs_build() -> bool:
+    if not GEMM_LIB_PATH.exists():
+        return True
+    mtime = GEMM_LIB_PATH.stat().st_mtime
+    deps = [CSRC_DIR / s for s in GEMM_SOURCES] + [INCLUDE_DIR / "eqf_b200.h"]
+    return any(p.stat().st_mtime > mtime for p in deps if p.name != "eqf_b200.h") or not GEMM_LIB_PATH.exists()
+
+
+def build_gemm(force: bool = False) -> Path:
+    """Compile the CUTLASS fast-fp32 (tcgen05) GEMM instantiations into ``libeqf_gemm.so`` (takes minutes)."""
+    if not force and not gemm_needs_build():
+        return GEMM_LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    tmp = GEMM_LIB_PATH.with_suffix(".so.tmp%d" % os.getpid())
+    inc = []
+    for d in cutlass_include_dirs():
+        inc += ["-I", str(d)]
+    cmd = [nvcc, *NVCC_FLAGS, "--expt-relaxed-constexpr", "-diag-suppress", "20012", *inc, "-I", str(INCLUDE_DIR),
+           "-o", str(tmp), *[str(CSRC_DIR / s) for s in GEMM_SOURCES]]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise EqfError("nvcc failed (gemm):\n" + proc.stdout[-4000:] + proc.stderr[-4000:])
+    os.replace(tmp, GEMM_LIB_PATH)
+    return GEMM_LIB_PATH
+
+
+_gemm_lib = None
+
+
+def load_gemm():
+    global _gemm_lib
+    if _gemm_lib is not None:
+        return _gemm_lib
+    with _lock:
+        if _gemm_lib is not None:
+            return _gemm_lib
+        if not GEMM_LIB_PATH.exists():
+            raise EqfError(f"{GEMM_LIB_PATH} is missing: run __graft_entry__.build()")
+        lib = ctypes.CDLL(str(GEMM_LIB_PATH))
+        for name, (restype, argtypes) in GEMM_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _gemm_lib = lib
+    return _gemm_lib
+
+
+def check_gemm(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = load_gemm().eqf_gemm_last_error()
+        raise EqfError(f"{what} failed (code {rc}): {msg.decode() if msg else '?'}")
 
 
 def load():

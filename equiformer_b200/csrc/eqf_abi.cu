@@ -1,5 +1,6 @@
 // eqf_abi.cu - plan construction, error reporting and misc entry points of libeqf_b200.so.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -128,6 +129,44 @@ extern "C" int eqf_plan_create(const EqfPathDesc* paths, int32_t n_paths, const 
   h.n_wtasks = (int)wtasks.size() / 2;
   h.n_xtasks = (int)xtasks.size() / 2;
 
+  // tile size: largest of {8,4,2,1} edges whose scratch fits comfortably beside the tables (env override for tuning)
+  int te = 8;
+  if (const char* env = std::getenv("EQF_TILE_EDGES")) { int v = std::atoi(env); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16) te = v; }
+  const size_t fixed_words = (size_t)n_paths * (sizeof(PathDev) / 4) + cg_len + m_size + 4 * (size_t)n_paths + 64;
+  auto scalar_smem = [&](int t) {
+    size_t extra = (size_t)std::max(weight_numel, t * m_size);
+    return sizeof(uint32_t) * (fixed_words + (size_t)t * m_size + (size_t)t * d_y + extra);
+  };
+  while (te > 1 && scalar_smem(te) > 40 * 1024) te >>= 1;
+  h.te = te;
+
+  // vector (float4-per-lane) task tables for one tile of `te` edges
+  bool vec_ok = true;
+  for (int b = 0; b < n_in1; ++b) vec_ok = vec_ok && (h.in1_mul[b] % 4 == 0);
+  for (int g = 0; g < n_out; ++g) vec_ok = vec_ok && (h.out_mul[g] % 4 == 0);
+  for (int p = 0; p < n_paths; ++p) vec_ok = vec_ok && (pd[p].koff % 4 == 0) && (pd[p].w_off % 4 == 0);
+  vec_ok = vec_ok && (weight_numel % 4 == 0);
+  h.vec_ok = vec_ok ? 1 : 0;
+  std::vector<int> vwtasks, vxtasks;
+  if (vec_ok) {
+    for (int b = 0; b < n_in1; ++b) {
+      const int nvec = h.in1_mul[b] / 4;
+      h.in1_lpe[b] = nvec < 32 ? nvec : 32;
+      h.in1_epw[b] = 32 / h.in1_lpe[b];
+    }
+    auto emit = [&](std::vector<int>& out, int id, int b) {
+      const int nvec = h.in1_mul[b] / 4;
+      const int chunks = (nvec + 31) / 32;
+      const int epw = h.in1_epw[b];
+      for (int e_start = 0; e_start < te; e_start += epw)
+        for (int c = 0; c < chunks; ++c) { out.push_back(id); out.push_back((e_start << 16) | c); }
+    };
+    for (int p = 0; p < n_paths; ++p) emit(vwtasks, p, pd[p].xb);
+    for (int b = 0; b < n_in1; ++b) emit(vxtasks, b, b);
+  }
+  h.n_vwtasks = (int)vwtasks.size() / 2;
+  h.n_vxtasks = (int)vxtasks.size() / 2;
+
   std::vector<uint32_t>& blob = plan->blob;
   auto align2 = [&]() { if (blob.size() & 1) blob.push_back(0); };
   auto append_ints = [&](const std::vector<int>& v) {
@@ -147,19 +186,22 @@ extern "C" int eqf_plan_create(const EqfPathDesc* paths, int32_t n_paths, const 
   align2(); h.off_xtasks = append_ints(xtasks);
   h.off_xbstart = append_ints(xbstart);
   h.off_xbpaths = append_ints(xbpaths);
+  align2(); h.off_vwtasks = append_ints(vwtasks);
+  align2(); h.off_vxtasks = append_ints(vxtasks);
   while (blob.size() & 3) blob.push_back(0);   // keep the float scratch behind it 16-byte aligned
   h.blob_words = (int)blob.size();
 
-  // tile size: largest of {8,4,2,1} edges whose scratch fits comfortably beside the tables
-  int te = 8;
+  auto al4 = [](size_t v) { return (v + 3) & ~(size_t)3; };
   auto smem_for = [&](int t) {
     size_t extra = (size_t)std::max(weight_numel, t * m_size);
     return sizeof(uint32_t) * ((size_t)h.blob_words + (size_t)t * m_size + (size_t)t * d_y + extra);
   };
-  while (te > 1 && smem_for(te) > 40 * 1024) te >>= 1;
   if (smem_for(te) > 200 * 1024) { delete plan; set_error("plan tables exceed shared memory"); return EQF_ERR_UNSUPPORTED; }
-  h.te = te;
   plan->smem_bytes = smem_for(te);
+  const size_t vec_base = (size_t)h.blob_words + al4((size_t)te * m_size) + al4((size_t)te * d_y) + al4(weight_numel);
+  plan->smem_bytes_vec_bwd = sizeof(uint32_t) * vec_base + 16;
+  plan->smem_bytes_vec_fwd = sizeof(uint32_t) * (vec_base + 2 * (size_t)te * weight_numel) + 32;
+  if (plan->smem_bytes_vec_fwd > 220 * 1024) h.vec_ok = 0;  // weight ring does not fit: scalar kernels
   *plan_out = plan;
   return EQF_OK;
 }
@@ -173,8 +215,8 @@ extern "C" void eqf_plan_destroy(EqfPlan* plan) {
 extern "C" int eqf_plan_info(const EqfPlan* plan, int32_t* out, int32_t n) {
   if (plan == nullptr || out == nullptr) { set_error("eqf_plan_info: null argument"); return EQF_ERR_INVALID; }
   const PlanHdr& h = plan->hdr;
-  const int32_t vals[8] = {h.n_paths, h.m_size, h.n_wtasks, h.n_xtasks, h.te, (int32_t)plan->smem_bytes, h.blob_words,
-                           h.w_numel};
-  for (int i = 0; i < n && i < 8; ++i) out[i] = vals[i];
+  const int32_t vals[12] = {h.n_paths, h.m_size, h.n_wtasks, h.n_xtasks, h.te, (int32_t)plan->smem_bytes, h.blob_words,
+                            h.w_numel, h.vec_ok, h.n_vwtasks, h.n_vxtasks, (int32_t)plan->smem_bytes_vec_fwd};
+  for (int i = 0; i < n && i < 12; ++i) out[i] = vals[i];
   return EQF_OK;
 }

@@ -38,6 +38,9 @@ struct PlanHdr {
   int blob_words;
   int off_paths, off_cg, off_mdesc, off_wtasks, off_xtasks, off_xbstart, off_xbpaths;
   int te;           // edges per tile
+  // vectorised kernels (eqf_dtp_vec.cu): per-tile task tables, lanes per edge / edges per warp of each in1 block
+  int vec_ok, n_vwtasks, n_vxtasks, off_vwtasks, off_vxtasks;
+  int in1_lpe[EQF_MAX_BLOCKS], in1_epw[EQF_MAX_BLOCKS];
   int in1_d[EQF_MAX_BLOCKS], in1_mul[EQF_MAX_BLOCKS];
   int out_d[EQF_MAX_BLOCKS], out_mul[EQF_MAX_BLOCKS];
 };
@@ -61,6 +64,9 @@ struct EdgeArgs {
 void set_error(const std::string& msg);
 int check_cuda(cudaError_t err, const char* what);
 int ensure_device(const EqfPlan* plan);  // uploads the table blob on first use
+int dtp_variant();                        // 0 scalar, 1 vec, 2 vec + TMA weights (env EQF_DTP_VARIANT)
+int launch_forward_vec(const EqfPlan* plan, const EdgeArgs& a, bool tma, cudaStream_t stream);
+int launch_grad_x_vec(const EqfPlan* plan, const EdgeArgs& a, bool with_w, cudaStream_t stream);
 
 }  // namespace eqf
 
@@ -70,5 +76,7 @@ struct EqfPlan {
   uint32_t* d_blob = nullptr;   // device copy
   int device = -1;
   int sm_count = 148;
-  size_t smem_bytes = 0;        // dynamic shared memory per CTA
+  size_t smem_bytes = 0;        // dynamic shared memory per CTA (scalar kernels)
+  size_t smem_bytes_vec_fwd = 0;  // vector forward (includes the TMA weight ring)
+  size_t smem_bytes_vec_bwd = 0;  // vector grad_x / grad_xw
 };

@@ -425,6 +425,8 @@ extern "C" int eqf_dtp_forward(const EqfPlan* plan, const EqfEdgeOperands* op, i
     if (out_groups == nullptr || out_groups[g] == nullptr) { set_error("null output group"); return EQF_ERR_INVALID; }
     a.out[g] = out_groups[g];
   }
+  if (plan->hdr.vec_ok && dtp_variant() > 0)
+    return launch_forward_vec(plan, a, dtp_variant() == 2 && !a.w_shared, (cudaStream_t)stream);
   const size_t smem = plan->smem_bytes;
   if ((rc = set_smem(dtp_forward_kernel, smem)) != EQF_OK) return rc;
   dtp_forward_kernel<<<grid_for(plan, n_edges), kThreads, smem, (cudaStream_t)stream>>>(plan->hdr, plan->d_blob, a);
@@ -453,6 +455,7 @@ extern "C" int eqf_dtp_grad_x(const EqfPlan* plan, const EqfEdgeOperands* op, in
     if (gx_blocks == nullptr || gx_blocks[b] == nullptr) { set_error("null gx block"); return EQF_ERR_INVALID; }
     a.gx[b] = gx_blocks[b];
   }
+  if (plan->hdr.vec_ok && dtp_variant() > 0) return launch_grad_x_vec(plan, a, false, (cudaStream_t)stream);
   const size_t smem = plan->smem_bytes;
   if ((rc = set_smem(dtp_grad_x_kernel<false>, smem)) != EQF_OK) return rc;
   dtp_grad_x_kernel<false><<<grid_for(plan, n_edges), kThreads, smem, (cudaStream_t)stream>>>(plan->hdr, plan->d_blob, a);
@@ -470,6 +473,7 @@ extern "C" int eqf_dtp_grad_xw(const EqfPlan* plan, const EqfEdgeOperands* op, i
     a.gx[b] = gx_blocks[b];
   }
   a.gw = gw;
+  if (plan->hdr.vec_ok && dtp_variant() > 0) return launch_grad_x_vec(plan, a, true, (cudaStream_t)stream);
   const size_t smem = plan->smem_bytes;
   if ((rc = set_smem(dtp_grad_x_kernel<true>, smem)) != EQF_OK) return rc;
   dtp_grad_x_kernel<true><<<grid_for(plan, n_edges), kThreads, smem, (cudaStream_t)stream>>>(plan->hdr, plan->d_blob, a);

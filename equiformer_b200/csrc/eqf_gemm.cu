@@ -1,0 +1,147 @@
+// eqf_gemm.cu - fp32-accurate tensor-core GEMM for the per-degree channel-mixing linears (sm_100a, tcgen05).
+//
+// The linears that follow each depth-wise tensor product (SeparableFCTP.lin / sep_alpha / proj / merge / FFN:
+// LinearRS, nets/tensor_product_rescale.py:165-174 -> e3nn 'uvw' einsum -> cuBLAS SGEMM in the reference) are plain
+// row-major GEMMs on the planar buffers: [rows*(2l+1), K_l] x [K_l, C_l].  They hold the FLOP majority of the layer
+//  and fp32 parity (1e-4) rules out single-pass TF32, so this file instantiates
+// CUTLASS's sm_100 "FastFP32" collective (vendored CUTLASS 4.5 headers): operands stay fp32 in HBM, TMA stages them
+// into shared memory, a transform warp-group splits every value into three bf16 terms, tcgen05.mma accumulates the
+// five significant cross products in TMEM (fp32 accuracy), and the epilogue reads TMEM back with tcgen05.ld.
+// This is library code in the sense of the task statement (like calling cuBLAS) - it replaces cuBLAS's SIMT SGEMM,
+// which ran at ~21 TFLOP/s on these skinny shapes.
+//
+// Three operand layouts cover forward, data gradient and weight gradient of Y = X W (all tensors row-major):
+//   NN: C[M,N] = A[M,K]  B[K,N]      TN-like dgrad: C[M,K'] = A[M,N'] B[K',N']^T     wgrad: C[K,N] = A[M,K]^T B[M,N]
+#include <cuda_runtime.h>
+
+#include "cutlass/cutlass.h"
+#include "cutlass/epilogue/collective/collective_builder.hpp"
+#include "cutlass/gemm/collective/collective_builder.hpp"
+#include "cutlass/gemm/device/gemm_universal_adapter.h"
+#include "cutlass/gemm/kernel/gemm_universal.hpp"
+#include "cutlass/util/packed_stride.hpp"
+#include "cute/tensor.hpp"
+
+#include <string>
+
+#include "../../include/eqf_b200.h"
+
+// self-contained (built into its own libeqf_gemm.so so that the CUTLASS instantiations are compiled once)
+namespace eqf {
+
+using namespace cute;
+
+static thread_local std::string g_gemm_error;
+static void set_error(const std::string& msg) { g_gemm_error = msg; }
+static int check_cuda(cudaError_t err, const char* what) {
+  if (err == cudaSuccess) return EQF_OK;
+  g_gemm_error = std::string(what) + ": " + cudaGetErrorString(err);
+  return EQF_ERR_CUDA;
+}
+
+template <class LayoutA, class LayoutB, int TileN>
+struct FastF32Gemm {
+  using ElementA = float;
+  using ElementB = float;
+  using ElementC = float;
+  using ElementAcc = float;
+  using LayoutC = cutlass::layout::RowMajor;
+  static constexpr int Align = 4;  // 128-bit
+  using MmaTile = Shape<_128, Int<TileN>, _16>;
+  using Cluster = Shape<_1, _1, _1>;
+
+  using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
+      cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, MmaTile, Cluster,
+      cutlass::epilogue::collective::EpilogueTileAuto, ElementAcc, ElementAcc, ElementC, LayoutC, Align, ElementC,
+      LayoutC, Align, cutlass::epilogue::collective::EpilogueScheduleAuto>::CollectiveOp;
+
+  using CollectiveMainloop = typename cutlass::gemm::collective::CollectiveBuilder<
+      cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, ElementA, LayoutA, Align, ElementB, LayoutB, Align,
+      ElementAcc, MmaTile, Cluster,
+      cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
+      cutlass::gemm::KernelTmaWarpSpecialized1SmFastFP32Sm100>::CollectiveOp;
+
+  using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue>;
+  using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
+
+  using StrideA = typename Gemm::GemmKernel::StrideA;
+  using StrideB = typename Gemm::GemmKernel::StrideB;
+  using StrideC = typename Gemm::GemmKernel::StrideC;
+  using StrideD = typename Gemm::GemmKernel::StrideD;
+
+  static int run(const float* A, const float* B, float* C, int M, int N, int K, long long lda, long long ldb,
+                 long long ldc, float beta, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    // leading dimensions: A row-major -> lda = elements between rows of A[M,K]; column-major -> between columns
+    StrideA sa = cutlass::make_cute_packed_stride(StrideA{}, make_shape(M, K, 1));
+    StrideB sb = cutlass::make_cute_packed_stride(StrideB{}, make_shape(N, K, 1));
+    StrideC sc = cutlass::make_cute_packed_stride(StrideC{}, make_shape(M, N, 1));
+    set_ld(sa, lda);
+    set_ld(sb, ldb);
+    set_ld(sc, ldc);
+    typename Gemm::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm,
+                                  {M, N, K, 1},
+                                  {A, sa, B, sb},
+                                  {{1.0f, beta}, C, sc, C, sc}};
+    Gemm gemm;
+    if (gemm.can_implement(args) != cutlass::Status::kSuccess) {
+      set_error("fast-fp32 GEMM: shape/alignment not supported (dims and leading dims must be multiples of 4)");
+      return EQF_ERR_UNSUPPORTED;
+    }
+    size_t need = Gemm::get_workspace_size(args);
+    if (need > workspace_bytes) { set_error("fast-fp32 GEMM: workspace too small"); return EQF_ERR_INVALID; }
+    if (gemm.initialize(args, workspace, stream) != cutlass::Status::kSuccess) {
+      set_error("fast-fp32 GEMM: initialize failed"); return EQF_ERR_CUDA;
+    }
+    if (gemm.run(stream) != cutlass::Status::kSuccess) { set_error("fast-fp32 GEMM: launch failed"); return EQF_ERR_CUDA; }
+    return check_cuda(cudaGetLastError(), "fast-fp32 GEMM launch");
+  }
+
+  // packed strides are (ld, 1, batch) or (1, ld, batch): overwrite whichever mode is the non-unit one
+  template <class Stride>
+  static void set_ld(Stride& s, long long ld) {
+    if constexpr (cute::is_static_v<decltype(get<0>(s))>) {
+      get<1>(s) = ld;
+    } else {
+      get<0>(s) = ld;
+    }
+  }
+};
+
+}  // namespace eqf
+
+using namespace eqf;
+using Row = cutlass::layout::RowMajor;
+using Col = cutlass::layout::ColumnMajor;
+
+// mode 0: C[M,N] = A[M,K] (row-major, lda) x B[K,N] (row-major, ldb)
+// mode 1: C[M,N] = A[M,K] (row-major, lda) x B^T where B is [N,K] row-major (ldb)          (data gradient)
+// mode 2: C[M,N] = A^T x B where A is [K,M] row-major (lda) and B is [K,N] row-major (ldb)   (weight gradient)
+// beta = 0 overwrites C, beta = 1 accumulates.  Workspace: device scratch of eqf_gemm_workspace_bytes().
+extern "C" int eqf_gemm_f32(int mode, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                            int64_t lda, int64_t ldb, int64_t ldc, float beta, void* workspace,
+                            int64_t workspace_bytes, void* stream) {
+  if (A == nullptr || B == nullptr || C == nullptr) { set_error("eqf_gemm_f32: null pointer"); return EQF_ERR_INVALID; }
+  if (M <= 0 || N <= 0 || K <= 0) return EQF_OK;
+  if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) { set_error("eqf_gemm_f32: dimension too large"); return EQF_ERR_UNSUPPORTED; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int m = (int)M, n = (int)N, k = (int)K;
+  const bool wide = n > 64;
+  switch (mode) {
+    case 0:
+      return wide ? FastF32Gemm<Row, Row, 128>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
+                  : FastF32Gemm<Row, Row, 64>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
+    case 1:
+      return wide ? FastF32Gemm<Row, Col, 128>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
+                  : FastF32Gemm<Row, Col, 64>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
+    case 2:
+      return wide ? FastF32Gemm<Col, Row, 128>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
+                  : FastF32Gemm<Col, Row, 64>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
+    default:
+      set_error("eqf_gemm_f32: mode must be 0, 1 or 2");
+      return EQF_ERR_INVALID;
+  }
+}
+
+extern "C" int64_t eqf_gemm_workspace_bytes(void) { return 4 << 20; }
+
+extern "C" const char* eqf_gemm_last_error(void) { return g_gemm_error.c_str(); }

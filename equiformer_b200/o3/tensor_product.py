@@ -191,6 +191,7 @@ class TensorProduct(torch.nn.Module):
         ``xs``: one block ``[R, 2l+1, mul]`` per ``irreps_in1`` entry; ``y``: ``[R, irreps_in2.dim]`` or None (== 1).
         Returns one block per ``irreps_out`` entry.
         """
+        from .. import ops
         w = self._get_weights(weight)
         if w.dim() != 1:
             raise NotImplementedError("per-row weights for 'uvw' are outside the hot path")
@@ -205,9 +206,9 @@ class TensorProduct(torch.nn.Module):
                 if m2 != 1:
                     raise ValueError("second operand required")
                 Weff = W[:, 0, :]
-                t = torch.matmul(x.reshape(R * d, -1), Weff).view(R, d, -1)
+                t = ops.matmul_f32(x.reshape(R * d, -1), Weff).view(R, d, -1)
             elif m2 == 1:
-                t = torch.matmul(x.reshape(R * d, -1), W[:, 0, :]).view(R, d, -1)
+                t = ops.matmul_f32(x.reshape(R * d, -1), W[:, 0, :]).view(R, d, -1)
                 t = t * y[:, in2_off[i2]].view(R, 1, 1)
             else:
                 yy = y[:, in2_off[i2]:in2_off[i2] + m2]

@@ -628,6 +628,112 @@ def segment_softmax(z: torch.Tensor, graph: Graph) -> torch.Tensor:
     return SegSoftmax.apply(z, graph)
 
 
+# ----------------------------------------------------------------------------- fp32-accurate tensor-core GEMM
+
+_GEMM_WORKSPACE = {}
+_GEMM_MODE = None
+
+
+def gemm_backend() -> str:
+    """'cutlass' (tcgen05 fast-fp32, libeqf_gemm.so) or 'torch' (cuBLAS SGEMM); env EQF_GEMM overrides."""
+    global _GEMM_MODE
+    if _GEMM_MODE is None:
+        import os
+        want = os.environ.get("EQF_GEMM", "cutlass")
+        if want == "cutlass" and not _lib.GEMM_LIB_PATH.exists():
+            raise _lib.EqfError(f"{_lib.GEMM_LIB_PATH} is missing: run __graft_entry__.build() (or set EQF_GEMM=torch)")
+        _GEMM_MODE = want
+    return _GEMM_MODE
+
+
+def _gemm_operand(t: torch.Tensor):
+    """Row-major 2-D operand with 16-byte aligned rows: returns (tensor, leading dimension)."""
+    if t.stride(1) != 1 or t.stride(0) % 4 != 0 or t.stride(0) < t.shape[1] or t.data_ptr() % 16 != 0:
+        t = t.contiguous()
+    return t, t.stride(0)
+
+
+def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+    """mode 0: A[M,K] B[K,N]; mode 1: A[M,K] B[N,K]^T; mode 2: A[K,M]^T B[K,N]  ->  C[M,N] (fp32 accurate)."""
+    if mode == 0:
+        (M, K), N = A.shape, B.shape[1]
+        ok = B.shape[0] == K
+    elif mode == 1:
+        (M, K), N = A.shape, B.shape[0]
+        ok = B.shape[1] == K
+    else:
+        (K, M), N = A.shape, B.shape[1]
+        ok = B.shape[0] == K
+    if not ok:
+        raise ValueError(f"gemm mode {mode}: incompatible shapes {tuple(A.shape)} {tuple(B.shape)}")
+    aligned = all(v % 4 == 0 for v in (A.shape[1], B.shape[1], N)) and min(M, N, K) > 0
+    if not (A.is_cuda and A.dtype == torch.float32 and aligned and gemm_backend() == "cutlass"):
+        if mode == 0:
+            return A @ B
+        return A @ B.t() if mode == 1 else A.t() @ B
+    A, lda = _gemm_operand(A)
+    B, ldb = _gemm_operand(B)
+    C = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    lib = _lib.load_gemm()
+    ws = _GEMM_WORKSPACE.get(A.device)
+    if ws is None:
+        ws = torch.empty(int(lib.eqf_gemm_workspace_bytes()), dtype=torch.uint8, device=A.device)
+        _GEMM_WORKSPACE[A.device] = ws
+    flops_bytes = 4 * (A.numel() + B.numel() + C.numel())
+    with torch.cuda.device(A.device), _kernel("gemm_fast_f32", flops_bytes):
+        rc = lib.eqf_gemm_f32(mode, A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, lda, ldb, N, 0.0,
+                              ws.data_ptr(), ws.numel(), _stream())
+    _lib.check_gemm(rc, "eqf_gemm_f32")
+    return C
+
+
+class Gemm(torch.autograd.Function):
+    """C = op(A) op(B) for the three layouts of :func:`gemm_raw`; closed under differentiation."""
+
+    @staticmethod
+    def forward(ctx, mode: int, A, B):
+        ctx.mode = mode
+        ctx.save_for_backward(A, B)
+        return gemm_raw(mode, A, B)
+
+    @staticmethod
+    def backward(ctx, dC):
+        A, B = ctx.saved_tensors
+        mode = ctx.mode
+        dA = dB = None
+        if mode == 0:      # C = A B
+            if ctx.needs_input_grad[1]:
+                dA = Gemm.apply(1, dC, B)
+            if ctx.needs_input_grad[2]:
+                dB = Gemm.apply(2, A, dC)
+        elif mode == 1:    # C = A B^T
+            if ctx.needs_input_grad[1]:
+                dA = Gemm.apply(0, dC, B)
+            if ctx.needs_input_grad[2]:
+                dB = Gemm.apply(2, dC, A)
+        else:              # C = A^T B
+            if ctx.needs_input_grad[1]:
+                dA = Gemm.apply(1, B, dC)
+            if ctx.needs_input_grad[2]:
+                dB = Gemm.apply(0, A, dC)
+        return None, dA, dB
+
+
+def matmul_f32(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """``x[M,K] @ w[K,N]`` through the fp32-accurate tensor-core GEMM on CUDA (plain matmul elsewhere)."""
+    if x.is_cuda and x.dtype == torch.float32:
+        return Gemm.apply(0, x, w)
+    return x @ w
+
+
+def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``F.linear``: ``x @ weight^T + bias`` with ``weight`` stored ``[out, in]`` like ``nn.Linear``."""
+    if x.is_cuda and x.dtype == torch.float32 and x.dim() == 2:
+        out = Gemm.apply(1, x, weight)
+        return out if bias is None else out + bias
+    return torch.nn.functional.linear(x, weight, bias)
+
+
 # ----------------------------------------------------------------------------- layout conversion
 
 

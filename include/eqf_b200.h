@@ -73,7 +73,8 @@ int eqf_plan_create(const EqfPathDesc* paths, int32_t n_paths,
                     int32_t d_y, int32_t weight_numel,
                     const float* cg, int32_t cg_len, EqfPlan** plan_out);
 void eqf_plan_destroy(EqfPlan* plan);
-/* host-side introspection: out[0..n) = {n_paths, m_size, n_wtasks, n_xtasks, tile_edges, smem_bytes, blob_words, weight_numel} */
+/* host-side introspection: out[0..n) = {n_paths, m_size, n_wtasks, n_xtasks, tile_edges, smem_bytes, blob_words,
+ * weight_numel, vec_ok, n_vwtasks, n_vxtasks, smem_bytes_vec_fwd} */
 int eqf_plan_info(const EqfPlan* plan, int32_t* out, int32_t n);
 /* number of CTAs eqf_dtp_grad_w launches (rows of the shared-weight partial buffer) */
 int eqf_plan_partial_rows(const EqfPlan* plan, int64_t n_edges);
@@ -128,6 +129,18 @@ int eqf_attn_edge_dot(const EqfHeadLayout* lay, const float* const* V, const flo
 /* out[g][e,j] = alpha[e,head(j)] * G[g][dst[e],j]                  (transpose w.r.t. V; alpha NULL: gather) */
 int eqf_attn_edge_scale(const EqfHeadLayout* lay, const float* alpha, const float* const* G,
                         const int64_t* dst, int64_t n_edges, float* const* out, void* stream);
+
+/* ---- libeqf_gemm.so: fp32-accurate tensor-core GEMM for the per-degree channel-mixing linears ------------------
+ * Replaces the cuBLAS SGEMMs behind LinearRS (nets/tensor_product_rescale.py:165-174) on planar buffers.
+ *   mode 0: C[M,N] = A[M,K] B[K,N]          (forward;   A, B row-major with leading dims lda, ldb)
+ *   mode 1: C[M,N] = A[M,K] B[N,K]^T        (data grad; B row-major [N,K])
+ *   mode 2: C[M,N] = A[K,M]^T B[K,N]        (weight grad; A row-major [K,M])
+ * beta = 0 overwrites C, 1 accumulates.  All dims / leading dims must be multiples of 4 floats (16-byte TMA rows). */
+int eqf_gemm_f32(int mode, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
+                 int64_t lda, int64_t ldb, int64_t ldc, float beta, void* workspace, int64_t workspace_bytes,
+                 void* stream);
+int64_t eqf_gemm_workspace_bytes(void);
+const char* eqf_gemm_last_error(void);
 
 #ifdef __cplusplus
 }

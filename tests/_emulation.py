@@ -116,7 +116,13 @@ def attn_edge_scale_raw(lay, alpha, Gs, graph):
     return outs
 
 
-_PATCHED = ["dtp_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
+def gemm_raw(mode, A, B):
+    if mode == 0:
+        return A @ B
+    return A @ B.t() if mode == 1 else A.t() @ B
+
+
+_PATCHED = ["gemm_raw", "dtp_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
             "seg_softmax_raw", "attn_aggregate_raw", "attn_edge_dot_raw", "attn_edge_scale_raw"]
 
 

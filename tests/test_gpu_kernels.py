@@ -158,3 +158,38 @@ def test_unsorted_edges_are_sorted_once(cuda_device):
     graph = ops.Graph(src.to(cuda_device), dst.to(cuda_device), 9)
     assert graph.perm is not None and bool((graph.dst[1:] >= graph.dst[:-1]).all())
     assert graph.row_ptr[-1].item() == 50
+
+
+@pytest.mark.parametrize("M,N,K", [(36000, 352, 224), (108000, 64, 384), (180000, 32, 352), (2304, 128, 128), (36000, 960, 64),
+                                   (1001 * 4, 480, 352), (12, 8, 4)])
+def test_fast_fp32_gemm_all_layouts(cuda_device, M, N, K):
+    """tcgen05 fast-fp32 GEMM (libeqf_gemm.so) vs fp64 matmul: forward, data-grad and weight-grad layouts."""
+    from equiformer_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(K, N, generator=g)
+    dC = torch.randn(M, N, generator=g)
+    d = lambda t: t.to(cuda_device)
+    tol = 2e-6   # fp32-level: far inside the 1e-4 end-to-end budget, single-pass TF32 would be ~1e-3
+    assert rel_err(ops.gemm_raw(0, d(A), d(B)), A.double() @ B.double()) < tol
+    assert rel_err(ops.gemm_raw(1, d(dC), d(B)), dC.double() @ B.double().t()) < tol      # dA = dC B^T
+    assert rel_err(ops.gemm_raw(2, d(A), d(dC)), A.double().t() @ dC.double()) < tol      # dB = A^T dC
+    # strided A (a channel slice of a wider planar buffer, as sep_alpha reads the DTP output)
+    wide = torch.randn(M, K + 8, generator=g)
+    view = d(wide)[:, 4:4 + K]
+    assert rel_err(ops.gemm_raw(0, view, d(B)), wide[:, 4:4 + K].double() @ B.double()) < tol
+
+
+def test_gemm_autograd_closure(cuda_device):
+    from equiformer_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    A = torch.randn(64, 32, generator=g).to(cuda_device).requires_grad_(True)
+    B = torch.randn(32, 16, generator=g).to(cuda_device).requires_grad_(True)
+    out = ops.matmul_f32(A, B)
+    (gA,) = torch.autograd.grad(out.pow(2).sum(), A, create_graph=True)
+    gA.pow(2).sum().backward()
+    A2 = A.detach().double().requires_grad_(True)
+    B2 = B.detach().double().requires_grad_(True)
+    (gA2,) = torch.autograd.grad((A2 @ B2).pow(2).sum(), A2, create_graph=True)
+    gA2.pow(2).sum().backward()
+    assert rel_err(A.grad, A2.grad) < 1e-5 and rel_err(B.grad, B2.grad) < 1e-5
