@@ -39,7 +39,7 @@ static int check_cuda(cudaError_t err, const char* what) {
   return EQF_ERR_CUDA;
 }
 
-template <class LayoutA, class LayoutB, int TileN>
+template <class LayoutA, class LayoutB, int TileN, int TileK = 16, class Scheduler = void>
 struct FastF32Gemm {
   using ElementA = float;
   using ElementB = float;
@@ -47,7 +47,7 @@ struct FastF32Gemm {
   using ElementAcc = float;
   using LayoutC = cutlass::layout::RowMajor;
   static constexpr int Align = 4;  // 128-bit
-  using MmaTile = Shape<_128, Int<TileN>, _16>;
+  using MmaTile = Shape<_128, Int<TileN>, Int<TileK>>;
   using Cluster = Shape<_1, _1, _1>;
 
   using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
@@ -61,7 +61,7 @@ struct FastF32Gemm {
       cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
       cutlass::gemm::KernelTmaWarpSpecialized1SmFastFP32Sm100>::CollectiveOp;
 
-  using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue>;
+  using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue, Scheduler>;
   using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
 
   using StrideA = typename Gemm::GemmKernel::StrideA;
@@ -134,14 +134,15 @@ extern "C" int eqf_gemm_f32(int mode, const float* A, const float* B, float* C, 
       return wide ? FastF32Gemm<Row, Col, 128>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
                   : FastF32Gemm<Row, Col, 64>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
     case 2:
-      return wide ? FastF32Gemm<Col, Row, 128>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
-                  : FastF32Gemm<Col, Row, 64>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
+      // weight gradient: tiny [K,N] output, reduction over all rows -> stream-K splits the reduction across SMs
+      return wide ? FastF32Gemm<Col, Row, 128, 16, cutlass::gemm::StreamKScheduler>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
+                  : FastF32Gemm<Col, Row, 64, 16, cutlass::gemm::StreamKScheduler>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
     default:
       set_error("eqf_gemm_f32: mode must be 0, 1 or 2");
       return EQF_ERR_INVALID;
   }
 }
 
-extern "C" int64_t eqf_gemm_workspace_bytes(void) { return 4 << 20; }
+extern "C" int64_t eqf_gemm_workspace_bytes(void) { return 64 << 20; }
 
 extern "C" const char* eqf_gemm_last_error(void) { return g_gemm_error.c_str(); }

@@ -170,14 +170,15 @@ def test_fast_fp32_gemm_all_layouts(cuda_device, M, N, K):
     B = torch.randn(K, N, generator=g)
     dC = torch.randn(M, N, generator=g)
     d = lambda t: t.to(cuda_device)
-    tol = 2e-6   # fp32-level: far inside the 1e-4 end-to-end budget, single-pass TF32 would be ~1e-3
-    assert rel_err(ops.gemm_raw(0, d(A), d(B)), A.double() @ B.double()) < tol
-    assert rel_err(ops.gemm_raw(1, d(dC), d(B)), dC.double() @ B.double().t()) < tol      # dA = dC B^T
-    assert rel_err(ops.gemm_raw(2, d(A), d(dC)), A.double().t() @ dC.double()) < tol      # dB = A^T dC
+    # fp32-level accuracy (fp32 accumulation error grows ~sqrt(reduction length)); single-pass TF32 would be ~1e-3
+    tol = lambda red: 2e-6 * max(1.0, (red / 256) ** 0.5)
+    assert rel_err(ops.gemm_raw(0, d(A), d(B)), A.double() @ B.double()) < tol(K)
+    assert rel_err(ops.gemm_raw(1, d(dC), d(B)), dC.double() @ B.double().t()) < tol(N)   # dA = dC B^T
+    assert rel_err(ops.gemm_raw(2, d(A), d(dC)), A.double().t() @ dC.double()) < tol(M)   # dB = A^T dC
     # strided A (a channel slice of a wider planar buffer, as sep_alpha reads the DTP output)
     wide = torch.randn(M, K + 8, generator=g)
     view = d(wide)[:, 4:4 + K]
-    assert rel_err(ops.gemm_raw(0, view, d(B)), wide[:, 4:4 + K].double() @ B.double()) < tol
+    assert rel_err(ops.gemm_raw(0, view, d(B)), wide[:, 4:4 + K].double() @ B.double()) < tol(K)
 
 
 def test_gemm_autograd_closure(cuda_device):
