@@ -15,6 +15,9 @@
 //
 // HBM-bound streaming kernels: per edge the forward moves 4*(D_in + D_y + W + D_out) bytes for about
 // 2*sum_p mul*(2l1+1)*(2l3+1) flops (QM9 Lmax=2: 18 340 B vs 17 kflop) - see DESIGN.md.
+#include <mutex>
+#include <unordered_map>
+
 #include "eqf_common.cuh"
 
 namespace eqf {
@@ -401,9 +404,18 @@ static int grid_for(const EqfPlan* plan, long long E) {
 
 template <typename K>
 static int set_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024)
-    return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
-                      "cudaFuncSetAttribute(smem)");
+  if (bytes <= 48 * 1024) return EQF_OK;
+  // raise the opt-in shared-memory limit once per (kernel, size), not per launch (and never inside a graph capture twice)
+  static std::mutex mu;
+  static std::unordered_map<const void*, size_t> configured;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = configured[reinterpret_cast<const void*>(kernel)];
+  if (bytes > have) {
+    int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
+                        "cudaFuncSetAttribute(smem)");
+    if (rc != EQF_OK) return rc;
+    have = bytes;
+  }
   return EQF_OK;
 }
 

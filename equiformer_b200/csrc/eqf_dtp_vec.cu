@@ -13,6 +13,9 @@
 // kernels of eqf_dtp.cu are used.
 #include <cstdlib>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "eqf_common.cuh"
 
 namespace eqf {
@@ -344,9 +347,18 @@ static int vgrid_bwd(const EqfPlan* plan, long long E) {
 
 template <typename K>
 static int vset_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024)
-    return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
-                      "cudaFuncSetAttribute(smem)");
+  if (bytes <= 48 * 1024) return EQF_OK;
+  // raise the opt-in shared-memory limit once per (kernel, size), not per launch (and never inside a graph capture twice)
+  static std::mutex mu;
+  static std::unordered_map<const void*, size_t> configured;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = configured[reinterpret_cast<const void*>(kernel)];
+  if (bytes > have) {
+    int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes),
+                        "cudaFuncSetAttribute(smem)");
+    if (rc != EQF_OK) return rc;
+    have = bytes;
+  }
   return EQF_OK;
 }
 

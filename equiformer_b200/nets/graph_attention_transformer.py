@@ -417,7 +417,9 @@ class NodeEmbeddingNetwork(torch.nn.Module):
         self.atom_type_lin.tp.weight.data.mul_(self.max_atom_type ** 0.5)
 
     def forward(self, node_atom):
-        onehot = torch.nn.functional.one_hot(node_atom, self.max_atom_type).to(self.atom_type_lin.tp.weight.dtype)
+        # one-hot without torch's range check (that check is a device synchronisation; keeps the step graph-capturable)
+        classes = torch.arange(self.max_atom_type, device=node_atom.device)
+        onehot = (node_atom.unsqueeze(-1) == classes).to(self.atom_type_lin.tp.weight.dtype)
         return self.atom_type_lin(onehot), onehot, onehot
 
 
@@ -519,6 +521,7 @@ class GraphAttentionTransformer(torch.nn.Module):
             Activation(self.irreps_feature, acts=[torch.nn.SiLU()]),
             LinearRS(self.irreps_feature, Irreps("1x0e"), rescale=_RESCALE))
         self.scale_scatter = ScaledScatter(_AVG_NUM_NODES)
+        self.register_buffer("_atom_remap", torch.tensor([-1, 0, -1, -1, -1, -1, 1, 2, 3, 4]), persistent=False)
         self.apply(self._init_weights)
 
     def build_blocks(self):
@@ -554,20 +557,20 @@ class GraphAttentionTransformer(torch.nn.Module):
                     skip.add(full)
         return skip
 
-    def edge_features(self, pos, batch):
-        """Graph + edge producers shared by every block (ref :866-878)."""
+    def forward(self, f_in, pos, batch, node_atom, **kwargs) -> torch.Tensor:
         edge_src, edge_dst = radius_graph(pos, r=self.max_radius, batch=batch, max_num_neighbors=1000)
+        return self.forward_edges(pos, batch, node_atom, edge_src, edge_dst, n_graphs=kwargs.get("n_graphs"))
+
+    def forward_edges(self, pos, batch, node_atom, edge_src, edge_dst, graph=None, n_graphs=None) -> torch.Tensor:
+        """Everything after neighbour search (ref :868-899); free of host synchronisation when ``graph`` (the CSR of
+        the destination-sorted edge list) and ``n_graphs`` are supplied, so it can be captured in a CUDA graph."""
         edge_vec = pos.index_select(0, edge_src) - pos.index_select(0, edge_dst)
         edge_sh = o3.spherical_harmonics(l=self.irreps_edge_attr, x=edge_vec, normalize=True, normalization="component")
         edge_length = edge_vec.norm(dim=1)
-        return edge_src, edge_dst, edge_sh, edge_length
-
-    def forward(self, f_in, pos, batch, node_atom, **kwargs) -> torch.Tensor:
-        edge_src, edge_dst, edge_sh, edge_length = self.edge_features(pos, batch)
-        remap = node_atom.new_tensor([-1, 0, -1, -1, -1, -1, 1, 2, 3, 4])
-        atom_embedding, _attr, _onehot = self.atom_embed(remap[node_atom])
+        atom_embedding, _attr, _onehot = self.atom_embed(self._atom_remap[node_atom])
         edge_length_embedding = self.rbf(edge_length)
-        graph = ops.Graph(edge_src, edge_dst, pos.shape[0], check_sorted=False)
+        if graph is None:
+            graph = ops.Graph(edge_src, edge_dst, pos.shape[0], check_sorted=False)
         edge_degree_embedding = self.edge_deg_embed(atom_embedding, edge_sh, edge_length_embedding, edge_src, edge_dst,
                                                     batch, graph=graph)
         node_features = atom_embedding + edge_degree_embedding
@@ -579,7 +582,7 @@ class GraphAttentionTransformer(torch.nn.Module):
         if self.out_dropout is not None:
             node_features = self.out_dropout(node_features)
         outputs = self.head(node_features)
-        outputs = self.scale_scatter(outputs, batch, dim=0)
+        outputs = self.scale_scatter(outputs, batch, dim=0, dim_size=n_graphs)
         if self.scale is not None:
             outputs = self.scale * outputs
         return outputs

@@ -59,6 +59,18 @@ def _ls_from(l: Union[int, Sequence[int], str, Irreps]) -> List[int]:
     return [int(v) for v in l]
 
 
+_COUPLING_CACHE = {}
+
+
+def _coupling_tensor(deg: int, dtype, device) -> torch.Tensor:
+    key = (deg, dtype, str(device))
+    t = _COUPLING_CACHE.get(key)
+    if t is None:  # uploaded once per (degree, dtype, device): no host-to-device copy on the hot path / inside CUDA graphs
+        t = torch.as_tensor(_coupling(deg), dtype=dtype, device=device)
+        _COUPLING_CACHE[key] = t
+    return t
+
+
 def spherical_harmonics(l, x: torch.Tensor, normalize: bool, normalization: str = "integral") -> torch.Tensor:
     """``[..., 3] -> [..., sum(2l+1)]``; same arguments as ``e3nn.o3.spherical_harmonics``."""
     if normalization not in ("integral", "component", "norm"):
@@ -75,7 +87,7 @@ def spherical_harmonics(l, x: torch.Tensor, normalize: bool, normalization: str 
     if lmax >= 1:
         ys.append(v)
     for deg in range(1, lmax):
-        a = torch.as_tensor(_coupling(deg), dtype=v.dtype, device=v.device)
+        a = _coupling_tensor(deg, v.dtype, v.device)
         t = torch.einsum("kji,ei->ekj", a, ys[deg])
         ys.append(torch.einsum("ekj,ej->ek", t, v))
     out = []
