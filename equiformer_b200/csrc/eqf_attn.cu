@@ -65,8 +65,11 @@ __device__ __forceinline__ int find_group(const HeadArgs& a, int chunk) {
 }
 
 // one warp per (node, 32-column chunk)
+// `perm` (optional): segment position -> edge id, for reducing by an index the edge list is NOT sorted by
+// (the CSC side: gradients of the gathered source rows).
 __global__ void __launch_bounds__(256) aggregate_kernel(HeadArgs a, const float* __restrict__ alpha,
-                                                        const long long* __restrict__ row_ptr, long long n_nodes) {
+                                                        const long long* __restrict__ row_ptr,
+                                                        const long long* __restrict__ perm, long long n_nodes) {
   const int n_chunks = a.chunk_start[a.n_groups];
   const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (wid >= n_nodes * n_chunks) return;
@@ -82,7 +85,14 @@ __global__ void __launch_bounds__(256) aggregate_kernel(HeadArgs a, const float*
   const float* __restrict__ v = a.V[g] + j;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
   long long e = r0;
-  if (alpha != nullptr) {
+  if (perm != nullptr) {
+    const int H = a.n_heads;
+    for (; e < r1; ++e) {
+      const long long id = __ldg(perm + e);
+      const float al = alpha ? __ldg(alpha + id * H + h) : 1.f;
+      acc0 = fmaf(al, __ldg(v + id * rowlen), acc0);
+    }
+  } else if (alpha != nullptr) {
     const float* __restrict__ al = alpha + h;
     const int H = a.n_heads;
     for (; e + 3 < r1; e += 4) {
@@ -189,7 +199,8 @@ extern "C" int eqf_seg_softmax(const float* z, const int64_t* row_ptr, int64_t n
 }
 
 extern "C" int eqf_attn_aggregate(const EqfHeadLayout* lay, const float* alpha, const float* const* V,
-                                  const int64_t* row_ptr, int64_t n_nodes, float* const* out, void* stream) {
+                                  const int64_t* row_ptr, const int64_t* perm, int64_t n_nodes, float* const* out,
+                                  void* stream) {
   HeadArgs a;
   int rc = fill_head_args(lay, a);
   if (rc != EQF_OK || n_nodes == 0) return rc;
@@ -202,7 +213,7 @@ extern "C" int eqf_attn_aggregate(const EqfHeadLayout* lay, const float* alpha, 
   const long long warps = n_nodes * a.chunk_start[a.n_groups];
   const long long blocks = (warps + wpb - 1) / wpb;
   aggregate_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(
-      a, alpha, reinterpret_cast<const long long*>(row_ptr), n_nodes);
+      a, alpha, reinterpret_cast<const long long*>(row_ptr), reinterpret_cast<const long long*>(perm), n_nodes);
   return check_cuda(cudaGetLastError(), "aggregate_kernel launch");
 }
 

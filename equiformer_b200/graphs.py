@@ -19,7 +19,7 @@ from .graph import radius_graph
 
 
 class _Captured:
-    __slots__ = ("graph", "pos", "batch", "z", "target", "src", "dst", "row_ptr", "csr", "loss")
+    __slots__ = ("graph", "pos", "batch", "z", "target", "src", "dst", "row_ptr", "src_perm", "src_row_ptr", "csr", "loss")
 
 
 class GraphedForwardBackward:
@@ -37,13 +37,15 @@ class GraphedForwardBackward:
         loss.backward()
         return loss.detach()
 
-    def _capture(self, pos, batch, z, target, src, dst, row_ptr) -> _Captured:
+    def _capture(self, pos, batch, z, target, src, dst, row_ptr, src_perm, src_row_ptr) -> _Captured:
         c = _Captured()
         c.pos, c.batch, c.z, c.target = pos.clone(), batch.clone(), z.clone(), target.clone()
         c.src, c.dst, c.row_ptr = src.clone(), dst.clone(), row_ptr.clone()
+        c.src_perm, c.src_row_ptr = src_perm.clone(), src_row_ptr.clone()
         csr = ops.Graph.__new__(ops.Graph)
         csr.n_nodes, csr.n_edges, csr.perm = int(pos.shape[0]), int(src.numel()), None
         csr.src, csr.dst, csr.row_ptr = c.src, c.dst, c.row_ptr
+        csr._src_perm, csr._src_row_ptr = c.src_perm, c.src_row_ptr
         c.csr = csr
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -64,12 +66,15 @@ class GraphedForwardBackward:
         counts = torch.bincount(dst, minlength=pos.shape[0])
         row_ptr = torch.zeros(pos.shape[0] + 1, dtype=torch.int64, device=pos.device)
         torch.cumsum(counts, 0, out=row_ptr[1:])
+        src_perm = torch.sort(src, stable=True).indices          # CSC view for the transpose of the source gather
+        src_row_ptr = torch.zeros(pos.shape[0] + 1, dtype=torch.int64, device=pos.device)
+        torch.cumsum(torch.bincount(src, minlength=pos.shape[0]), 0, out=src_row_ptr[1:])
         key = (int(pos.shape[0]), int(src.numel()), int(target.shape[0]))
         c = self._cache.get(key)
         if c is None:
             if len(self._cache) >= self.max_cached:
                 self._cache.pop(next(iter(self._cache)))
-            c = self._capture(pos, batch, z, target, src, dst, row_ptr)
+            c = self._capture(pos, batch, z, target, src, dst, row_ptr, src_perm, src_row_ptr)
             self._cache[key] = c
         c.pos.copy_(pos, non_blocking=True)
         c.batch.copy_(batch, non_blocking=True)
@@ -78,5 +83,7 @@ class GraphedForwardBackward:
         c.src.copy_(src)
         c.dst.copy_(dst)
         c.row_ptr.copy_(row_ptr)
+        c.src_perm.copy_(src_perm)
+        c.src_row_ptr.copy_(src_row_ptr)
         c.graph.replay()
         return c.loss

@@ -286,12 +286,12 @@ class GraphAttention(torch.nn.Module):
         xs = ops.to_planar(node_input, self.irreps_node_input)
         m_src = self.merge_src.planar(xs)
         m_dst = self.merge_dst.planar(xs)
-        message = [a.index_select(0, graph.src) + b.index_select(0, graph.dst) for a, b in zip(m_src, m_dst)]
+        # the gather + add of ref :487 happens inside the DTP kernel's operand load (node tables stay L2-resident)
 
         if self.nonlinear_message:
             sa = self.sep_act
             weight = sa.dtp_rad(edge_scalars)                                             # [ref :490]
-            f = sa.dtp.planar(message, edge_attr, weight)                                 # [ref :491]  DTP #1
+            f = sa.dtp.tp.planar_depthwise_gathered(graph, m_src, m_dst, edge_attr, weight)   # [ref :487+:491]  DTP #1
             alpha = self.sep_alpha.planar(_entries_from_groups(f, sa.dtp.tp.plan))[0]     # [ref :492]
             value = sa.lin.planar(f)                                                      # [ref :494]
             value = sa.gate.planar(value) if isinstance(sa.gate, Gate) else [sa.gate(v) for v in value]  # [:495]
@@ -300,7 +300,8 @@ class GraphAttention(torch.nn.Module):
             value = self.sep_value.lin.planar(f2)
             alpha = alpha.reshape(E, H, A)                                                # [ref :493]
         else:
-            out = self.sep.planar(message, edge_attr, edge_scalars)                       # [ref :499]
+            weight = self.sep.dtp_rad(edge_scalars)
+            out = self.sep.lin.planar(self.sep.dtp.tp.planar_depthwise_gathered(graph, m_src, m_dst, edge_attr, weight))  # [ref :487+:499]
             first = out[0]                                                                # 0e entry: alpha | value scalars
             if first.shape[1] != 1:
                 raise NotImplementedError("attention logits need a leading 0e entry")
@@ -462,7 +463,7 @@ class EdgeDegreeEmbeddingNetwork(torch.nn.Module):
         ones = torch.ones((n_nodes, 1, 1), dtype=node_input.dtype, device=node_input.device)
         node_feats = self.exp.planar([ones])
         weight = self.rad(edge_scalars)
-        edge_feats = self.dw.planar([t.index_select(0, graph.src) for t in node_feats], edge_attr, weight)
+        edge_feats = self.dw.tp.planar_depthwise_gathered(graph, node_feats, None, edge_attr, weight)
         edge_feats = self.proj.planar(edge_feats)
         summed = ops.attention_aggregate(self._sum_layout, graph, None, [t.contiguous() for t in edge_feats])
         return ops.from_planar(summed).div(self.scale_scatter.avg_aggregate_num ** 0.5)

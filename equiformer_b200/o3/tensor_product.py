@@ -174,6 +174,12 @@ class TensorProduct(torch.nn.Module):
         w = self._get_weights(weight)
         return ops.depthwise_tensor_product(self.plan, xs, y, w)
 
+    def planar_depthwise_gathered(self, graph, As, Bs, y, weight=None):
+        """Planar DTP on ``A[src] (+ B[dst])`` with the gather folded into the kernel's operand load."""
+        from .. import ops
+        w = self._get_weights(weight)
+        return ops.depthwise_tensor_product_gathered(self.plan, graph, As, Bs, y, w)
+
     def linear_weight_blocks(self, weight=None):
         """``[(i_in1, i_in2, i_out, W[mul_in, mul_in2, mul_out] * path constant)]`` for the scalar-in2 'uvw' kind."""
         if self._kind != "linear":

@@ -55,11 +55,19 @@ def _ptr_array(ts: Sequence[torch.Tensor]):
     return arr
 
 
-def _operands(plan: DtpPlan, xs, y, w, gs, w_shared: bool) -> _lib.EqfEdgeOperands:
+def _operands(plan: DtpPlan, xs, y, w, gs, w_shared: bool, gather=None) -> _lib.EqfEdgeOperands:
+    """``gather = (src, dst, x2s)``: x rows are ``xs[b][src[e]] (+ x2s[b][dst[e]])`` instead of ``xs[b][e]``."""
     op = _lib.EqfEdgeOperands()
     if xs is not None:
         for i, t in enumerate(xs):
             op.x[i] = t.data_ptr()
+    if gather is not None:
+        src, dst, x2s = gather
+        op.src = src.data_ptr()
+        if x2s is not None:
+            op.dst = dst.data_ptr()
+            for i, t in enumerate(x2s):
+                op.x2[i] = t.data_ptr()
     if gs is not None:
         for i, t in enumerate(gs):
             op.g[i] = t.data_ptr()
@@ -181,11 +189,27 @@ def _attn_bytes(lay: "HeadLayout", rows_edge: int, rows_node: int, kind: str) ->
 # ----------------------------------------------------------------------------- raw kernel calls
 
 
-def dtp_forward_raw(plan: DtpPlan, xs, y, w) -> List[torch.Tensor]:
+def _check_gather(plan: DtpPlan, xs, gather, E: int, what: str):
+    """Validate gathered operands; returns (xs, gather) with contiguous CUDA tensors."""
+    if gather is None:
+        return _check_blocks(plan, xs, E, what), None
+    src, dst, x2s = gather
+    n_rows = xs[0].shape[0]
+    xs = _check_blocks(plan, xs, n_rows, what)
+    src = _require_index(src, "edge_src")
+    if src.numel() != E:
+        raise ValueError(f"{what}: gather index has {src.numel()} entries for {E} edges")
+    if x2s is not None:
+        x2s = _check_blocks(plan, x2s, x2s[0].shape[0], what)
+        dst = _require_index(dst, "edge_dst")
+    return xs, (src, dst, x2s)
+
+
+def dtp_forward_raw(plan: DtpPlan, xs, y, w, gather=None) -> List[torch.Tensor]:
     y, w, E, shared = _check_yw(plan, y, w)
-    xs = _check_blocks(plan, xs, E, "dtp_forward x")
+    xs, gather = _check_gather(plan, xs, gather, E, "dtp_forward x")
     outs = [torch.empty((E, 2 * l + 1, mul), device=y.device, dtype=torch.float32) for l, _p, mul in plan.out_groups]
-    op = _operands(plan, xs, y, w, None, shared)
+    op = _operands(plan, xs, y, w, None, shared, gather)
     with torch.cuda.device(y.device), _kernel("dtp_forward", _dtp_bytes(plan, E, shared, "forward")):
         rc = _lib.load().eqf_dtp_forward(plan.handle, ctypes.byref(op), E, _ptr_array(outs), _stream())
     _lib.check(rc, "eqf_dtp_forward")
@@ -236,15 +260,15 @@ def dtp_grad_y_raw(plan: DtpPlan, xs, w, gs, y_like) -> torch.Tensor:
     return gy
 
 
-def dtp_grad_xw_raw(plan: DtpPlan, xs, y, w, gs) -> Tuple[List[torch.Tensor], torch.Tensor]:
+def dtp_grad_xw_raw(plan: DtpPlan, xs, y, w, gs, gather=None) -> Tuple[List[torch.Tensor], torch.Tensor]:
     y, w, E, shared = _check_yw(plan, y, w)
-    xs = _check_blocks(plan, xs, E, "dtp_grad_xw x")
+    xs, gather = _check_gather(plan, xs, gather, E, "dtp_grad_xw x")
     gs = _check_groups(plan, gs, E, "dtp_grad_xw g")
     gxs = [torch.empty((E, 2 * l + 1, mul), device=y.device, dtype=torch.float32) for l, mul in plan.in1_blocks]
     if E == 0:
         return gxs, torch.zeros_like(w)
     gw = _gw_buffer(plan, E, shared, y.device)
-    op = _operands(plan, xs, y, w, gs, shared)
+    op = _operands(plan, xs, y, w, gs, shared, gather)
     with torch.cuda.device(y.device), _kernel("dtp_grad_xw", _dtp_bytes(plan, E, shared, "grad_xw")):
         rc = _lib.load().eqf_dtp_grad_xw(plan.handle, ctypes.byref(op), E, _ptr_array(gxs),
                                          ctypes.c_void_p(gw.data_ptr()), _stream())
@@ -399,6 +423,76 @@ class DtpGradY(torch.autograd.Function):
         return (None, None, gw, *gxs, *ggs)
 
 
+class DtpOutGathered(torch.autograd.Function):
+    """DTP whose in1 operand is gathered inside the kernel: ``x_e = A[src_e] (+ B[dst_e])`` (ref :487 fused into :491).
+
+    apply(plan, graph, n_b, y, w, *As, *Bs) with ``n_b`` = 0 (no B tables) or len(As).  First-order backward is two
+    kernels (grad_xw with the same gather, then segment sums to the node tables by dst and - through the CSC - by src);
+    under ``create_graph`` the backward re-expresses itself with the differentiable primitives instead.
+    """
+
+    @staticmethod
+    def forward(ctx, plan: DtpPlan, graph: "Graph", n_b: int, y, w, *AB):
+        nb = len(plan.in1_blocks)
+        As, Bs = AB[:nb], (AB[nb:] if n_b else None)
+        ctx.plan, ctx.graph, ctx.n_b = plan, graph, n_b
+        outs = dtp_forward_raw(plan, As, y, w, gather=(graph.src, graph.dst, Bs))
+        ctx.save_for_backward(y, w, *AB)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        plan, graph, n_b = ctx.plan, ctx.graph, ctx.n_b
+        y, w, *AB = ctx.saved_tensors
+        nb = len(plan.in1_blocks)
+        As, Bs = AB[:nb], (AB[nb:] if n_b else None)
+        E = y.shape[0]
+        gs = [g if g is not None else torch.zeros((E, 2 * l + 1, m), device=y.device)
+              for g, (l, _p, m) in zip(gs, plan.out_groups)]
+        need_y, need_w = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+        need_x = any(ctx.needs_input_grad[5:])
+        if torch.is_grad_enabled():   # higher-order: differentiable composition of the primitive family
+            xs = [a.index_select(0, graph.src) for a in As]
+            if Bs is not None:
+                xs = [x + b.index_select(0, graph.dst) for x, b in zip(xs, Bs)]
+            gy = DtpGradY.apply(plan, y, w, *xs, *gs) if need_y else None
+            gw = DtpGradW.apply(plan, y, w.dim() == 1, *xs, *gs) if need_w else None
+            gA = [None] * nb
+            gB = [None] * nb
+            if need_x:
+                gxs = DtpGradX.apply(plan, y, w, *gs)
+                gA = [torch.zeros_like(a).index_add(0, graph.src, g) for a, g in zip(As, gxs)]
+                if Bs is not None:
+                    gB = [torch.zeros_like(b).index_add(0, graph.dst, g) for b, g in zip(Bs, gxs)]
+            return (None, None, None, gy, gw, *gA, *(gB if Bs is not None else []))
+        gs = [g.contiguous() for g in gs]
+        gather = (graph.src, graph.dst, Bs)
+        gy = gw = None
+        gA = [None] * nb
+        gB = [None] * nb
+        if need_x or need_w:
+            gxs, gw_full = dtp_grad_xw_raw(plan, As, y, w, gs, gather=gather)
+            gw = gw_full if need_w else None
+            if need_x:
+                lay = HeadLayout([2 * l + 1 for l, _ in plan.in1_blocks], [m for _, m in plan.in1_blocks], 1)
+                gA = attn_aggregate_raw(lay, None, gxs, graph, by_src=True)
+                if Bs is not None:
+                    gB = attn_aggregate_raw(lay, None, gxs, graph)
+        if need_y:
+            xs = [a.index_select(0, graph.src) for a in As]
+            if Bs is not None:
+                xs = [x + b.index_select(0, graph.dst) for x, b in zip(xs, Bs)]
+            gy = dtp_grad_y_raw(plan, xs, w, gs, y)
+        return (None, None, None, gy, gw, *gA, *(gB if Bs is not None else []))
+
+
+def depthwise_tensor_product_gathered(plan: DtpPlan, graph: "Graph", As, Bs, y, w):
+    """``DTP(A[src] (+ B[dst]), y; w)`` with the gather done inside the kernel.  ``Bs`` may be None."""
+    if Bs is None:
+        return list(DtpOutGathered.apply(plan, graph, 0, y, w, *As))
+    return list(DtpOutGathered.apply(plan, graph, len(Bs), y, w, *As, *Bs))
+
+
 def depthwise_tensor_product(plan: DtpPlan, xs: Sequence[torch.Tensor], y: torch.Tensor, w: torch.Tensor):
     """Planar DTP: ``xs`` per in1 block ``[E, 2l+1, mul]`` -> list per output group ``[E, 2l+1, K]``."""
     return list(DtpOut.apply(plan, y, w, *xs))
@@ -458,6 +552,25 @@ class Graph:
     def sort_edges(self, t: torch.Tensor) -> torch.Tensor:
         return t if self.perm is None else t.index_select(0, self.perm)
 
+    def build_csc(self) -> None:
+        """Source-sorted view of the same edge list: ``src_perm`` (segment position -> edge id) and ``src_row_ptr``."""
+        self._src_perm = torch.sort(self.src, stable=True).indices
+        counts = torch.bincount(self.src, minlength=self.n_nodes)
+        self._src_row_ptr = torch.zeros(self.n_nodes + 1, dtype=torch.int64, device=self.src.device)
+        torch.cumsum(counts, 0, out=self._src_row_ptr[1:])
+
+    @property
+    def src_perm(self) -> torch.Tensor:
+        if getattr(self, "_src_perm", None) is None:
+            self.build_csc()
+        return self._src_perm
+
+    @property
+    def src_row_ptr(self) -> torch.Tensor:
+        if getattr(self, "_src_row_ptr", None) is None:
+            self.build_csc()
+        return self._src_row_ptr
+
 
 def seg_softmax_raw(z: torch.Tensor, graph: Graph) -> torch.Tensor:
     z = _require_cuda(z, "attention logits")
@@ -471,7 +584,8 @@ def seg_softmax_raw(z: torch.Tensor, graph: Graph) -> torch.Tensor:
     return alpha
 
 
-def attn_aggregate_raw(lay: HeadLayout, alpha, Vs, graph: Graph) -> List[torch.Tensor]:
+def attn_aggregate_raw(lay: HeadLayout, alpha, Vs, graph: Graph, by_src: bool = False) -> List[torch.Tensor]:
+    """Segment reduction over destination segments (default) or, with ``by_src``, over source segments via the CSC."""
     Vs = lay.check(Vs, graph.n_edges, "aggregate V")
     if alpha is not None:
         alpha = _require_cuda(alpha, "alpha")
@@ -479,9 +593,14 @@ def attn_aggregate_raw(lay: HeadLayout, alpha, Vs, graph: Graph) -> List[torch.T
             raise ValueError("alpha must be [E, H]")
     dev = Vs[0].device
     outs = [torch.empty((graph.n_nodes, d, C), device=dev, dtype=torch.float32) for d, C in zip(lay.ds, lay.Cs)]
+    if by_src:
+        row_ptr, perm = graph.src_row_ptr, graph.src_perm
+    else:
+        row_ptr, perm = graph.row_ptr, None
     with torch.cuda.device(dev), _kernel("attn_aggregate", _attn_bytes(lay, graph.n_edges, graph.n_nodes, "aggregate")):
         rc = _lib.load().eqf_attn_aggregate(ctypes.byref(lay.c), alpha.data_ptr() if alpha is not None else None,
-                                            _ptr_array(Vs), graph.row_ptr.data_ptr(), graph.n_nodes,
+                                            _ptr_array(Vs), row_ptr.data_ptr(),
+                                            perm.data_ptr() if perm is not None else None, graph.n_nodes,
                                             _ptr_array(outs), _stream())
     _lib.check(rc, "eqf_attn_aggregate")
     return outs

@@ -118,9 +118,11 @@ int eqf_seg_softmax(const float* z, const int64_t* row_ptr, int64_t n_nodes, int
                     float* alpha, void* stream);
 
 /* out[g][t,j] = sum_{e in seg(t)} alpha[e,head(j)] * V[g][e,j]   (alpha NULL: plain segment sum)
- * == value*alpha followed by torch_scatter.scatter(..., edge_dst) (:512-513).                     */
+ * == value*alpha followed by torch_scatter.scatter(..., edge_dst) (:512-513).
+ * perm (optional, NULL = identity): segment position -> edge id, for segments of an index the edge list is not
+ * sorted by (the transpose of `message_src[edge_src]`, :487, in the backward pass).                */
 int eqf_attn_aggregate(const EqfHeadLayout* lay, const float* alpha, const float* const* V,
-                       const int64_t* row_ptr, int64_t n_nodes, float* const* out, void* stream);
+                       const int64_t* row_ptr, const int64_t* perm, int64_t n_nodes, float* const* out, void* stream);
 
 /* galpha[e,h] = sum_{j in head h} V[g][e,j] * G[g][dst[e],j]       (transpose of aggregate w.r.t. alpha) */
 int eqf_attn_edge_dot(const EqfHeadLayout* lay, const float* const* V, const float* const* G,

@@ -25,7 +25,18 @@ def _w(plan, p, w):
     return wv if wv.dim() == 2 else wv[None, :]
 
 
-def dtp_forward_raw(plan, xs, y, w):
+def _gathered(xs, gather):
+    if gather is None:
+        return xs
+    src, dst, x2s = gather
+    xs = [x.index_select(0, src) for x in xs]
+    if x2s is not None:
+        xs = [x + b.index_select(0, dst) for x, b in zip(xs, x2s)]
+    return xs
+
+
+def dtp_forward_raw(plan, xs, y, w, gather=None):
+    xs = _gathered(xs, gather)
     E = y.shape[0]
     outs = [y.new_zeros((E, 2 * l + 1, mul)) for l, _p, mul in plan.out_groups]
     for p in plan.paths:
@@ -67,7 +78,8 @@ def dtp_grad_y_raw(plan, xs, w, gs, y_like):
     return gy
 
 
-def dtp_grad_xw_raw(plan, xs, y, w, gs):
+def dtp_grad_xw_raw(plan, xs, y, w, gs, gather=None):
+    xs = _gathered(xs, gather)
     return dtp_grad_x_raw(plan, gs, y, w), dtp_grad_w_raw(plan, xs, y, gs, w.dim() == 1)
 
 
@@ -88,12 +100,13 @@ def seg_softmax_raw(z, graph):
     return out
 
 
-def attn_aggregate_raw(lay, alpha, Vs, graph):
+def attn_aggregate_raw(lay, alpha, Vs, graph, by_src=False):
     outs = []
+    index = graph.src if by_src else graph.dst
     for g, V in enumerate(Vs):
         val = V if alpha is None else V * alpha[:, _head_of(lay, g)][:, None, :]
         out = V.new_zeros((graph.n_nodes,) + tuple(V.shape[1:]))
-        outs.append(out.index_add(0, graph.dst, val))
+        outs.append(out.index_add(0, index, val))
     return outs
 
 

@@ -194,3 +194,34 @@ def test_gemm_autograd_closure(cuda_device):
     (gA2,) = torch.autograd.grad((A2 @ B2).pow(2).sum(), A2, create_graph=True)
     gA2.pow(2).sum().backward()
     assert rel_err(A.grad, A2.grad) < 1e-5 and rel_err(B.grad, B2.grad) < 1e-5
+
+
+@pytest.mark.parametrize("with_b", [True, False])
+def test_dtp_gather_fused_and_csc_aggregate(cuda_device, with_b):
+    """x = A[src] (+ B[dst]) gathered inside the kernels (ref :487 folded into :491) and the CSC segment sum."""
+    from equiformer_b200 import ops
+    plan = _dtp("qm9_l2").tp.plan
+    n_nodes, E = 53, 611
+    graph, src, dst = _graph(n_nodes, E, 11, cuda_device)
+    g = torch.Generator().manual_seed(3)
+    As = [torch.randn(n_nodes, 2 * l + 1, m, generator=g) for l, m in plan.in1_blocks]
+    Bs = [torch.randn(n_nodes, 2 * l + 1, m, generator=g) for l, m in plan.in1_blocks] if with_b else None
+    y = torch.randn(E, plan.d_y, generator=g)
+    w = torch.randn(E, plan.weight_numel, generator=g)
+    gs = [torch.randn(E, 2 * l + 1, m, generator=g) for l, _p, m in plan.out_groups]
+    d = lambda t: t.to(cuda_device)
+    dB = [d(t) for t in Bs] if with_b else None
+    xs64 = [a.double()[src] + (b.double()[dst] if with_b else 0) for a, b in zip(As, Bs or As)]
+    out = ops.dtp_forward_raw(plan, [d(t) for t in As], d(y), d(w), gather=(graph.src, graph.dst, dB))
+    for a, b in zip(out, emu.dtp_forward_raw(plan, xs64, y.double(), w.double())):
+        assert rel_err(a, b) < TOL
+    gx, gw = ops.dtp_grad_xw_raw(plan, [d(t) for t in As], d(y), d(w), [d(t) for t in gs], gather=(graph.src, graph.dst, dB))
+    gx_ref = emu.dtp_grad_x_raw(plan, [t.double() for t in gs], y.double(), w.double())
+    for a, b in zip(gx, gx_ref):
+        assert rel_err(a, b) < TOL
+    assert rel_err(gw, emu.dtp_grad_w_raw(plan, xs64, y.double(), [t.double() for t in gs], False)) < TOL
+    lay = ops.HeadLayout([2 * l + 1 for l, _ in plan.in1_blocks], [m for _, m in plan.in1_blocks], 1)
+    by_src = ops.attn_aggregate_raw(lay, None, gx, graph, by_src=True)
+    for a, ref in zip(by_src, gx_ref):
+        exp = torch.zeros(n_nodes, *ref.shape[1:], dtype=torch.float64).index_add_(0, src, ref)
+        assert rel_err(a, exp) < TOL
