@@ -140,6 +140,9 @@ extern "C" int eqf_plan_create(const EqfPathDesc* paths, int32_t n_paths, const 
   while (te > 1 && scalar_smem(te) > 40 * 1024) te >>= 1;
   h.te = te;
 
+  h.d_in = 0;
+  for (int b = 0; b < n_in1; ++b) { h.in1_off[b] = h.d_in; h.d_in += h.in1_d[b] * h.in1_mul[b]; }
+
   // vector (float4-per-lane) task tables for one tile of `te` edges
   bool vec_ok = true;
   for (int b = 0; b < n_in1; ++b) vec_ok = vec_ok && (h.in1_mul[b] % 4 == 0);
@@ -153,6 +156,8 @@ extern "C" int eqf_plan_create(const EqfPathDesc* paths, int32_t n_paths, const 
       const int nvec = h.in1_mul[b] / 4;
       h.in1_lpe[b] = nvec < 32 ? nvec : 32;
       h.in1_epw[b] = 32 / h.in1_lpe[b];
+      h.in1_lpe_shift[b] = -1;
+      for (int sft = 0; sft <= 5; ++sft) if ((1 << sft) == h.in1_lpe[b]) h.in1_lpe_shift[b] = sft;
     }
     auto emit = [&](std::vector<int>& out, int id, int b) {
       const int nvec = h.in1_mul[b] / 4;

@@ -41,6 +41,9 @@ struct PlanHdr {
   // vectorised kernels (eqf_dtp_vec.cu): per-tile task tables, lanes per edge / edges per warp of each in1 block
   int vec_ok, n_vwtasks, n_vxtasks, off_vwtasks, off_vxtasks;
   int in1_lpe[EQF_MAX_BLOCKS], in1_epw[EQF_MAX_BLOCKS];
+  int in1_lpe_shift[EQF_MAX_BLOCKS];   // log2(lanes per edge) or -1 when not a power of two
+  int in1_off[EQF_MAX_BLOCKS];         // float offset of each in1 block inside one [d_in] row
+  int d_in;                            // floats per in1 row (all blocks)
   int in1_d[EQF_MAX_BLOCKS], in1_mul[EQF_MAX_BLOCKS];
   int out_d[EQF_MAX_BLOCKS], out_mul[EQF_MAX_BLOCKS];
 };
@@ -64,9 +67,12 @@ struct EdgeArgs {
 void set_error(const std::string& msg);
 int check_cuda(cudaError_t err, const char* what);
 int ensure_device(const EqfPlan* plan);  // uploads the table blob on first use
-int dtp_variant();                        // 0 scalar, 1 vec, 2 vec + TMA weights (env EQF_DTP_VARIANT)
+int dtp_variant();                        // 0 scalar, 1 vec, 2 vec + TMA weights, 3 pipelined v3 (env EQF_DTP_VARIANT)
 int launch_forward_vec(const EqfPlan* plan, const EdgeArgs& a, bool tma, cudaStream_t stream);
 int launch_grad_x_vec(const EqfPlan* plan, const EdgeArgs& a, bool with_w, cudaStream_t stream);
+int launch_forward_v3(const EqfPlan* plan, const EdgeArgs& a, cudaStream_t stream);
+int launch_backward_v3(const EqfPlan* plan, const EdgeArgs& a, bool with_w, cudaStream_t stream);
+int backward_v3_grid(const EqfPlan* plan, long long E);
 
 }  // namespace eqf
 

@@ -319,12 +319,12 @@ __global__ void __launch_bounds__(kThreads) dtp_grad_x_vec_kernel(PlanHdr h, con
 
 // ---------------------------------------------------------------------------------------------- host side
 int dtp_variant() {
-  // EQF_DTP_VARIANT = scalar | vec | tma (default tma); read once
+  // EQF_DTP_VARIANT = scalar | vec | tma | v3 (default v3); read once
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("EQF_DTP_VARIANT");
-    std::string s = e ? e : "tma";
-    v = (s == "scalar") ? 0 : (s == "vec") ? 1 : 2;
+    std::string s = e ? e : "v3";
+    v = (s == "scalar") ? 0 : (s == "vec") ? 1 : (s == "tma") ? 2 : 3;
   }
   return v;
 }
