@@ -107,7 +107,14 @@ _lib = None
 
 
 def sources():
-    return [CSRC_DIR / s for s in SOURCES if (CSRC_DIR / s).exists()]
+    gen = sorted((CSRC_DIR / "gen").glob("dtp_gen_*.cu")) if (CSRC_DIR / "gen").exists() else []
+    return [CSRC_DIR / s for s in SOURCES if (CSRC_DIR / s).exists()] + gen
+
+
+def generate_sources():
+    """Emit the plan-specialised kernels for the registered model configurations (csrc/gen/*.cu)."""
+    from . import codegen
+    return codegen.write_all()
 
 
 def needs_build() -> bool:
@@ -120,6 +127,7 @@ def needs_build() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile ``csrc/*.cu`` for sm_100a into ``equiformer_b200/libeqf_b200.so`` (in-tree)."""
+    generate_sources()
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"

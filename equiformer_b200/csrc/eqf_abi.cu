@@ -20,6 +20,22 @@ int check_cuda(cudaError_t err, const char* what) {
 
 static std::mutex g_upload_mutex;
 
+static std::vector<const GeneratedKernels*>& generated_registry() {
+  static std::vector<const GeneratedKernels*> reg;
+  return reg;
+}
+int register_generated(const GeneratedKernels* k) { generated_registry().push_back(k); return (int)generated_registry().size(); }
+const GeneratedKernels* find_generated(unsigned long long signature) {
+  for (const GeneratedKernels* k : generated_registry()) if (k->signature == signature) return k;
+  return nullptr;
+}
+
+static unsigned long long fnv1a(unsigned long long h, const void* data, size_t n) {
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 0x100000001B3ULL; }
+  return h;
+}
+
 // Upload the table blob on first use (plan creation itself needs no GPU).
 int ensure_device(const EqfPlan* cplan) {
   EqfPlan* plan = const_cast<EqfPlan*>(cplan);
@@ -207,6 +223,23 @@ extern "C" int eqf_plan_create(const EqfPathDesc* paths, int32_t n_paths, const 
   plan->smem_bytes_vec_bwd = sizeof(uint32_t) * vec_base + 16;
   plan->smem_bytes_vec_fwd = sizeof(uint32_t) * (vec_base + 2 * (size_t)te * weight_numel) + 32;
   if (plan->smem_bytes_vec_fwd > 220 * 1024) h.vec_ok = 0;  // weight ring does not fit: scalar kernels
+  {  // canonical image hashed exactly like codegen.plan_signature
+    std::vector<int32_t> words;
+    words.push_back(n_in1);
+    for (int b = 0; b < n_in1; ++b) { words.push_back(in1_l[b]); words.push_back(in1_mul[b]); }
+    words.push_back(n_out);
+    for (int g = 0; g < n_out; ++g) { words.push_back(out_l[g]); words.push_back(out_mul[g]); }
+    words.push_back(d_y); words.push_back(weight_numel); words.push_back(n_paths);
+    for (int p = 0; p < n_paths; ++p) {
+      const EqfPathDesc& s = paths[p];
+      const int32_t v[10] = {s.l1, s.l2, s.l3, s.mul, s.in1_block, s.in2_off, s.out_group, s.out_chan_off, s.w_off, s.cg_off};
+      words.insert(words.end(), v, v + 10);
+    }
+    unsigned long long hsh = fnv1a(0xCBF29CE484222325ULL, words.data(), words.size() * sizeof(int32_t));
+    hsh = fnv1a(hsh, cg, (size_t)cg_len * sizeof(float));
+    plan->signature = hsh;
+    plan->gen = find_generated(hsh);
+  }
   *plan_out = plan;
   return EQF_OK;
 }
@@ -220,8 +253,9 @@ extern "C" void eqf_plan_destroy(EqfPlan* plan) {
 extern "C" int eqf_plan_info(const EqfPlan* plan, int32_t* out, int32_t n) {
   if (plan == nullptr || out == nullptr) { set_error("eqf_plan_info: null argument"); return EQF_ERR_INVALID; }
   const PlanHdr& h = plan->hdr;
-  const int32_t vals[12] = {h.n_paths, h.m_size, h.n_wtasks, h.n_xtasks, h.te, (int32_t)plan->smem_bytes, h.blob_words,
-                            h.w_numel, h.vec_ok, h.n_vwtasks, h.n_vxtasks, (int32_t)plan->smem_bytes_vec_fwd};
-  for (int i = 0; i < n && i < 12; ++i) out[i] = vals[i];
+  const int32_t vals[13] = {h.n_paths, h.m_size, h.n_wtasks, h.n_xtasks, h.te, (int32_t)plan->smem_bytes, h.blob_words,
+                            h.w_numel, h.vec_ok, h.n_vwtasks, h.n_vxtasks, (int32_t)plan->smem_bytes_vec_fwd,
+                            plan->gen != nullptr ? 1 : 0};
+  for (int i = 0; i < n && i < 13; ++i) out[i] = vals[i];
   return EQF_OK;
 }

@@ -67,7 +67,17 @@ struct EdgeArgs {
 void set_error(const std::string& msg);
 int check_cuda(cudaError_t err, const char* what);
 int ensure_device(const EqfPlan* plan);  // uploads the table blob on first use
-int dtp_variant();                        // 0 scalar, 1 vec, 2 vec + TMA weights, 3 pipelined v3 (env EQF_DTP_VARIANT)
+// plan-specialised kernels emitted by equiformer_b200/codegen.py (csrc/gen/*.cu), matched by plan hash
+struct GeneratedKernels {
+  unsigned long long signature;
+  const char* tag;
+  int (*forward)(const EqfPlan*, const EdgeArgs&, cudaStream_t);
+  int (*backward)(const EqfPlan*, const EdgeArgs&, bool with_w, cudaStream_t);
+  int (*partial_rows)(const EqfPlan*, long long);
+};
+int register_generated(const GeneratedKernels* k);
+const GeneratedKernels* find_generated(unsigned long long signature);
+int dtp_variant();                        // 0 scalar, 1 vec, 2 vec + TMA weights, 3 pipelined v3, 4 generated (env EQF_DTP_VARIANT)
 int launch_forward_vec(const EqfPlan* plan, const EdgeArgs& a, bool tma, cudaStream_t stream);
 int launch_grad_x_vec(const EqfPlan* plan, const EdgeArgs& a, bool with_w, cudaStream_t stream);
 int launch_forward_v3(const EqfPlan* plan, const EdgeArgs& a, cudaStream_t stream);
@@ -85,4 +95,6 @@ struct EqfPlan {
   size_t smem_bytes = 0;        // dynamic shared memory per CTA (scalar kernels)
   size_t smem_bytes_vec_fwd = 0;  // vector forward (includes the TMA weight ring)
   size_t smem_bytes_vec_bwd = 0;  // vector grad_x / grad_xw
+  unsigned long long signature = 0;            // FNV-1a of the path table (codegen.plan_signature)
+  const eqf::GeneratedKernels* gen = nullptr;  // plan-specialised kernels when the signature is known
 };

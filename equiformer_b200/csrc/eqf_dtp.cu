@@ -426,8 +426,11 @@ using namespace eqf;
 extern "C" int eqf_plan_partial_rows(const EqfPlan* plan, int64_t n_edges) {
   if (plan == nullptr) return EQF_ERR_INVALID;
   // upper bound over the kernel generations that may write the shared-weight partial buffer
-  const int a = grid_for(plan, n_edges), b = backward_v3_grid(plan, n_edges);
-  return a > b ? a : b;
+  int rows = grid_for(plan, n_edges);
+  const int b = backward_v3_grid(plan, n_edges);
+  if (b > rows) rows = b;
+  if (plan->gen != nullptr) { const int c = plan->gen->partial_rows(plan, n_edges); if (c > rows) rows = c; }
+  return rows;
 }
 
 extern "C" int eqf_dtp_forward(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_edges,
@@ -439,6 +442,7 @@ extern "C" int eqf_dtp_forward(const EqfPlan* plan, const EqfEdgeOperands* op, i
     if (out_groups == nullptr || out_groups[g] == nullptr) { set_error("null output group"); return EQF_ERR_INVALID; }
     a.out[g] = out_groups[g];
   }
+  if (plan->gen != nullptr && dtp_variant() == 4) return plan->gen->forward(plan, a, (cudaStream_t)stream);
   if (plan->hdr.vec_ok && dtp_variant() == 3) return launch_forward_v3(plan, a, (cudaStream_t)stream);
   if (plan->hdr.vec_ok && dtp_variant() > 0)
     return launch_forward_vec(plan, a, dtp_variant() == 2 && !a.w_shared, (cudaStream_t)stream);
@@ -470,6 +474,7 @@ extern "C" int eqf_dtp_grad_x(const EqfPlan* plan, const EqfEdgeOperands* op, in
     if (gx_blocks == nullptr || gx_blocks[b] == nullptr) { set_error("null gx block"); return EQF_ERR_INVALID; }
     a.gx[b] = gx_blocks[b];
   }
+  if (plan->gen != nullptr && dtp_variant() == 4) return plan->gen->backward(plan, a, false, (cudaStream_t)stream);
   if (plan->hdr.vec_ok && dtp_variant() == 3) return launch_backward_v3(plan, a, false, (cudaStream_t)stream);
   if (plan->hdr.vec_ok && dtp_variant() > 0) return launch_grad_x_vec(plan, a, false, (cudaStream_t)stream);
   const size_t smem = plan->smem_bytes;
@@ -489,6 +494,7 @@ extern "C" int eqf_dtp_grad_xw(const EqfPlan* plan, const EqfEdgeOperands* op, i
     a.gx[b] = gx_blocks[b];
   }
   a.gw = gw;
+  if (plan->gen != nullptr && dtp_variant() == 4) return plan->gen->backward(plan, a, true, (cudaStream_t)stream);
   if (plan->hdr.vec_ok && dtp_variant() == 3) return launch_backward_v3(plan, a, true, (cudaStream_t)stream);
   if (plan->hdr.vec_ok && dtp_variant() > 0) return launch_grad_x_vec(plan, a, true, (cudaStream_t)stream);
   const size_t smem = plan->smem_bytes;

@@ -319,12 +319,13 @@ __global__ void __launch_bounds__(kThreads) dtp_grad_x_vec_kernel(PlanHdr h, con
 
 // ---------------------------------------------------------------------------------------------- host side
 int dtp_variant() {
-  // EQF_DTP_VARIANT = scalar | vec | tma | v3 (default v3); read once
+  // EQF_DTP_VARIANT = scalar | vec | tma | v3 | gen (default gen: plan-specialised kernels when the plan is known,
+  // otherwise the fastest generic variant, tma); read once
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("EQF_DTP_VARIANT");
-    std::string s = e ? e : "v3";
-    v = (s == "scalar") ? 0 : (s == "vec") ? 1 : (s == "tma") ? 2 : 3;
+    std::string s = e ? e : "gen";
+    v = (s == "scalar") ? 0 : (s == "vec") ? 1 : (s == "v3") ? 3 : (s == "tma") ? 2 : 4;
   }
   return v;
 }

@@ -269,6 +269,16 @@ class GraphAttention(torch.nn.Module):
         self.proj = LinearRS(irreps_attn_heads, self.irreps_node_output)
         self.proj_drop = EquivariantDropout(self.irreps_node_input, drop_prob=proj_drop) if proj_drop != 0.0 else None
 
+        # sep_alpha reads only the 0e entries of the DTP output; when they form the first output group (always, after the
+        # even-first sort) its per-entry weights are one contiguous [K0, mul_alpha] matrix -> a single GEMM
+        self._alpha_single_gemm = False
+        if self.nonlinear_message:
+            plan_out = self.sep_act.dtp.irreps_out
+            n0 = sum(1 for _, ir in plan_out if ir.is_scalar())
+            ins = [(i.i_in1, i.i_in2, i.i_out) for i in self.sep_alpha.tp.instructions]
+            if n0 > 0 and all(ir.is_scalar() for _, ir in plan_out[:n0]) and ins == [(i, 0, 0) for i in range(n0)]:
+                self._alpha_single_gemm = True
+
         if not _is_sorted_simplified(self.irreps_head):
             raise NotImplementedError("irreps_head must be sorted (l ascending, even first) with one entry per irrep")
         self._head_layout = ops.HeadLayout([ir.dim for _, ir in irreps_attn_heads],
@@ -292,7 +302,14 @@ class GraphAttention(torch.nn.Module):
             sa = self.sep_act
             weight = sa.dtp_rad(edge_scalars)                                             # [ref :490]
             f = sa.dtp.tp.planar_depthwise_gathered(graph, m_src, m_dst, edge_attr, weight)   # [ref :487+:491]  DTP #1
-            alpha = self.sep_alpha.planar(_entries_from_groups(f, sa.dtp.tp.plan))[0]     # [ref :492]
+            if self._alpha_single_gemm:                                                   # [ref :492]
+                k0 = f[0].shape[2]
+                w_alpha = self.sep_alpha.tp.weight.view(k0, -1)
+                alpha = ops.matmul_f32(f[0].reshape(E, k0), w_alpha)
+                if len(self.sep_alpha.bias) > 0:
+                    alpha = alpha + self.sep_alpha.bias[0]
+            else:
+                alpha = self.sep_alpha.planar(_entries_from_groups(f, sa.dtp.tp.plan))[0]
             value = sa.lin.planar(f)                                                      # [ref :494]
             value = sa.gate.planar(value) if isinstance(sa.gate, Gate) else [sa.gate(v) for v in value]  # [:495]
             value = _reblock(value, sa.gate.irreps_out, self.sep_value.irreps_node_input)

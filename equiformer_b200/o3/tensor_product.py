@@ -126,15 +126,13 @@ class TensorProduct(torch.nn.Module):
 
     # ------------------------------------------------------------------ weights
     def weight_views(self, weight: Optional[torch.Tensor] = None, yield_instruction: bool = False):
+        from .. import ops
         w = self._get_weights(weight)
         batch = w.shape[:-1]
-        off = 0
-        for idx, ins in enumerate(self.instructions):
-            if not ins.has_weight:
-                continue
-            n = _prod(ins.path_shape)
-            view = w.narrow(-1, off, n).view(batch + ins.path_shape)
-            off += n
+        weighted = [(idx, ins) for idx, ins in enumerate(self.instructions) if ins.has_weight]
+        chunks = ops.split_flat(w, [_prod(ins.path_shape) for _, ins in weighted])
+        for (idx, ins), chunk in zip(weighted, chunks):
+            view = chunk.view(batch + ins.path_shape)
             yield (idx, ins, view) if yield_instruction else view
 
     def _get_weights(self, weight: Optional[torch.Tensor]) -> torch.Tensor:

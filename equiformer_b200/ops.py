@@ -229,8 +229,9 @@ def dtp_grad_x_raw(plan: DtpPlan, gs, y, w) -> List[torch.Tensor]:
 
 def _gw_buffer(plan: DtpPlan, E: int, shared: bool, device) -> torch.Tensor:
     if shared:
+        # upper bound on the CTAs of whichever kernel generation runs; rows a launch does not write must read as zero
         rows = _lib.load().eqf_plan_partial_rows(plan.handle, E)
-        return torch.empty((max(rows, 1), plan.weight_numel), device=device, dtype=torch.float32)
+        return torch.zeros((max(rows, 1), plan.weight_numel), device=device, dtype=torch.float32)
     return torch.empty((E, plan.weight_numel), device=device, dtype=torch.float32)
 
 
@@ -765,6 +766,11 @@ def gemm_backend() -> str:
     return _GEMM_MODE
 
 
+def gemm_backend_forced() -> bool:
+    import os
+    return os.environ.get("EQF_GEMM_FORCE", "0") == "1"
+
+
 def _gemm_operand(t: torch.Tensor):
     """Row-major 2-D operand with 16-byte aligned rows: returns (tensor, leading dimension)."""
     if t.stride(1) != 1 or t.stride(0) % 4 != 0 or t.stride(0) < t.shape[1] or t.data_ptr() % 16 != 0:
@@ -786,7 +792,12 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     if not ok:
         raise ValueError(f"gemm mode {mode}: incompatible shapes {tuple(A.shape)} {tuple(B.shape)}")
     aligned = all(v % 4 == 0 for v in (A.shape[1], B.shape[1], N)) and min(M, N, K) > 0
-    if not (A.is_cuda and A.dtype == torch.float32 and aligned and gemm_backend() == "cutlass"):
+    # measured policy (profiles/r1_gemm_microbench.jsonl): the tcgen05 fast-fp32 kernel wins on the tall edge-level
+    # products (forward / data gradient, 1.3-1.6x over cuBLAS SGEMM); the weight gradient (tiny output, reduction over
+    # all rows) and node-level products are faster in cuBLAS.
+    use_cutlass = (A.is_cuda and A.dtype == torch.float32 and aligned and gemm_backend() == "cutlass"
+                   and (gemm_backend_forced() or (mode != 2 and M >= 16384)))
+    if not use_cutlass:
         if mode == 0:
             return A @ B
         return A @ B.t() if mode == 1 else A.t() @ B
@@ -856,20 +867,89 @@ def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
 # ----------------------------------------------------------------------------- layout conversion
 
 
-def to_planar(x: torch.Tensor, irreps) -> List[torch.Tensor]:
-    """e3nn row layout ``[R, sum mul*(2l+1)]`` -> one ``[R, 2l+1, mul]`` block per irreps entry."""
-    out = []
-    off = 0
-    R = x.shape[0]
-    for mul, ir in irreps:
-        d = ir.dim
+def _to_planar_impl(x: torch.Tensor, dims) -> List[torch.Tensor]:
+    out, off, R = [], 0, x.shape[0]
+    for mul, d in dims:
         blk = x.narrow(1, off, mul * d).reshape(R, mul, d)
-        out.append(blk.transpose(1, 2).contiguous() if d > 1 else blk.reshape(R, 1, mul))
+        out.append(blk.transpose(1, 2).contiguous() if d > 1 else blk.reshape(R, 1, mul).contiguous())
         off += mul * d
     return out
 
 
-def from_planar(blocks: Sequence[torch.Tensor]) -> torch.Tensor:
-    """Inverse of :func:`to_planar` (entries concatenated in order)."""
+def _from_planar_impl(blocks: Sequence[torch.Tensor]) -> torch.Tensor:
     R = blocks[0].shape[0]
     return torch.cat([b.transpose(1, 2).reshape(R, -1) for b in blocks], dim=1)
+
+
+class _ToPlanar(torch.autograd.Function):
+    """Layout change with a hand-written transpose: the backward is ONE concatenation instead of autograd's
+    zero-fill + slice-copy + add per entry (launch-count hygiene on the node path)."""
+
+    @staticmethod
+    def forward(ctx, x, dims):
+        ctx.dims = dims
+        return tuple(_to_planar_impl(x, dims))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        R = next(g for g in gs if g is not None).shape[0]
+        ref = next(g for g in gs if g is not None)
+        gs = [g if g is not None else ref.new_zeros((R, d, mul)) for g, (mul, d) in zip(gs, ctx.dims)]
+        return _FromPlanar.apply(ctx.dims, *gs), None
+
+
+class _FromPlanar(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dims, *blocks):
+        ctx.dims = dims
+        return _from_planar_impl(blocks)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None, *_ToPlanar.apply(g, ctx.dims))
+
+
+def to_planar(x: torch.Tensor, irreps) -> List[torch.Tensor]:
+    """e3nn row layout ``[R, sum mul*(2l+1)]`` -> one ``[R, 2l+1, mul]`` block per irreps entry."""
+    dims = tuple((mul, ir.dim) for mul, ir in irreps)
+    if not x.requires_grad:
+        return _to_planar_impl(x, dims)
+    return list(_ToPlanar.apply(x, dims))
+
+
+def from_planar(blocks: Sequence[torch.Tensor]) -> torch.Tensor:
+    """Inverse of :func:`to_planar` (entries concatenated in order)."""
+    if not any(b.requires_grad for b in blocks):
+        return _from_planar_impl(blocks)
+    dims = tuple((b.shape[2], b.shape[1]) for b in blocks)
+    return _FromPlanar.apply(dims, *blocks)
+
+
+class _SplitFlat(torch.autograd.Function):
+    """Views of consecutive chunks of a flat parameter; backward = one ``cat`` (instead of zero-fill + copy + add per
+    chunk, which is what autograd does for ``narrow``)."""
+
+    @staticmethod
+    def forward(ctx, w, sizes):
+        ctx.sizes = sizes
+        out, off = [], 0
+        for n in sizes:
+            out.append(w.narrow(0, off, n))
+            off += n
+        return tuple(out)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        ref = next(g for g in gs if g is not None)
+        parts = [g.reshape(-1) if g is not None else ref.new_zeros(n) for g, n in zip(gs, ctx.sizes)]
+        return torch.cat(parts), None
+
+
+def split_flat(w: torch.Tensor, sizes: Sequence[int]) -> List[torch.Tensor]:
+    if not w.requires_grad or w.dim() != 1:
+        out, off = [], 0
+        for n in sizes:
+            out.append(w.narrow(-1, off, n))
+            off += n
+        return out
+    return list(_SplitFlat.apply(w, tuple(sizes)))

@@ -134,10 +134,10 @@ class DtpPlan:
         return self._handle
 
     def info(self) -> dict:
-        out = (ctypes.c_int32 * 12)()
-        _lib.check(_lib.load().eqf_plan_info(self.handle, out, 12), "eqf_plan_info")
+        out = (ctypes.c_int32 * 13)()
+        _lib.check(_lib.load().eqf_plan_info(self.handle, out, 13), "eqf_plan_info")
         keys = ("n_paths", "m_size", "n_wtasks", "n_xtasks", "tile_edges", "smem_bytes", "blob_words", "weight_numel",
-                "vec_ok", "n_vwtasks", "n_vxtasks", "smem_bytes_vec_fwd")
+                "vec_ok", "n_vwtasks", "n_vxtasks", "smem_bytes_vec_fwd", "generated")
         return dict(zip(keys, list(out)))
 
     def __del__(self):

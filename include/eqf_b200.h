@@ -74,7 +74,7 @@ int eqf_plan_create(const EqfPathDesc* paths, int32_t n_paths,
                     const float* cg, int32_t cg_len, EqfPlan** plan_out);
 void eqf_plan_destroy(EqfPlan* plan);
 /* host-side introspection: out[0..n) = {n_paths, m_size, n_wtasks, n_xtasks, tile_edges, smem_bytes, blob_words,
- * weight_numel, vec_ok, n_vwtasks, n_vxtasks, smem_bytes_vec_fwd} */
+ * weight_numel, vec_ok, n_vwtasks, n_vxtasks, smem_bytes_vec_fwd, has_generated_kernels} */
 int eqf_plan_info(const EqfPlan* plan, int32_t* out, int32_t n);
 /* number of CTAs eqf_dtp_grad_w launches (rows of the shared-weight partial buffer) */
 int eqf_plan_partial_rows(const EqfPlan* plan, int64_t n_edges);

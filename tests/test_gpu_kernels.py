@@ -162,9 +162,10 @@ def test_unsorted_edges_are_sorted_once(cuda_device):
 
 @pytest.mark.parametrize("M,N,K", [(36000, 352, 224), (108000, 64, 384), (180000, 32, 352), (2304, 128, 128), (36000, 960, 64),
                                    (1001 * 4, 480, 352), (12, 8, 4)])
-def test_fast_fp32_gemm_all_layouts(cuda_device, M, N, K):
+def test_fast_fp32_gemm_all_layouts(cuda_device, M, N, K, monkeypatch):
     """tcgen05 fast-fp32 GEMM (libeqf_gemm.so) vs fp64 matmul: forward, data-grad and weight-grad layouts."""
     from equiformer_b200 import ops
+    monkeypatch.setenv("EQF_GEMM_FORCE", "1")   # exercise the CUTLASS kernel for every layout / size, not just the policy's picks
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g)
     B = torch.randn(K, N, generator=g)

@@ -1,0 +1,21 @@
+#!/bin/bash
+set -u
+TAG=${1:-r1f}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+echo "== kernel tests (gen default)"; timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_golden.py -m gpu -q -x 2>&1 | tail -6
+echo "== kernel tests (tma generic)"; EQF_DTP_VARIANT=tma timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "dtp" 2>&1 | tail -3
+echo "== kernel tests (v3 generic)"; EQF_DTP_VARIANT=v3 timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "dtp" 2>&1 | tail -3
+echo "== dtp microbench"
+for v in gen tma; do
+  EQF_DTP_VARIANT=$v timeout 120 python tools/dtp_microbench.py qm9_l2 32560 20 2>&1 | tail -1 | tee -a $OUT/dtp_microbench.jsonl
+done
+EQF_DTP_VARIANT=gen timeout 120 python tools/dtp_microbench.py qm9_l2 500000 5 2>&1 | tail -1 | tee -a $OUT/dtp_microbench.jsonl
+EQF_DTP_VARIANT=gen timeout 120 python tools/dtp_microbench.py md17_l3 20000 10 2>&1 | tail -1 | tee -a $OUT/dtp_microbench.jsonl
+EQF_DTP_VARIANT=gen timeout 120 python tools/dtp_microbench.py oc20_l1 58000 10 2>&1 | tail -1 | tee -a $OUT/dtp_microbench.jsonl
+echo "== model tests"; timeout 900 python -m pytest tests/test_gpu_model.py -m gpu -q -x 2>&1 | tail -6
+echo "== bench (graph)"; timeout 600 python bench.py --steps 10 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err; echo "rc=$?"; tail -3 $OUT/bench.err; cat $OUT/bench.json
+echo "== bench (graph, torch gemm)"; EQF_GEMM=torch timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_graph_torch.json 2> $OUT/bench_graph_torch.err; echo "rc=$?"; cat $OUT/bench_graph_torch.json | python -c "import json,sys; d=json.load(sys.stdin); print(d['ms_per_step'], d['value'], d['config']['eager_ms_per_step'])"
+echo "== ncu full gen kernels"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:forward_kernel -s 3 -c 1 -o $OUT/prof_gen_forward python tools/dtp_microbench.py qm9_l2 32560 1 > $OUT/ncu_fwd.log 2>&1; echo "rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:backward_kernel -s 3 -c 1 -o $OUT/prof_gen_backward python tools/dtp_microbench.py qm9_l2 32560 1 > $OUT/ncu_bwd.log 2>&1; echo "rc=$?"
