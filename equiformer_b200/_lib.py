@@ -19,7 +19,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC_DIR = PKG_DIR / "csrc"
 INCLUDE_DIR = PKG_DIR.parent / "include"
 LIB_PATH = PKG_DIR / "libeqf_b200.so"
-SOURCES = ("eqf_abi.cu", "eqf_dtp.cu", "eqf_dtp_vec.cu", "eqf_dtp_v3.cu", "eqf_attn.cu")
+SOURCES = ("eqf_abi.cu", "eqf_dtp.cu", "eqf_dtp_vec.cu", "eqf_dtp_v3.cu", "eqf_attn.cu", "eqf_pointwise.cu")
 GEMM_LIB_PATH = PKG_DIR / "libeqf_gemm.so"
 GEMM_SOURCES = ("eqf_gemm.cu",)
 
@@ -50,6 +50,16 @@ class EqfEdgeOperands(ctypes.Structure):
         ("w", c_void_p),
         ("w_shared", c_int32),
         ("g", c_void_p * EQF_MAX_BLOCKS),
+    ]
+
+
+class EqfGateLayout(ctypes.Structure):
+    _fields_ = [
+        ("n_gated", c_int32),
+        ("d", c_int32 * EQF_MAX_BLOCKS),
+        ("C", c_int32 * EQF_MAX_BLOCKS),
+        ("n_alpha", c_int32), ("n_scalars", c_int32), ("n_heads", c_int32),
+        ("c_silu", c_float), ("c_sigmoid", c_float), ("c_slr", c_float), ("slr_slope", c_float),
     ]
 
 
@@ -87,6 +97,16 @@ SIGNATURES = {
                                     c_void_p, c_void_p]),
     "eqf_attn_edge_scale": (c_int32, [POINTER(EqfHeadLayout), c_void_p, POINTER(c_void_p), c_void_p, c_int64,
                                       POINTER(c_void_p), c_void_p]),
+    "eqf_pointwise_rows": (c_int32, [c_int64]),
+    "eqf_ln_silu_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_float, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
+                                  c_void_p]),
+    "eqf_ln_silu_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
+    "eqf_gate_logits_fwd": (c_int32, [POINTER(EqfGateLayout), c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_int64,
+                                      c_void_p, c_void_p, POINTER(c_void_p), c_void_p]),
+    "eqf_gate_logits_bwd": (c_int32, [POINTER(EqfGateLayout), c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p,
+                                      c_void_p, POINTER(c_void_p), c_int64, c_void_p, POINTER(c_void_p), c_void_p,
+                                      c_void_p]),
 }
 
 

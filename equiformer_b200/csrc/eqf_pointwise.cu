@@ -1,0 +1,323 @@
+// eqf_pointwise.cu - fused per-edge pointwise kernels around the GEMMs of the attention path (sm_100a).
+//
+// Reference work replaced:
+//   * RadialProfile's hidden layers (nets/radial_func.py:24-35): LayerNorm -> SiLU on [E, 64] after each Linear -
+//     eager: native_layer_norm + silu (+ in backward layer_norm_backward whose gamma/beta reduction alone cost 240 us
+//     per call on B200, profiles/r1_launches_all_kernels_v2.csv) -> ln_silu_{fwd,bwd}_kernel, one warp per row;
+//   * the middle of GraphAttention.forward (nets/graph_attention_transformer.py:492-495,506-507): bias adds, the Gate
+//     (SiLU on scalars, sigmoid gates x gated irreps, e3nn normalize2mom constants) and the attention logits
+//     (SmoothLeakyReLU . alpha_dot) -> gate_logits_{fwd,bwd}_kernel, one warp per edge;
+// all HBM-streaming: every input element is read once, every output written once.
+#include "eqf_common.cuh"
+
+namespace eqf {
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------ LayerNorm + SiLU
+// y = silu(z), z = (x - mean) * rstd * gamma + beta ; C <= 32 * kMaxPerLane, one warp per row
+constexpr int kMaxPerLane = 8;
+
+__global__ void __launch_bounds__(256) ln_silu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, float eps, long long R, int C,
+                                                          float* __restrict__ y, float* __restrict__ mean,
+                                                          float* __restrict__ rstd) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 8;
+  for (long long r = warp; r < R; r += n_warps) {
+    float v[kMaxPerLane];
+    float s = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxPerLane; ++q) {
+      const int c = lane + 32 * q;
+      v[q] = (c < C) ? __ldg(x + r * C + c) : 0.f;
+      s += v[q];
+    }
+    const float m = wsum(s) / C;
+    float ss = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxPerLane; ++q) {
+      const int c = lane + 32 * q;
+      const float d = (c < C) ? v[q] - m : 0.f;
+      ss += d * d;
+    }
+    const float rs = rsqrtf(wsum(ss) / C + eps);
+#pragma unroll
+    for (int q = 0; q < kMaxPerLane; ++q) {
+      const int c = lane + 32 * q;
+      if (c < C) {
+        const float z = (v[q] - m) * rs * __ldg(gamma + c) + __ldg(beta + c);
+        y[r * C + c] = z * sigmoidf_(z);
+      }
+    }
+    if (lane == 0) { mean[r] = m; rstd[r] = rs; }
+  }
+}
+
+// gx, and per-CTA partial sums of dgamma / dbeta (rows = gridDim.x)
+__global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, const float* __restrict__ mean,
+                                                          const float* __restrict__ rstd, const float* __restrict__ gy,
+                                                          long long R, int C, float* __restrict__ gx,
+                                                          float* __restrict__ dgamma_part, float* __restrict__ dbeta_part) {
+  __shared__ float sg[32 * kMaxPerLane], sb[32 * kMaxPerLane];
+  for (int i = threadIdx.x; i < 32 * kMaxPerLane; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 8;
+  float ag[kMaxPerLane], ab[kMaxPerLane];
+#pragma unroll
+  for (int q = 0; q < kMaxPerLane; ++q) { ag[q] = 0.f; ab[q] = 0.f; }
+  for (long long r = warp; r < R; r += n_warps) {
+    const float m = __ldg(mean + r), rs = __ldg(rstd + r);
+    float xh[kMaxPerLane], gz[kMaxPerLane];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < kMaxPerLane; ++q) {
+      const int c = lane + 32 * q;
+      xh[q] = 0.f; gz[q] = 0.f;
+      if (c < C) {
+        const float g = __ldg(gamma + c);
+        xh[q] = (__ldg(x + r * C + c) - m) * rs;
+        const float z = xh[q] * g + __ldg(beta + c);
+        const float sg_ = sigmoidf_(z);
+        const float dz = __ldg(gy + r * C + c) * (sg_ * (1.f + z * (1.f - sg_)));   // d silu / dz
+        ag[q] += dz * xh[q];
+        ab[q] += dz;
+        gz[q] = dz * g;
+        s1 += gz[q];
+        s2 += gz[q] * xh[q];
+      }
+    }
+    s1 = wsum(s1) / C;
+    s2 = wsum(s2) / C;
+#pragma unroll
+    for (int q = 0; q < kMaxPerLane; ++q) {
+      const int c = lane + 32 * q;
+      if (c < C) gx[r * C + c] = rs * (gz[q] - s1 - xh[q] * s2);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < kMaxPerLane; ++q) {
+    const int c = lane + 32 * q;
+    if (c < C) { atomicAdd(&sg[c], ag[q]); atomicAdd(&sb[c], ab[q]); }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    dgamma_part[(long long)blockIdx.x * C + c] = sg[c];
+    dbeta_part[(long long)blockIdx.x * C + c] = sb[c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ gate + logits
+// Inputs (planar): t0 [E, A0 + S + Gt]  = [alpha pre-activations | scalars | gates]   (biases already added)
+//                  gated blocks g_b [E, d_b, C_b] (b < n_gated), sum_b C_b == Gt, gates consumed in block order
+// Outputs: z [E, H] attention logits; v0 [E, S]; v_b [E, d_b, C_b]
+struct GateArgs {
+  const float* t0;
+  const float* gated[EQF_MAX_BLOCKS];
+  float* v0;
+  float* vout[EQF_MAX_BLOCKS];
+  float* z;
+  const float* alpha_dot;  // [H, A0/H]
+  const float* bias;       // optional [A0 + S + Gt], added to t0 on the fly
+  // backward
+  const float* gz;               // [E, H]
+  const float* gv0;              // [E, S]
+  const float* gvout[EQF_MAX_BLOCKS];
+  float* gt0;                    // [E, A0 + S + Gt]
+  float* ggated[EQF_MAX_BLOCKS];
+  float* gdot_part;              // [grid, A0]
+  int n_gated, A0, S, Gt, H;
+  int d[EQF_MAX_BLOCKS], C[EQF_MAX_BLOCKS];
+  float c_silu, c_sig, c_slr, slope;
+  long long E;
+};
+
+__global__ void __launch_bounds__(256) gate_logits_fwd_kernel(GateArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 8;
+  const int T0 = a.A0 + a.S + a.Gt, ah = a.A0 / a.H;
+  const float k1 = 0.5f * (1.f + a.slope), k2 = 0.5f * (1.f - a.slope);
+  const float* bs = a.bias;
+  for (long long e = warp; e < a.E; e += n_warps) {
+    const float* t = a.t0 + e * T0;
+    // logits: z[h] = sum_k c_slr * slr(t[h*ah + k]) * alpha_dot[h, k]
+    for (int h = 0; h < a.H; ++h) {
+      float acc = 0.f;
+      for (int k = lane; k < ah; k += 32) {
+        const float xv = __ldg(t + h * ah + k) + (bs ? __ldg(bs + h * ah + k) : 0.f);
+        const float s = sigmoidf_(xv);
+        acc = fmaf(a.c_slr * (k1 * xv + k2 * xv * (2.f * s - 1.f)), __ldg(a.alpha_dot + h * ah + k), acc);
+      }
+      acc = wsum(acc);
+      if (lane == 0) a.z[e * a.H + h] = acc;
+    }
+    for (int c = lane; c < a.S; c += 32) {
+      const float xv = __ldg(t + a.A0 + c) + (bs ? __ldg(bs + a.A0 + c) : 0.f);
+      a.v0[e * a.S + c] = a.c_silu * xv * sigmoidf_(xv);
+    }
+    int goff = a.A0 + a.S;
+    for (int b = 0; b < a.n_gated; ++b) {
+      const int C = a.C[b], d = a.d[b];
+      const float* gb = a.gated[b] + e * d * C;
+      float* vb = a.vout[b] + e * d * C;
+      for (int c = lane; c < C; c += 32) {
+        const float gate = a.c_sig * sigmoidf_(__ldg(t + goff + c) + (bs ? __ldg(bs + goff + c) : 0.f));
+        for (int i = 0; i < d; ++i) vb[i * C + c] = __ldg(gb + i * C + c) * gate;
+      }
+      goff += C;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gate_logits_bwd_kernel(GateArgs a) {
+  extern __shared__ float sdot[];  // [A0]
+  for (int i = threadIdx.x; i < a.A0; i += blockDim.x) sdot[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 8;
+  const int T0 = a.A0 + a.S + a.Gt, ah = a.A0 / a.H;
+  const float k1 = 0.5f * (1.f + a.slope), k2 = 0.5f * (1.f - a.slope);
+  const float* bs = a.bias;
+  const bool reg_acc = (ah <= 32 && a.H <= EQF_MAX_HEADS);   // alpha_dot gradient in registers (no shared atomics per edge)
+  float adot[EQF_MAX_HEADS];
+#pragma unroll
+  for (int h = 0; h < EQF_MAX_HEADS; ++h) adot[h] = 0.f;
+  for (long long e = warp; e < a.E; e += n_warps) {
+    const float* t = a.t0 + e * T0;
+    float* gt = a.gt0 + e * T0;
+#pragma unroll
+    for (int h = 0; h < EQF_MAX_HEADS; ++h) {
+      if (h < a.H) {
+        const float gzh = __ldg(a.gz + e * a.H + h);
+        for (int k = lane; k < ah; k += 32) {
+          const float xv = __ldg(t + h * ah + k) + (bs ? __ldg(bs + h * ah + k) : 0.f);
+          const float s = sigmoidf_(xv);
+          const float act = a.c_slr * (k1 * xv + k2 * xv * (2.f * s - 1.f));
+          const float dact = a.c_slr * (k1 + k2 * ((2.f * s - 1.f) + 2.f * xv * s * (1.f - s)));
+          const float ad = __ldg(a.alpha_dot + h * ah + k);
+          gt[h * ah + k] = gzh * ad * dact;
+          if (reg_acc) adot[h] += gzh * act;
+          else atomicAdd(&sdot[h * ah + k], gzh * act);
+        }
+      }
+    }
+    for (int c = lane; c < a.S; c += 32) {
+      const float xv = __ldg(t + a.A0 + c) + (bs ? __ldg(bs + a.A0 + c) : 0.f);
+      const float s = sigmoidf_(xv);
+      gt[a.A0 + c] = __ldg(a.gv0 + e * a.S + c) * a.c_silu * (s * (1.f + xv * (1.f - s)));
+    }
+    int goff = a.A0 + a.S;
+    for (int b = 0; b < a.n_gated; ++b) {
+      const int C = a.C[b], d = a.d[b];
+      const float* gb = a.gated[b] + e * d * C;
+      const float* gvb = a.gvout[b] + e * d * C;
+      float* ggb = a.ggated[b] + e * d * C;
+      for (int c = lane; c < C; c += 32) {
+        const float s = sigmoidf_(__ldg(t + goff + c) + (bs ? __ldg(bs + goff + c) : 0.f));
+        const float gate = a.c_sig * s;
+        float acc = 0.f;
+        for (int i = 0; i < d; ++i) {
+          const float gv = __ldg(gvb + i * C + c);
+          ggb[i * C + c] = gv * gate;
+          acc = fmaf(gv, __ldg(gb + i * C + c), acc);
+        }
+        gt[goff + c] = acc * a.c_sig * s * (1.f - s);
+      }
+      goff += C;
+    }
+  }
+  if (reg_acc && lane < ah) {
+#pragma unroll
+    for (int h = 0; h < EQF_MAX_HEADS; ++h)
+      if (h < a.H) atomicAdd(&sdot[h * ah + lane], adot[h]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.A0; i += blockDim.x) a.gdot_part[(long long)blockIdx.x * a.A0 + i] = sdot[i];
+}
+
+static int pointwise_grid(long long rows) {
+  long long blocks = (rows + 7) / 8;
+  const long long cap = 148LL * 8;
+  if (blocks > cap) blocks = cap;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace eqf
+
+using namespace eqf;
+
+extern "C" int eqf_pointwise_rows(int64_t rows) { return pointwise_grid(rows); }
+
+extern "C" int eqf_ln_silu_fwd(const float* x, const float* gamma, const float* beta, float eps, int64_t R, int32_t C,
+                               float* y, float* mean, float* rstd, void* stream) {
+  if (R == 0) return EQF_OK;
+  if (!x || !gamma || !beta || !y || !mean || !rstd) { set_error("eqf_ln_silu_fwd: null pointer"); return EQF_ERR_INVALID; }
+  if (C < 1 || C > 32 * kMaxPerLane) { set_error("eqf_ln_silu: C must be in 1..256"); return EQF_ERR_UNSUPPORTED; }
+  ln_silu_fwd_kernel<<<pointwise_grid(R), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, R, C, y, mean, rstd);
+  return check_cuda(cudaGetLastError(), "ln_silu_fwd_kernel launch");
+}
+
+extern "C" int eqf_ln_silu_bwd(const float* x, const float* gamma, const float* beta, const float* mean, const float* rstd,
+                               const float* gy, int64_t R, int32_t C, float* gx, float* dgamma_part, float* dbeta_part,
+                               void* stream) {
+  if (R == 0) return EQF_OK;
+  if (!x || !gamma || !beta || !mean || !rstd || !gy || !gx || !dgamma_part || !dbeta_part) {
+    set_error("eqf_ln_silu_bwd: null pointer"); return EQF_ERR_INVALID;
+  }
+  if (C < 1 || C > 32 * kMaxPerLane) { set_error("eqf_ln_silu: C must be in 1..256"); return EQF_ERR_UNSUPPORTED; }
+  ln_silu_bwd_kernel<<<pointwise_grid(R), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, mean, rstd, gy, R, C, gx,
+                                                                          dgamma_part, dbeta_part);
+  return check_cuda(cudaGetLastError(), "ln_silu_bwd_kernel launch");
+}
+
+static int fill_gate(const EqfGateLayout* lay, GateArgs& a) {
+  if (lay == nullptr) { set_error("null gate layout"); return EQF_ERR_INVALID; }
+  if (lay->n_gated < 0 || lay->n_gated > EQF_MAX_BLOCKS || lay->n_heads < 1 || lay->n_alpha % lay->n_heads != 0) {
+    set_error("bad gate layout"); return EQF_ERR_INVALID;
+  }
+  a.n_gated = lay->n_gated; a.A0 = lay->n_alpha; a.S = lay->n_scalars; a.H = lay->n_heads;
+  a.Gt = 0;
+  for (int b = 0; b < lay->n_gated; ++b) { a.d[b] = lay->d[b]; a.C[b] = lay->C[b]; a.Gt += lay->C[b]; }
+  a.c_silu = lay->c_silu; a.c_sig = lay->c_sigmoid; a.c_slr = lay->c_slr; a.slope = lay->slr_slope;
+  return EQF_OK;
+}
+
+extern "C" int eqf_gate_logits_fwd(const EqfGateLayout* lay, const float* t0, const float* bias,
+                                   const float* const* gated, const float* alpha_dot, int64_t n_edges, float* z,
+                                   float* v0, float* const* vout, void* stream) {
+  GateArgs a;
+  int rc = fill_gate(lay, a);
+  if (rc != EQF_OK || n_edges == 0) return rc;
+  if (!t0 || !alpha_dot || !z || !v0) { set_error("eqf_gate_logits_fwd: null pointer"); return EQF_ERR_INVALID; }
+  a.t0 = t0; a.bias = bias; a.alpha_dot = alpha_dot; a.z = z; a.v0 = v0; a.E = n_edges;
+  for (int b = 0; b < a.n_gated; ++b) {
+    if (!gated || !vout || !gated[b] || !vout[b]) { set_error("eqf_gate_logits_fwd: null block"); return EQF_ERR_INVALID; }
+    a.gated[b] = gated[b]; a.vout[b] = vout[b];
+  }
+  gate_logits_fwd_kernel<<<pointwise_grid(n_edges), 256, 0, (cudaStream_t)stream>>>(a);
+  return check_cuda(cudaGetLastError(), "gate_logits_fwd_kernel launch");
+}
+
+extern "C" int eqf_gate_logits_bwd(const EqfGateLayout* lay, const float* t0, const float* bias,
+                                   const float* const* gated, const float* alpha_dot, const float* gz, const float* gv0,
+                                   const float* const* gvout, int64_t n_edges, float* gt0, float* const* ggated,
+                                   float* gdot_part, void* stream) {
+  GateArgs a;
+  int rc = fill_gate(lay, a);
+  if (rc != EQF_OK || n_edges == 0) return rc;
+  if (!t0 || !alpha_dot || !gz || !gv0 || !gt0 || !gdot_part) { set_error("eqf_gate_logits_bwd: null pointer"); return EQF_ERR_INVALID; }
+  a.t0 = t0; a.bias = bias; a.alpha_dot = alpha_dot; a.gz = gz; a.gv0 = gv0; a.gt0 = gt0; a.gdot_part = gdot_part; a.E = n_edges;
+  for (int b = 0; b < a.n_gated; ++b) {
+    if (!gated || !gvout || !ggated || !gated[b] || !gvout[b] || !ggated[b]) { set_error("eqf_gate_logits_bwd: null block"); return EQF_ERR_INVALID; }
+    a.gated[b] = gated[b]; a.gvout[b] = gvout[b]; a.ggated[b] = ggated[b];
+  }
+  gate_logits_bwd_kernel<<<pointwise_grid(n_edges), 256, a.A0 * sizeof(float), (cudaStream_t)stream>>>(a);
+  return check_cuda(cudaGetLastError(), "gate_logits_bwd_kernel launch");
+}

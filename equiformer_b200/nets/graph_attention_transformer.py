@@ -279,6 +279,24 @@ class GraphAttention(torch.nn.Module):
             if n0 > 0 and all(ir.is_scalar() for _, ir in plan_out[:n0]) and ins == [(i, 0, 0) for i in range(n0)]:
                 self._alpha_single_gemm = True
 
+        # fused bias + Gate + logits kernel (ops.GateLogits) when the layer has the canonical structure:
+        # lin outputs [(scalars+gates) x 0e | gated entries], one instruction per output entry, single-GEMM alpha
+        self._gate_layout = None
+        if self.nonlinear_message and self._alpha_single_gemm and isinstance(self.sep_act.gate, Gate):
+            gate, lin = self.sep_act.gate, self.sep_act.lin
+            ins = [(i.i_in1, i.i_out) for i in lin.tp.instructions]
+            n_out = len(lin.irreps_out)
+            canonical = (len(gate.irreps_scalars) == 1 and ins == [(i, i) for i in range(n_out)]
+                         and lin.irreps_out[0].ir.is_scalar()
+                         and lin.irreps_out[0].mul == gate.irreps_scalars.dim + gate.irreps_gates.dim
+                         and [m for m, _ in lin.irreps_out[1:]] == [m for m, _ in gate.irreps_gated]
+                         and len(lin.bias) == 1 and len(self.sep_alpha.bias) == 1 and mul_alpha_head <= 32)
+            if canonical:
+                self._gate_layout = ops.GateLayout(
+                    mul_alpha, gate.irreps_scalars.dim, num_heads, [ir.dim for _, ir in gate.irreps_gated],
+                    [m for m, _ in gate.irreps_gated], gate.act_scalars.acts[0].cst, gate.act_gates.acts[0].cst,
+                    self.alpha_act.acts[0].cst, 0.2)
+
         if not _is_sorted_simplified(self.irreps_head):
             raise NotImplementedError("irreps_head must be sorted (l ascending, even first) with one entry per irrep")
         self._head_layout = ops.HeadLayout([ir.dim for _, ir in irreps_attn_heads],
@@ -302,7 +320,24 @@ class GraphAttention(torch.nn.Module):
             sa = self.sep_act
             weight = sa.dtp_rad(edge_scalars)                                             # [ref :490]
             f = sa.dtp.tp.planar_depthwise_gathered(graph, m_src, m_dst, edge_attr, weight)   # [ref :487+:491]  DTP #1
-            if self._alpha_single_gemm:                                                   # [ref :492]
+            logits = None
+            if self._gate_layout is not None and ops.fused_ok(f[0]):
+                # one GEMM for alpha and the 0e part of the value linear ([K0, A0 | S + Gates]), then ONE kernel for
+                # the bias adds, the gate and the attention logits                           [ref :492-495, :506-507]
+                lay = self._gate_layout
+                k0 = f[0].shape[2]
+                blocks = {io: (W, c) for _i1, _i2, io, W, c in sa.lin.tp.linear_weight_blocks()}
+                w_cat = torch.cat([self.sep_alpha.tp.weight.view(k0, -1), blocks[0][0][:, 0, :]], dim=1)
+                t0 = ops.matmul_f32(f[0].reshape(E, k0), w_cat)
+                bias = torch.cat([self.sep_alpha.bias[0], sa.lin.bias[0]])
+                gated = [ops.matmul_f32(f[g].reshape(E * f[g].shape[1], f[g].shape[2]), blocks[g][0][:, 0, :])
+                         .view(E, f[g].shape[1], -1) for g in range(1, len(f))]
+                logits, v0, *vs = ops.GateLogits.apply(lay, t0, bias, self.alpha_dot.view(H, A), *gated)
+                value = _reblock([v0.view(E, 1, -1), *vs], sa.gate.irreps_out, self.sep_value.irreps_node_input)
+                f2 = self.sep_value.dtp.planar(value, edge_attr, None)                    # [ref :496]  DTP #2
+                value = self.sep_value.lin.planar(f2)
+                alpha = None
+            elif self._alpha_single_gemm:                                                 # [ref :492]
                 k0 = f[0].shape[2]
                 w_alpha = self.sep_alpha.tp.weight.view(k0, -1)
                 alpha = ops.matmul_f32(f[0].reshape(E, k0), w_alpha)
@@ -310,14 +345,16 @@ class GraphAttention(torch.nn.Module):
                     alpha = alpha + self.sep_alpha.bias[0]
             else:
                 alpha = self.sep_alpha.planar(_entries_from_groups(f, sa.dtp.tp.plan))[0]
-            value = sa.lin.planar(f)                                                      # [ref :494]
-            value = sa.gate.planar(value) if isinstance(sa.gate, Gate) else [sa.gate(v) for v in value]  # [:495]
-            value = _reblock(value, sa.gate.irreps_out, self.sep_value.irreps_node_input)
-            f2 = self.sep_value.dtp.planar(value, edge_attr, None)                        # [ref :496]  DTP #2
-            value = self.sep_value.lin.planar(f2)
-            alpha = alpha.reshape(E, H, A)                                                # [ref :493]
+            if logits is None:
+                value = sa.lin.planar(f)                                                  # [ref :494]
+                value = sa.gate.planar(value) if isinstance(sa.gate, Gate) else [sa.gate(v) for v in value]  # [:495]
+                value = _reblock(value, sa.gate.irreps_out, self.sep_value.irreps_node_input)
+                f2 = self.sep_value.dtp.planar(value, edge_attr, None)                    # [ref :496]  DTP #2
+                value = self.sep_value.lin.planar(f2)
+                alpha = alpha.reshape(E, H, A)                                            # [ref :493]
         else:
             weight = self.sep.dtp_rad(edge_scalars)
+            logits = None
             out = self.sep.lin.planar(self.sep.dtp.tp.planar_depthwise_gathered(graph, m_src, m_dst, edge_attr, weight))  # [ref :487+:499]
             first = out[0]                                                                # 0e entry: alpha | value scalars
             if first.shape[1] != 1:
@@ -328,7 +365,7 @@ class GraphAttention(torch.nn.Module):
             value = ([per_head.narrow(2, A, rest).reshape(E, 1, H * rest)] if rest > 0 else []) + list(out[1:])
 
         # logits -> segment softmax -> weighted aggregation                               [ref :506-513]
-        z = (self.alpha_act(alpha) * self.alpha_dot).sum(dim=-1)
+        z = logits if logits is not None else (self.alpha_act(alpha) * self.alpha_dot).sum(dim=-1)
         attn = ops.segment_softmax(z.contiguous(), graph)
         if self.alpha_dropout is not None:
             attn = self.alpha_dropout(attn)

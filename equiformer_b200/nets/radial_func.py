@@ -35,8 +35,20 @@ class RadialProfile(nn.Module):
     def forward(self, f_in):
         from .. import ops
         out = f_in
-        for layer in self.net:   # same modules/keys as nn.Sequential; Linear layers go through the tcgen05 GEMM on CUDA
-            out = ops.linear_f32(out, layer.weight, layer.bias) if isinstance(layer, nn.Linear) else layer(out)
+        mods = list(self.net)    # same modules / state_dict keys as nn.Sequential; executed with fused kernels on CUDA
+        i = 0
+        while i < len(mods):
+            m = mods[i]
+            if isinstance(m, nn.Linear):
+                out = ops.linear_f32(out, m.weight, m.bias)
+                i += 1
+            elif isinstance(m, nn.LayerNorm) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.SiLU) \
+                    and m.elementwise_affine and len(m.normalized_shape) == 1:
+                out = ops.ln_silu(out, m.weight, m.bias, m.eps)      # LayerNorm + SiLU in one pass
+                i += 2
+            else:
+                out = m(out)
+                i += 1
         if self.offset is not None:
             out = out + self.offset.reshape(1, -1)
         return out

@@ -864,6 +864,196 @@ def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     return torch.nn.functional.linear(x, weight, bias)
 
 
+# ----------------------------------------------------------------------------- fused pointwise ops
+
+
+def _higher_order_grads(fn, inputs, grad_outputs):
+    """Backward of a fused op under ``create_graph``: rebuild the op from differentiable torch ops on the saved inputs
+    and differentiate that (slow path, used only for second-order training such as MD17 force losses)."""
+    with torch.enable_grad():
+        outs = fn(*inputs)
+        outs = outs if isinstance(outs, (tuple, list)) else (outs,)
+        pairs = [(o, g) for o, g in zip(outs, grad_outputs) if g is not None and o.requires_grad]
+        need = [t for t in inputs if isinstance(t, torch.Tensor) and t.requires_grad]
+        grads = torch.autograd.grad([o for o, _ in pairs], need, [g for _, g in pairs], create_graph=True,
+                                    allow_unused=True)
+    it = iter(grads)
+    return [next(it) if (isinstance(t, torch.Tensor) and t.requires_grad) else None for t in inputs]
+
+
+def ln_silu_torch(x, gamma, beta, eps):
+    return torch.nn.functional.silu(torch.nn.functional.layer_norm(x, x.shape[-1:], gamma, beta, eps))
+
+
+def ln_silu_fwd_raw(x, gamma, beta, eps):
+    x = _require_cuda(x, "ln_silu x")
+    R, C = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(R, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(R, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device), _kernel("ln_silu_fwd", 8 * x.numel()):
+        rc = _lib.load().eqf_ln_silu_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, R, C, y.data_ptr(),
+                                         mean.data_ptr(), rstd.data_ptr(), _stream())
+    _lib.check(rc, "eqf_ln_silu_fwd")
+    return y, mean, rstd
+
+
+def ln_silu_bwd_raw(x, gamma, beta, mean, rstd, gy):
+    gy = _require_cuda(gy, "ln_silu gy")
+    R, C = x.shape
+    rows = _lib.load().eqf_pointwise_rows(R)
+    gx = torch.empty_like(x)
+    dg = torch.empty((rows, C), device=x.device, dtype=torch.float32)
+    db = torch.empty((rows, C), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device), _kernel("ln_silu_bwd", 12 * x.numel()):
+        rc = _lib.load().eqf_ln_silu_bwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                         gy.data_ptr(), R, C, gx.data_ptr(), dg.data_ptr(), db.data_ptr(), _stream())
+    _lib.check(rc, "eqf_ln_silu_bwd")
+    return gx, dg.sum(0), db.sum(0)
+
+
+class LnSilu(torch.autograd.Function):
+    """``silu(layer_norm(x))`` on ``[rows, C]`` (RadialProfile hidden layers, ref radial_func.py:24-35)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps: float):
+        y, mean, rstd = ln_silu_fwd_raw(x, gamma, beta, eps)
+        ctx.eps = eps
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        if torch.is_grad_enabled():
+            gx, gg, gb = _higher_order_grads(lambda a, b, c: ln_silu_torch(a, b, c, ctx.eps), (x, gamma, beta), (gy,))
+            return gx, gg, gb, None
+        gx, gg, gb = ln_silu_bwd_raw(x, gamma, beta, mean, rstd, gy)
+        return gx, gg, gb, None
+
+
+FUSED_ON_ANY_DEVICE = False   # tests/_emulation.py flips this so the fused Functions are exercised on CPU stand-ins
+
+
+def fused_ok(t: torch.Tensor) -> bool:
+    return FUSED_ON_ANY_DEVICE or (t.is_cuda and t.dtype == torch.float32)
+
+
+def ln_silu(x, gamma, beta, eps: float = 1e-5):
+    if fused_ok(x) and x.dim() == 2 and x.shape[1] <= 256:
+        return LnSilu.apply(x.contiguous(), gamma, beta, eps)
+    return ln_silu_torch(x, gamma, beta, eps)
+
+
+class GateLayout:
+    """Static description of the fused gate + logits op (see ``eqf_gate_logits_fwd`` in include/eqf_b200.h)."""
+
+    def __init__(self, n_alpha: int, n_scalars: int, n_heads: int, ds: Sequence[int], Cs: Sequence[int],
+                 c_silu: float, c_sigmoid: float, c_slr: float, slope: float):
+        if len(ds) > _lib.EQF_MAX_BLOCKS or n_heads > _lib.EQF_MAX_HEADS or n_alpha % n_heads:
+            raise NotImplementedError("gate layout exceeds kernel limits")
+        self.n_alpha, self.n_scalars, self.n_heads = n_alpha, n_scalars, n_heads
+        self.ds, self.Cs = tuple(ds), tuple(Cs)
+        self.c_silu, self.c_sigmoid, self.c_slr, self.slope = c_silu, c_sigmoid, c_slr, slope
+        c = _lib.EqfGateLayout()
+        c.n_gated, c.n_alpha, c.n_scalars, c.n_heads = len(ds), n_alpha, n_scalars, n_heads
+        for i, (d, C) in enumerate(zip(ds, Cs)):
+            c.d[i], c.C[i] = d, C
+        c.c_silu, c.c_sigmoid, c.c_slr, c.slr_slope = c_silu, c_sigmoid, c_slr, slope
+        self.c = c
+
+    @property
+    def width(self) -> int:
+        return self.n_alpha + self.n_scalars + sum(self.Cs)
+
+
+def gate_logits_torch(lay: GateLayout, t0, bias, alpha_dot, *gated):
+    """Differentiable torch statement of the fused op (higher-order path and the CPU test stand-in)."""
+    t = t0 if bias is None else t0 + bias
+    E, H, A0, S = t.shape[0], lay.n_heads, lay.n_alpha, lay.n_scalars
+    a = t[:, :A0].reshape(E, H, A0 // H)
+    slr = 0.5 * (1 + lay.slope) * a + 0.5 * (1 - lay.slope) * a * (2 * torch.sigmoid(a) - 1)
+    z = (lay.c_slr * slr * alpha_dot.reshape(1, H, A0 // H)).sum(-1)
+    v0 = lay.c_silu * torch.nn.functional.silu(t[:, A0:A0 + S])
+    gates = lay.c_sigmoid * torch.sigmoid(t[:, A0 + S:])
+    outs, off = [], 0
+    for g, C in zip(gated, lay.Cs):
+        outs.append(g * gates[:, off:off + C].unsqueeze(1))
+        off += C
+    return (z, v0, *outs)
+
+
+def gate_logits_fwd_raw(lay: GateLayout, t0, bias, alpha_dot, gated):
+    t0 = _require_cuda(t0, "gate t0")
+    E = t0.shape[0]
+    if t0.shape[1] != lay.width:
+        raise ValueError(f"gate input must be [E, {lay.width}]")
+    gated = [_require_cuda(g, "gated block") for g in gated]
+    z = torch.empty((E, lay.n_heads), device=t0.device, dtype=torch.float32)
+    v0 = torch.empty((E, lay.n_scalars), device=t0.device, dtype=torch.float32)
+    vout = [torch.empty_like(g) for g in gated]
+    nbytes = 4 * (t0.numel() + 2 * sum(g.numel() for g in gated) + v0.numel() + z.numel())
+    with torch.cuda.device(t0.device), _kernel("gate_logits_fwd", nbytes):
+        rc = _lib.load().eqf_gate_logits_fwd(ctypes.byref(lay.c), t0.data_ptr(),
+                                             bias.data_ptr() if bias is not None else None, _ptr_array(gated),
+                                             alpha_dot.data_ptr(), E, z.data_ptr(), v0.data_ptr(), _ptr_array(vout),
+                                             _stream())
+    _lib.check(rc, "eqf_gate_logits_fwd")
+    return z, v0, vout
+
+
+def gate_logits_bwd_raw(lay: GateLayout, t0, bias, alpha_dot, gated, gz, gv0, gvout):
+    E = t0.shape[0]
+    gz, gv0 = _require_cuda(gz, "gz"), _require_cuda(gv0, "gv0")
+    gvout = [_require_cuda(g, "gvout") for g in gvout]
+    rows = _lib.load().eqf_pointwise_rows(E)
+    gt0 = torch.empty_like(t0)
+    ggated = [torch.empty_like(g) for g in gated]
+    gdot = torch.empty((rows, lay.n_alpha), device=t0.device, dtype=torch.float32)
+    nbytes = 4 * (2 * t0.numel() + 3 * sum(g.numel() for g in gated) + gv0.numel() + gz.numel())
+    with torch.cuda.device(t0.device), _kernel("gate_logits_bwd", nbytes):
+        rc = _lib.load().eqf_gate_logits_bwd(ctypes.byref(lay.c), t0.data_ptr(),
+                                             bias.data_ptr() if bias is not None else None, _ptr_array(gated),
+                                             alpha_dot.data_ptr(), gz.data_ptr(), gv0.data_ptr(), _ptr_array(gvout), E,
+                                             gt0.data_ptr(), _ptr_array(ggated), gdot.data_ptr(), _stream())
+    _lib.check(rc, "eqf_gate_logits_bwd")
+    return gt0, ggated, gdot.sum(0)
+
+
+class GateLogits(torch.autograd.Function):
+    """(z, v0, *vout) = fused bias + Gate + attention logits (ref :492-495, :506-507).  apply(lay, t0, bias, alpha_dot, *gated)."""
+
+    @staticmethod
+    def forward(ctx, lay: GateLayout, t0, bias, alpha_dot, *gated):
+        ctx.lay = lay
+        ctx.has_bias = bias is not None
+        alpha_dot = alpha_dot.contiguous()
+        z, v0, vout = gate_logits_fwd_raw(lay, t0, bias, alpha_dot, gated)
+        ctx.save_for_backward(t0, alpha_dot, *gated, *([bias] if bias is not None else []))
+        return (z, v0, *vout)
+
+    @staticmethod
+    def backward(ctx, gz, gv0, *gvout):
+        lay = ctx.lay
+        saved = ctx.saved_tensors
+        n = len(lay.ds)
+        t0, alpha_dot, gated = saved[0], saved[1], saved[2:2 + n]
+        bias = saved[2 + n] if ctx.has_bias else None
+        zeros = lambda like: torch.zeros_like(like)
+        gz = gz if gz is not None else t0.new_zeros((t0.shape[0], lay.n_heads))
+        gv0 = gv0 if gv0 is not None else t0.new_zeros((t0.shape[0], lay.n_scalars))
+        gvout = [g if g is not None else zeros(b) for g, b in zip(gvout, gated)]
+        if torch.is_grad_enabled():
+            ins = (t0, bias, alpha_dot, *gated)
+            fn = lambda t, b, ad, *gs: gate_logits_torch(lay, t, b, ad, *gs)
+            grads = _higher_order_grads(fn, ins, (gz, gv0, *gvout))
+            return (None, *grads)
+        gt0, ggated, gdot = gate_logits_bwd_raw(lay, t0, bias, alpha_dot, gated, gz.contiguous(), gv0.contiguous(),
+                                                [g.contiguous() for g in gvout])
+        gbias = gt0.sum(0) if bias is not None else None
+        return (None, gt0, gbias, gdot.view_as(alpha_dot), *ggated)
+
+
 # ----------------------------------------------------------------------------- layout conversion
 
 

@@ -132,6 +132,33 @@ int eqf_attn_edge_dot(const EqfHeadLayout* lay, const float* const* V, const flo
 int eqf_attn_edge_scale(const EqfHeadLayout* lay, const float* alpha, const float* const* G,
                         const int64_t* dst, int64_t n_edges, float* const* out, void* stream);
 
+/* ---- fused pointwise kernels around the GEMMs -------------------------------------------------------------------
+ * y = silu(LayerNorm(x)) on [R, C] rows (C <= 256): the hidden layers of RadialProfile (nets/radial_func.py:24-35).
+ * The backward returns per-CTA partial sums of d gamma / d beta in [eqf_pointwise_rows(R), C] buffers.            */
+int eqf_pointwise_rows(int64_t rows);
+int eqf_ln_silu_fwd(const float* x, const float* gamma, const float* beta, float eps, int64_t R, int32_t C,
+                    float* y, float* mean, float* rstd, void* stream);
+int eqf_ln_silu_bwd(const float* x, const float* gamma, const float* beta, const float* mean, const float* rstd,
+                    const float* gy, int64_t R, int32_t C, float* gx, float* dgamma_part, float* dbeta_part,
+                    void* stream);
+
+/* Gate + attention logits of GraphAttention.forward (graph_attention_transformer.py:492-495, 506-507) in one pass:
+ *   t0[e] = [alpha | scalars | gates] pre-activations (+ optional bias), gated[b] planar blocks [E, d, C];
+ *   z[e,h] = sum_k c_slr * SmoothLeakyReLU(alpha[e,h,k]) * alpha_dot[h,k];  v0 = c_silu * silu(scalars);
+ *   vout[b][e,i,c] = gated[b][e,i,c] * c_sigmoid * sigmoid(gate[c]).  Constants are e3nn's normalize2mom factors. */
+typedef struct {
+  int32_t n_gated;
+  int32_t d[EQF_MAX_BLOCKS];
+  int32_t C[EQF_MAX_BLOCKS];
+  int32_t n_alpha, n_scalars, n_heads;
+  float c_silu, c_sigmoid, c_slr, slr_slope;
+} EqfGateLayout;
+int eqf_gate_logits_fwd(const EqfGateLayout* lay, const float* t0, const float* bias, const float* const* gated,
+                        const float* alpha_dot, int64_t n_edges, float* z, float* v0, float* const* vout, void* stream);
+int eqf_gate_logits_bwd(const EqfGateLayout* lay, const float* t0, const float* bias, const float* const* gated,
+                        const float* alpha_dot, const float* gz, const float* gv0, const float* const* gvout,
+                        int64_t n_edges, float* gt0, float* const* ggated, float* gdot_part, void* stream);
+
 /* ---- libeqf_gemm.so: fp32-accurate tensor-core GEMM for the per-degree channel-mixing linears ------------------
  * Replaces the cuBLAS SGEMMs behind LinearRS (nets/tensor_product_rescale.py:165-174) on planar buffers.
  *   mode 0: C[M,N] = A[M,K] B[K,N]          (forward;   A, B row-major with leading dims lda, ldb)

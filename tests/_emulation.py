@@ -135,7 +135,35 @@ def gemm_raw(mode, A, B):
     return A @ B.t() if mode == 1 else A.t() @ B
 
 
-_PATCHED = ["gemm_raw", "dtp_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
+def ln_silu_fwd_raw(x, gamma, beta, eps):
+    mean = x.mean(-1)
+    rstd = (x.var(-1, unbiased=False) + eps).rsqrt()
+    return ops.ln_silu_torch(x, gamma, beta, eps), mean, rstd
+
+
+def ln_silu_bwd_raw(x, gamma, beta, mean, rstd, gy):
+    with torch.enable_grad():
+        xs = [t.detach().requires_grad_(True) for t in (x, gamma, beta)]
+        y = torch.nn.functional.silu(torch.nn.functional.layer_norm(xs[0], xs[0].shape[-1:], xs[1], xs[2], 1e-5))
+        return torch.autograd.grad(y, xs, gy)
+
+
+def gate_logits_fwd_raw(lay, t0, bias, alpha_dot, gated):
+    z, v0, *vout = ops.gate_logits_torch(lay, t0, bias, alpha_dot, *gated)
+    return z, v0, list(vout)
+
+
+def gate_logits_bwd_raw(lay, t0, bias, alpha_dot, gated, gz, gv0, gvout):
+    with torch.enable_grad():
+        t = t0.detach().requires_grad_(True)
+        ad = alpha_dot.detach().requires_grad_(True)
+        gs = [g.detach().requires_grad_(True) for g in gated]
+        outs = ops.gate_logits_torch(lay, t, bias.detach() if bias is not None else None, ad, *gs)
+        grads = torch.autograd.grad(outs, [t, ad, *gs], [gz, gv0, *gvout])
+    return grads[0], list(grads[2:]), grads[1].reshape(-1)
+
+
+_PATCHED = ["ln_silu_fwd_raw", "ln_silu_bwd_raw", "gate_logits_fwd_raw", "gate_logits_bwd_raw", "gemm_raw", "dtp_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
             "seg_softmax_raw", "attn_aggregate_raw", "attn_edge_dot_raw", "attn_edge_scale_raw"]
 
 
@@ -151,7 +179,9 @@ def emulated_kernels():
             setattr(ops, name, g[name])
         ops._require_cuda = lambda t, name: t.contiguous()
         ops._require_index = lambda t, name: t.to(torch.int64).contiguous()
+        ops.FUSED_ON_ANY_DEVICE = True
         yield
     finally:
+        ops.FUSED_ON_ANY_DEVICE = False
         for name, fn in saved.items():
             setattr(ops, name, fn)

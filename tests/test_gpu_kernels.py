@@ -226,3 +226,50 @@ def test_dtp_gather_fused_and_csc_aggregate(cuda_device, with_b):
     for a, ref in zip(by_src, gx_ref):
         exp = torch.zeros(n_nodes, *ref.shape[1:], dtype=torch.float64).index_add_(0, src, ref)
         assert rel_err(a, exp) < TOL
+
+
+@pytest.mark.parametrize("R,C", [(1, 64), (1000, 64), (4097, 96), (33, 256)])
+def test_ln_silu_fused(cuda_device, R, C):
+    """silu(LayerNorm(x)) forward and (gx, dgamma, dbeta) backward vs fp64 torch (RadialProfile hidden layers)."""
+    from equiformer_b200 import ops
+    g = torch.Generator().manual_seed(R + C)
+    x = torch.randn(R, C, generator=g) * 2 + 0.3
+    gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    gy = torch.randn(R, C, generator=g)
+    d = lambda t: t.to(cuda_device)
+    y, mean, rstd = ops.ln_silu_fwd_raw(d(x), d(gamma), d(beta), 1e-5)
+    xs = [t.double().requires_grad_(True) for t in (x, gamma, beta)]
+    ref = ops.ln_silu_torch(xs[0], xs[1], xs[2], 1e-5)
+    assert rel_err(y, ref) < TOL
+    gx, gg, gb = ops.ln_silu_bwd_raw(d(x), d(gamma), d(beta), mean, rstd, d(gy))
+    rx, rg, rb = torch.autograd.grad(ref, xs, gy.double())
+    assert rel_err(gx, rx) < 5e-5 and rel_err(gg, rg) < 5e-5 and rel_err(gb, rb) < 5e-5
+
+
+@pytest.mark.parametrize("cfg", [dict(A0=128, S=128, H=4, ds=(3, 5), Cs=(64, 32)), dict(A0=256, S=256, H=8, ds=(3,), Cs=(128,)),
+                                 dict(A0=128, S=128, H=4, ds=(3, 5, 7), Cs=(64, 64, 32))])
+def test_gate_logits_fused(cuda_device, cfg):
+    """bias + Gate + attention logits in one kernel (ref :492-495, :506-507) vs the fp64 torch statement, fwd and bwd."""
+    from equiformer_b200 import ops
+    lay = ops.GateLayout(cfg["A0"], cfg["S"], cfg["H"], cfg["ds"], cfg["Cs"], 1.6791767923989418, 1.8467055342154763,
+                         1.531320475574866, 0.2)
+    E = 777
+    g = torch.Generator().manual_seed(1)
+    t0 = torch.randn(E, lay.width, generator=g)
+    bias = torch.randn(lay.width, generator=g) * 0.3
+    ad = torch.randn(cfg["H"], cfg["A0"] // cfg["H"], generator=g)
+    gated = [torch.randn(E, d_, c, generator=g) for d_, c in zip(cfg["ds"], cfg["Cs"])]
+    d = lambda t: t.to(cuda_device)
+    z, v0, vout = ops.gate_logits_fwd_raw(lay, d(t0), d(bias), d(ad), [d(t) for t in gated])
+    ins = [t.double().requires_grad_(True) for t in (t0, bias, ad, *gated)]
+    ref = ops.gate_logits_torch(lay, ins[0], ins[1], ins[2], *ins[3:])
+    for a, b in zip((z, v0, *vout), ref):
+        assert rel_err(a, b) < TOL
+    gouts = [torch.randn(r.shape, generator=g) for r in ref]
+    gt0, ggated, gdot = ops.gate_logits_bwd_raw(lay, d(t0), d(bias), d(ad), [d(t) for t in gated], d(gouts[0]), d(gouts[1]),
+                                                [d(t) for t in gouts[2:]])
+    rg = torch.autograd.grad(ref, ins, [t.double() for t in gouts])
+    assert rel_err(gt0, rg[0]) < 5e-5 and rel_err(gt0.sum(0), rg[1]) < 5e-5
+    assert rel_err(gdot.view_as(ad), rg[2]) < 5e-5
+    for a, b in zip(ggated, rg[3:]):
+        assert rel_err(a, b) < 5e-5
