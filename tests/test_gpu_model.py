@@ -163,3 +163,51 @@ def test_cuda_graph_replay_matches_eager(cuda_device):
         assert rel_err(loss_g, loss_e) < 1e-6
         assert rel_err(grads_g, bucket.flat) < 1e-5
     assert gfb.captures <= 2
+
+
+def test_oc20_l1_layer_vs_oracle(cuda_device):
+    """BASELINE config 4 shapes (l1_256_nonlinear: 256x0e+128x1e, 8 heads of 32x0e+16x1e): one GraphAttention layer."""
+    R = _oracle()
+    from oracle import e3nn_ref as e3
+    from equiformer_b200 import o3
+    from equiformer_b200.graph import radius_graph
+    from equiformer_b200.nets import GraphAttention
+    torch.manual_seed(0)
+    irreps, sh, head = "256x0e+128x1e", "1x0e+1x1e", "32x0e+16x1e"
+    ga = GraphAttention(irreps, "1x0e", sh, irreps, [128, 64, 64], head, 8, nonlinear_message=True, alpha_drop=0.0,
+                        proj_drop=0.0).to(cuda_device).eval()
+    _perturb(ga)
+    g = torch.Generator().manual_seed(6)
+    pos = torch.rand(73, 3, generator=g) * 9.0
+    batch = torch.zeros(73, dtype=torch.long)
+    src, dst = radius_graph(pos, 5.0, batch, max_num_neighbors=1000)
+    sh_e = o3.spherical_harmonics(sh, pos[src] - pos[dst], True, "component")
+    x = torch.randn(73, 640, generator=g)
+    rbf = torch.randn(src.numel(), 128, generator=g)
+    d = lambda t: t.to(cuda_device)
+    out = ga(d(x), None, d(src), d(dst), d(sh_e), d(rbf), d(batch))
+    params = {"ga." + k: v for k, v in R.cast_params(ga.state_dict(), torch.float64).items()}
+    ir = e3.parse_irreps(irreps)
+    ref = R.graph_attention(params, "ga", ir, e3.parse_irreps(sh), e3.parse_irreps(head), 8, ir, True, x.double(), src, dst,
+                            sh_e.double(), rbf.double())
+    assert rel_err(out, ref) < 1e-4
+
+
+def test_stress_cell_rotation_invariance(cuda_device):
+    """BASELINE config 5 size (10 k atoms, ~50 neighbours, E ~ 5e5, Lmax=2): forward energies are rotation invariant."""
+    model = _build("graph_attention_transformer_nonlinear_l2", cuda_device)
+    g = torch.Generator().manual_seed(0)
+    n = 10000
+    side = (n / (50.0 / (4.0 / 3.0 * 3.141592653589793 * 125.0))) ** (1.0 / 3.0)
+    pos = torch.rand(n, 3, generator=g, dtype=torch.float64) * side
+    z = torch.tensor([1, 6, 7, 8, 9])[torch.randint(0, 5, (n,), generator=g)]
+    batch = torch.zeros(n, dtype=torch.long)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g, dtype=torch.float64))
+    if torch.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    d = lambda t: t.to(cuda_device)
+    with torch.no_grad():
+        e0 = model(f_in=None, pos=d(pos.float()), batch=d(batch), node_atom=d(z))
+        e1 = model(f_in=None, pos=d((pos @ q.T).float()), batch=d(batch), node_atom=d(z))
+    assert torch.isfinite(e0).all()
+    assert rel_err(e1, e0) < 1e-4
