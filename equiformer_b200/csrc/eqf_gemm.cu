@@ -17,11 +17,13 @@
 #include "cutlass/cutlass.h"
 #include "cutlass/epilogue/collective/collective_builder.hpp"
 #include "cutlass/gemm/collective/collective_builder.hpp"
+#include "cutlass/gemm/device/gemm_universal.h"
 #include "cutlass/gemm/device/gemm_universal_adapter.h"
 #include "cutlass/gemm/kernel/gemm_universal.hpp"
 #include "cutlass/util/packed_stride.hpp"
 #include "cute/tensor.hpp"
 
+#include <cstdlib>
 #include <string>
 
 #include "../../include/eqf_b200.h"
@@ -39,7 +41,7 @@ static int check_cuda(cudaError_t err, const char* what) {
   return EQF_ERR_CUDA;
 }
 
-template <class LayoutA, class LayoutB, int TileN, int TileK = 16, class Scheduler = void>
+template <class LayoutA, class LayoutB, int TileN, int TileK = 16, class Scheduler = void, bool TwoSm = false>
 struct FastF32Gemm {
   using ElementA = float;
   using ElementB = float;
@@ -47,8 +49,11 @@ struct FastF32Gemm {
   using ElementAcc = float;
   using LayoutC = cutlass::layout::RowMajor;
   static constexpr int Align = 4;  // 128-bit
-  using MmaTile = Shape<_128, Int<TileN>, Int<TileK>>;
-  using Cluster = Shape<_1, _1, _1>;
+  // 1-SM: 128 x N MMA atoms, no cluster; 2-SM: cta_group::2 pairs (256 x N per pair), cluster 2x1
+  using MmaTile = Shape<Int<TwoSm ? 256 : 128>, Int<TileN>, Int<TileK>>;
+  using Cluster = Shape<Int<TwoSm ? 2 : 1>, _1, _1>;
+  using Schedule = cute::conditional_t<TwoSm, cutlass::gemm::KernelTmaWarpSpecialized2SmFastFP32Sm100,
+                                       cutlass::gemm::KernelTmaWarpSpecialized1SmFastFP32Sm100>;
 
   using CollectiveEpilogue = typename cutlass::epilogue::collective::CollectiveBuilder<
       cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, MmaTile, Cluster,
@@ -59,7 +64,7 @@ struct FastF32Gemm {
       cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, ElementA, LayoutA, Align, ElementB, LayoutB, Align,
       ElementAcc, MmaTile, Cluster,
       cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
-      cutlass::gemm::KernelTmaWarpSpecialized1SmFastFP32Sm100>::CollectiveOp;
+      Schedule>::CollectiveOp;
 
   using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue, Scheduler>;
   using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
@@ -107,6 +112,43 @@ struct FastF32Gemm {
   }
 };
 
+// ------------------------------------------------------------------------------------------------------------------
+// Weight gradient dW[K,N] = X[M,K]^T dY[M,N]: tiny output, reduction over all rows.  The sm_100 fast-fp32 collective
+// (even with the stream-K scheduler) and cuBLAS's SIMT SGEMM both run this shape at 8-25 TFLOP/s
+// (profiles/r1_gemm_microbench.jsonl).  CUTLASS's 3xTF32 tensor-op kernel (error-compensated, fp32-accurate) with
+// serial split-K parallelises the reduction over the SMs; it uses mma.sync - adequate here because the product is
+// bound by streaming X and dY once, not by tensor throughput.
+struct WgradGemm3xTF32 {
+  using Gemm = cutlass::gemm::device::GemmUniversal<
+      float, cutlass::layout::ColumnMajor,      // A = X^T  (element (i, m) = X[m, i])
+      float, cutlass::layout::RowMajor,         // B = dY
+      float, cutlass::layout::RowMajor,         // C / D = dW
+      float, cutlass::arch::OpClassTensorOp, cutlass::arch::Sm80,
+      cutlass::gemm::GemmShape<128, 64, 16>, cutlass::gemm::GemmShape<64, 32, 16>, cutlass::gemm::GemmShape<16, 8, 8>,
+      cutlass::epilogue::thread::LinearCombination<float, 4, float, float>,
+      cutlass::gemm::threadblock::GemmIdentityThreadblockSwizzle<>, 3, 4, 4, cutlass::arch::OpMultiplyAddFastF32>;
+
+  static int run(const float* X, const float* dY, float* dW, int rows, int N, int K, long long ldx, long long ldy,
+                 long long ldw, float beta, void* workspace, size_t workspace_bytes, int sm_count, cudaStream_t stream) {
+    // split the row reduction so that tiles x slices covers the machine about twice
+    const int tiles = ((K + 127) / 128) * ((N + 63) / 64);
+    int slices = (2 * sm_count + tiles - 1) / tiles;
+    const int max_slices = (rows + 511) / 512;
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
+    typename Gemm::Arguments args(cutlass::gemm::GemmUniversalMode::kGemm, {K, N, rows}, slices, {1.0f, beta}, X, dY, dW,
+                                  dW, 0, 0, 0, 0, ldx, ldy, ldw, ldw);
+    Gemm gemm;
+    if (gemm.can_implement(args) != cutlass::Status::kSuccess) {
+      set_error("3xTF32 weight-gradient GEMM: shape/alignment not supported"); return EQF_ERR_UNSUPPORTED;
+    }
+    if (Gemm::get_workspace_size(args) > workspace_bytes) { set_error("3xTF32 weight-gradient GEMM: workspace too small"); return EQF_ERR_INVALID; }
+    if (gemm.initialize(args, workspace, stream) != cutlass::Status::kSuccess) { set_error("3xTF32 weight-gradient GEMM: initialize failed"); return EQF_ERR_CUDA; }
+    if (gemm.run(stream) != cutlass::Status::kSuccess) { set_error("3xTF32 weight-gradient GEMM: launch failed"); return EQF_ERR_CUDA; }
+    return check_cuda(cudaGetLastError(), "3xTF32 weight-gradient GEMM launch");
+  }
+};
+
 }  // namespace eqf
 
 using namespace eqf;
@@ -126,6 +168,14 @@ extern "C" int eqf_gemm_f32(int mode, const float* A, const float* B, float* C, 
   cudaStream_t s = (cudaStream_t)stream;
   const int m = (int)M, n = (int)N, k = (int)K;
   const bool wide = n > 64;
+  static const bool two_sm = [] { const char* e = std::getenv("EQF_GEMM_2SM"); return e != nullptr && e[0] == '1'; }();
+  if (two_sm && mode != 2) {
+    if (mode == 0)
+      return wide ? FastF32Gemm<Row, Row, 128, 16, void, true>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
+                  : FastF32Gemm<Row, Row, 64, 16, void, true>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
+    return wide ? FastF32Gemm<Row, Col, 128, 16, void, true>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
+                : FastF32Gemm<Row, Col, 64, 16, void, true>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
+  }
   switch (mode) {
     case 0:
       return wide ? FastF32Gemm<Row, Row, 128>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
@@ -133,10 +183,11 @@ extern "C" int eqf_gemm_f32(int mode, const float* A, const float* B, float* C, 
     case 1:
       return wide ? FastF32Gemm<Row, Col, 128>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
                   : FastF32Gemm<Row, Col, 64>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
-    case 2:
-      // weight gradient: tiny [K,N] output, reduction over all rows -> stream-K splits the reduction across SMs
-      return wide ? FastF32Gemm<Col, Row, 128, 16, cutlass::gemm::StreamKScheduler>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
-                  : FastF32Gemm<Col, Row, 64, 16, cutlass::gemm::StreamKScheduler>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
+    case 2: {
+      // weight gradient: C[m, n] = A[k, m]^T B[k, n] with k = all rows -> split-K 3xTF32 tensor-op kernel
+      static const int sms = [] { int d = 0, v = 148; if (cudaGetDevice(&d) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v > 0 ? v : 148; }();
+      return WgradGemm3xTF32::run(A, B, C, k, n, m, lda, ldb, ldc, beta, workspace, workspace_bytes, sms, s);
+    }
     default:
       set_error("eqf_gemm_f32: mode must be 0, 1 or 2");
       return EQF_ERR_INVALID;

@@ -130,8 +130,11 @@ class KernelProfile:
     while the profile is installed (events are recorded on the launching stream, around the launch only).
     """
 
-    def __init__(self, time_events: bool = True):
+    def __init__(self, time_events: bool = True, presleep_cycles: int = 0):
         self.time_events = time_events
+        # GPU-side delay queued before each timed launch so that the host has enqueued start-event, kernel and end-event
+        # before the GPU reaches them: in a host-bound eager pass the event pair would otherwise include launch gaps.
+        self.presleep_cycles = presleep_cycles
         self.launches = 0
         self.records = []
 
@@ -161,6 +164,8 @@ def _kernel(name: str, nbytes: int):
         return
     s = torch.cuda.Event(enable_timing=True)
     e = torch.cuda.Event(enable_timing=True)
+    if prof.presleep_cycles:
+        torch.cuda._sleep(prof.presleep_cycles)
     s.record()
     yield
     e.record()
@@ -796,7 +801,7 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     # products (forward / data gradient, 1.3-1.6x over cuBLAS SGEMM); the weight gradient (tiny output, reduction over
     # all rows) and node-level products are faster in cuBLAS.
     use_cutlass = (A.is_cuda and A.dtype == torch.float32 and aligned and gemm_backend() == "cutlass"
-                   and (gemm_backend_forced() or (mode != 2 and M >= 16384)))
+                   and (gemm_backend_forced() or (mode != 2 and M >= 16384) or (mode == 2 and K >= 8192)))
     if not use_cutlass:
         if mode == 0:
             return A @ B

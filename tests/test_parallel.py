@@ -61,3 +61,28 @@ def test_bench_reference_arm_ranks_other_than_zero_exit_quietly(monkeypatch, cap
         gpus, steps, warmup, ref_graphs = 2, 1, 0, 1
     bench.run_reference(A())
     assert capsys.readouterr().out == ""
+
+
+def test_flat_adamw_matches_torch_adamw():
+    """FlatAdamW (one flat buffer, six element-wise kernels) == torch.optim.AdamW with the same decay groups."""
+    from equiformer_b200.parallel import FlatAdamW, FlatGradAllReduce
+    torch.manual_seed(0)
+    make = lambda: torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.SiLU(), torch.nn.Linear(5, 3)).double()
+    a, b = make(), make()
+    b.load_state_dict(a.state_dict())
+    bucket = FlatGradAllReduce(a.parameters())
+    opt_a = FlatAdamW(a.named_parameters(), bucket, lr=1e-2, weight_decay=0.1)
+    decay = [p for p in b.parameters() if p.dim() > 1]
+    no_decay = [p for p in b.parameters() if p.dim() <= 1]
+    opt_b = torch.optim.AdamW([{"params": decay, "weight_decay": 0.1}, {"params": no_decay, "weight_decay": 0.0}], lr=1e-2)
+    g = torch.Generator().manual_seed(1)
+    for _ in range(5):
+        x = torch.randn(7, 6, generator=g, dtype=torch.float64)
+        bucket.zero_grad()
+        a(x).pow(2).sum().backward()
+        opt_a.step()
+        opt_b.zero_grad()
+        b(x).pow(2).sum().backward()
+        opt_b.step()
+    for pa, pb in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(pa, pb, atol=1e-12), (pa - pb).abs().max()
