@@ -113,6 +113,8 @@ SIGNATURES = {
 GEMM_SIGNATURES = {
     "eqf_gemm_f32": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                                 c_int64, c_float, c_void_p, c_int64, c_void_p]),
+    "eqf_gemm_f32_wgrad_sliced": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                            c_int64, c_void_p, c_int64, c_void_p]),
     "eqf_gemm_workspace_bytes": (c_int64, []),
     "eqf_gemm_last_error": (c_char_p, []),
 }

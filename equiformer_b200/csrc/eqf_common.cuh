@@ -73,6 +73,7 @@ struct GeneratedKernels {
   const char* tag;
   int (*forward)(const EqfPlan*, const EdgeArgs&, cudaStream_t);
   int (*backward)(const EqfPlan*, const EdgeArgs&, bool with_w, cudaStream_t);
+  int (*grad_y)(const EqfPlan*, const EdgeArgs&, cudaStream_t);
   int (*partial_rows)(const EqfPlan*, long long);
 };
 int register_generated(const GeneratedKernels* k);

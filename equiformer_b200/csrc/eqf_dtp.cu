@@ -510,6 +510,7 @@ extern "C" int eqf_dtp_grad_y(const EqfPlan* plan, const EqfEdgeOperands* op, in
   if (rc != EQF_OK || n_edges == 0) return rc;
   if (gy == nullptr) { set_error("null gy"); return EQF_ERR_INVALID; }
   a.gy = gy;
+  if (plan->gen != nullptr && dtp_variant() == 4) return plan->gen->grad_y(plan, a, (cudaStream_t)stream);
   const size_t smem = plan->smem_bytes;
   if ((rc = set_smem(dtp_grad_y_kernel, smem)) != EQF_OK) return rc;
   dtp_grad_y_kernel<<<grid_for(plan, n_edges), kThreads, smem, (cudaStream_t)stream>>>(plan->hdr, plan->d_blob, a);

@@ -17,7 +17,6 @@
 #include "cutlass/cutlass.h"
 #include "cutlass/epilogue/collective/collective_builder.hpp"
 #include "cutlass/gemm/collective/collective_builder.hpp"
-#include "cutlass/gemm/device/gemm_universal.h"
 #include "cutlass/gemm/device/gemm_universal_adapter.h"
 #include "cutlass/gemm/kernel/gemm_universal.hpp"
 #include "cutlass/util/packed_stride.hpp"
@@ -74,17 +73,21 @@ struct FastF32Gemm {
   using StrideC = typename Gemm::GemmKernel::StrideC;
   using StrideD = typename Gemm::GemmKernel::StrideD;
 
+  // batch > 1: `batch` independent products with operand strides (batch_a, batch_b, batch_c) elements apart -
+  // used to split the row reduction of the weight gradient into slices that fill the machine.
   static int run(const float* A, const float* B, float* C, int M, int N, int K, long long lda, long long ldb,
-                 long long ldc, float beta, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+                 long long ldc, float beta, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                 int batch = 1, long long batch_a = 0, long long batch_b = 0, long long batch_c = 0) {
     // leading dimensions: A row-major -> lda = elements between rows of A[M,K]; column-major -> between columns
-    StrideA sa = cutlass::make_cute_packed_stride(StrideA{}, make_shape(M, K, 1));
-    StrideB sb = cutlass::make_cute_packed_stride(StrideB{}, make_shape(N, K, 1));
-    StrideC sc = cutlass::make_cute_packed_stride(StrideC{}, make_shape(M, N, 1));
+    StrideA sa = cutlass::make_cute_packed_stride(StrideA{}, make_shape(M, K, batch));
+    StrideB sb = cutlass::make_cute_packed_stride(StrideB{}, make_shape(N, K, batch));
+    StrideC sc = cutlass::make_cute_packed_stride(StrideC{}, make_shape(M, N, batch));
     set_ld(sa, lda);
     set_ld(sb, ldb);
     set_ld(sc, ldc);
+    if (batch > 1) { get<2>(sa) = batch_a; get<2>(sb) = batch_b; get<2>(sc) = batch_c; }
     typename Gemm::Arguments args{cutlass::gemm::GemmUniversalMode::kGemm,
-                                  {M, N, K, 1},
+                                  {M, N, K, batch},
                                   {A, sa, B, sb},
                                   {{1.0f, beta}, C, sc, C, sc}};
     Gemm gemm;
@@ -112,43 +115,6 @@ struct FastF32Gemm {
   }
 };
 
-// ------------------------------------------------------------------------------------------------------------------
-// Weight gradient dW[K,N] = X[M,K]^T dY[M,N]: tiny output, reduction over all rows.  The sm_100 fast-fp32 collective
-// (even with the stream-K scheduler) and cuBLAS's SIMT SGEMM both run this shape at 8-25 TFLOP/s
-// (profiles/r1_gemm_microbench.jsonl).  CUTLASS's 3xTF32 tensor-op kernel (error-compensated, fp32-accurate) with
-// serial split-K parallelises the reduction over the SMs; it uses mma.sync - adequate here because the product is
-// bound by streaming X and dY once, not by tensor throughput.
-struct WgradGemm3xTF32 {
-  using Gemm = cutlass::gemm::device::GemmUniversal<
-      float, cutlass::layout::ColumnMajor,      // A = X^T  (element (i, m) = X[m, i])
-      float, cutlass::layout::RowMajor,         // B = dY
-      float, cutlass::layout::RowMajor,         // C / D = dW
-      float, cutlass::arch::OpClassTensorOp, cutlass::arch::Sm80,
-      cutlass::gemm::GemmShape<128, 64, 16>, cutlass::gemm::GemmShape<64, 32, 16>, cutlass::gemm::GemmShape<16, 8, 8>,
-      cutlass::epilogue::thread::LinearCombination<float, 4, float, float>,
-      cutlass::gemm::threadblock::GemmIdentityThreadblockSwizzle<>, 3, 4, 4, cutlass::arch::OpMultiplyAddFastF32>;
-
-  static int run(const float* X, const float* dY, float* dW, int rows, int N, int K, long long ldx, long long ldy,
-                 long long ldw, float beta, void* workspace, size_t workspace_bytes, int sm_count, cudaStream_t stream) {
-    // split the row reduction so that tiles x slices covers the machine about twice
-    const int tiles = ((K + 127) / 128) * ((N + 63) / 64);
-    int slices = (2 * sm_count + tiles - 1) / tiles;
-    const int max_slices = (rows + 511) / 512;
-    if (slices > max_slices) slices = max_slices;
-    if (slices < 1) slices = 1;
-    typename Gemm::Arguments args(cutlass::gemm::GemmUniversalMode::kGemm, {K, N, rows}, slices, {1.0f, beta}, X, dY, dW,
-                                  dW, 0, 0, 0, 0, ldx, ldy, ldw, ldw);
-    Gemm gemm;
-    if (gemm.can_implement(args) != cutlass::Status::kSuccess) {
-      set_error("3xTF32 weight-gradient GEMM: shape/alignment not supported"); return EQF_ERR_UNSUPPORTED;
-    }
-    if (Gemm::get_workspace_size(args) > workspace_bytes) { set_error("3xTF32 weight-gradient GEMM: workspace too small"); return EQF_ERR_INVALID; }
-    if (gemm.initialize(args, workspace, stream) != cutlass::Status::kSuccess) { set_error("3xTF32 weight-gradient GEMM: initialize failed"); return EQF_ERR_CUDA; }
-    if (gemm.run(stream) != cutlass::Status::kSuccess) { set_error("3xTF32 weight-gradient GEMM: launch failed"); return EQF_ERR_CUDA; }
-    return check_cuda(cudaGetLastError(), "3xTF32 weight-gradient GEMM launch");
-  }
-};
-
 }  // namespace eqf
 
 using namespace eqf;
@@ -164,11 +130,16 @@ extern "C" int eqf_gemm_f32(int mode, const float* A, const float* B, float* C, 
                             int64_t workspace_bytes, void* stream) {
   if (A == nullptr || B == nullptr || C == nullptr) { set_error("eqf_gemm_f32: null pointer"); return EQF_ERR_INVALID; }
   if (M <= 0 || N <= 0 || K <= 0) return EQF_OK;
+  if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15 || (lda | ldb | ldc) & 3) {
+    set_error("eqf_gemm_f32: operands must be 16-byte aligned with leading dimensions that are multiples of 4 floats");
+    return EQF_ERR_INVALID;
+  }
   if (M > 0x7fffffffLL || N > 0x7fffffffLL || K > 0x7fffffffLL) { set_error("eqf_gemm_f32: dimension too large"); return EQF_ERR_UNSUPPORTED; }
   cudaStream_t s = (cudaStream_t)stream;
   const int m = (int)M, n = (int)N, k = (int)K;
   const bool wide = n > 64;
-  static const bool two_sm = [] { const char* e = std::getenv("EQF_GEMM_2SM"); return e != nullptr && e[0] == '1'; }();
+  // cta_group::2 tiles measured 3-5 % faster than 1-SM tiles on every layer shape (profiles/r1_gemm_microbench*.jsonl)
+  static const bool two_sm = [] { const char* e = std::getenv("EQF_GEMM_2SM"); return e == nullptr || e[0] != '0'; }();
   if (two_sm && mode != 2) {
     if (mode == 0)
       return wide ? FastF32Gemm<Row, Row, 128, 16, void, true>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
@@ -183,11 +154,9 @@ extern "C" int eqf_gemm_f32(int mode, const float* A, const float* B, float* C, 
     case 1:
       return wide ? FastF32Gemm<Row, Col, 128>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
                   : FastF32Gemm<Row, Col, 64>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
-    case 2: {
-      // weight gradient: C[m, n] = A[k, m]^T B[k, n] with k = all rows -> split-K 3xTF32 tensor-op kernel
-      static const int sms = [] { int d = 0, v = 148; if (cudaGetDevice(&d) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d); return v > 0 ? v : 148; }();
-      return WgradGemm3xTF32::run(A, B, C, k, n, m, lda, ldb, ldc, beta, workspace, workspace_bytes, sms, s);
-    }
+    case 2:
+      return wide ? FastF32Gemm<Col, Row, 128>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
+                  : FastF32Gemm<Col, Row, 64>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
     default:
       set_error("eqf_gemm_f32: mode must be 0, 1 or 2");
       return EQF_ERR_INVALID;
@@ -197,3 +166,26 @@ extern "C" int eqf_gemm_f32(int mode, const float* A, const float* B, float* C, 
 extern "C" int64_t eqf_gemm_workspace_bytes(void) { return 64 << 20; }
 
 extern "C" const char* eqf_gemm_last_error(void) { return g_gemm_error.c_str(); }
+
+
+// Weight gradient with the row reduction split into `slices` equal chunks of `chunk` rows (slices * chunk <= K rows):
+// part[s][M, N] = A[s*chunk : (s+1)*chunk, :M]^T  B[s*chunk : (s+1)*chunk, :N]   for s < slices  (one batched launch of
+// the tcgen05 fast-fp32 kernel - the batch dimension supplies the parallelism the tiny [M, N] output lacks).
+// The caller reduces `part` over s (and adds the tail rows, if any, with one more mode-2 call).
+extern "C" int eqf_gemm_f32_wgrad_sliced(const float* A, const float* B, float* part, int64_t M, int64_t N, int64_t chunk,
+                                         int64_t slices, int64_t lda, int64_t ldb, void* workspace,
+                                         int64_t workspace_bytes, void* stream) {
+  if (A == nullptr || B == nullptr || part == nullptr) { set_error("eqf_gemm_f32_wgrad_sliced: null pointer"); return EQF_ERR_INVALID; }
+  if (M <= 0 || N <= 0 || chunk <= 0 || slices <= 0) return EQF_OK;
+  if (((uintptr_t)A | (uintptr_t)B | (uintptr_t)part) & 15 || (lda | ldb | N) & 3 || (chunk & 3)) {
+    set_error("eqf_gemm_f32_wgrad_sliced: operands must be 16-byte aligned (dims / chunk multiples of 4)");
+    return EQF_ERR_INVALID;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  const int m = (int)M, n = (int)N, k = (int)chunk, L = (int)slices;
+  if (n > 64)
+    return FastF32Gemm<Col, Row, 128>::run(A, B, part, m, n, k, lda, ldb, N, 0.f, workspace, workspace_bytes, s, L,
+                                           chunk * lda, chunk * ldb, M * N);
+  return FastF32Gemm<Col, Row, 64>::run(A, B, part, m, n, k, lda, ldb, N, 0.f, workspace, workspace_bytes, s, L,
+                                        chunk * lda, chunk * ldb, M * N);
+}

@@ -778,8 +778,10 @@ def gemm_backend_forced() -> bool:
 
 def _gemm_operand(t: torch.Tensor):
     """Row-major 2-D operand with 16-byte aligned rows: returns (tensor, leading dimension)."""
-    if t.stride(1) != 1 or t.stride(0) % 4 != 0 or t.stride(0) < t.shape[1] or t.data_ptr() % 16 != 0:
+    if t.stride(1) != 1 or t.stride(0) % 4 != 0 or t.stride(0) < t.shape[1]:
         t = t.contiguous()
+    if t.data_ptr() % 16 != 0:      # e.g. a view at an odd offset of a flat parameter buffer: TMA needs 16-byte rows
+        t = t.clone(memory_format=torch.contiguous_format)
     return t, t.stride(0)
 
 
@@ -801,25 +803,54 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     # products (forward / data gradient, 1.3-1.6x over cuBLAS SGEMM); the weight gradient (tiny output, reduction over
     # all rows) and node-level products are faster in cuBLAS.
     use_cutlass = (A.is_cuda and A.dtype == torch.float32 and aligned and gemm_backend() == "cutlass"
-                   and (gemm_backend_forced() or (mode != 2 and M >= 16384) or (mode == 2 and K >= 8192)))
+                   and (gemm_backend_forced() or (mode != 2 and M >= 16384) or (mode == 2 and K >= 16384)))
     if not use_cutlass:
         if mode == 0:
             return A @ B
         return A @ B.t() if mode == 1 else A.t() @ B
     A, lda = _gemm_operand(A)
     B, ldb = _gemm_operand(B)
-    C = torch.empty((M, N), device=A.device, dtype=torch.float32)
     lib = _lib.load_gemm()
     ws = _GEMM_WORKSPACE.get(A.device)
     if ws is None:
         ws = torch.empty(int(lib.eqf_gemm_workspace_bytes()), dtype=torch.uint8, device=A.device)
         _GEMM_WORKSPACE[A.device] = ws
+    if mode == 2 and K >= 4096:
+        return _wgrad_sliced(lib, ws, A, B, lda, ldb, M, N, K)
+    C = torch.empty((M, N), device=A.device, dtype=torch.float32)
     flops_bytes = 4 * (A.numel() + B.numel() + C.numel())
     with torch.cuda.device(A.device), _kernel("gemm_fast_f32", flops_bytes):
         rc = lib.eqf_gemm_f32(mode, A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, lda, ldb, N, 0.0,
                               ws.data_ptr(), ws.numel(), _stream())
     _lib.check_gemm(rc, "eqf_gemm_f32")
     return C
+
+
+def _wgrad_sliced(lib, ws, A, B, lda, ldb, M, N, K):
+    """dW[M,N] = A[K,M]^T B[K,N] with the K rows cut into slices: one batched tcgen05 launch + a sum over slices.
+
+    The output is tiny ([224..384] x [32..352]) and the reduction long (all edges x components), so a plain GEMM
+    launches only a handful of CTAs; the batch dimension restores the parallelism (same trick as split-K, but the
+    partial products are independent batches of the same fast-fp32 kernel)."""
+    import os
+    tiles = ((M + 127) // 128) * ((N + 127) // 128 if N > 64 else 1)
+    waves = float(os.environ.get("EQF_WGRAD_WAVES", "2"))          # CTAs per SM to aim for (tuning knob)
+    slices = max(1, min(int(-(-waves * 148 // tiles)), K // 256))
+    chunk = (K // slices) & ~15                      # multiple of the 16-row k-tile; the rest is the tail
+    slices = K // chunk
+    tail = K - slices * chunk
+    part = torch.empty((slices + (1 if tail else 0), M, N), device=A.device, dtype=torch.float32)
+    nbytes = 4 * (A.numel() + B.numel() + 2 * part.numel())
+    with torch.cuda.device(A.device), _kernel("gemm_fast_f32_wgrad", nbytes):
+        rc = lib.eqf_gemm_f32_wgrad_sliced(A.data_ptr(), B.data_ptr(), part.data_ptr(), M, N, chunk, slices, lda, ldb,
+                                           ws.data_ptr(), ws.numel(), _stream())
+        _lib.check_gemm(rc, "eqf_gemm_f32_wgrad_sliced")
+        if tail:
+            off = slices * chunk
+            rc = lib.eqf_gemm_f32(2, A.data_ptr() + 4 * off * lda, B.data_ptr() + 4 * off * ldb, part[slices].data_ptr(),
+                                  M, N, tail, lda, ldb, N, 0.0, ws.data_ptr(), ws.numel(), _stream())
+            _lib.check_gemm(rc, "eqf_gemm_f32 (tail)")
+    return part.sum(dim=0)
 
 
 class Gemm(torch.autograd.Function):

@@ -43,14 +43,15 @@ class FlatGradAllReduce:
         if not self.params:
             raise ValueError("no trainable parameters")
         first = self.params[0]
-        total = sum(p.numel() for p in self.params)
+        # every tensor starts on a 256-byte boundary of the flat buffer (TMA / vector loads need 16-byte aligned rows)
+        self.offsets, total = [], 0
+        for p in self.params:
+            self.offsets.append(total)
+            total += (p.numel() + 63) // 64 * 64
         self.flat = torch.zeros(total, dtype=first.dtype, device=first.device)
         self.group = process_group
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
         self.world = dist.get_world_size(process_group) if dist.is_initialized() else 1
 
     def zero_grad(self) -> None:
@@ -62,11 +63,8 @@ class FlatGradAllReduce:
                 break
 
     def _reattach(self) -> None:
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+        for p, off in zip(self.params, self.offsets):
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
 
     def reduce(self, async_op: bool = False):
         """Average gradients over ranks (no-op for a single process)."""
@@ -104,16 +102,14 @@ class FlatAdamW:
         if [p for _, p in named] != bucket.params and any(a is not b for (_, a), b in zip(named, bucket.params)):
             raise ValueError("FlatAdamW: parameter order must match the gradient bucket")
         self.bucket, self.lr, self.betas, self.eps = bucket, lr, betas, eps
-        flat = torch.empty_like(bucket.flat)
-        decay = torch.empty_like(bucket.flat)
-        off = 0
+        flat = torch.zeros_like(bucket.flat)
+        decay = torch.zeros_like(bucket.flat)
         with torch.no_grad():
-            for name, p in named:
+            for (name, p), off in zip(named, bucket.offsets):
                 n = p.numel()
                 flat[off:off + n].copy_(p.reshape(-1))
                 p.data = flat[off:off + n].view_as(p)
                 decay[off:off + n] = 0.0 if (name in no_decay or p.dim() <= 1) else weight_decay
-                off += n
         self.flat, self.decay = flat, decay
         self.m = torch.zeros_like(flat)
         self.v = torch.zeros_like(flat)

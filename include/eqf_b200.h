@@ -168,6 +168,11 @@ int eqf_gate_logits_bwd(const EqfGateLayout* lay, const float* t0, const float* 
 int eqf_gemm_f32(int mode, const float* A, const float* B, float* C, int64_t M, int64_t N, int64_t K,
                  int64_t lda, int64_t ldb, int64_t ldc, float beta, void* workspace, int64_t workspace_bytes,
                  void* stream);
+/* weight gradient with the row reduction split into `slices` chunks of `chunk` rows (batched launch):
+ * part[s][M,N] = A[s*chunk:(s+1)*chunk, :M]^T B[s*chunk:(s+1)*chunk, :N]; the caller sums over s. */
+int eqf_gemm_f32_wgrad_sliced(const float* A, const float* B, float* part, int64_t M, int64_t N, int64_t chunk,
+                              int64_t slices, int64_t lda, int64_t ldb, void* workspace, int64_t workspace_bytes,
+                              void* stream);
 int64_t eqf_gemm_workspace_bytes(void);
 const char* eqf_gemm_last_error(void);
 

@@ -29,7 +29,7 @@ def _worker(rank, world, port, ret):
     bucket.zero_grad()
     (model(shard).sum() / data.shape[0] * world).backward()       # so that the rank-average equals the full-batch grad
     bucket.reduce()
-    flat = bucket.flat.clone()
+    flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])   # the bucket itself is padded per tensor
     # single-process reference on the full batch
     ref_model = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.SiLU(), torch.nn.Linear(5, 1)).double()
     ref_model.load_state_dict(model.state_dict())
