@@ -834,7 +834,9 @@ def _wgrad_sliced(lib, ws, A, B, lda, ldb, M, N, K):
     partial products are independent batches of the same fast-fp32 kernel)."""
     import os
     tiles = ((M + 127) // 128) * ((N + 127) // 128 if N > 64 else 1)
-    waves = float(os.environ.get("EQF_WGRAD_WAVES", "2"))          # CTAs per SM to aim for (tuning knob)
+    # CTAs per SM to aim for: measured best 4 for the narrow outputs (<= 3 tiles), 2 for wider ones
+    # (profiles/r1_gemm_wgrad_slices.jsonl); EQF_WGRAD_WAVES overrides
+    waves = float(os.environ.get("EQF_WGRAD_WAVES", "4" if tiles <= 3 else "2"))
     slices = max(1, min(int(-(-waves * 148 // tiles)), K // 256))
     chunk = (K // slices) & ~15                      # multiple of the 16-row k-tile; the rest is the tail
     slices = K // chunk
