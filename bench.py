@@ -151,6 +151,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun pins OMP_NUM_THREADS=1; the CPU arm may use every core
     threads = torch.get_num_threads()
     n_sample = args.ref_graphs
     params, cfg, pos, batch, z, target, n_graphs, edges = cpu_sample(n_sample)
@@ -309,6 +310,7 @@ def run_ours(args):
                                 "a GPU-side delay queued before each pair keeps host launch gaps out of the interval"}
         cpu = None
         if not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
             params, cfg, cpos, cbatch, cz, ctgt, cgraphs, cedges = cpu_sample(args.ref_graphs)
             oracle_step(params, cfg, cpos, cbatch, cz, ctgt, cgraphs)
             t0 = time.perf_counter()

@@ -164,6 +164,106 @@ __global__ void __launch_bounds__(256) edge_scale_kernel(HeadArgs a, const float
   }
 }
 
+// ------------------------------------------------------------------------------------------------ 128-bit variants
+// Used when every group has rowlen % 4 == 0 and (C / H) % 4 == 0 (all shipped configs): a lane owns four consecutive
+// channels (same head), a warp instruction moves 512 contiguous bytes.
+__device__ __forceinline__ float4 ldv(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+
+// one warp per (node, 128-column chunk)
+__global__ void __launch_bounds__(256) aggregate_vec_kernel(HeadArgs a, const float* __restrict__ alpha,
+                                                            const long long* __restrict__ row_ptr,
+                                                            const long long* __restrict__ perm, long long n_nodes) {
+  const int n_chunks = a.chunk_start[a.n_groups];   // here: chunks of 128 columns
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= n_nodes * n_chunks) return;
+  const long long t = wid / n_chunks;
+  const int chunk = (int)(wid - t * n_chunks);
+  const int g = find_group(a, chunk);
+  const int j = (chunk - a.chunk_start[g]) * 128 + (threadIdx.x & 31) * 4;
+  const int rowlen = a.rowlen[g];
+  if (j >= rowlen) return;
+  const int H = a.n_heads;
+  const int h = (j % a.C[g]) / (a.C[g] / H);
+  const long long r0 = row_ptr[t], r1 = row_ptr[t + 1];
+  const float* __restrict__ v = a.V[g] + j;
+  float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+  long long e = r0;
+  for (; e + 1 < r1; e += 2) {
+    const long long i0 = perm ? __ldg(perm + e) : e, i1 = perm ? __ldg(perm + e + 1) : e + 1;
+    const float a0 = alpha ? __ldg(alpha + i0 * H + h) : 1.f, a1 = alpha ? __ldg(alpha + i1 * H + h) : 1.f;
+    const float4 v0 = ldv(v + i0 * rowlen), v1 = ldv(v + i1 * rowlen);
+    acc0.x = fmaf(a0, v0.x, acc0.x); acc0.y = fmaf(a0, v0.y, acc0.y); acc0.z = fmaf(a0, v0.z, acc0.z); acc0.w = fmaf(a0, v0.w, acc0.w);
+    acc1.x = fmaf(a1, v1.x, acc1.x); acc1.y = fmaf(a1, v1.y, acc1.y); acc1.z = fmaf(a1, v1.z, acc1.z); acc1.w = fmaf(a1, v1.w, acc1.w);
+  }
+  if (e < r1) {
+    const long long i0 = perm ? __ldg(perm + e) : e;
+    const float a0 = alpha ? __ldg(alpha + i0 * H + h) : 1.f;
+    const float4 v0 = ldv(v + i0 * rowlen);
+    acc0.x = fmaf(a0, v0.x, acc0.x); acc0.y = fmaf(a0, v0.y, acc0.y); acc0.z = fmaf(a0, v0.z, acc0.z); acc0.w = fmaf(a0, v0.w, acc0.w);
+  }
+  *reinterpret_cast<float4*>(a.out[g] + t * rowlen + j) =
+      make_float4(acc0.x + acc1.x, acc0.y + acc1.y, acc0.z + acc1.z, acc0.w + acc1.w);
+}
+
+// one warp per edge, H accumulators per lane
+template <int H>
+__global__ void __launch_bounds__(256) edge_dot_vec_kernel(HeadArgs a, const long long* __restrict__ dst, long long n_edges,
+                                                           float* __restrict__ galpha) {
+  const long long e = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (e >= n_edges) return;
+  const int lane = threadIdx.x & 31;
+  const long long t = dst[e];
+  float acc[H];
+#pragma unroll
+  for (int h = 0; h < H; ++h) acc[h] = 0.f;
+  for (int g = 0; g < a.n_groups; ++g) {
+    const int rowlen = a.rowlen[g], C = a.C[g], ch = C / H;
+    const float* __restrict__ v = a.V[g] + e * rowlen;
+    const float* __restrict__ gg = a.G[g] + t * rowlen;
+    for (int j = lane * 4; j < rowlen; j += 128) {
+      const float4 x = ldv(v + j), y = ldv(gg + j);
+      const float p = x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+      const int h = (j % C) / ch;
+#pragma unroll
+      for (int q = 0; q < H; ++q) acc[q] += (q == h) ? p : 0.f;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < H; ++q) {
+    const float r = warp_add(acc[q]);
+    if (lane == 0) galpha[e * H + q] = r;
+  }
+}
+
+// one warp per edge: out[g][e, j] = alpha[e, head(j)] * G[g][dst[e], j]
+__global__ void __launch_bounds__(256) edge_scale_vec_kernel(HeadArgs a, const float* __restrict__ alpha,
+                                                             const long long* __restrict__ dst, long long n_edges) {
+  const int lane = threadIdx.x & 31;
+  const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long e = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n_edges; e += n_warps) {
+    const long long t = dst[e];
+    for (int g = 0; g < a.n_groups; ++g) {
+      const int rowlen = a.rowlen[g], C = a.C[g], ch = C / a.n_heads;
+      const float* __restrict__ gg = a.G[g] + t * rowlen;
+      float* __restrict__ o = a.out[g] + e * rowlen;
+      for (int j = lane * 4; j < rowlen; j += 128) {
+        float4 v = ldv(gg + j);
+        if (alpha != nullptr) {
+          const float s = __ldg(alpha + e * a.n_heads + (j % C) / ch);
+          v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+        }
+        *reinterpret_cast<float4*>(o + j) = v;
+      }
+    }
+  }
+}
+
+static bool vec_ok(const HeadArgs& a) {
+  for (int g = 0; g < a.n_groups; ++g)
+    if (a.rowlen[g] % 4 != 0 || (a.C[g] / a.n_heads) % 4 != 0) return false;
+  return true;
+}
+
 static int fill_head_args(const EqfHeadLayout* lay, HeadArgs& a) {
   if (lay == nullptr) { set_error("null head layout"); return EQF_ERR_INVALID; }
   if (lay->n_groups < 1 || lay->n_groups > EQF_MAX_BLOCKS) { set_error("bad n_groups"); return EQF_ERR_INVALID; }
@@ -210,6 +310,13 @@ extern "C" int eqf_attn_aggregate(const EqfHeadLayout* lay, const float* alpha, 
     a.V[g] = V[g]; a.out[g] = out[g];
   }
   const int wpb = 8;
+  if (vec_ok(a)) {
+    for (int g = 0; g < a.n_groups; ++g) a.chunk_start[g + 1] = a.chunk_start[g] + (a.rowlen[g] + 127) / 128;
+    const long long warps = n_nodes * a.chunk_start[a.n_groups];
+    aggregate_vec_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+        a, alpha, reinterpret_cast<const long long*>(row_ptr), reinterpret_cast<const long long*>(perm), n_nodes);
+    return check_cuda(cudaGetLastError(), "aggregate_vec_kernel launch");
+  }
   const long long warps = n_nodes * a.chunk_start[a.n_groups];
   const long long blocks = (warps + wpb - 1) / wpb;
   aggregate_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(
@@ -229,8 +336,19 @@ extern "C" int eqf_attn_edge_dot(const EqfHeadLayout* lay, const float* const* V
   }
   const int wpb = 8;
   const long long blocks = (n_edges + wpb - 1) / wpb;
-  edge_dot_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(
-      a, reinterpret_cast<const long long*>(dst), n_edges, galpha);
+  const long long* d = reinterpret_cast<const long long*>(dst);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (vec_ok(a) && (a.n_heads == 1 || a.n_heads == 2 || a.n_heads == 4 || a.n_heads == 8 || a.n_heads == 16)) {
+    switch (a.n_heads) {
+      case 1: edge_dot_vec_kernel<1><<<(unsigned)blocks, wpb * 32, 0, st>>>(a, d, n_edges, galpha); break;
+      case 2: edge_dot_vec_kernel<2><<<(unsigned)blocks, wpb * 32, 0, st>>>(a, d, n_edges, galpha); break;
+      case 4: edge_dot_vec_kernel<4><<<(unsigned)blocks, wpb * 32, 0, st>>>(a, d, n_edges, galpha); break;
+      case 8: edge_dot_vec_kernel<8><<<(unsigned)blocks, wpb * 32, 0, st>>>(a, d, n_edges, galpha); break;
+      default: edge_dot_vec_kernel<16><<<(unsigned)blocks, wpb * 32, 0, st>>>(a, d, n_edges, galpha); break;
+    }
+    return check_cuda(cudaGetLastError(), "edge_dot_vec_kernel launch");
+  }
+  edge_dot_kernel<<<(unsigned)blocks, wpb * 32, 0, st>>>(a, d, n_edges, galpha);
   return check_cuda(cudaGetLastError(), "edge_dot_kernel launch");
 }
 
@@ -245,6 +363,13 @@ extern "C" int eqf_attn_edge_scale(const EqfHeadLayout* lay, const float* alpha,
     if (G[g] == nullptr || out[g] == nullptr) { set_error("eqf_attn_edge_scale: null group"); return EQF_ERR_INVALID; }
     a.G[g] = G[g]; a.out[g] = out[g];
     if (a.rowlen[g] > max_rowlen) max_rowlen = a.rowlen[g];
+  }
+  if (vec_ok(a)) {
+    long long vb = (n_edges + 7) / 8;
+    if (vb > 148LL * 16) vb = 148LL * 16;
+    edge_scale_vec_kernel<<<(unsigned)(vb < 1 ? 1 : vb), 256, 0, (cudaStream_t)stream>>>(
+        a, alpha, reinterpret_cast<const long long*>(dst), n_edges);
+    return check_cuda(cudaGetLastError(), "edge_scale_vec_kernel launch");
   }
   long long blocks = (n_edges * max_rowlen + 255) / 256;
   if (blocks > 148LL * 32) blocks = 148LL * 32;

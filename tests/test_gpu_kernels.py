@@ -113,7 +113,7 @@ def _graph(n_nodes, E, seed, device, with_empty=True):
 
 
 @pytest.mark.parametrize("H,dims,chans", [(4, (1, 3, 5), (128, 64, 32)), (8, (1, 3), (256, 128)), (1, (1, 3, 5), (20, 12, 4)),
-                                          (4, (1, 3, 5, 7), (128, 64, 64, 32))])
+                                          (4, (1, 3, 5, 7), (128, 64, 64, 32)), (2, (1, 3), (6, 2))])   # last: scalar kernels
 def test_attention_family(cuda_device, H, dims, chans):
     """seg_softmax (PyG semantics, :508), aggregate (:512-513), edge_dot, edge_scale vs fp64 torch on ragged segments."""
     from equiformer_b200 import ops
