@@ -242,6 +242,141 @@ __global__ void __launch_bounds__(256) gate_logits_bwd_kernel(GateArgs a) {
   for (int i = threadIdx.x; i < a.A0; i += blockDim.x) a.gdot_part[(long long)blockIdx.x * a.A0 + i] = sdot[i];
 }
 
+// ------------------------------------------------------------------------------------------------ 128-bit gate/logits
+// Same math, float4 lanes: requires A0, S, every C and A0/H to be multiples of 4 and (A0/H)/4 a power of two <= 32
+// (all shipped configs).  Phase 1: lanes over alpha float4s (head partial sums combined with shuffles); phase 2: lanes
+// over scalar float4s; phase 3: lanes over gate float4s, each lane walking the 2l+1 components of its gated channels.
+__device__ __forceinline__ float4 ld4p(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4p(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 add4(const float4& a, const float4& b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+struct GateBlockRef { int b; int c; };
+__device__ __forceinline__ GateBlockRef gate_block(const GateArgs& a, int q4) {   // q4: float4 index inside the gates
+  int b = 0, c = q4 * 4;
+  while (b + 1 < a.n_gated && c >= a.C[b]) { c -= a.C[b]; ++b; }
+  return {b, c};
+}
+
+__device__ __forceinline__ float slr_act(float x, float k1, float k2, float c) {
+  const float s = sigmoidf_(x);
+  return c * (k1 * x + k2 * x * (2.f * s - 1.f));
+}
+__device__ __forceinline__ float slr_dact(float x, float k1, float k2, float c) {
+  const float s = sigmoidf_(x);
+  return c * (k1 + k2 * ((2.f * s - 1.f) + 2.f * x * s * (1.f - s)));
+}
+
+__global__ void __launch_bounds__(256) gate_logits_fwd_vec_kernel(GateArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 8;
+  const int T0 = a.A0 + a.S + a.Gt, ah = a.A0 / a.H, lph = ah / 4;   // lanes per head
+  const float k1 = 0.5f * (1.f + a.slope), k2 = 0.5f * (1.f - a.slope);
+  const float* bs = a.bias;
+  for (long long e = warp; e < a.E; e += n_warps) {
+    const float* t = a.t0 + e * T0;
+    for (int q = lane; q < a.A0 / 4; q += 32) {           // ---- logits
+      float4 x = ld4p(t + 4 * q);
+      if (bs) x = add4(x, ld4p(bs + 4 * q));
+      const float4 ad = ld4p(a.alpha_dot + 4 * q);
+      float p = slr_act(x.x, k1, k2, a.c_slr) * ad.x + slr_act(x.y, k1, k2, a.c_slr) * ad.y +
+                slr_act(x.z, k1, k2, a.c_slr) * ad.z + slr_act(x.w, k1, k2, a.c_slr) * ad.w;
+      for (int o = lph >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+      if ((q % lph) == 0) a.z[e * a.H + q / lph] = p;
+    }
+    for (int q = lane; q < a.S / 4; q += 32) {            // ---- scalars
+      float4 x = ld4p(t + a.A0 + 4 * q);
+      if (bs) x = add4(x, ld4p(bs + a.A0 + 4 * q));
+      st4p(a.v0 + e * a.S + 4 * q, make_float4(a.c_silu * x.x * sigmoidf_(x.x), a.c_silu * x.y * sigmoidf_(x.y),
+                                               a.c_silu * x.z * sigmoidf_(x.z), a.c_silu * x.w * sigmoidf_(x.w)));
+    }
+    for (int q = lane; q < a.Gt / 4; q += 32) {           // ---- gates x gated irreps
+      float4 x = ld4p(t + a.A0 + a.S + 4 * q);
+      if (bs) x = add4(x, ld4p(bs + a.A0 + a.S + 4 * q));
+      const float4 gate = make_float4(a.c_sig * sigmoidf_(x.x), a.c_sig * sigmoidf_(x.y), a.c_sig * sigmoidf_(x.z),
+                                      a.c_sig * sigmoidf_(x.w));
+      const GateBlockRef r = gate_block(a, q);
+      const int C = a.C[r.b], d = a.d[r.b];
+      const float* gb = a.gated[r.b] + e * d * C + r.c;
+      float* vb = a.vout[r.b] + e * d * C + r.c;
+      for (int i = 0; i < d; ++i) {
+        const float4 g = ld4p(gb + i * C);
+        st4p(vb + i * C, make_float4(g.x * gate.x, g.y * gate.y, g.z * gate.z, g.w * gate.w));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) gate_logits_bwd_vec_kernel(GateArgs a) {
+  extern __shared__ float sdot[];  // [A0]
+  for (int i = threadIdx.x; i < a.A0; i += blockDim.x) sdot[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 8;
+  const int T0 = a.A0 + a.S + a.Gt, ah = a.A0 / a.H, lph = ah / 4;
+  const float k1 = 0.5f * (1.f + a.slope), k2 = 0.5f * (1.f - a.slope);
+  const float* bs = a.bias;
+  float4 adot = make_float4(0.f, 0.f, 0.f, 0.f);       // alpha_dot gradient of this lane's four (h, k) (A0/4 <= 32 lanes)
+  const bool reg_acc = a.A0 / 4 <= 32;
+  for (long long e = warp; e < a.E; e += n_warps) {
+    const float* t = a.t0 + e * T0;
+    float* gt = a.gt0 + e * T0;
+    for (int q = lane; q < a.A0 / 4; q += 32) {
+      float4 x = ld4p(t + 4 * q);
+      if (bs) x = add4(x, ld4p(bs + 4 * q));
+      const float4 ad = ld4p(a.alpha_dot + 4 * q);
+      const float gzh = __ldg(a.gz + e * a.H + q / lph);
+      st4p(gt + 4 * q, make_float4(gzh * ad.x * slr_dact(x.x, k1, k2, a.c_slr), gzh * ad.y * slr_dact(x.y, k1, k2, a.c_slr),
+                                   gzh * ad.z * slr_dact(x.z, k1, k2, a.c_slr), gzh * ad.w * slr_dact(x.w, k1, k2, a.c_slr)));
+      const float4 act = make_float4(gzh * slr_act(x.x, k1, k2, a.c_slr), gzh * slr_act(x.y, k1, k2, a.c_slr),
+                                     gzh * slr_act(x.z, k1, k2, a.c_slr), gzh * slr_act(x.w, k1, k2, a.c_slr));
+      if (reg_acc) adot = add4(adot, act);
+      else { atomicAdd(&sdot[4 * q], act.x); atomicAdd(&sdot[4 * q + 1], act.y); atomicAdd(&sdot[4 * q + 2], act.z); atomicAdd(&sdot[4 * q + 3], act.w); }
+    }
+    for (int q = lane; q < a.S / 4; q += 32) {
+      float4 x = ld4p(t + a.A0 + 4 * q);
+      if (bs) x = add4(x, ld4p(bs + a.A0 + 4 * q));
+      const float4 gv = ld4p(a.gv0 + e * a.S + 4 * q);
+      const float sx = sigmoidf_(x.x), sy = sigmoidf_(x.y), sz = sigmoidf_(x.z), sw = sigmoidf_(x.w);
+      st4p(gt + a.A0 + 4 * q, make_float4(gv.x * a.c_silu * sx * (1.f + x.x * (1.f - sx)), gv.y * a.c_silu * sy * (1.f + x.y * (1.f - sy)),
+                                          gv.z * a.c_silu * sz * (1.f + x.z * (1.f - sz)), gv.w * a.c_silu * sw * (1.f + x.w * (1.f - sw))));
+    }
+    for (int q = lane; q < a.Gt / 4; q += 32) {
+      float4 x = ld4p(t + a.A0 + a.S + 4 * q);
+      if (bs) x = add4(x, ld4p(bs + a.A0 + a.S + 4 * q));
+      const float sx = sigmoidf_(x.x), sy = sigmoidf_(x.y), sz = sigmoidf_(x.z), sw = sigmoidf_(x.w);
+      const float4 gate = make_float4(a.c_sig * sx, a.c_sig * sy, a.c_sig * sz, a.c_sig * sw);
+      const GateBlockRef r = gate_block(a, q);
+      const int C = a.C[r.b], d = a.d[r.b];
+      const float* gb = a.gated[r.b] + e * d * C + r.c;
+      const float* gvb = a.gvout[r.b] + e * d * C + r.c;
+      float* ggb = a.ggated[r.b] + e * d * C + r.c;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < d; ++i) {
+        const float4 gv = ld4p(gvb + i * C), g = ld4p(gb + i * C);
+        st4p(ggb + i * C, make_float4(gv.x * gate.x, gv.y * gate.y, gv.z * gate.z, gv.w * gate.w));
+        acc.x = fmaf(gv.x, g.x, acc.x); acc.y = fmaf(gv.y, g.y, acc.y); acc.z = fmaf(gv.z, g.z, acc.z); acc.w = fmaf(gv.w, g.w, acc.w);
+      }
+      st4p(gt + a.A0 + a.S + 4 * q, make_float4(acc.x * a.c_sig * sx * (1.f - sx), acc.y * a.c_sig * sy * (1.f - sy),
+                                                acc.z * a.c_sig * sz * (1.f - sz), acc.w * a.c_sig * sw * (1.f - sw)));
+    }
+  }
+  if (reg_acc && lane < a.A0 / 4) {
+    atomicAdd(&sdot[4 * lane], adot.x); atomicAdd(&sdot[4 * lane + 1], adot.y);
+    atomicAdd(&sdot[4 * lane + 2], adot.z); atomicAdd(&sdot[4 * lane + 3], adot.w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < a.A0; i += blockDim.x) a.gdot_part[(long long)blockIdx.x * a.A0 + i] = sdot[i];
+}
+
+static bool gate_vec_ok(const GateArgs& a) {
+  if (a.A0 % 4 || a.S % 4 || (a.A0 / a.H) % 4) return false;
+  const int lph = a.A0 / a.H / 4;
+  if (lph < 1 || lph > 32 || (lph & (lph - 1))) return false;
+  if (lph > 1 && (a.A0 / 4) % 32 != 0) return false;   // head sums use full-warp shuffles: every lane must take part
+  for (int b = 0; b < a.n_gated; ++b) if (a.C[b] % 4) return false;
+  return true;
+}
+
 static int pointwise_grid(long long rows) {
   long long blocks = (rows + 7) / 8;
   const long long cap = 148LL * 8;
@@ -301,7 +436,8 @@ extern "C" int eqf_gate_logits_fwd(const EqfGateLayout* lay, const float* t0, co
     if (!gated || !vout || !gated[b] || !vout[b]) { set_error("eqf_gate_logits_fwd: null block"); return EQF_ERR_INVALID; }
     a.gated[b] = gated[b]; a.vout[b] = vout[b];
   }
-  gate_logits_fwd_kernel<<<pointwise_grid(n_edges), 256, 0, (cudaStream_t)stream>>>(a);
+  if (gate_vec_ok(a)) gate_logits_fwd_vec_kernel<<<pointwise_grid(n_edges), 256, 0, (cudaStream_t)stream>>>(a);
+  else gate_logits_fwd_kernel<<<pointwise_grid(n_edges), 256, 0, (cudaStream_t)stream>>>(a);
   return check_cuda(cudaGetLastError(), "gate_logits_fwd_kernel launch");
 }
 
@@ -318,6 +454,7 @@ extern "C" int eqf_gate_logits_bwd(const EqfGateLayout* lay, const float* t0, co
     if (!gated || !gvout || !ggated || !gated[b] || !gvout[b] || !ggated[b]) { set_error("eqf_gate_logits_bwd: null block"); return EQF_ERR_INVALID; }
     a.gated[b] = gated[b]; a.gvout[b] = gvout[b]; a.ggated[b] = ggated[b];
   }
-  gate_logits_bwd_kernel<<<pointwise_grid(n_edges), 256, a.A0 * sizeof(float), (cudaStream_t)stream>>>(a);
+  if (gate_vec_ok(a)) gate_logits_bwd_vec_kernel<<<pointwise_grid(n_edges), 256, a.A0 * sizeof(float), (cudaStream_t)stream>>>(a);
+  else gate_logits_bwd_kernel<<<pointwise_grid(n_edges), 256, a.A0 * sizeof(float), (cudaStream_t)stream>>>(a);
   return check_cuda(cudaGetLastError(), "gate_logits_bwd_kernel launch");
 }

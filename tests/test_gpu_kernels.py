@@ -247,7 +247,9 @@ def test_ln_silu_fused(cuda_device, R, C):
 
 
 @pytest.mark.parametrize("cfg", [dict(A0=128, S=128, H=4, ds=(3, 5), Cs=(64, 32)), dict(A0=256, S=256, H=8, ds=(3,), Cs=(128,)),
-                                 dict(A0=128, S=128, H=4, ds=(3, 5, 7), Cs=(64, 64, 32))])
+                                 dict(A0=128, S=128, H=4, ds=(3, 5, 7), Cs=(64, 64, 32)),
+                                 dict(A0=16, S=16, H=4, ds=(3, 5), Cs=(8, 4)),       # tiny heads: one lane per head
+                                 dict(A0=64, S=20, H=4, ds=(3,), Cs=(6,))])          # falls back to the scalar kernels
 def test_gate_logits_fused(cuda_device, cfg):
     """bias + Gate + attention logits in one kernel (ref :492-495, :506-507) vs the fp64 torch statement, fwd and bwd."""
     from equiformer_b200 import ops
