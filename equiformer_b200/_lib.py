@@ -63,6 +63,16 @@ class EqfGateLayout(ctypes.Structure):
     ]
 
 
+class EqfNormLayout(ctypes.Structure):
+    _fields_ = [
+        ("n_entries", c_int32),
+        ("mul", c_int32 * EQF_MAX_BLOCKS),
+        ("d", c_int32 * EQF_MAX_BLOCKS),
+        ("is_scalar", c_int32 * EQF_MAX_BLOCKS),
+        ("eps", c_float),
+    ]
+
+
 class EqfHeadLayout(ctypes.Structure):
     _fields_ = [
         ("n_groups", c_int32),
@@ -102,6 +112,10 @@ SIGNATURES = {
                                   c_void_p]),
     "eqf_ln_silu_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
                                   c_void_p, c_void_p, c_void_p]),
+    "eqf_eln_rows": (c_int32, [c_int64]),
+    "eqf_eln_fwd": (c_int32, [POINTER(EqfNormLayout), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "eqf_eln_bwd": (c_int32, [POINTER(EqfNormLayout), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                              c_void_p, c_void_p]),
     "eqf_gate_logits_fwd": (c_int32, [POINTER(EqfGateLayout), c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_int64,
                                       c_void_p, c_void_p, POINTER(c_void_p), c_void_p]),
     "eqf_gate_logits_bwd": (c_int32, [POINTER(EqfGateLayout), c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p,
@@ -220,9 +234,10 @@ def load_gemm():
     with _lock:
         if _gemm_lib is not None:
             return _gemm_lib
-        if not GEMM_LIB_PATH.exists():
-            raise EqfError(f"{GEMM_LIB_PATH} is missing: run __graft_entry__.build()")
-        lib = ctypes.CDLL(str(GEMM_LIB_PATH))
+        path = Path(os.environ.get("EQF_GEMM_LIB", GEMM_LIB_PATH))     # override: tuning variants (tools/gemm_microbench.py)
+        if not path.exists():
+            raise EqfError(f"{path} is missing: run __graft_entry__.build()")
+        lib = ctypes.CDLL(str(path))
         for name, (restype, argtypes) in GEMM_SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = restype

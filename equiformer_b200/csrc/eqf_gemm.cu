@@ -40,7 +40,33 @@ static int check_cuda(cudaError_t err, const char* what) {
   return EQF_ERR_CUDA;
 }
 
-template <class LayoutA, class LayoutB, int TileN, int TileK = 16, class Scheduler = void, bool TwoSm = false>
+// The stock builder fixes NumBandsToCompute = 5 (all nine bf16 cross products) and AccPromotionInterval = 1.
+// Bands 4 and 5 (A1*B2 + A2*B1, A2*B2) carry terms below 2^-24 of the product - under the fp32 rounding of the
+// result - so the policy is rebound here with a compile-time band count (3 keeps six of the nine MMAs).
+#ifndef EQF_GEMM_BANDS
+#define EQF_GEMM_BANDS 5
+#endif
+#ifndef EQF_GEMM_PROMO
+#define EQF_GEMM_PROMO 1
+#endif
+#ifndef EQF_GEMM_TILEK
+#define EQF_GEMM_TILEK 16
+#endif
+
+template <class Op, int Bands, int Promo>
+struct RebindBands { using type = Op; };
+
+template <int L2T, int T2M, int Sch, int Acc, int NB, int SF, int API, class CS, class ACA, class Arch, int Bands,
+          int Promo, class... Rest>
+struct RebindBands<cutlass::gemm::collective::CollectiveMma<
+                       cutlass::gemm::MainloopSm100TmaUmmaWarpSpecializedFastF32<L2T, T2M, Sch, Acc, NB, SF, API, CS, ACA, Arch>,
+                       Rest...>,
+                   Bands, Promo> {
+  using type = cutlass::gemm::collective::CollectiveMma<
+      cutlass::gemm::MainloopSm100TmaUmmaWarpSpecializedFastF32<L2T, T2M, Sch, Acc, Bands, SF, Promo, CS, ACA, Arch>, Rest...>;
+};
+
+template <class LayoutA, class LayoutB, int TileN, int TileK = EQF_GEMM_TILEK, class Scheduler = void, bool TwoSm = false>
 struct FastF32Gemm {
   using ElementA = float;
   using ElementB = float;
@@ -59,11 +85,13 @@ struct FastF32Gemm {
       cutlass::epilogue::collective::EpilogueTileAuto, ElementAcc, ElementAcc, ElementC, LayoutC, Align, ElementC,
       LayoutC, Align, cutlass::epilogue::collective::EpilogueScheduleAuto>::CollectiveOp;
 
-  using CollectiveMainloop = typename cutlass::gemm::collective::CollectiveBuilder<
+  using StockMainloop = typename cutlass::gemm::collective::CollectiveBuilder<
       cutlass::arch::Sm100, cutlass::arch::OpClassTensorOp, ElementA, LayoutA, Align, ElementB, LayoutB, Align,
       ElementAcc, MmaTile, Cluster,
       cutlass::gemm::collective::StageCountAutoCarveout<static_cast<int>(sizeof(typename CollectiveEpilogue::SharedStorage))>,
       Schedule>::CollectiveOp;
+  using CollectiveMainloop = typename RebindBands<StockMainloop, EQF_GEMM_BANDS, EQF_GEMM_PROMO>::type;
+  static_assert(CollectiveMainloop::DispatchPolicy::NumBandsToCompute == EQF_GEMM_BANDS, "band rebinding did not apply");
 
   using GemmKernel = cutlass::gemm::kernel::GemmUniversal<Shape<int, int, int, int>, CollectiveMainloop, CollectiveEpilogue, Scheduler>;
   using Gemm = cutlass::gemm::device::GemmUniversalAdapter<GemmKernel>;
@@ -142,10 +170,10 @@ extern "C" int eqf_gemm_f32(int mode, const float* A, const float* B, float* C, 
   static const bool two_sm = [] { const char* e = std::getenv("EQF_GEMM_2SM"); return e == nullptr || e[0] != '0'; }();
   if (two_sm && mode != 2) {
     if (mode == 0)
-      return wide ? FastF32Gemm<Row, Row, 128, 16, void, true>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
-                  : FastF32Gemm<Row, Row, 64, 16, void, true>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
-    return wide ? FastF32Gemm<Row, Col, 128, 16, void, true>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
-                : FastF32Gemm<Row, Col, 64, 16, void, true>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
+      return wide ? FastF32Gemm<Row, Row, 128, EQF_GEMM_TILEK, void, true>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
+                  : FastF32Gemm<Row, Row, 64, EQF_GEMM_TILEK, void, true>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
+    return wide ? FastF32Gemm<Row, Col, 128, EQF_GEMM_TILEK, void, true>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s)
+                : FastF32Gemm<Row, Col, 64, EQF_GEMM_TILEK, void, true>::run(A, B, C, m, n, k, lda, ldb, ldc, beta, workspace, workspace_bytes, s);
   }
   switch (mode) {
     case 0:
@@ -188,4 +216,12 @@ extern "C" int eqf_gemm_f32_wgrad_sliced(const float* A, const float* B, float* 
                                            chunk * lda, chunk * ldb, M * N);
   return FastF32Gemm<Col, Row, 64>::run(A, B, part, m, n, k, lda, ldb, N, 0.f, workspace, workspace_bytes, s, L,
                                         chunk * lda, chunk * ldb, M * N);
+}
+
+
+extern "C" int eqf_gemm_config(int* bands, int* promo, int* tile_k) {
+  if (bands) *bands = EQF_GEMM_BANDS;
+  if (promo) *promo = EQF_GEMM_PROMO;
+  if (tile_k) *tile_k = EQF_GEMM_TILEK;
+  return EQF_OK;
 }

@@ -1,6 +1,7 @@
 """Equivariant layer normalisation (drop-in for ``EquivariantLayerNormV2``, ``nets/layer_norm.py:62-152``).
 
-Node-level, O(N*D) work: kept in torch.  Per irreps entry ``[N, mul, 2l+1]``: scalars are
+Node-level, O(N*D) work; the affine 'component' case runs as one fused kernel forward and one backward
+(``ops.equivariant_layer_norm`` -> ``eqf_eln_fwd/bwd``), everything else as the torch statement below.  Per irreps entry ``[N, mul, 2l+1]``: scalars are
 mean-centred over channels; every entry is divided by the RMS over (channels, components)
 (``normalization='component'``) or the channel mean of squared norms (``'norm'``), scaled by a per-channel
 affine weight; scalars get an affine bias.  ``state_dict`` keys ``affine_weight`` / ``affine_bias``.
@@ -10,6 +11,7 @@ from __future__ import annotations
 import torch
 from torch import nn
 
+from .. import ops
 from ..o3 import Irreps
 
 
@@ -29,6 +31,9 @@ class EquivariantLayerNormV2(nn.Module):
         if normalization not in ("norm", "component"):
             raise AssertionError("normalization needs to be 'norm' or 'component'")
         self.normalization = normalization
+        self._layout = None
+        if affine and normalization == "component" and len(self.irreps) <= 8:
+            self._layout = ops.NormLayout([(mul, ir.dim, ir.l == 0 and ir.p == 1) for mul, ir in self.irreps], eps)
 
     def __repr__(self) -> str:
         return f"{self.__class__.__name__}({self.irreps}, eps={self.eps})"
@@ -38,6 +43,8 @@ class EquivariantLayerNormV2(nn.Module):
         if x.shape[-1] != self.irreps.dim:
             raise AssertionError(f"`ix` should have reached node_input.size(-1) ({x.shape[-1]}), "
                                  f"but it ended at {self.irreps.dim}")
+        if self._layout is not None and x.dim() == 2:
+            return ops.equivariant_layer_norm(self._layout, x, self.affine_weight, self.affine_bias)
         out, off, iw, ib = [], 0, 0, 0
         for mul, ir in self.irreps:
             d = ir.dim

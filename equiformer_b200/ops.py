@@ -983,6 +983,94 @@ def ln_silu(x, gamma, beta, eps: float = 1e-5):
     return ln_silu_torch(x, gamma, beta, eps)
 
 
+class NormLayout:
+    """Static description of an ``EquivariantLayerNormV2`` ('component', affine) for ``eqf_eln_fwd/bwd``."""
+
+    def __init__(self, entries: Sequence[tuple], eps: float):
+        # entries: (mul, dim, is_scalar) per irreps entry, in e3nn order
+        if len(entries) > _lib.EQF_MAX_BLOCKS:
+            raise NotImplementedError("norm layout exceeds kernel limits")
+        self.entries, self.eps = tuple(entries), float(eps)
+        self.dim = sum(m * d for m, d, _ in entries)
+        self.n_w = sum(m for m, _, _ in entries)
+        self.n_b = sum(m for m, _, sc in entries if sc)
+        c = _lib.EqfNormLayout()
+        c.n_entries, c.eps = len(entries), float(eps)
+        for i, (m, d, sc) in enumerate(entries):
+            c.mul[i], c.d[i], c.is_scalar[i] = m, d, int(bool(sc))
+        self.c = c
+
+
+def eln_torch(lay: NormLayout, x, w, b):
+    """Differentiable torch statement of the fused equivariant LayerNorm (ref nets/layer_norm.py:104-152)."""
+    out, off, iw, ib = [], 0, 0, 0
+    for mul, d, scalar in lay.entries:
+        f = x.narrow(1, off, mul * d).reshape(-1, mul, d)
+        off += mul * d
+        if scalar:
+            f = f - f.mean(dim=1, keepdim=True)
+        scale = (f.pow(2).mean(-1).mean(dim=1, keepdim=True) + lay.eps).pow(-0.5) * w[None, iw:iw + mul]
+        iw += mul
+        f = f * scale.unsqueeze(-1)
+        if scalar:
+            f = f + b[ib:ib + mul].reshape(mul, 1)
+            ib += mul
+        out.append(f.reshape(-1, mul * d))
+    return torch.cat(out, dim=-1)
+
+
+def eln_fwd_raw(lay: NormLayout, x, w, b):
+    x = _require_cuda(x, "eln x")
+    N = x.shape[0]
+    y = torch.empty_like(x)
+    rstd = torch.empty((N, len(lay.entries)), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device), _kernel("eln_fwd", 8 * x.numel()):
+        rc = _lib.load().eqf_eln_fwd(ctypes.byref(lay.c), x.data_ptr(), w.data_ptr(), b.data_ptr(), N, y.data_ptr(),
+                                     rstd.data_ptr(), _stream())
+    _lib.check(rc, "eqf_eln_fwd")
+    return y, rstd
+
+
+def eln_bwd_raw(lay: NormLayout, x, w, rstd, gy):
+    gy = _require_cuda(gy, "eln gy")
+    N = x.shape[0]
+    rows = _lib.load().eqf_eln_rows(N)
+    gx = torch.empty_like(x)
+    dw = torch.empty((rows, lay.n_w), device=x.device, dtype=torch.float32)
+    db = torch.empty((rows, max(lay.n_b, 1)), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device), _kernel("eln_bwd", 12 * x.numel()):
+        rc = _lib.load().eqf_eln_bwd(ctypes.byref(lay.c), x.data_ptr(), w.data_ptr(), rstd.data_ptr(), gy.data_ptr(), N,
+                                     gx.data_ptr(), dw.data_ptr(), db.data_ptr(), _stream())
+    _lib.check(rc, "eqf_eln_bwd")
+    return gx, dw.sum(0), db.sum(0)[:lay.n_b]
+
+
+class EquivLayerNorm(torch.autograd.Function):
+    """Fused ``EquivariantLayerNormV2`` forward/backward on e3nn-layout node rows."""
+
+    @staticmethod
+    def forward(ctx, lay: NormLayout, x, w, b):
+        y, rstd = eln_fwd_raw(lay, x, w, b)
+        ctx.lay = lay
+        ctx.save_for_backward(x, w, b, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w, b, rstd = ctx.saved_tensors
+        if torch.is_grad_enabled():
+            gx, gw, gb = _higher_order_grads(lambda a, c, e: eln_torch(ctx.lay, a, c, e), (x, w, b), (gy,))
+            return None, gx, gw, gb
+        gx, gw, gb = eln_bwd_raw(ctx.lay, x, w, rstd, gy.contiguous())
+        return None, gx, gw, gb
+
+
+def equivariant_layer_norm(lay: NormLayout, x, w, b):
+    if fused_ok(x) and x.dim() == 2 and x.shape[0] > 0:
+        return EquivLayerNorm.apply(lay, x.contiguous(), w, b)
+    return eln_torch(lay, x, w, b)
+
+
 class GateLayout:
     """Static description of the fused gate + logits op (see ``eqf_gate_logits_fwd`` in include/eqf_b200.h)."""
 

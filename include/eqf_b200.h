@@ -142,6 +142,21 @@ int eqf_ln_silu_bwd(const float* x, const float* gamma, const float* beta, const
                     const float* gy, int64_t R, int32_t C, float* gx, float* dgamma_part, float* dbeta_part,
                     void* stream);
 
+/* EquivariantLayerNormV2 ('component' normalisation, affine; nets/layer_norm.py:89-152) on e3nn-layout rows:
+ * one fused kernel forward, one backward (per-CTA partial sums of the affine gradients in [eqf_eln_rows(N), .]). */
+typedef struct {
+  int32_t n_entries;
+  int32_t mul[EQF_MAX_BLOCKS];
+  int32_t d[EQF_MAX_BLOCKS];
+  int32_t is_scalar[EQF_MAX_BLOCKS];   /* 0e entries: mean-centred, carry the affine bias */
+  float eps;
+} EqfNormLayout;
+int eqf_eln_rows(int64_t rows);
+int eqf_eln_fwd(const EqfNormLayout* lay, const float* x, const float* w, const float* b, int64_t N, float* y,
+                float* rstd, void* stream);
+int eqf_eln_bwd(const EqfNormLayout* lay, const float* x, const float* w, const float* rstd, const float* gy,
+                int64_t N, float* gx, float* dw_part, float* db_part, void* stream);
+
 /* Gate + attention logits of GraphAttention.forward (graph_attention_transformer.py:492-495, 506-507) in one pass:
  *   t0[e] = [alpha | scalars | gates] pre-activations (+ optional bias), gated[b] planar blocks [E, d, C];
  *   z[e,h] = sum_k c_slr * SmoothLeakyReLU(alpha[e,h,k]) * alpha_dot[h,k];  v0 = c_silu * silu(scalars);

@@ -141,6 +141,22 @@ def ln_silu_fwd_raw(x, gamma, beta, eps):
     return ops.ln_silu_torch(x, gamma, beta, eps), mean, rstd
 
 
+def eln_fwd_raw(lay, x, w, b):
+    return ops.eln_torch(lay, x, w, b), torch.zeros(x.shape[0], len(lay.entries))
+
+
+def eln_bwd_raw(lay, x, w, rstd, gy):
+    xs = [t.detach().requires_grad_(True) for t in (x, w, b_like(lay, x))]
+    with torch.enable_grad():
+        y = ops.eln_torch(lay, *xs)
+    gx, gw, gb = torch.autograd.grad(y, xs, gy, allow_unused=True)
+    return gx, gw, gb if gb is not None else torch.zeros(lay.n_b)
+
+
+def b_like(lay, x):
+    return torch.zeros(lay.n_b, dtype=x.dtype)
+
+
 def ln_silu_bwd_raw(x, gamma, beta, mean, rstd, gy):
     with torch.enable_grad():
         xs = [t.detach().requires_grad_(True) for t in (x, gamma, beta)]
@@ -163,7 +179,7 @@ def gate_logits_bwd_raw(lay, t0, bias, alpha_dot, gated, gz, gv0, gvout):
     return grads[0], list(grads[2:]), grads[1].reshape(-1)
 
 
-_PATCHED = ["ln_silu_fwd_raw", "ln_silu_bwd_raw", "gate_logits_fwd_raw", "gate_logits_bwd_raw", "gemm_raw", "dtp_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
+_PATCHED = ["eln_fwd_raw", "eln_bwd_raw", "ln_silu_fwd_raw", "ln_silu_bwd_raw", "gate_logits_fwd_raw", "gate_logits_bwd_raw", "gemm_raw", "dtp_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
             "seg_softmax_raw", "attn_aggregate_raw", "attn_edge_dot_raw", "attn_edge_scale_raw"]
 
 

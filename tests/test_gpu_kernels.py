@@ -246,6 +246,34 @@ def test_ln_silu_fused(cuda_device, R, C):
     assert rel_err(gx, rx) < 5e-5 and rel_err(gg, rg) < 5e-5 and rel_err(gb, rb) < 5e-5
 
 
+@pytest.mark.parametrize("entries", [[(128, 1, True), (64, 3, False), (32, 5, False)],
+                                     [(128, 1, True), (64, 3, False), (64, 5, False), (32, 7, False)],
+                                     [(256, 1, True), (128, 3, False)],
+                                     [(8, 1, True), (8, 1, False), (5, 3, False)]])
+@pytest.mark.parametrize("N", [1, 1461, 5000])
+def test_equivariant_layer_norm_fused(cuda_device, entries, N):
+    """EquivariantLayerNormV2 ('component', affine; ref nets/layer_norm.py:104-152) fused fwd / bwd vs fp64 torch."""
+    from equiformer_b200 import ops
+    lay = ops.NormLayout(entries, 1e-5)
+    g = torch.Generator().manual_seed(N)
+    x = torch.randn(N, lay.dim, generator=g) * 1.5 + 0.2
+    w, b = torch.randn(lay.n_w, generator=g), torch.randn(lay.n_b, generator=g)
+    gy = torch.randn(N, lay.dim, generator=g)
+    d = lambda t: t.to(cuda_device)
+    y, rstd = ops.eln_fwd_raw(lay, d(x), d(w), d(b))
+    xs = [t.double().requires_grad_(True) for t in (x, w, b)]
+    ref = ops.eln_torch(lay, *xs)
+    assert rel_err(y, ref) < TOL
+    gx, gw, gb = ops.eln_bwd_raw(lay, d(x), d(w), rstd, d(gy))
+    rx, rw, rb = torch.autograd.grad(ref, xs, gy.double())
+    assert rel_err(gx, rx) < 5e-5 and rel_err(gw, rw) < 5e-5 and rel_err(gb, rb) < 5e-5
+    # through the module, autograd wiring included
+    xd, wd, bd = (d(t).requires_grad_(True) for t in (x, w, b))
+    out = ops.equivariant_layer_norm(lay, xd, wd, bd)
+    ax, aw, ab = torch.autograd.grad(out, (xd, wd, bd), d(gy))
+    assert rel_err(ax, rx) < 5e-5 and rel_err(aw, rw) < 5e-5 and rel_err(ab, rb) < 5e-5
+
+
 @pytest.mark.parametrize("cfg", [dict(A0=128, S=128, H=4, ds=(3, 5), Cs=(64, 32)), dict(A0=256, S=256, H=8, ds=(3,), Cs=(128,)),
                                  dict(A0=128, S=128, H=4, ds=(3, 5, 7), Cs=(64, 64, 32)),
                                  dict(A0=16, S=16, H=4, ds=(3, 5), Cs=(8, 4)),       # tiny heads: one lane per head
