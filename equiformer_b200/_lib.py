@@ -131,6 +131,7 @@ GEMM_SIGNATURES = {
                                             c_int64, c_void_p, c_int64, c_void_p]),
     "eqf_gemm_workspace_bytes": (c_int64, []),
     "eqf_gemm_last_error": (c_char_p, []),
+    "eqf_gemm_config": (c_int32, [POINTER(c_int32), POINTER(c_int32), POINTER(c_int32)]),
 }
 
 

@@ -43,14 +43,17 @@ static int check_cuda(cudaError_t err, const char* what) {
 // The stock builder fixes NumBandsToCompute = 5 (all nine bf16 cross products) and AccPromotionInterval = 1.
 // Bands 4 and 5 (A1*B2 + A2*B1, A2*B2) carry terms below 2^-24 of the product - under the fp32 rounding of the
 // result - so the policy is rebound here with a compile-time band count (3 keeps six of the nine MMAs).
+// Measured on the layer shapes (profiles/r1_gemm_variants.md): the band count barely matters (the kernel is not
+// MMA-bound), promoting the TMEM accumulator into registers every 2 k-blocks instead of every one is worth 20 %;
+// rel. error vs fp64 stays 2.7e-7 (cuBLAS SGEMM: 8e-7).  K tile 64 / interval 4 does not fit shared memory.
 #ifndef EQF_GEMM_BANDS
-#define EQF_GEMM_BANDS 5
+#define EQF_GEMM_BANDS 3
 #endif
 #ifndef EQF_GEMM_PROMO
-#define EQF_GEMM_PROMO 1
+#define EQF_GEMM_PROMO 2
 #endif
 #ifndef EQF_GEMM_TILEK
-#define EQF_GEMM_TILEK 16
+#define EQF_GEMM_TILEK 32
 #endif
 
 template <class Op, int Bands, int Promo>

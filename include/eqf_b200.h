@@ -190,6 +190,8 @@ int eqf_gemm_f32_wgrad_sliced(const float* A, const float* B, float* part, int64
                               void* stream);
 int64_t eqf_gemm_workspace_bytes(void);
 const char* eqf_gemm_last_error(void);
+/* compile-time tuning of the fast-fp32 mainloop: bf16 bands kept (3..5), accumulator promotion interval, K tile */
+int eqf_gemm_config(int* bands, int* promo, int* tile_k);
 
 #ifdef __cplusplus
 }
