@@ -377,6 +377,87 @@ static bool gate_vec_ok(const GateArgs& a) {
   return true;
 }
 
+// ------------------------------------------------------------------------------------------------ column sum
+// out[c] = sum_r x[r, c]: bias / offset gradients (sum over all edges), reduction of per-CTA partial rows and of the
+// sliced weight-gradient partials.  torch's reduce_kernel ran these at 1-2 TB/s (a single CTA for the narrow ones):
+// 201 launches, 4.1 ms of a 27 ms step (profiles/r1_launches_final.csv).  Threads run along the columns (coalesced,
+// float4 when aligned), rows are split over blockIdx.y; the last CTA to finish a column tile adds the partial rows in
+// a fixed order (deterministic) and resets the tile's counter, so the buffer is reusable without a memset.
+template <int VEC>
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long rows, long long cols, long long ld,
+                                                     float* __restrict__ out, float* __restrict__ part,
+                                                     unsigned int* __restrict__ counters) {
+  __shared__ float red[8][32 * VEC];
+  __shared__ bool last;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const long long c0 = ((long long)blockIdx.x * 32 + tx) * VEC;
+  const bool active = c0 < cols;
+  float acc[4][VEC];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[u][v] = 0.f;
+  const long long stride = (long long)gridDim.y * 8;
+  long long r = (long long)blockIdx.y * 8 + ty;
+  if (active) {
+    for (; r + 3 * stride < rows; r += 4 * stride) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float* p = x + (r + u * stride) * ld + c0;
+        if constexpr (VEC == 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+          acc[u][0] += v.x; acc[u][1] += v.y; acc[u][2] += v.z; acc[u][3] += v.w;
+        } else {
+          acc[u][0] += __ldg(p);
+        }
+      }
+    }
+    for (; r < rows; r += stride) {
+      const float* p = x + r * ld + c0;
+      if constexpr (VEC == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        acc[0][0] += v.x; acc[0][1] += v.y; acc[0][2] += v.z; acc[0][3] += v.w;
+      } else {
+        acc[0][0] += __ldg(p);
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) red[ty][tx * VEC + v] = (acc[0][v] + acc[1][v]) + (acc[2][v] + acc[3][v]);
+  __syncthreads();
+  const int t = ty * 32 + tx;                       // 256 threads over the 32*VEC columns of the tile
+  const long long tile0 = (long long)blockIdx.x * 32 * VEC;
+  if (t < 32 * VEC && tile0 + t < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][t];
+    if (gridDim.y == 1) out[tile0 + t] = s;
+    else part[(long long)blockIdx.y * cols + tile0 + t] = s;
+  }
+  if (gridDim.y == 1) return;
+  __threadfence();
+  __syncthreads();
+  if (t == 0) last = (atomicAdd(&counters[blockIdx.x], 1u) == gridDim.y - 1);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (t < 32 * VEC && tile0 + t < cols) {
+    float s = 0.f;
+    for (unsigned int k = 0; k < gridDim.y; ++k) s += __ldcg(part + (long long)k * cols + tile0 + t);
+    out[tile0 + t] = s;
+  }
+  if (t == 0) counters[blockIdx.x] = 0u;
+}
+
+static void colsum_shape(long long rows, long long cols, int vec, long long& tiles, long long& splits) {
+  tiles = (cols + 32 * vec - 1) / (32 * vec);
+  splits = (148LL * 6) / tiles;
+  const long long max_splits = (rows + 31) / 32;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  if (splits > 65535) splits = 65535;
+}
+
 // ------------------------------------------------------------------------------------------------ equivariant LayerNorm
 // EquivariantLayerNormV2 ('component', nets/layer_norm.py:89-152) on e3nn-layout rows [N, sum mul*(2l+1)]:
 // per entry: scalars are mean-centred over channels; n = mean over (channel, component) of field^2;
@@ -597,4 +678,33 @@ extern "C" int eqf_eln_bwd(const EqfNormLayout* lay, const float* x, const float
   a.x = x; a.w = w; a.b = nullptr; a.rstd = const_cast<float*>(rstd); a.gy = gy; a.gx = gx; a.dw_part = dw_part; a.db_part = db_part; a.N = N;
   eln_bwd_kernel<<<eln_grid(N), 256, (a.n_w + a.n_b) * sizeof(float), (cudaStream_t)stream>>>(a);
   return check_cuda(cudaGetLastError(), "eln_bwd_kernel launch");
+}
+
+
+// out[cols] = column sums of x[rows, cols] (row stride ld).  `part` needs eqf_colsum_scratch_floats(rows, cols) floats,
+// `counters` EQF_COLSUM_COUNTERS zero-initialised uint32 (left zeroed on return: reusable across calls on one stream).
+extern "C" int64_t eqf_colsum_scratch_floats(int64_t rows, int64_t cols) {
+  long long tiles, splits;
+  colsum_shape(rows, cols, 1, tiles, splits);       // the scalar layout has the most tiles -> fewest splits; bound both
+  long long t4, s4;
+  colsum_shape(rows, cols, 4, t4, s4);
+  const long long m = splits > s4 ? splits : s4;
+  return m * cols;
+}
+
+extern "C" int eqf_colsum(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out, float* part,
+                          uint32_t* counters, void* stream) {
+  if (cols <= 0) return EQF_OK;
+  if (!out) { set_error("eqf_colsum: null output"); return EQF_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (rows <= 0) return check_cuda(cudaMemsetAsync(out, 0, cols * sizeof(float), s), "eqf_colsum memset");
+  if (!x || !part || !counters || ld < cols) { set_error("eqf_colsum: bad arguments"); return EQF_ERR_INVALID; }
+  const bool vec = (cols % 4 == 0) && (ld % 4 == 0) && ((uintptr_t)x % 16 == 0);
+  long long tiles, splits;
+  colsum_shape(rows, cols, vec ? 4 : 1, tiles, splits);
+  if (tiles > EQF_COLSUM_COUNTERS) { set_error("eqf_colsum: too many column tiles"); return EQF_ERR_UNSUPPORTED; }
+  dim3 grid((unsigned)tiles, (unsigned)splits), block(32, 8);
+  if (vec) colsum_kernel<4><<<grid, block, 0, s>>>(x, rows, cols, ld, out, part, counters);
+  else colsum_kernel<1><<<grid, block, 0, s>>>(x, rows, cols, ld, out, part, counters);
+  return check_cuda(cudaGetLastError(), "colsum_kernel launch");
 }

@@ -397,17 +397,33 @@ class FeedForwardNetwork(torch.nn.Module):
         self.fctp_2 = FullyConnectedTensorProductRescale(
             self.irreps_mlp_mid, self.irreps_node_attr, self.irreps_node_output, bias=True, rescale=_RESCALE)
         self.proj_drop = EquivariantDropout(self.irreps_node_output, drop_prob=proj_drop) if proj_drop != 0.0 else None
+        # bias + Gate in one kernel when fctp_1 has the canonical structure (one instruction per output entry)
+        self._gate_layout = None
+        gate, f1 = self.fctp_1.gate, self.fctp_1
+        ins = [(i.i_in1, i.i_out) for i in f1.tp.instructions]
+        if (isinstance(gate, Gate) and ins == [(i, i) for i in range(len(f1.irreps_out))] and len(f1.bias) == 1
+                and self.irreps_node_attr.dim == 1):
+            lay = ops.gate_only_layout(gate, f1.irreps_out)
+            self._gate_layout = lay if (lay is not None and f1.bias[0].numel() == lay.width) else None
 
     def forward(self, node_input, node_attr, **kwargs):
         # planar end to end: entries of fctp_1's gate input -> gate -> fctp_2
         xs = ops.to_planar(node_input, self.irreps_node_input)
-        h = self.fctp_1.planar(xs, node_attr)
+        # the models feed the constant scalar 1 as node_attr (ref :869): the multiply by it is skipped when marked so
+        y = None if (getattr(node_attr, "_eqf_all_ones", False) and self.irreps_node_attr.dim == 1) else node_attr
         gate = self.fctp_1.gate
-        if isinstance(gate, Gate):
-            h = _reblock(gate.planar(h), gate.irreps_out, self.fctp_2.irreps_in1)
+        if self._gate_layout is not None and y is None and ops.fused_ok(xs[0]):
+            pre = self.fctp_1.tp.planar_linear(xs, None, None)                  # bias is added inside the gate kernel
+            N = pre[0].shape[0]
+            h = ops.gate_fused(self._gate_layout, pre[0].reshape(N, -1), self.fctp_1.bias[0], pre[1:])
+            h = _reblock([h[0].view(N, 1, -1), *h[1:]], gate.irreps_out, self.fctp_2.irreps_in1)
         else:
-            h = [gate(t) for t in h]
-        node_output = ops.from_planar(self.fctp_2.planar(h, node_attr))
+            h = self.fctp_1.planar(xs, y)
+            if isinstance(gate, Gate):
+                h = _reblock(gate.planar(h), gate.irreps_out, self.fctp_2.irreps_in1)
+            else:
+                h = [gate(t) for t in h]
+        node_output = ops.from_planar(self.fctp_2.planar(h, y))
         if self.proj_drop is not None:
             node_output = self.proj_drop(node_output)
         return node_output
@@ -630,6 +646,7 @@ class GraphAttentionTransformer(torch.nn.Module):
                                                     batch, graph=graph)
         node_features = atom_embedding + edge_degree_embedding
         node_attr = torch.ones_like(node_features.narrow(1, 0, 1))
+        node_attr._eqf_all_ones = True          # lets the node-level FCTPs skip the multiply by the constant 1
         for blk in self.blocks:
             node_features = blk(node_input=node_features, node_attr=node_attr, edge_src=edge_src, edge_dst=edge_dst,
                                 edge_attr=edge_sh, edge_scalars=edge_length_embedding, batch=batch, graph=graph)

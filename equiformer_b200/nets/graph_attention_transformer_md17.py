@@ -128,6 +128,7 @@ class GraphAttentionTransformerMD17(torch.nn.Module):
                                                     batch, graph=graph)
         node_features = atom_embedding + edge_degree_embedding
         node_attr = torch.ones_like(node_features.narrow(1, 0, 1))
+        node_attr._eqf_all_ones = True
         for blk in self.blocks:
             node_features = blk(node_input=node_features, node_attr=node_attr, edge_src=edge_src, edge_dst=edge_dst,
                                 edge_attr=edge_sh, edge_scalars=edge_length_embedding, batch=batch, graph=graph)

@@ -50,5 +50,5 @@ class RadialProfile(nn.Module):
                 out = m(out)
                 i += 1
         if self.offset is not None:
-            out = out + self.offset.reshape(1, -1)
+            out = ops.add_bias(out, self.offset)
         return out

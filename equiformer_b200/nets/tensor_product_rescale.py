@@ -23,6 +23,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from .. import o3
+from .. import ops
 from ..o3 import Irreps
 
 
@@ -120,7 +121,7 @@ class TensorProductRescale(torch.nn.Module):
         res = []
         for t, (b_idx, off) in zip(outs, self._entry_bias):
             if b_idx is not None:
-                t = t + self.bias[b_idx].narrow(0, off, t.shape[-1])
+                t = ops.add_bias(t, self.bias[b_idx].narrow(0, off, t.shape[-1]))
             res.append(t)
         return res
 

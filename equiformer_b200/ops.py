@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import contextlib
 import ctypes
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -251,7 +252,7 @@ def dtp_grad_w_raw(plan: DtpPlan, xs, y, gs, shared: bool) -> torch.Tensor:
     with torch.cuda.device(y.device), _kernel("dtp_grad_w", _dtp_bytes(plan, E, shared, "grad_w")):
         rc = _lib.load().eqf_dtp_grad_w(plan.handle, ctypes.byref(op), E, ctypes.c_void_p(gw.data_ptr()), _stream())
     _lib.check(rc, "eqf_dtp_grad_w")
-    return gw.sum(dim=0) if shared else gw
+    return _colsum(gw) if shared else gw
 
 
 def dtp_grad_y_raw(plan: DtpPlan, xs, w, gs, y_like) -> torch.Tensor:
@@ -279,7 +280,7 @@ def dtp_grad_xw_raw(plan: DtpPlan, xs, y, w, gs, gather=None) -> Tuple[List[torc
         rc = _lib.load().eqf_dtp_grad_xw(plan.handle, ctypes.byref(op), E, _ptr_array(gxs),
                                          ctypes.c_void_p(gw.data_ptr()), _stream())
     _lib.check(rc, "eqf_dtp_grad_xw")
-    return gxs, (gw.sum(dim=0) if shared else gw)
+    return gxs, (_colsum(gw) if shared else gw)
 
 
 # ----------------------------------------------------------------------------- DTP autograd family
@@ -785,6 +786,9 @@ def _gemm_operand(t: torch.Tensor):
     return t, t.stride(0)
 
 
+_WGRAD_MIN_K = int(os.environ.get("EQF_WGRAD_MIN_K", "16384"))   # reduction length from which the weight gradient uses tcgen05
+
+
 def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     """mode 0: A[M,K] B[K,N]; mode 1: A[M,K] B[N,K]^T; mode 2: A[K,M]^T B[K,N]  ->  C[M,N] (fp32 accurate)."""
     if mode == 0:
@@ -803,7 +807,7 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     # products (forward / data gradient, 1.3-1.6x over cuBLAS SGEMM); the weight gradient (tiny output, reduction over
     # all rows) and node-level products are faster in cuBLAS.
     use_cutlass = (A.is_cuda and A.dtype == torch.float32 and aligned and gemm_backend() == "cutlass"
-                   and (gemm_backend_forced() or (mode != 2 and M >= 16384) or (mode == 2 and K >= 16384)))
+                   and (gemm_backend_forced() or (mode != 2 and M >= 16384) or (mode == 2 and K >= _WGRAD_MIN_K)))
     if not use_cutlass:
         if mode == 0:
             return A @ B
@@ -815,7 +819,7 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     if ws is None:
         ws = torch.empty(int(lib.eqf_gemm_workspace_bytes()), dtype=torch.uint8, device=A.device)
         _GEMM_WORKSPACE[A.device] = ws
-    if mode == 2 and K >= 4096:
+    if mode == 2 and K >= min(4096, _WGRAD_MIN_K):
         return _wgrad_sliced(lib, ws, A, B, lda, ldb, M, N, K)
     C = torch.empty((M, N), device=A.device, dtype=torch.float32)
     flops_bytes = 4 * (A.numel() + B.numel() + C.numel())
@@ -838,7 +842,12 @@ def _wgrad_sliced(lib, ws, A, B, lda, ldb, M, N, K):
     # (profiles/r1_gemm_wgrad_slices.jsonl); EQF_WGRAD_WAVES overrides
     waves = float(os.environ.get("EQF_WGRAD_WAVES", "4" if tiles <= 3 else "2"))
     slices = max(1, min(int(-(-waves * 148 // tiles)), K // 256))
-    chunk = (K // slices) & ~15                      # multiple of the 16-row k-tile; the rest is the tail
+    chunk = max((K // slices) & ~15, 16)             # multiple of the 16-row k-tile; the rest is the tail
+    # an exact divisor of K near the target (multiple of 4 rows keeps every slice 16-byte aligned) avoids the tail launch
+    for c in range(chunk + (-chunk % 4), min(2 * chunk, K) + 1, 4):
+        if K % c == 0:
+            chunk = c
+            break
     slices = K // chunk
     tail = K - slices * chunk
     part = torch.empty((slices + (1 if tail else 0), M, N), device=A.device, dtype=torch.float32)
@@ -852,7 +861,7 @@ def _wgrad_sliced(lib, ws, A, B, lda, ldb, M, N, K):
             rc = lib.eqf_gemm_f32(2, A.data_ptr() + 4 * off * lda, B.data_ptr() + 4 * off * ldb, part[slices].data_ptr(),
                                   M, N, tail, lda, ldb, N, 0.0, ws.data_ptr(), ws.numel(), _stream())
             _lib.check_gemm(rc, "eqf_gemm_f32 (tail)")
-    return part.sum(dim=0)
+    return colsum_raw(part.view(part.shape[0], M * N)).view(M, N)
 
 
 class Gemm(torch.autograd.Function):
@@ -898,8 +907,77 @@ def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     """``F.linear``: ``x @ weight^T + bias`` with ``weight`` stored ``[out, in]`` like ``nn.Linear``."""
     if x.is_cuda and x.dtype == torch.float32 and x.dim() == 2:
         out = Gemm.apply(1, x, weight)
-        return out if bias is None else out + bias
+        return out if bias is None else add_bias(out, bias)
     return torch.nn.functional.linear(x, weight, bias)
+
+
+# ----------------------------------------------------------------------------- column sums / bias adds
+_COLSUM_COUNTERS = {}
+
+
+def colsum_raw(x: torch.Tensor) -> torch.Tensor:
+    """``x.sum(0)`` of a 2-D fp32 CUDA tensor (unit column stride) through ``eqf_colsum`` (deterministic)."""
+    x = _require_cuda(x, "colsum x")
+    if x.dim() != 2:
+        raise ValueError("colsum expects a 2-D tensor")
+    if x.stride(1) != 1 and x.shape[1] > 1:
+        x = x.contiguous()
+    rows, cols = x.shape
+    ld = x.stride(0) if rows > 1 else max(cols, 1)
+    lib = _lib.load()
+    if ld < cols or -(-cols // 32) > _lib.EQF_COLSUM_COUNTERS:
+        return x.sum(0)
+    out = torch.empty(cols, device=x.device, dtype=torch.float32)
+    if cols == 0:
+        return out
+    counters = _COLSUM_COUNTERS.get(x.device)
+    if counters is None:
+        counters = torch.zeros(_lib.EQF_COLSUM_COUNTERS, device=x.device, dtype=torch.int32)
+        _COLSUM_COUNTERS[x.device] = counters
+    part = torch.empty(max(int(lib.eqf_colsum_scratch_floats(rows, cols)), 1), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device), _kernel("colsum", 4 * x.numel()):
+        rc = lib.eqf_colsum(x.data_ptr(), rows, cols, ld, out.data_ptr(), part.data_ptr(), counters.data_ptr(), _stream())
+    _lib.check(rc, "eqf_colsum")
+    return out
+
+
+def _colsum(x: torch.Tensor) -> torch.Tensor:
+    """Column sum of kernel partials: the CUDA kernel on fp32 device tensors, ``sum(0)`` for the CPU test stand-ins."""
+    return colsum_raw(x) if fused_ok(x) else x.sum(0)
+
+
+class ColSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.rows = x.shape[0]
+        return colsum_raw(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.unsqueeze(0).expand(ctx.rows, -1)
+
+
+class AddBias(torch.autograd.Function):
+    """``x + b`` with ``b`` broadcast along the last dimension; the bias gradient is one ``eqf_colsum`` launch instead
+    of autograd's generic broadcast reduction (ref: bias adds of tensor_product_rescale.py:120-134, radial offset)."""
+
+    @staticmethod
+    def forward(ctx, x, b):
+        return x + b
+
+    @staticmethod
+    def backward(ctx, g):
+        gb = None
+        if ctx.needs_input_grad[1]:
+            g2 = g.reshape(-1, g.shape[-1])
+            gb = ColSum.apply(g2 if g2.stride(-1) == 1 else g2.contiguous())
+        return g, gb
+
+
+def add_bias(x: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    if fused_ok(x) and b.dim() == 1 and b.shape[0] == x.shape[-1] and x.numel() > 0:
+        return AddBias.apply(x, b)
+    return x + b
 
 
 # ----------------------------------------------------------------------------- fused pointwise ops
@@ -947,7 +1025,7 @@ def ln_silu_bwd_raw(x, gamma, beta, mean, rstd, gy):
         rc = _lib.load().eqf_ln_silu_bwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                          gy.data_ptr(), R, C, gx.data_ptr(), dg.data_ptr(), db.data_ptr(), _stream())
     _lib.check(rc, "eqf_ln_silu_bwd")
-    return gx, dg.sum(0), db.sum(0)
+    return gx, colsum_raw(dg), colsum_raw(db)
 
 
 class LnSilu(torch.autograd.Function):
@@ -1042,7 +1120,7 @@ def eln_bwd_raw(lay: NormLayout, x, w, rstd, gy):
         rc = _lib.load().eqf_eln_bwd(ctypes.byref(lay.c), x.data_ptr(), w.data_ptr(), rstd.data_ptr(), gy.data_ptr(), N,
                                      gx.data_ptr(), dw.data_ptr(), db.data_ptr(), _stream())
     _lib.check(rc, "eqf_eln_bwd")
-    return gx, dw.sum(0), db.sum(0)[:lay.n_b]
+    return gx, colsum_raw(dw), colsum_raw(db)[:lay.n_b]
 
 
 class EquivLayerNorm(torch.autograd.Function):
@@ -1097,9 +1175,12 @@ def gate_logits_torch(lay: GateLayout, t0, bias, alpha_dot, *gated):
     """Differentiable torch statement of the fused op (higher-order path and the CPU test stand-in)."""
     t = t0 if bias is None else t0 + bias
     E, H, A0, S = t.shape[0], lay.n_heads, lay.n_alpha, lay.n_scalars
-    a = t[:, :A0].reshape(E, H, A0 // H)
-    slr = 0.5 * (1 + lay.slope) * a + 0.5 * (1 - lay.slope) * a * (2 * torch.sigmoid(a) - 1)
-    z = (lay.c_slr * slr * alpha_dot.reshape(1, H, A0 // H)).sum(-1)
+    if A0 > 0:
+        a = t[:, :A0].reshape(E, H, A0 // H)
+        slr = 0.5 * (1 + lay.slope) * a + 0.5 * (1 - lay.slope) * a * (2 * torch.sigmoid(a) - 1)
+        z = (lay.c_slr * slr * alpha_dot.reshape(1, H, A0 // H)).sum(-1)
+    else:                                   # gate-only layout (node-level FFN): no logits
+        z = t.new_zeros((E, H))
     v0 = lay.c_silu * torch.nn.functional.silu(t[:, A0:A0 + S])
     gates = lay.c_sigmoid * torch.sigmoid(t[:, A0 + S:])
     outs, off = [], 0
@@ -1135,7 +1216,7 @@ def gate_logits_bwd_raw(lay: GateLayout, t0, bias, alpha_dot, gated, gz, gv0, gv
     rows = _lib.load().eqf_pointwise_rows(E)
     gt0 = torch.empty_like(t0)
     ggated = [torch.empty_like(g) for g in gated]
-    gdot = torch.empty((rows, lay.n_alpha), device=t0.device, dtype=torch.float32)
+    gdot = torch.empty((rows, max(lay.n_alpha, 1)), device=t0.device, dtype=torch.float32)
     nbytes = 4 * (2 * t0.numel() + 3 * sum(g.numel() for g in gated) + gv0.numel() + gz.numel())
     with torch.cuda.device(t0.device), _kernel("gate_logits_bwd", nbytes):
         rc = _lib.load().eqf_gate_logits_bwd(ctypes.byref(lay.c), t0.data_ptr(),
@@ -1143,7 +1224,37 @@ def gate_logits_bwd_raw(lay: GateLayout, t0, bias, alpha_dot, gated, gz, gv0, gv
                                              alpha_dot.data_ptr(), gz.data_ptr(), gv0.data_ptr(), _ptr_array(gvout), E,
                                              gt0.data_ptr(), _ptr_array(ggated), gdot.data_ptr(), _stream())
     _lib.check(rc, "eqf_gate_logits_bwd")
-    return gt0, ggated, gdot.sum(0)
+    return gt0, ggated, (colsum_raw(gdot) if lay.n_alpha > 0 else None)
+
+
+def gate_only_layout(gate, lin_out_irreps) -> Optional[GateLayout]:
+    """Layout for ``bias + Gate`` without logits (FFN), or None when the Gate is not in the canonical form
+    ``[(scalars + gates) x 0e | gated entries]`` the kernel reads."""
+    try:
+        scal, gates, gated = gate.irreps_scalars, gate.irreps_gates, gate.irreps_gated
+        canonical = (len(scal) == 1 and lin_out_irreps[0].ir.is_scalar()
+                     and lin_out_irreps[0].mul == scal.dim + gates.dim
+                     and [m for m, _ in lin_out_irreps[1:]] == [m for m, _ in gated]
+                     and len(gated) <= _lib.EQF_MAX_BLOCKS)
+        if not canonical:
+            return None
+        return GateLayout(0, scal.dim, 1, [ir.dim for _, ir in gated], [m for m, _ in gated],
+                          gate.act_scalars.acts[0].cst, gate.act_gates.acts[0].cst, 1.0, 0.2)
+    except (AttributeError, IndexError, NotImplementedError):
+        return None
+
+
+_GATE_DUMMY = {}
+
+
+def gate_fused(lay: GateLayout, t0, bias, gated):
+    """``Gate(bias + [t0 | gated])`` in one kernel (gate-only use of :class:`GateLogits`): returns (scalars, *gated)."""
+    dummy = _GATE_DUMMY.get(t0.device)
+    if dummy is None:
+        dummy = torch.zeros(1, 1, device=t0.device, dtype=t0.dtype)
+        _GATE_DUMMY[t0.device] = dummy
+    _z, v0, *vs = GateLogits.apply(lay, t0, bias, dummy, *gated)
+    return (v0, *vs)
 
 
 class GateLogits(torch.autograd.Function):
@@ -1176,8 +1287,8 @@ class GateLogits(torch.autograd.Function):
             return (None, *grads)
         gt0, ggated, gdot = gate_logits_bwd_raw(lay, t0, bias, alpha_dot, gated, gz.contiguous(), gv0.contiguous(),
                                                 [g.contiguous() for g in gvout])
-        gbias = gt0.sum(0) if bias is not None else None
-        return (None, gt0, gbias, gdot.view_as(alpha_dot), *ggated)
+        gbias = _colsum(gt0) if bias is not None else None
+        return (None, gt0, gbias, gdot.view_as(alpha_dot) if lay.n_alpha > 0 else None, *ggated)
 
 
 # ----------------------------------------------------------------------------- layout conversion

@@ -142,6 +142,14 @@ int eqf_ln_silu_bwd(const float* x, const float* gamma, const float* beta, const
                     const float* gy, int64_t R, int32_t C, float* gx, float* dgamma_part, float* dbeta_part,
                     void* stream);
 
+/* Column sums out[c] = sum_r x[r, c] (row stride ld): the bias / radial-offset gradients the reference gets from
+ * autograd's broadcast reduction (nets/tensor_product_rescale.py:120-134, radial_func.py:45-49), and the final
+ * reduction of per-CTA partial rows.  Deterministic (fixed summation order). */
+#define EQF_COLSUM_COUNTERS 16384
+int64_t eqf_colsum_scratch_floats(int64_t rows, int64_t cols);
+int eqf_colsum(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out, float* part, uint32_t* counters,
+               void* stream);
+
 /* EquivariantLayerNormV2 ('component' normalisation, affine; nets/layer_norm.py:89-152) on e3nn-layout rows:
  * one fused kernel forward, one backward (per-CTA partial sums of the affine gradients in [eqf_eln_rows(N), .]). */
 typedef struct {

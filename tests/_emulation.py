@@ -141,6 +141,10 @@ def ln_silu_fwd_raw(x, gamma, beta, eps):
     return ops.ln_silu_torch(x, gamma, beta, eps), mean, rstd
 
 
+def colsum_raw(x):
+    return x.sum(0)
+
+
 def eln_fwd_raw(lay, x, w, b):
     return ops.eln_torch(lay, x, w, b), torch.zeros(x.shape[0], len(lay.entries))
 
@@ -175,11 +179,12 @@ def gate_logits_bwd_raw(lay, t0, bias, alpha_dot, gated, gz, gv0, gvout):
         ad = alpha_dot.detach().requires_grad_(True)
         gs = [g.detach().requires_grad_(True) for g in gated]
         outs = ops.gate_logits_torch(lay, t, bias.detach() if bias is not None else None, ad, *gs)
-        grads = torch.autograd.grad(outs, [t, ad, *gs], [gz, gv0, *gvout])
-    return grads[0], list(grads[2:]), grads[1].reshape(-1)
+        pairs = [(o, g) for o, g in zip(outs, [gz, gv0, *gvout]) if o.requires_grad]
+        grads = torch.autograd.grad([o for o, _ in pairs], [t, ad, *gs], [g for _, g in pairs], allow_unused=True)
+    return grads[0], list(grads[2:]), (grads[1].reshape(-1) if lay.n_alpha > 0 else None)
 
 
-_PATCHED = ["eln_fwd_raw", "eln_bwd_raw", "ln_silu_fwd_raw", "ln_silu_bwd_raw", "gate_logits_fwd_raw", "gate_logits_bwd_raw", "gemm_raw", "dtp_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
+_PATCHED = ["colsum_raw", "eln_fwd_raw", "eln_bwd_raw", "ln_silu_fwd_raw", "ln_silu_bwd_raw", "gate_logits_fwd_raw", "gate_logits_bwd_raw", "gemm_raw", "dtp_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
             "seg_softmax_raw", "attn_aggregate_raw", "attn_edge_dot_raw", "attn_edge_scale_raw"]
 
 

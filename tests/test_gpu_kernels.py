@@ -246,6 +246,42 @@ def test_ln_silu_fused(cuda_device, R, C):
     assert rel_err(gx, rx) < 5e-5 and rel_err(gg, rg) < 5e-5 and rel_err(gb, rb) < 5e-5
 
 
+@pytest.mark.parametrize("rows,cols", [(1, 1), (7, 3), (32560, 64), (32560, 352), (32560, 960), (1184, 64), (197, 24576),
+                                       (2324, 130), (100000, 5), (3, 86016)])
+def test_colsum(cuda_device, rows, cols):
+    """Column sums (bias / offset gradients, reduction of kernel partials) vs fp64, contiguous and row-strided input;
+    repeated calls share the self-resetting tile counters."""
+    from equiformer_b200 import ops
+    g = torch.Generator().manual_seed(rows + cols)
+    x = torch.randn(rows, cols, generator=g) + 0.1
+    ref = x.double().sum(0)
+    scale = ref.abs().max().clamp_min(1.0)
+    for _ in range(3):
+        out = ops.colsum_raw(x.to(cuda_device))
+        assert ((out.cpu().double() - ref).abs().max() / scale) < 2e-6
+    wide = torch.randn(rows, cols + 12, generator=g).to(cuda_device)
+    view = wide[:, 4:4 + cols]
+    out = ops.colsum_raw(view)
+    ref = view.cpu().double().sum(0)
+    assert ((out.cpu().double() - ref).abs().max() / ref.abs().max().clamp_min(1.0)) < 2e-6
+
+
+def test_add_bias_autograd(cuda_device):
+    from equiformer_b200 import ops
+    x = torch.randn(5000, 3, 96, device=cuda_device, requires_grad=True)
+    b = torch.randn(96, device=cuda_device, requires_grad=True)
+    g = torch.randn(5000, 3, 96, device=cuda_device)
+    gx, gb = torch.autograd.grad(ops.add_bias(x, b), (x, b), g)
+    assert torch.equal(gx, g)
+    assert rel_err(gb, g.double().sum((0, 1))) < 1e-6
+    # second order: d/dg of <colsum(g), v> is v broadcast
+    gg = g.clone().requires_grad_(True)
+    (gb2,) = torch.autograd.grad(ops.add_bias(x, b), (b,), gg, create_graph=True)
+    v = torch.randn(96, device=cuda_device)
+    (back,) = torch.autograd.grad((gb2 * v).sum(), gg)
+    assert torch.allclose(back, v.expand_as(back))
+
+
 @pytest.mark.parametrize("entries", [[(128, 1, True), (64, 3, False), (32, 5, False)],
                                      [(128, 1, True), (64, 3, False), (64, 5, False), (32, 7, False)],
                                      [(256, 1, True), (128, 3, False)],

@@ -35,7 +35,7 @@ def main():
     torch.cuda.synchronize()
     from torch.profiler import ProfilerActivity, profile
     n = 3
-    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
+    with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], record_shapes=True) as prof:
         for _ in range(n):
             step()
         torch.cuda.synchronize()
@@ -59,6 +59,18 @@ def main():
     print(text)
     with open(os.path.join(out_dir, "profile_step.txt"), "w") as f:
         f.write(text + "\n")
+    # which torch ops (by input shape) hold the device time that is not in our kernels
+    shaped = []
+    for e in prof.key_averages(group_by_input_shape=True):
+        t = getattr(e, "self_device_time_total", None)
+        if t is None:
+            t = getattr(e, "self_cuda_time_total", 0.0)
+        if t > 0 and e.key.startswith("aten::"):
+            shaped.append((t / n / 1e3, e.count / n, e.key, str(e.input_shapes)[:150]))
+    shaped.sort(reverse=True)
+    with open(os.path.join(out_dir, "profile_step_shapes.txt"), "w") as f:
+        for t, c, k, sh in shaped[:120]:
+            f.write(f"{t:8.3f} ms/step n/step={c:6.1f} {k:28s} {sh}\n")
 
 
 if __name__ == "__main__":
