@@ -51,6 +51,7 @@ class EqfEdgeOperands(ctypes.Structure):
         ("w", c_void_p),
         ("w_shared", c_int32),
         ("g", c_void_p * EQF_MAX_BLOCKS),
+        ("w_offset", c_void_p),
     ]
 
 

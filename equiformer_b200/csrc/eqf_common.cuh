@@ -55,6 +55,7 @@ struct EdgeArgs {
   const long long* dst;
   const float* y;
   const float* w;
+  const float* w_off;            // optional [W] offset added to every row of w (radial offset, fused into the load)
   int w_shared;
   const float* g[EQF_MAX_BLOCKS];
   float* out[EQF_MAX_BLOCKS];   // forward outputs (per output group)

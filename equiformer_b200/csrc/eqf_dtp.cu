@@ -383,8 +383,12 @@ static int fill_args(const EqfPlan* plan, const EqfEdgeOperands* op, long long E
   }
   a.src = reinterpret_cast<const long long*>(op->src);
   a.dst = reinterpret_cast<const long long*>(op->dst);
-  a.y = op->y; a.w = op->w; a.w_shared = op->w_shared; a.gw = nullptr; a.gy = nullptr; a.E = E;
+  a.y = op->y; a.w = op->w; a.w_off = op->w_offset; a.w_shared = op->w_shared; a.gw = nullptr; a.gy = nullptr; a.E = E;
   if (E == 0) return EQF_OK;
+  if (a.w_off != nullptr && !(plan->gen != nullptr && dtp_variant() == 4)) {
+    set_error("w_offset is only supported by the plan-specialised kernels");
+    return EQF_ERR_UNSUPPORTED;
+  }
   if (a.y == nullptr) { set_error("edge_attr (y) pointer is null"); return EQF_ERR_INVALID; }
   if (need_w && a.w == nullptr) { set_error("weight pointer is null"); return EQF_ERR_INVALID; }
   if (need_x) for (int b = 0; b < h.n_in1; ++b) {

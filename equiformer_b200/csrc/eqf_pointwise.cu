@@ -441,9 +441,29 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
   __syncthreads();
   if (!last) return;
   __threadfence();
+  // final pass: the 8 row groups each add every 8th partial row (fixed order -> deterministic), then one smem reduce
+  float fin[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) fin[v] = 0.f;
+  if (active) {
+    for (unsigned int k = ty; k < gridDim.y; k += 8) {
+      const float* p = part + (long long)k * cols + c0;
+      if constexpr (VEC == 4) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(p));
+        fin[0] += v.x; fin[1] += v.y; fin[2] += v.z; fin[3] += v.w;
+      } else {
+        fin[0] += __ldcg(p);
+      }
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) red[ty][tx * VEC + v] = fin[v];
+  __syncthreads();
   if (t < 32 * VEC && tile0 + t < cols) {
     float s = 0.f;
-    for (unsigned int k = 0; k < gridDim.y; ++k) s += __ldcg(part + (long long)k * cols + tile0 + t);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][t];
     out[tile0 + t] = s;
   }
   if (t == 0) counters[blockIdx.x] = 0u;
@@ -451,11 +471,11 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 
 static void colsum_shape(long long rows, long long cols, int vec, long long& tiles, long long& splits) {
   tiles = (cols + 32 * vec - 1) / (32 * vec);
-  splits = (148LL * 6) / tiles;
-  const long long max_splits = (rows + 31) / 32;
+  splits = (148LL * 4) / tiles;                     // ~4 CTAs per SM in flight ...
+  const long long max_splits = (rows + 63) / 64;    // ... each with at least 64 rows (8 per row group)
   if (splits > max_splits) splits = max_splits;
+  if (splits > 256) splits = 256;                   // bounds the final pass (32 partial rows per row group)
   if (splits < 1) splits = 1;
-  if (splits > 65535) splits = 65535;
 }
 
 // ------------------------------------------------------------------------------------------------ equivariant LayerNorm

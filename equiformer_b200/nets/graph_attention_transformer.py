@@ -276,7 +276,8 @@ class GraphAttention(torch.nn.Module):
             plan_out = self.sep_act.dtp.irreps_out
             n0 = sum(1 for _, ir in plan_out if ir.is_scalar())
             ins = [(i.i_in1, i.i_in2, i.i_out) for i in self.sep_alpha.tp.instructions]
-            if n0 > 0 and all(ir.is_scalar() for _, ir in plan_out[:n0]) and ins == [(i, 0, 0) for i in range(n0)]:
+            if (n0 > 0 and all(ir.is_scalar() for _, ir in plan_out[:n0]) and ins == [(i, 0, 0) for i in range(n0)]
+                    and all(c == 1.0 for *_i, _W, c in self.sep_alpha.tp.linear_weight_blocks())):
                 self._alpha_single_gemm = True
 
         # fused bias + Gate + logits kernel (ops.GateLogits) when the layer has the canonical structure:
@@ -290,7 +291,10 @@ class GraphAttention(torch.nn.Module):
                          and lin.irreps_out[0].ir.is_scalar()
                          and lin.irreps_out[0].mul == gate.irreps_scalars.dim + gate.irreps_gates.dim
                          and [m for m, _ in lin.irreps_out[1:]] == [m for m, _ in gate.irreps_gated]
-                         and len(lin.bias) == 1 and len(self.sep_alpha.bias) == 1 and mul_alpha_head <= 32)
+                         and len(lin.bias) == 1 and len(self.sep_alpha.bias) == 1 and mul_alpha_head <= 32
+                         # the fused path feeds the raw weight blocks to the GEMMs: every path constant must be 1
+                         and all(c == 1.0 for *_i, _W, c in lin.tp.linear_weight_blocks())
+                         and all(c == 1.0 for *_i, _W, c in self.sep_alpha.tp.linear_weight_blocks()))
             if canonical:
                 self._gate_layout = ops.GateLayout(
                     mul_alpha, gate.irreps_scalars.dim, num_heads, [ir.dim for _, ir in gate.irreps_gated],
@@ -318,8 +322,10 @@ class GraphAttention(torch.nn.Module):
 
         if self.nonlinear_message:
             sa = self.sep_act
-            weight = sa.dtp_rad(edge_scalars)                                             # [ref :490]
-            f = sa.dtp.tp.planar_depthwise_gathered(graph, m_src, m_dst, edge_attr, weight)   # [ref :487+:491]  DTP #1
+            # [ref :490] radial weights; the radial offset is added inside the DTP kernel's weight load
+            weight = sa.dtp_rad(edge_scalars, add_offset=False)
+            f = sa.dtp.tp.planar_depthwise_gathered(graph, m_src, m_dst, edge_attr, weight,
+                                                    sa.dtp_rad.offset)                    # [ref :487+:491]  DTP #1
             logits = None
             if self._gate_layout is not None and ops.fused_ok(f[0]):
                 # one GEMM for alpha and the 0e part of the value linear ([K0, A0 | S + Gates]), then ONE kernel for
@@ -353,9 +359,10 @@ class GraphAttention(torch.nn.Module):
                 value = self.sep_value.lin.planar(f2)
                 alpha = alpha.reshape(E, H, A)                                            # [ref :493]
         else:
-            weight = self.sep.dtp_rad(edge_scalars)
+            weight = self.sep.dtp_rad(edge_scalars, add_offset=False)
             logits = None
-            out = self.sep.lin.planar(self.sep.dtp.tp.planar_depthwise_gathered(graph, m_src, m_dst, edge_attr, weight))  # [ref :487+:499]
+            out = self.sep.lin.planar(self.sep.dtp.tp.planar_depthwise_gathered(
+                graph, m_src, m_dst, edge_attr, weight, self.sep.dtp_rad.offset))         # [ref :487+:499]
             first = out[0]                                                                # 0e entry: alpha | value scalars
             if first.shape[1] != 1:
                 raise NotImplementedError("attention logits need a leading 0e entry")

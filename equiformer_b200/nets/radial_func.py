@@ -32,7 +32,9 @@ class RadialProfile(nn.Module):
             bound = 1.0 / math.sqrt(fan_in) if fan_in > 0 else 0.0
             nn.init.uniform_(self.offset, -bound, bound)
 
-    def forward(self, f_in):
+    def forward(self, f_in, add_offset: bool = True):
+        """``add_offset=False`` returns the MLP output without ``offset``: the caller hands ``self.offset`` to the
+        tensor-product kernel, which adds it while loading the weights (no extra pass over ``[E, weight_numel]``)."""
         from .. import ops
         out = f_in
         mods = list(self.net)    # same modules / state_dict keys as nn.Sequential; executed with fused kernels on CUDA
@@ -49,6 +51,6 @@ class RadialProfile(nn.Module):
             else:
                 out = m(out)
                 i += 1
-        if self.offset is not None:
+        if self.offset is not None and add_offset:
             out = ops.add_bias(out, self.offset)
         return out

@@ -172,11 +172,12 @@ class TensorProduct(torch.nn.Module):
         w = self._get_weights(weight)
         return ops.depthwise_tensor_product(self.plan, xs, y, w)
 
-    def planar_depthwise_gathered(self, graph, As, Bs, y, weight=None):
-        """Planar DTP on ``A[src] (+ B[dst])`` with the gather folded into the kernel's operand load."""
+    def planar_depthwise_gathered(self, graph, As, Bs, y, weight=None, weight_offset=None):
+        """Planar DTP on ``A[src] (+ B[dst])`` with the gather folded into the kernel's operand load; the weights are
+        ``weight (+ weight_offset)`` with the ``[weight_numel]`` offset added inside the kernel when it can be."""
         from .. import ops
         w = self._get_weights(weight)
-        return ops.depthwise_tensor_product_gathered(self.plan, graph, As, Bs, y, w)
+        return ops.depthwise_tensor_product_gathered(self.plan, graph, As, Bs, y, w, weight_offset)
 
     def linear_weight_blocks(self, weight=None):
         """``[(i_in1, i_in2, i_out, W[mul_in, mul_in2, mul_out] * path constant)]`` for the scalar-in2 'uvw' kind."""
@@ -186,6 +187,8 @@ class TensorProduct(torch.nn.Module):
         for _idx, ins, view in self.weight_views(weight, yield_instruction=True):
             ir1 = self.irreps_in1[ins.i_in1].ir
             c = ins.path_weight * float(wigner_3j_np(ir1.l, 0, ir1.l)[0, 0, 0])  # w3j(l,0,l) = delta / sqrt(2l+1)
+            if abs(c - 1.0) < 1e-12:     # sqrt(2l+1) / sqrt(2l+1) in floating point: not a reason for an extra pass
+                c = 1.0
             out.append((ins.i_in1, ins.i_in2, ins.i_out, view, c))
         return out
 
@@ -206,6 +209,8 @@ class TensorProduct(torch.nn.Module):
             x = xs[i1]
             d = x.shape[1]
             m2 = W.shape[1]
+            if c != 1.0:
+                W = W * c                    # the path constant goes onto the [mul_in, mul_out] weights, not the rows
             if y is None:
                 if m2 != 1:
                     raise ValueError("second operand required")
@@ -217,8 +222,6 @@ class TensorProduct(torch.nn.Module):
             else:
                 yy = y[:, in2_off[i2]:in2_off[i2] + m2]
                 t = torch.einsum("rdu,rv,uvw->rdw", x, yy, W)
-            if c != 1.0:
-                t = t * c
             outs[io] = t if outs[io] is None else outs[io] + t
         for io, (mul, ir) in enumerate(self.irreps_out):
             if outs[io] is None:

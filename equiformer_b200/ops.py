@@ -56,9 +56,15 @@ def _ptr_array(ts: Sequence[torch.Tensor]):
     return arr
 
 
-def _operands(plan: DtpPlan, xs, y, w, gs, w_shared: bool, gather=None) -> _lib.EqfEdgeOperands:
-    """``gather = (src, dst, x2s)``: x rows are ``xs[b][src[e]] (+ x2s[b][dst[e]])`` instead of ``xs[b][e]``."""
+def _operands(plan: DtpPlan, xs, y, w, gs, w_shared: bool, gather=None, w_offset=None) -> _lib.EqfEdgeOperands:
+    """``gather = (src, dst, x2s)``: x rows are ``xs[b][src[e]] (+ x2s[b][dst[e]])`` instead of ``xs[b][e]``;
+    ``w_offset`` ``[W]``: the kernels read ``w[e] + w_offset`` (plan-specialised kernels only)."""
     op = _lib.EqfEdgeOperands()
+    if w_offset is not None:
+        w_offset = _require_cuda(w_offset, "w_offset")
+        if w_shared or tuple(w_offset.shape) != (plan.weight_numel,):
+            raise ValueError("w_offset must be [weight_numel] and needs per-edge weights")
+        op.w_offset = w_offset.data_ptr()
     if xs is not None:
         for i, t in enumerate(xs):
             op.x[i] = t.data_ptr()
@@ -211,11 +217,11 @@ def _check_gather(plan: DtpPlan, xs, gather, E: int, what: str):
     return xs, (src, dst, x2s)
 
 
-def dtp_forward_raw(plan: DtpPlan, xs, y, w, gather=None) -> List[torch.Tensor]:
+def dtp_forward_raw(plan: DtpPlan, xs, y, w, gather=None, w_offset=None) -> List[torch.Tensor]:
     y, w, E, shared = _check_yw(plan, y, w)
     xs, gather = _check_gather(plan, xs, gather, E, "dtp_forward x")
     outs = [torch.empty((E, 2 * l + 1, mul), device=y.device, dtype=torch.float32) for l, _p, mul in plan.out_groups]
-    op = _operands(plan, xs, y, w, None, shared, gather)
+    op = _operands(plan, xs, y, w, None, shared, gather, w_offset)
     with torch.cuda.device(y.device), _kernel("dtp_forward", _dtp_bytes(plan, E, shared, "forward")):
         rc = _lib.load().eqf_dtp_forward(plan.handle, ctypes.byref(op), E, _ptr_array(outs), _stream())
     _lib.check(rc, "eqf_dtp_forward")
@@ -267,7 +273,7 @@ def dtp_grad_y_raw(plan: DtpPlan, xs, w, gs, y_like) -> torch.Tensor:
     return gy
 
 
-def dtp_grad_xw_raw(plan: DtpPlan, xs, y, w, gs, gather=None) -> Tuple[List[torch.Tensor], torch.Tensor]:
+def dtp_grad_xw_raw(plan: DtpPlan, xs, y, w, gs, gather=None, w_offset=None) -> Tuple[List[torch.Tensor], torch.Tensor]:
     y, w, E, shared = _check_yw(plan, y, w)
     xs, gather = _check_gather(plan, xs, gather, E, "dtp_grad_xw x")
     gs = _check_groups(plan, gs, E, "dtp_grad_xw g")
@@ -275,7 +281,7 @@ def dtp_grad_xw_raw(plan: DtpPlan, xs, y, w, gs, gather=None) -> Tuple[List[torc
     if E == 0:
         return gxs, torch.zeros_like(w)
     gw = _gw_buffer(plan, E, shared, y.device)
-    op = _operands(plan, xs, y, w, gs, shared, gather)
+    op = _operands(plan, xs, y, w, gs, shared, gather, w_offset)
     with torch.cuda.device(y.device), _kernel("dtp_grad_xw", _dtp_bytes(plan, E, shared, "grad_xw")):
         rc = _lib.load().eqf_dtp_grad_xw(plan.handle, ctypes.byref(op), E, _ptr_array(gxs),
                                          ctypes.c_void_p(gw.data_ptr()), _stream())
@@ -493,11 +499,61 @@ class DtpOutGathered(torch.autograd.Function):
         return (None, None, None, gy, gw, *gA, *(gB if Bs is not None else []))
 
 
-def depthwise_tensor_product_gathered(plan: DtpPlan, graph: "Graph", As, Bs, y, w):
-    """``DTP(A[src] (+ B[dst]), y; w)`` with the gather done inside the kernel.  ``Bs`` may be None."""
-    if Bs is None:
-        return list(DtpOutGathered.apply(plan, graph, 0, y, w, *As))
-    return list(DtpOutGathered.apply(plan, graph, len(Bs), y, w, *As, *Bs))
+class DtpOutGatheredOffset(torch.autograd.Function):
+    """:class:`DtpOutGathered` with per-edge weights ``w + offset`` where the ``[W]`` offset is added inside the kernels'
+    weight load (the radial ``offset`` of ref radial_func.py:45-49 never takes its own pass over ``[E, W]``).
+
+    apply(plan, graph, n_b, y, w, offset, *As, *Bs)."""
+
+    @staticmethod
+    def forward(ctx, plan: DtpPlan, graph: "Graph", n_b: int, y, w, offset, *AB):
+        nb = len(plan.in1_blocks)
+        As, Bs = AB[:nb], (AB[nb:] if n_b else None)
+        ctx.plan, ctx.graph, ctx.n_b = plan, graph, n_b
+        outs = dtp_forward_raw(plan, As, y, w, gather=(graph.src, graph.dst, Bs), w_offset=offset)
+        ctx.save_for_backward(y, w, offset, *AB)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        plan, graph, n_b = ctx.plan, ctx.graph, ctx.n_b
+        y, w, offset, *AB = ctx.saved_tensors
+        nb = len(plan.in1_blocks)
+        As, Bs = AB[:nb], (AB[nb:] if n_b else None)
+        E = y.shape[0]
+        gs = [g if g is not None else torch.zeros((E, 2 * l + 1, m), device=y.device)
+              for g, (l, _p, m) in zip(gs, plan.out_groups)]
+        need_y, need_w, need_off = ctx.needs_input_grad[3:6]
+        need_x = any(ctx.needs_input_grad[6:])
+        if torch.is_grad_enabled() or need_y:    # higher order / forces: the differentiable family on w + offset
+            fn = lambda yy, ww, oo, *ab: DtpOutGathered.apply(plan, graph, n_b, yy, ww + oo, *ab)
+            grads = _higher_order_grads(fn, (y, w, offset, *AB), gs)
+            return (None, None, None, *grads)
+        gs = [g.contiguous() for g in gs]
+        gw = goff = None
+        gA = [None] * nb
+        gB = [None] * nb
+        if need_x or need_w or need_off:
+            gxs, gw = dtp_grad_xw_raw(plan, As, y, w, gs, gather=(graph.src, graph.dst, Bs), w_offset=offset)
+            if need_off:
+                goff = colsum_raw(gw)
+            if need_x:
+                lay = HeadLayout([2 * l + 1 for l, _ in plan.in1_blocks], [m for _, m in plan.in1_blocks], 1)
+                gA = attn_aggregate_raw(lay, None, gxs, graph, by_src=True)
+                if Bs is not None:
+                    gB = attn_aggregate_raw(lay, None, gxs, graph)
+        return (None, None, None, None, gw if need_w else None, goff, *gA, *(gB if Bs is not None else []))
+
+
+def depthwise_tensor_product_gathered(plan: DtpPlan, graph: "Graph", As, Bs, y, w, w_offset=None):
+    """``DTP(A[src] (+ B[dst]), y; w (+ w_offset))`` with the gather done inside the kernel.  ``Bs`` may be None."""
+    AB = (*As, *(Bs if Bs is not None else ()))
+    n_b = 0 if Bs is None else len(Bs)
+    if w_offset is not None:
+        if plan.generated and w.dim() == 2 and fused_ok(y):
+            return list(DtpOutGatheredOffset.apply(plan, graph, n_b, y, w, w_offset, *AB))
+        w = w + w_offset
+    return list(DtpOutGathered.apply(plan, graph, n_b, y, w, *AB))
 
 
 def depthwise_tensor_product(plan: DtpPlan, xs: Sequence[torch.Tensor], y: torch.Tensor, w: torch.Tensor):
@@ -786,7 +842,9 @@ def _gemm_operand(t: torch.Tensor):
     return t, t.stride(0)
 
 
-_WGRAD_MIN_K = int(os.environ.get("EQF_WGRAD_MIN_K", "16384"))   # reduction length from which the weight gradient uses tcgen05
+# reduction length from which the weight gradient runs as the sliced tcgen05 launch; node-level products (2 324 atoms x
+# (2l+1) rows) included: 24.6 -> 22.9 ms/step against cuBLAS's single-wave SIMT kernel there (gpurun r1n)
+_WGRAD_MIN_K = int(os.environ.get("EQF_WGRAD_MIN_K", "2048"))
 
 
 def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
@@ -987,6 +1045,9 @@ def _higher_order_grads(fn, inputs, grad_outputs):
     """Backward of a fused op under ``create_graph``: rebuild the op from differentiable torch ops on the saved inputs
     and differentiate that (slow path, used only for second-order training such as MD17 force losses)."""
     with torch.enable_grad():
+        # differentiate with respect to fresh views: one input may be an ancestor of another in the outer graph (the
+        # edge harmonics feed the node tables), and the partial derivative asked for here must not follow that route
+        inputs = [t.view_as(t) if (isinstance(t, torch.Tensor) and t.requires_grad) else t for t in inputs]
         outs = fn(*inputs)
         outs = outs if isinstance(outs, (tuple, list)) else (outs,)
         pairs = [(o, g) for o, g in zip(outs, grad_outputs) if g is not None and o.requires_grad]

@@ -140,6 +140,16 @@ class DtpPlan:
                 "vec_ok", "n_vwtasks", "n_vxtasks", "smem_bytes_vec_fwd", "generated")
         return dict(zip(keys, list(out)))
 
+    @property
+    def generated(self) -> bool:
+        """True when the plan-specialised kernels (codegen.py) will run for this plan."""
+        g = getattr(self, "_generated", None)
+        if g is None:
+            import os
+            g = bool(self.info()["generated"]) and os.environ.get("EQF_DTP_VARIANT", "gen") not in ("scalar", "vec", "v3", "tma")
+            self._generated = g
+        return g
+
     def __del__(self):
         h, self._handle = getattr(self, "_handle", None), None
         if h is not None:

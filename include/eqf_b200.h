@@ -59,6 +59,9 @@ typedef struct {
   const float* w;                    /* per-edge weights [E][W] or shared [W]                     */
   int32_t w_shared;                  /* 1: w is [W] (internal weights), 0: [E][W]                 */
   const float* g[EQF_MAX_BLOCKS];    /* output-group tensors (cotangents), planar [E][2l3+1][K]   */
+  const float* w_offset;             /* optional [W]: the kernels use w[e] + w_offset (RadialProfile's offset,
+                                        nets/radial_func.py:45-49, folded into the weight load); may be NULL.
+                                        Only the plan-specialised kernels take it (EQF_ERR_UNSUPPORTED otherwise) */
 } EqfEdgeOperands;
 
 int eqf_version(void);

@@ -35,8 +35,10 @@ def _gathered(xs, gather):
     return xs
 
 
-def dtp_forward_raw(plan, xs, y, w, gather=None):
+def dtp_forward_raw(plan, xs, y, w, gather=None, w_offset=None):
     xs = _gathered(xs, gather)
+    if w_offset is not None:
+        w = w + w_offset
     E = y.shape[0]
     outs = [y.new_zeros((E, 2 * l + 1, mul)) for l, _p, mul in plan.out_groups]
     for p in plan.paths:
@@ -78,8 +80,10 @@ def dtp_grad_y_raw(plan, xs, w, gs, y_like):
     return gy
 
 
-def dtp_grad_xw_raw(plan, xs, y, w, gs, gather=None):
+def dtp_grad_xw_raw(plan, xs, y, w, gs, gather=None, w_offset=None):
     xs = _gathered(xs, gather)
+    if w_offset is not None:
+        w = w + w_offset
     return dtp_grad_x_raw(plan, gs, y, w), dtp_grad_w_raw(plan, xs, y, gs, w.dim() == 1)
 
 

@@ -77,3 +77,32 @@ def test_unsorted_edge_list_gives_same_layer_output():
         a = ga(x, None, src, dst, sh, rbf, None)
         b = ga(x, None, src[perm], dst[perm], sh[perm], rbf[perm], None)
     assert (a - b).abs().max() < 1e-12
+
+
+def test_dtp_gathered_offset_gradcheck_with_dependent_inputs():
+    """DtpOutGatheredOffset: first and second order, including the case that broke a nested-autograd backward once:
+    the node tables are themselves functions of the edge harmonics (edge-degree embedding), so a partial derivative
+    taken with autograd.grad on the saved tensors must not follow that ancestry."""
+    plan = _plan()
+    n_nodes, E = 4, 9
+    dst = torch.tensor([0, 0, 0, 1, 1, 3, 3, 3, 3])
+    src = torch.tensor([1, 2, 3, 0, 2, 0, 1, 2, 0])
+    g = torch.Generator().manual_seed(4)
+    nb = len(plan.in1_blocks)
+    A0 = [torch.randn(n_nodes, 2 * l + 1, m, generator=g, dtype=torch.float64, requires_grad=True) for l, m in plan.in1_blocks]
+    B0 = [torch.randn(n_nodes, 2 * l + 1, m, generator=g, dtype=torch.float64, requires_grad=True) for l, m in plan.in1_blocks]
+    y = torch.randn(E, plan.d_y, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(E, plan.weight_numel, generator=g, dtype=torch.float64, requires_grad=True)
+    off = torch.randn(plan.weight_numel, generator=g, dtype=torch.float64, requires_grad=True)
+
+    with emulated_kernels():
+        graph = ops.Graph(src, dst, n_nodes, check_sorted=False)
+
+        def f(y, w, off, *AB):
+            # node tables depend on y (like node features built from the edge-degree embedding)
+            s = torch.zeros(n_nodes, dtype=y.dtype).index_add(0, dst, y.sum(1))
+            AB = [t * (1.0 + 0.1 * s.view(-1, 1, 1)) for t in AB]
+            return tuple(ops.DtpOutGatheredOffset.apply(plan, graph, nb, y, w * (1.0 + y[:, :1]), off, *AB))
+
+        assert torch.autograd.gradcheck(f, (y, w, off, *A0, *B0), atol=1e-7)
+        assert torch.autograd.gradgradcheck(f, (y, w, off, *A0, *B0), atol=1e-6)

@@ -228,6 +228,42 @@ def test_dtp_gather_fused_and_csc_aggregate(cuda_device, with_b):
         assert rel_err(a, exp) < TOL
 
 
+@pytest.mark.parametrize("cfg", ["qm9_l2", "md17_l3"])
+def test_dtp_weight_offset_fused(cuda_device, cfg):
+    """w[e] + offset added inside the generated kernels' weight load (radial offset, ref radial_func.py:45-49):
+    forward and grad_xw vs the fp64 statement on w + offset; the autograd wrapper returns colsum(gw) for the offset."""
+    from equiformer_b200 import ops
+    plan = _dtp(cfg).tp.plan
+    if not plan.generated:
+        pytest.skip("no plan-specialised kernels for this configuration")
+    n_nodes, E = 41, 523
+    graph, src, dst = _graph(n_nodes, E, 5, cuda_device)
+    g = torch.Generator().manual_seed(9)
+    As = [torch.randn(n_nodes, 2 * l + 1, m, generator=g) for l, m in plan.in1_blocks]
+    Bs = [torch.randn(n_nodes, 2 * l + 1, m, generator=g) for l, m in plan.in1_blocks]
+    y = torch.randn(E, plan.d_y, generator=g)
+    w = torch.randn(E, plan.weight_numel, generator=g)
+    off = torch.randn(plan.weight_numel, generator=g)
+    gs = [torch.randn(E, 2 * l + 1, m, generator=g) for l, _p, m in plan.out_groups]
+    d = lambda t: t.to(cuda_device)
+    xs64 = [a.double()[src] + b.double()[dst] for a, b in zip(As, Bs)]
+    w64 = w.double() + off.double()
+    gather = (graph.src, graph.dst, [d(t) for t in Bs])
+    out = ops.dtp_forward_raw(plan, [d(t) for t in As], d(y), d(w), gather=gather, w_offset=d(off))
+    for a, b in zip(out, emu.dtp_forward_raw(plan, xs64, y.double(), w64)):
+        assert rel_err(a, b) < TOL
+    gx, gw = ops.dtp_grad_xw_raw(plan, [d(t) for t in As], d(y), d(w), [d(t) for t in gs], gather=gather, w_offset=d(off))
+    for a, b in zip(gx, emu.dtp_grad_x_raw(plan, [t.double() for t in gs], y.double(), w64)):
+        assert rel_err(a, b) < TOL
+    gw_ref = emu.dtp_grad_w_raw(plan, xs64, y.double(), [t.double() for t in gs], False)
+    assert rel_err(gw, gw_ref) < TOL
+    # autograd wrapper
+    leaves = [d(t).requires_grad_(True) for t in (w, off, *As, *Bs)]
+    outs = ops.depthwise_tensor_product_gathered(plan, graph, leaves[2:2 + len(As)], leaves[2 + len(As):], d(y), leaves[0], leaves[1])
+    grads = torch.autograd.grad(outs, leaves, [d(t) for t in gs])
+    assert rel_err(grads[0], gw_ref) < TOL and rel_err(grads[1], gw_ref.sum(0)) < 1e-5
+
+
 @pytest.mark.parametrize("R,C", [(1, 64), (1000, 64), (4097, 96), (33, 256)])
 def test_ln_silu_fused(cuda_device, R, C):
     """silu(LayerNorm(x)) forward and (gx, dgamma, dbeta) backward vs fp64 torch (RadialProfile hidden layers)."""
