@@ -888,6 +888,33 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     return C
 
 
+_TF32X3_SPLIT = {}
+
+
+def gemm_tf32x3_raw(A: torch.Tensor, Bt: torch.Tensor) -> torch.Tensor:
+    """``A[M, K] @ Bt[N, K]^T`` through the hand-written tcgen05 3xTF32 kernel (``eqf_gemm_tf32x3``)."""
+    A = _require_cuda(A, "gemm A")
+    Bt = _require_cuda(Bt, "gemm Bt")
+    (M, K), N = A.shape, Bt.shape[0]
+    if Bt.shape[1] != K:
+        raise ValueError(f"gemm_tf32x3: incompatible shapes {tuple(A.shape)} {tuple(Bt.shape)}")
+    A, lda = _gemm_operand(A)
+    Bt = Bt.contiguous()
+    if Bt.data_ptr() % 16:
+        Bt = Bt.clone()
+    C = torch.empty((M, N), device=A.device, dtype=torch.float32)
+    need = 2 * N * K
+    split = _TF32X3_SPLIT.get(A.device)
+    if split is None or split.numel() < need:
+        split = torch.empty(max(need, 1 << 20), device=A.device, dtype=torch.float32)
+        _TF32X3_SPLIT[A.device] = split
+    with torch.cuda.device(A.device), _kernel("gemm_tf32x3", 4 * (A.numel() + Bt.numel() + C.numel())):
+        rc = _lib.load().eqf_gemm_tf32x3(A.data_ptr(), Bt.data_ptr(), C.data_ptr(), M, N, K, lda, K, N, split.data_ptr(),
+                                         _stream())
+    _lib.check(rc, "eqf_gemm_tf32x3")
+    return C
+
+
 def _wgrad_sliced(lib, ws, A, B, lda, ldb, M, N, K):
     """dW[M,N] = A[K,M]^T B[K,N] with the K rows cut into slices: one batched tcgen05 launch + a sum over slices.
 

@@ -145,6 +145,13 @@ int eqf_ln_silu_bwd(const float* x, const float* gamma, const float* beta, const
                     const float* gy, int64_t R, int32_t C, float* gx, float* dgamma_part, float* dbeta_part,
                     void* stream);
 
+/* Hand-written tcgen05 GEMM (3xTF32, fp32-level accuracy) for the tall per-degree linears:
+ * C[M, N] = A[M, K] x Bt[N, K]^T, all row-major fp32; `split` = device scratch of 2*N*K floats (hi / lo planes of Bt).
+ * Replaces the e3nn 'uvw' einsum -> cuBLAS SGEMM of LinearRS (nets/tensor_product_rescale.py:165-174) on the
+ * forward (Bt = W^T) and data-gradient (Bt = W) products. */
+int eqf_gemm_tf32x3(const float* A, const float* Bt, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
+                    int64_t ldb, int64_t ldc, float* split, void* stream);
+
 /* Column sums out[c] = sum_r x[r, c] (row stride ld): the bias / radial-offset gradients the reference gets from
  * autograd's broadcast reduction (nets/tensor_product_rescale.py:120-134, radial_func.py:45-49), and the final
  * reduction of per-CTA partial rows.  Deterministic (fixed summation order). */
