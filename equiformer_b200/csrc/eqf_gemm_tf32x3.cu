@@ -7,11 +7,12 @@
 // 9xBF16 collective (eqf_gemm.cu) keeps the tensor pipe 33 % busy on them: every value is split three ways by a
 // transform warp-group and the TMEM accumulator is promoted to registers every other k-block.  This kernel uses the
 // 3xTF32 scheme instead:
-//   a = a_hi + a_lo,  a_hi = the top 19 bits of a (what a kind::tf32 MMA reads from a raw fp32 operand),
-//   a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi          (the dropped a_lo*b_lo term is 2^-22 relative)
-// so the *raw* TMA-written fp32 tile is the hi operand as is, the only transform is lo = x - trunc19(x) on the A tile
-// (the weights' hi / lo planes are split once per call by a tiny kernel), and all three products accumulate in one
-// TMEM accumulator over the whole K loop - no promotion.
+//   a = a_hi + a_lo,  a_hi = a rounded to nearest tf32 (19 bits), a_lo = a - a_hi (exact),
+//   a*b ~= a_lo*b_hi + a_hi*b_lo + a_hi*b_hi          (the dropped a_lo*b_lo term is 2^-24 relative)
+// The transform warps rewrite the TMA-written A tile in place with a_hi and write a_lo next to it (masking the raw
+// bits instead - what the MMA does to a raw fp32 operand - is biased and cost 10x in accuracy at K ~ 1000); the
+// weights' hi / lo planes are split once per call by a tiny kernel; all three products accumulate in one TMEM
+// accumulator over the whole K loop - no promotion.
 //
 // One CTA per SM, persistent over 128 x BN output tiles, warp-specialised:
 //   warps 0-3  epilogue   (tcgen05.ld TMEM -> registers -> st.global; warp w owns TMEM lanes 32w..32w+31)
@@ -32,11 +33,18 @@
 namespace eqf {
 namespace tf32x3 {
 
-constexpr int BM = 128;          // rows per tile (UMMA M)
-constexpr int BK = 32;           // fp32 per k-tile row = 128 bytes = one SWIZZLE_128B atom
-constexpr int UMMA_K = 8;        // tf32 MMA depth
+#ifndef EQF_TF32X3_BK
+#define EQF_TF32X3_BK 16
+#endif
+constexpr int BM = 128;              // rows per tile (UMMA M)
+constexpr int BK = EQF_TF32X3_BK;    // fp32 per k-tile row: 32 -> 128-byte rows (SWIZZLE_128B), 16 -> 64-byte rows (SWIZZLE_64B)
+constexpr int kRowBytes = BK * 4;
+constexpr int UMMA_K = 8;            // tf32 MMA depth
+constexpr int kStoreCols = 32;       // epilogue chunk: 32 columns = 128-byte rows in the staging buffers (SWIZZLE_128B)
+static_assert(BK == 16 || BK == 32, "BK must be 16 or 32");
 constexpr int kThreads = 320;
 constexpr int kEpilogueWarps = 4, kProducerWarp = 4, kMmaWarp = 5, kTransformWarp0 = 6, kTransformWarps = 4;
+constexpr int kTransformThreads = kTransformWarps * 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -66,10 +74,12 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {   // arrives on `ba
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// K-major operand tile in shared memory: rows of 128 bytes, 8-row groups 1024 bytes apart, SWIZZLE_128B
-// (cute UMMA::SmemDescriptor: start>>4 | LBO(=1)<<16 | SBO(=64)<<32 | version(=1)<<46 | layout SWIZZLE_128B(=2)<<61)
+// K-major operand tile in shared memory: rows of kRowBytes, 8-row groups 8*kRowBytes apart, swizzle span = row length
+// (cute UMMA::SmemDescriptor: start>>4 | LBO(=1)<<16 | SBO<<32 | version(=1)<<46 | layout<<61; SWIZZLE_128B = 2, _64B = 4)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
-  return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+  constexpr uint64_t sbo = (8 * kRowBytes) >> 4;
+  constexpr uint64_t layout = (BK == 32) ? 2 : 4;
+  return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
 }
 // kind::tf32, fp32 accumulate, K-major A and B, M = 128, N = n  (cute UMMA::InstrDescriptor)
 __device__ __forceinline__ uint32_t instr_desc(int n) {
@@ -82,35 +92,73 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
 
+// round to nearest tf32 (10-bit mantissa), low 13 bits zero: an unbiased split, unlike masking the raw bits
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// x -> (hi, lo): hi = x rounded to tf32 written back in place (the MMA truncates its fp32 operand, so it must be
+// handed the rounded value explicitly), lo = x - hi written `lo_offset` bytes further
+__device__ __forceinline__ void split_store(uint32_t addr, uint32_t lo_offset, const float4& v) {
+  float4 h, r;
+  h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+  r.x = v.x - h.x; r.y = v.y - h.y; r.z = v.z - h.z; r.w = v.w - h.w;
+  sts128(addr, h);
+  sts128(addr + lo_offset, r);
+}
+
 struct Params {
   float* C;
   long long M, N, K, ldc;
   int n_tile;        // columns per output tile (multiple of 16, <= BN)
   int n_blocks;      // ceil(N / n_tile)
   long long m_blocks;
+  long long* dbg;    // optional timeline of CTA 0 (clock64 stamps), see tools/tf32x3_timeline.py
 };
+
+// dbg layout: role r in {0 producer, 1 mma, 2 transform, 3 epilogue}: dbg[r * 1024 + n] = n-th stamp of that role
+__device__ __forceinline__ void stamp(const Params& p, int role, int& n) {
+  if (p.dbg != nullptr && blockIdx.x == 0 && n < 1024) p.dbg[role * 1024 + n] = clock64();
+  ++n;
+}
 
 template <int BN>
 struct Smem {
-  static constexpr int kStages = (BN >= 256) ? 2 : (BN >= 128 ? 3 : 4);
-  static constexpr int kABytes = BM * BK * 4;      // 16 KB
-  static constexpr int kBBytes = BN * BK * 4;
-  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kABytes = BM * kRowBytes;
+  static constexpr int kBBytes = BN * kRowBytes;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;       // A hi | A lo | B hi | B lo
+  static constexpr int kStoreBytes = kEpilogueWarps * 2 * 32 * kStoreCols * 4;   // per warp: 2 buffers of 32 rows x 128 B
   static constexpr int kBarrierBytes = 1024;
-  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024 /* alignment slack */;
+  static constexpr int kBudget = 227 * 1024 - 1024 /* alignment slack */;
+  static constexpr int kStagesRaw = (kBudget - kStoreBytes - kBarrierBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static_assert(kStages >= 2, "tile does not fit shared memory");
+  static constexpr int kTotal = kStages * kStageBytes + kStoreBytes + kBarrierBytes + 1024;
 };
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-                   const __grid_constant__ CUtensorMap map_blo, Params p) {
+                   const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c, Params p) {
   using S = Smem<BN>;
   constexpr int kStages = S::kStages;
   constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * S::kStageBytes);
+  uint8_t* store_base = smem + kStages * S::kStageBytes;     // epilogue staging (1024-byte aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(store_base + S::kStoreBytes);
   uint64_t* full = bars;                       // [kStages] TMA landed
   uint64_t* lo_ready = bars + kStages;         // [kStages] A_lo written
   uint64_t* empty = bars + 2 * kStages;        // [kStages] MMAs reading the stage have finished
@@ -126,6 +174,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_bhi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_blo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_c)) : "memory");
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&lo_ready[s], kTransformWarps);
@@ -150,7 +199,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // ===================================================================================== TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      const uint32_t tx = (uint32_t)(S::kABytes + 2 * p.n_tile * BK * 4);
+      int n_stamp = 0;
+      const uint32_t tx = (uint32_t)(S::kABytes + 2 * p.n_tile * kRowBytes);
       for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
         const long long mb = tile / p.n_blocks;
         const int nb = (int)(tile % p.n_blocks);
@@ -158,6 +208,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
+          stamp(p, 0, n_stamp);
           uint8_t* st = stage_base + (size_t)s * S::kStageBytes;
           mbar_expect_tx(&full[s], tx);
           tma_load_2d(st, &map_a, (int)(kt * BK), (int)(mb * BM), &full[s]);
@@ -171,6 +222,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (lane == 0) {
       const uint32_t idesc = instr_desc(p.n_tile);
       uint32_t it = 0, acc_it = 0;
+      int n_stamp = 0;
       for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
         const int a = acc_it & 1;
         const uint32_t aph = (acc_it >> 1) & 1;
@@ -181,90 +233,109 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&full[s], ph);
+          stamp(p, 1, n_stamp);
           mbar_wait(&lo_ready[s], ph);
+          stamp(p, 1, n_stamp);
           tc_fence_after();
           const uint32_t st = smem_u32(stage_base + (size_t)s * S::kStageBytes);
           const uint64_t a_hi = smem_desc(st), a_lo = smem_desc(st + S::kABytes);
           const uint64_t b_hi = smem_desc(st + 2 * S::kABytes), b_lo = smem_desc(st + 2 * S::kABytes + S::kBBytes);
 #pragma unroll
           for (int kb = 0; kb < BK / UMMA_K; ++kb) {
-            const uint64_t adv = (uint64_t)((kb * UMMA_K * 4) >> 4);     // 32 bytes per k-block inside the 128-byte row
+            const uint64_t adv = (uint64_t)((kb * UMMA_K * 4) >> 4);     // 32 bytes per k-block inside the swizzled row
             umma_tf32(d_tmem, a_lo + adv, b_hi + adv, idesc, (kt > 0 || kb > 0) ? 1u : 0u);
             umma_tf32(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
             umma_tf32(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
           }
           umma_commit(&empty[s]);                    // frees the smem stage once these MMAs have read it
+          stamp(p, 1, n_stamp);
         }
         umma_commit(&tmem_full[a]);                  // accumulator complete
       }
     }
   } else if (warp >= kTransformWarp0) {
-    // ===================================================================================== transform: A_lo = A - trunc19(A)
+    // ===================================================================================== transform: A -> (A_hi, A_lo)
     const int t = threadIdx.x - kTransformWarp0 * 32;   // 0..127
     uint32_t it = 0;
+    int n_stamp = 0;
     for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
       for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(&full[s], ph);
-        const float4* raw = reinterpret_cast<const float4*>(stage_base + (size_t)s * S::kStageBytes);
-        float4* lo = reinterpret_cast<float4*>(stage_base + (size_t)s * S::kStageBytes + S::kABytes);
+        if (t == 0) stamp(p, 2, n_stamp);
+        // loads are batched ahead of the stores (explicit ld/st.shared: with generic pointers the compiler serialised
+        // load -> use -> store and the transform, not the tensor pipe, set the pace)
+        const uint32_t st_addr = smem_u32(stage_base + (size_t)s * S::kStageBytes);
+        {   // A tile: BM rows
+          const uint32_t raw_addr = st_addr + (uint32_t)t * 16u;
+          constexpr int kPer = (BM * BK / 4) / kTransformThreads;
+          float4 v[kPer];
 #pragma unroll
-        for (int i = 0; i < (BM * BK / 4) / (kTransformWarps * 32); ++i) {
-          const int idx = i * (kTransformWarps * 32) + t;
-          const float4 v = raw[idx];
-          float4 r;
-          r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-          r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-          r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-          r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-          lo[idx] = r;
+          for (int i = 0; i < kPer; ++i) v[i] = lds128(raw_addr + (uint32_t)i * (kTransformThreads * 16));
+#pragma unroll
+          for (int i = 0; i < kPer; ++i) split_store(raw_addr + (uint32_t)i * (kTransformThreads * 16), S::kABytes, v[i]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA's async proxy
         __syncwarp();
         if (lane == 0) mbar_arrive(&lo_ready[s]);
+        if (t == 0) stamp(p, 2, n_stamp);
       }
     }
   } else {
     // ===================================================================================== epilogue (warps 0-3)
-    uint32_t acc_it = 0;
+    uint32_t acc_it = 0, chunk_it = 0;
+    int n_stamp = 0;
     for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
       const long long mb = tile / p.n_blocks;
       const int nb = (int)(tile % p.n_blocks);
       const int a = acc_it & 1;
       const uint32_t aph = (acc_it >> 1) & 1;
       mbar_wait(&tmem_full[a], aph);
+      if (threadIdx.x == 0) stamp(p, 3, n_stamp);
       tc_fence_after();
-      const long long row = mb * BM + warp * 32 + lane;
-      const long long col0 = (long long)nb * p.n_tile;
-      float* crow = p.C + row * p.ldc + col0;
+      // TMEM -> registers -> swizzled staging rows (this warp's 32 rows x 32 columns) -> TMA store; two staging buffers
+      // per warp so the store of chunk c overlaps the TMEM read of chunk c+1.  (Direct st.global of a thread's own row
+      // made every warp store touch 32 different lines: 13-15k cycles per tile, more than the main loop.)
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * BN);
-      for (int c = 0; c < p.n_tile; c += 16) {
-        uint32_t v[16];
+      const int row0 = (int)(mb * BM) + warp * 32;
+      const int col0 = nb * p.n_tile;
+      uint8_t* wbuf = store_base + warp * (2 * 32 * kStoreCols * 4);
+      for (int c = 0; c < p.n_tile; c += kStoreCols, ++chunk_it) {
+        const uint32_t buf = smem_u32(wbuf + (chunk_it & 1) * (32 * kStoreCols * 4));
+        uint32_t v[32];
         asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr + (uint32_t)c));
+        // the buffer about to be overwritten was handed to a TMA store two chunks ago: wait until that store has read it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (row < p.M) {
-          if (col0 + c + 16 <= p.N) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              *reinterpret_cast<float4*>(crow + c + 4 * q) =
-                  make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
-                              __uint_as_float(v[4 * q + 3]));
-          } else {
-#pragma unroll
-            for (int q = 0; q < 16; ++q)
-              if (col0 + c + q < p.N) crow[c + q] = __uint_as_float(v[q]);
-          }
+        for (int j = 0; j < 8; ++j) {       // 16-byte chunk j of this lane's 128-byte row, SWIZZLE_128B position
+          const uint32_t dst = buf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+          sts128(dst, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                  __uint_as_float(v[4 * j + 3])));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                       ::"l"(reinterpret_cast<uint64_t>(&map_c)), "r"(col0 + c), "r"(row0), "r"(buf) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[a]);
+      if (threadIdx.x == 0) stamp(p, 3, n_stamp);
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all of this warp's stores have landed
   }
 
   tc_fence_before();
@@ -274,11 +345,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 }
 
-// hi / lo planes of the (small) weight operand: hi = top 19 bits, lo = w - hi
+// hi / lo planes of the (small) weight operand: hi = w rounded to tf32, lo = w - hi
 __global__ void split_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = w[i];
-    const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    const float h = tf32_rn(v);
     hi[i] = h;
     lo[i] = v - h;
   }
@@ -299,23 +370,26 @@ static EncodeTiled encode_fn() {
   return fn;
 }
 
-// 2-D fp32 tensor [rows, cols] with row stride ld (elements), box = [box_rows, 32 columns], 128-byte swizzle, zero OOB fill
-static int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+// 2-D fp32 tensor [rows, cols] with row stride ld (elements), box = [box_rows, box_cols], swizzle span = box row bytes
+// (64 or 128), zero fill out of bounds (loads) / clipping (stores)
+static int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows,
+                    int box_cols) {
   EncodeTiled enc = encode_fn();
   if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return EQF_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = (box_cols * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")"); return EQF_ERR_CUDA; }
   return EQF_OK;
 }
 
 template <int BN>
-static int launch(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const Params& p, cudaStream_t s) {
+static int launch(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mc,
+                  const Params& p, cudaStream_t s) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -328,7 +402,7 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMa
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long tiles = p.m_blocks * p.n_blocks;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  gemm_tf32x3_kernel<BN><<<grid, kThreads, Smem<BN>::kTotal, s>>>(ma, mh, ml, p);
+  gemm_tf32x3_kernel<BN><<<grid, kThreads, Smem<BN>::kTotal, s>>>(ma, mh, ml, mc, p);
   return check_cuda(cudaGetLastError(), "gemm_tf32x3_kernel launch");
 }
 
@@ -336,6 +410,10 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMa
 }  // namespace eqf
 
 using namespace eqf;
+
+static long long* g_tf32x3_dbg = nullptr;
+// debugging aid: device buffer of 4 * 1024 int64 that receives CTA 0's clock64 timeline on the next launches (NULL = off)
+extern "C" void eqf_gemm_tf32x3_set_timeline(long long* device_buffer) { g_tf32x3_dbg = device_buffer; }
 
 // C[M, N] = A[M, K] (row-major, lda) x Bt[N, K]^T (row-major, ldb), 3xTF32 on tcgen05.  `split` is device scratch of
 // 2 * N * K floats for the hi / lo planes of Bt.  All pointers 16-byte aligned, K, lda, ldb, ldc multiples of 4.
@@ -351,29 +429,32 @@ extern "C" int eqf_gemm_tf32x3(const float* A, const float* Bt, float* C, int64_
     return EQF_ERR_INVALID;
   }
   cudaStream_t s = (cudaStream_t)stream;
-  // hi / lo planes of the weights, packed [N, K]
+  // hi / lo planes of the weights, packed [N, K] (loading precomputed planes costs L2 bandwidth; splitting the raw
+  // tile in shared memory instead was tried and lost: the transform's shared-memory traffic became the limiter)
   float* hi = split;
   float* lo = split + N * K;
-  if (ldb == K) {
-    split_kernel<<<(unsigned)((N * K + 255) / 256 < 1184 ? (N * K + 255) / 256 : 1184), 256, 0, s>>>(Bt, hi, lo, N * K);
-  } else {
-    set_error("eqf_gemm_tf32x3: Bt must be packed (ldb == K)");
-    return EQF_ERR_UNSUPPORTED;
+  {
+    const long long n = N * K;
+    const unsigned blocks = (unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    if (ldb == K) split_kernel<<<blocks, 256, 0, s>>>(Bt, hi, lo, n);
+    else { set_error("eqf_gemm_tf32x3: Bt must be packed (ldb == K)"); return EQF_ERR_UNSUPPORTED; }
   }
   int rc = check_cuda(cudaGetLastError(), "split_kernel launch");
   if (rc != EQF_OK) return rc;
-  // tile the columns: at most 256 per tile, multiples of 16, as even as possible
+  // column tiles: one tile of round_up(N, 16) columns when N <= 256, else tiles of 256 (the last one narrower: its
+  // out-of-range weight rows load as zeros and its out-of-range columns are clipped by the TMA store)
   const int n_blocks = (int)((N + 255) / 256);
-  int n_tile = (int)((N + n_blocks - 1) / n_blocks);
-  n_tile = (n_tile + 15) & ~15;
+  const int n_tile = n_blocks == 1 ? (int)((N + 15) & ~15LL) : 256;
   Params p;
-  p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.n_tile = n_tile; p.n_blocks = (int)((N + n_tile - 1) / n_tile);
+  p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.n_tile = n_tile; p.n_blocks = n_blocks;
   p.m_blocks = (M + BM - 1) / BM;
-  CUtensorMap ma, mh, ml;
-  if ((rc = make_map(&ma, A, M, K, lda, BM)) != EQF_OK) return rc;
-  if ((rc = make_map(&mh, hi, N, K, K, n_tile)) != EQF_OK) return rc;
-  if ((rc = make_map(&ml, lo, N, K, K, n_tile)) != EQF_OK) return rc;
-  if (n_tile <= 64) return launch<64>(ma, mh, ml, p, s);
-  if (n_tile <= 128) return launch<128>(ma, mh, ml, p, s);
-  return launch<256>(ma, mh, ml, p, s);
+  p.dbg = g_tf32x3_dbg;
+  CUtensorMap ma, mh, ml, mc;
+  if ((rc = make_map(&ma, A, M, K, lda, BM, BK)) != EQF_OK) return rc;
+  if ((rc = make_map(&mh, hi, N, K, K, n_tile, BK)) != EQF_OK) return rc;
+  if ((rc = make_map(&ml, lo, N, K, K, n_tile, BK)) != EQF_OK) return rc;
+  if ((rc = make_map(&mc, C, M, N, ldc, 32, kStoreCols)) != EQF_OK) return rc;
+  if (n_tile <= 64) return launch<64>(ma, mh, ml, mc, p, s);
+  if (n_tile <= 128) return launch<128>(ma, mh, ml, mc, p, s);
+  return launch<256>(ma, mh, ml, mc, p, s);
 }

@@ -31,10 +31,11 @@ class GraphedForwardBackward:
         self.captures = 0
 
     def _fwd_bwd(self, c: _Captured) -> torch.Tensor:
-        self.bucket.flat.zero_()
         out = self.model.forward_edges(c.pos, c.batch, c.z, c.src, c.dst, graph=c.csr, n_graphs=c.target.shape[0])
         loss = self.loss_fn(out, c.target)
-        loss.backward()
+        # gradients as a list + one multi-tensor copy into the flat bucket (autograd's per-parameter accumulation into
+        # the bucket views would be ~290 tiny `grad += g` launches per step)
+        self.bucket.store(torch.autograd.grad(loss, self.bucket.params, allow_unused=True))
         return loss.detach()
 
     def _capture(self, pos, batch, z, target, src, dst, row_ptr, src_perm, src_row_ptr) -> _Captured:

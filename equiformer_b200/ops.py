@@ -870,6 +870,10 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
         if mode == 0:
             return A @ B
         return A @ B.t() if mode == 1 else A.t() @ B
+    # forward / data-gradient products with a wide output run on the hand-written 3xTF32 tcgen05 kernel (1.2-1.6x the
+    # CUTLASS collective there, profiles/r1_tf32x3_microbench.jsonl); narrow outputs stay on the CUTLASS kernel
+    if mode != 2 and _TF32X3 and N >= 128 and M >= 16384 and not gemm_backend_forced():
+        return gemm_tf32x3_raw(A, B if mode == 1 else B.t().contiguous())
     A, lda = _gemm_operand(A)
     B, ldb = _gemm_operand(B)
     lib = _lib.load_gemm()
@@ -888,6 +892,7 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     return C
 
 
+_TF32X3 = os.environ.get("EQF_GEMM_TF32X3", "1") != "0"
 _TF32X3_SPLIT = {}
 
 

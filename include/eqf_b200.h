@@ -151,6 +151,8 @@ int eqf_ln_silu_bwd(const float* x, const float* gamma, const float* beta, const
  * forward (Bt = W^T) and data-gradient (Bt = W) products. */
 int eqf_gemm_tf32x3(const float* A, const float* Bt, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                     int64_t ldb, int64_t ldc, float* split, void* stream);
+/* debugging aid: device buffer of 4*1024 int64 receiving CTA 0's clock64 timeline on later launches (NULL = off) */
+void eqf_gemm_tf32x3_set_timeline(long long* device_buffer);
 
 /* Column sums out[c] = sum_r x[r, c] (row stride ld): the bias / radial-offset gradients the reference gets from
  * autograd's broadcast reduction (nets/tensor_product_rescale.py:120-134, radial_func.py:45-49), and the final

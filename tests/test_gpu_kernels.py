@@ -182,6 +182,29 @@ def test_fast_fp32_gemm_all_layouts(cuda_device, M, N, K, monkeypatch):
     assert rel_err(ops.gemm_raw(0, view, d(B)), wide[:, 4:4 + K].double() @ B.double()) < tol(K)
 
 
+@pytest.mark.parametrize("M,N,K", [(100, 16, 32), (1000, 48, 64), (3001, 72, 100), (36000, 224, 224), (36000, 352, 224),
+                                   (36000, 960, 64), (108000, 384, 64), (33000, 128, 960), (129, 256, 16), (128, 272, 36)])
+def test_tf32x3_tcgen05_gemm(cuda_device, M, N, K):
+    """Hand-written tcgen05 3xTF32 GEMM C = A Bt^T vs fp64: ragged rows, K tails, single and multiple column tiles,
+    strided A.  Accuracy: 2-3e-6 of max|C| at K ~ 224 (TMEM accumulation), far from single-pass TF32's 1e-3."""
+    from equiformer_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    Bt = torch.randn(N, K, generator=g)
+    d = lambda t: t.to(cuda_device)
+    tol = 6e-6 * max(1.0, (K / 256) ** 0.5)
+    ref = A.double() @ Bt.double().t()
+    out = ops.gemm_tf32x3_raw(d(A), d(Bt))
+    assert out.shape == (M, N) and rel_err(out, ref) < tol
+    wide = torch.randn(M, K + 8, generator=g)
+    out = ops.gemm_tf32x3_raw(d(wide)[:, 4:4 + K], d(Bt))
+    assert rel_err(out, wide[:, 4:4 + K].double() @ Bt.double().t()) < tol
+    # exactly representable inputs (small integers) must give the exact product
+    Ai = torch.randint(-8, 9, (M, K), generator=g).float()
+    Bi = torch.randint(-8, 9, (N, K), generator=g).float()
+    assert torch.equal(ops.gemm_tf32x3_raw(d(Ai), d(Bi)).cpu(), Ai @ Bi.t())
+
+
 def test_gemm_autograd_closure(cuda_device):
     from equiformer_b200 import ops
     g = torch.Generator().manual_seed(0)

@@ -86,3 +86,23 @@ def test_flat_adamw_matches_torch_adamw():
         opt_b.step()
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert torch.allclose(pa, pb, atol=1e-12), (pa - pb).abs().max()
+
+
+def test_flat_bucket_store_matches_backward_accumulation():
+    """FlatGradAllReduce.store(autograd.grad(...)) fills the bucket exactly like loss.backward() into the views."""
+    import torch
+    from equiformer_b200.parallel import FlatGradAllReduce
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.SiLU(), torch.nn.Linear(7, 3))
+    unused = torch.nn.Parameter(torch.randn(4))
+    params = list(net.parameters()) + [unused]
+    bucket = FlatGradAllReduce(params)
+    x = torch.randn(11, 5)
+    bucket.zero_grad()
+    net(x).square().sum().backward()
+    ref = bucket.flat.clone()
+    bucket.flat.fill_(123.0)
+    bucket.store(torch.autograd.grad(net(x).square().sum(), bucket.params, allow_unused=True))
+    live = torch.cat([p.grad.reshape(-1) for p in params])
+    assert torch.equal(live, torch.cat([ref[o:o + p.numel()] for p, o in zip(params, bucket.offsets)]))
+    assert torch.count_nonzero(unused.grad) == 0
