@@ -118,6 +118,8 @@ __device__ __forceinline__ void split_store(uint32_t addr, uint32_t lo_offset, c
   sts128(addr + lo_offset, r);
 }
 
+__device__ __forceinline__ uint8_t* stage_base_of(uint8_t* smem, int s, int stage_bytes) { return smem + (size_t)s * stage_bytes; }
+
 struct Params {
   float* C;
   long long M, N, K, ldc;
@@ -373,14 +375,16 @@ static EncodeTiled encode_fn() {
 // 2-D fp32 tensor [rows, cols] with row stride ld (elements), box = [box_rows, box_cols], swizzle span = box row bytes
 // (64 or 128), zero fill out of bounds (loads) / clipping (stores)
 static int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows,
-                    int box_cols) {
+                    int box_cols, bool atom_32b = false) {
   EncodeTiled enc = encode_fn();
   if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return EQF_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapSwizzle sw = (box_cols * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  // atom_32b: 32-byte chunks swizzled within the 128-byte span - the only layout the MMA accepts for MN-major tf32 operands
+  const CUtensorMapSwizzle sw = atom_32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                : (box_cols * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")"); return EQF_ERR_CUDA; }
@@ -406,6 +410,256 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMa
   return check_cuda(cudaGetLastError(), "gemm_tf32x3_kernel launch");
 }
 
+
+// ================================================================================================ weight gradient
+//   W[K1, N] = A[R, K1]^T G[R, N]        (reduction over the R = edges x (2l+1) rows; tiny output)
+// Both operands are "MN-major" for the MMA (the non-reduction dimension is the contiguous one in HBM): a tile is a
+// row of TMA boxes [BKR reduction rows x 32 columns] (128-byte rows, swizzle 128B_ATOM_32B), i.e. canonical UMMA
+// MN-major atoms of 4 rows x 128 bytes; LBO = distance between the 32-column blocks, SBO = distance between atoms.
+// grid = (output tiles of 128 x n_tile) x (row slices): every CTA reduces its slice of rows into one TMEM accumulator
+// and writes a partial [K1, N] block; the caller sums the partials over slices (eqf_colsum).  Same warp roles and
+// 3xTF32 split as the forward kernel; here the transform warps split both operand tiles.
+namespace wg {
+
+constexpr int BKR = 16;                       // reduction rows per stage = two k-blocks of 8
+constexpr int kBlockBytes = BKR * 128;        // one [BKR x 32] box
+constexpr int kMBlocks = BM / 32;             // 4 boxes for the 128 output rows
+
+struct WParams {
+  long long R, rows_per_slice;
+  int n_tile, n_tiles;                        // output columns per CTA (multiple of 32), number of column tiles
+};
+
+template <int BN>
+struct WSmem {
+  static constexpr int kABytes = kMBlocks * kBlockBytes;           // 8 KB
+  static constexpr int kGBytes = (BN / 32) * kBlockBytes;
+  static constexpr int kRaw = kABytes + kGBytes;                   // hi (raw) part of a stage; the lo part follows
+  static constexpr int kStageBytes = 2 * kRaw;
+  static constexpr int kStoreBytes = kEpilogueWarps * 2 * 32 * kStoreCols * 4;
+  static constexpr int kBudget = 227 * 1024 - 1024;
+  static constexpr int kStagesRaw = (kBudget - kStoreBytes - 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kTotal = kStages * kStageBytes + kStoreBytes + 1024 + 1024;
+};
+
+// MN-major tf32 operands exist only in the SWIZZLE_128B_BASE32B layout (cute: Layout_MN_SW128_32B_Atom, TMA swizzle
+// 128B_ATOM_32B): atoms of 4 reduction rows x 128 bytes; SBO = distance between the 4-row atoms (512 B), LBO = distance
+// between the 32-column blocks; one MMA (K = 8) spans two atoms.
+__device__ __forceinline__ uint64_t smem_desc_mn(uint32_t addr) {
+  constexpr uint64_t lbo = kBlockBytes >> 4, sbo = 512 >> 4;
+  return (uint64_t)((addr >> 4) & 0x3FFF) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (1ull << 61);
+}
+__device__ __forceinline__ uint32_t instr_desc_mn(int n) {    // as instr_desc, with A and B MN-major (bits 15, 16)
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_g,
+                    const __grid_constant__ CUtensorMap map_p, WParams p) {
+  using S = WSmem<BN>;
+  constexpr int kStages = S::kStages;
+  constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* store_base = smem + kStages * S::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(store_base + S::kStoreBytes);
+  uint64_t* full = bars;
+  uint64_t* lo_ready = bars + kStages;
+  uint64_t* empty = bars + 2 * kStages;
+  uint64_t* tmem_full = bars + 3 * kStages;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x / p.n_tiles, nt = blockIdx.x % p.n_tiles;
+  const long long r0 = (long long)blockIdx.y * p.rows_per_slice;
+  long long rows = p.R - r0;
+  if (rows > p.rows_per_slice) rows = p.rows_per_slice;
+  const int k_tiles = (int)((rows + BKR - 1) / BKR);       // >= 1 (host guarantees non-empty slices)
+  const int g_blocks = p.n_tile / 32;
+
+  if (warp == kProducerWarp && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_g)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_p)) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&lo_ready[s], kTransformWarps);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)((kMBlocks + g_blocks) * kBlockBytes);
+      for (int kt = 0; kt < k_tiles; ++kt) {
+        const int s = kt % kStages;
+        const uint32_t ph = (kt / kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = stage_base_of(smem, s, S::kStageBytes);
+        mbar_expect_tx(&full[s], tx);
+        const int row = (int)(r0 + (long long)kt * BKR);
+        for (int j = 0; j < kMBlocks; ++j) tma_load_2d(st + j * kBlockBytes, &map_a, mt * BM + 32 * j, row, &full[s]);
+        for (int j = 0; j < g_blocks; ++j)
+          tma_load_2d(st + S::kABytes + j * kBlockBytes, &map_g, nt * p.n_tile + 32 * j, row, &full[s]);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc_mn(p.n_tile);
+      for (int kt = 0; kt < k_tiles; ++kt) {
+        const int s = kt % kStages;
+        const uint32_t ph = (kt / kStages) & 1;
+        mbar_wait(&full[s], ph);
+        mbar_wait(&lo_ready[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(stage_base_of(smem, s, S::kStageBytes));
+#pragma unroll
+        for (int kb = 0; kb < BKR / UMMA_K; ++kb) {
+          const uint32_t off = (uint32_t)kb * 1024u;              // next 8-row group inside every 32-column block
+          const uint64_t a_hi = smem_desc_mn(st + off), g_hi = smem_desc_mn(st + S::kABytes + off);
+          const uint64_t a_lo = smem_desc_mn(st + S::kRaw + off), g_lo = smem_desc_mn(st + S::kRaw + S::kABytes + off);
+          umma_tf32(tmem_base, a_lo, g_hi, idesc, (kt > 0 || kb > 0) ? 1u : 0u);
+          umma_tf32(tmem_base, a_hi, g_lo, idesc, 1u);
+          umma_tf32(tmem_base, a_hi, g_hi, idesc, 1u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else if (warp >= kTransformWarp0) {
+    const int t = threadIdx.x - kTransformWarp0 * 32;
+    const int n_piece = (kMBlocks + g_blocks) * kBlockBytes / 16;     // 16-byte pieces of the raw part (A then G)
+    for (int kt = 0; kt < k_tiles; ++kt) {
+      const int s = kt % kStages;
+      const uint32_t ph = (kt / kStages) & 1;
+      mbar_wait(&full[s], ph);
+      const uint32_t st = smem_u32(stage_base_of(smem, s, S::kStageBytes));
+      for (int base = 0; base < n_piece; base += 4 * kTransformThreads) {
+        float4 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int idx = base + i * kTransformThreads + t;
+          if (idx < n_piece) v[i] = lds128(st + (uint32_t)idx * 16u);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int idx = base + i * kTransformThreads + t;
+          if (idx < n_piece) split_store(st + (uint32_t)idx * 16u, S::kRaw, v[i]);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&lo_ready[s]);
+    }
+  } else {
+    // epilogue: partial[slice][mt * 128 + row][nt * n_tile + col]
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint8_t* wbuf = store_base + warp * (2 * 32 * kStoreCols * 4);
+    uint32_t chunk_it = 0;
+    for (int c = 0; c < p.n_tile; c += kStoreCols, ++chunk_it) {
+      const uint32_t buf = smem_u32(wbuf + (chunk_it & 1) * (32 * kStoreCols * 4));
+      uint32_t v[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr + (uint32_t)c));
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t dst = buf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+        sts128(dst, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                __uint_as_float(v[4 * j + 3])));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                     ::"l"(reinterpret_cast<uint64_t>(&map_p)), "r"(nt * p.n_tile + c), "r"(mt * BM + warp * 32),
+                       "r"((int)blockIdx.y), "r"(buf) : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// partial[slices][K1][N] (packed): 3-D map, box = [1, 32 rows, 32 columns]
+static int make_map3(CUtensorMap* map, const float* base, long long slices, long long K1, long long N) {
+  EncodeTiled enc = encode_fn();
+  if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return EQF_ERR_CUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)N, (cuuint64_t)K1, (cuuint64_t)slices};
+  cuuint64_t strides[2] = {(cuuint64_t)N * sizeof(float), (cuuint64_t)N * K1 * sizeof(float)};
+  cuuint32_t box[3] = {(cuuint32_t)kStoreCols, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (3-D) failed (code " + std::to_string((int)r) + ")"); return EQF_ERR_CUDA; }
+  return EQF_OK;
+}
+
+struct Shape { int n_tile, n_tiles, m_tiles; long long slices, rows_per_slice; };
+
+static Shape plan(long long R, long long K1, long long N) {
+  Shape sh;
+  sh.n_tiles = (int)((N + 255) / 256);
+  sh.n_tile = sh.n_tiles == 1 ? (int)((N + 31) & ~31LL) : 256;
+  sh.m_tiles = (int)((K1 + BM - 1) / BM);
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long slices = sms / ((long long)sh.m_tiles * sh.n_tiles);     // one wave of CTAs (one CTA per SM)
+  if (slices < 1) slices = 1;
+  long long rps = (R + slices - 1) / slices;
+  if (rps < 64) rps = 64;
+  rps = (rps + BKR - 1) / BKR * BKR;
+  sh.rows_per_slice = rps;
+  sh.slices = (R + rps - 1) / rps;                                    // every slice non-empty
+  return sh;
+}
+
+template <int BN>
+static int launch(const CUtensorMap& ma, const CUtensorMap& mg, const CUtensorMap& mp, const WParams& p, const Shape& sh,
+                  cudaStream_t s) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(wgrad_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WSmem<BN>::kTotal);
+  });
+  if (attr_err != cudaSuccess) return check_cuda(attr_err, "wgrad_tf32x3 smem attribute");
+  dim3 grid((unsigned)(sh.m_tiles * sh.n_tiles), (unsigned)sh.slices);
+  wgrad_tf32x3_kernel<BN><<<grid, kThreads, WSmem<BN>::kTotal, s>>>(ma, mg, mp, p);
+  return check_cuda(cudaGetLastError(), "wgrad_tf32x3_kernel launch");
+}
+
+}  // namespace wg
 }  // namespace tf32x3
 }  // namespace eqf
 
@@ -457,4 +711,38 @@ extern "C" int eqf_gemm_tf32x3(const float* A, const float* Bt, float* C, int64_
   if (n_tile <= 64) return launch<64>(ma, mh, ml, mc, p, s);
   if (n_tile <= 128) return launch<128>(ma, mh, ml, mc, p, s);
   return launch<256>(ma, mh, ml, mc, p, s);
+}
+
+
+// number of row slices eqf_gemm_tf32x3_wgrad will use (= leading dimension of its `partial` scratch [slices, K1, N])
+extern "C" int64_t eqf_gemm_tf32x3_wgrad_slices(int64_t R, int64_t K1, int64_t N) {
+  if (R <= 0 || K1 <= 0 || N <= 0) return 0;
+  return eqf::tf32x3::wg::plan(R, K1, N).slices;
+}
+
+// partial[s] = A[rows of slice s, :K1]^T G[rows of slice s, :N]  for every slice s; the weight gradient is the sum over s.
+// A [R, K1] (lda), G [R, N] (ldg) row-major fp32, 16-byte aligned, K1, N, lda, ldg multiples of 4.
+extern "C" int eqf_gemm_tf32x3_wgrad(const float* A, const float* G, float* partial, int64_t R, int64_t K1, int64_t N,
+                                     int64_t lda, int64_t ldg, void* stream) {
+  using namespace eqf::tf32x3;
+  if (R <= 0 || K1 <= 0 || N <= 0) return EQF_OK;
+  if (!A || !G || !partial) { set_error("eqf_gemm_tf32x3_wgrad: null pointer"); return EQF_ERR_INVALID; }
+  if ((((uintptr_t)A | (uintptr_t)G | (uintptr_t)partial) & 15) || ((K1 | N | lda | ldg) & 3) || lda < K1 || ldg < N) {
+    set_error("eqf_gemm_tf32x3_wgrad: operands must be 16-byte aligned, dimensions multiples of 4");
+    return EQF_ERR_INVALID;
+  }
+  if (R > 0x7fffffffLL) { set_error("eqf_gemm_tf32x3_wgrad: too many rows"); return EQF_ERR_UNSUPPORTED; }
+  const wg::Shape sh = wg::plan(R, K1, N);
+  wg::WParams p;
+  p.R = R; p.rows_per_slice = sh.rows_per_slice; p.n_tile = sh.n_tile; p.n_tiles = sh.n_tiles;
+  CUtensorMap ma, mg, mp;
+  int rc;
+  if ((rc = make_map(&ma, A, R, K1, lda, wg::BKR, 32, true)) != EQF_OK) return rc;
+  if ((rc = make_map(&mg, G, R, N, ldg, wg::BKR, 32, true)) != EQF_OK) return rc;
+  if ((rc = wg::make_map3(&mp, partial, sh.slices, K1, N)) != EQF_OK) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (sh.n_tile <= 32) return wg::launch<32>(ma, mg, mp, p, sh, s);
+  if (sh.n_tile <= 64) return wg::launch<64>(ma, mg, mp, p, sh, s);
+  if (sh.n_tile <= 128) return wg::launch<128>(ma, mg, mp, p, sh, s);
+  return wg::launch<256>(ma, mg, mp, p, sh, s);
 }

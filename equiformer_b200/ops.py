@@ -874,6 +874,10 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     # CUTLASS collective there, profiles/r1_tf32x3_microbench.jsonl); narrow outputs stay on the CUTLASS kernel
     if mode != 2 and _TF32X3 and N >= 128 and M >= 16384 and not gemm_backend_forced():
         return gemm_tf32x3_raw(A, B if mode == 1 else B.t().contiguous())
+    # weight gradient: the hand-written kernel (one TMEM accumulator per row slice) wins for wide outputs and for the
+    # short node-level reductions; long reductions into narrow outputs stay on the sliced CUTLASS launch
+    if mode == 2 and _TF32X3 and (N >= 128 or K < 16384) and not gemm_backend_forced():
+        return gemm_tf32x3_wgrad_raw(A, B)
     A, lda = _gemm_operand(A)
     B, ldb = _gemm_operand(B)
     lib = _lib.load_gemm()
@@ -918,6 +922,27 @@ def gemm_tf32x3_raw(A: torch.Tensor, Bt: torch.Tensor) -> torch.Tensor:
                                          _stream())
     _lib.check(rc, "eqf_gemm_tf32x3")
     return C
+
+
+def gemm_tf32x3_wgrad_raw(A: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
+    """``A[R, K1]^T @ G[R, N]`` (weight gradient) through the hand-written tcgen05 3xTF32 kernel: per-slice partial
+    products (one CTA per row slice and output tile) + one deterministic column sum over the slices."""
+    A = _require_cuda(A, "wgrad A")
+    G = _require_cuda(G, "wgrad G")
+    (R, K1), N = A.shape, G.shape[1]
+    if G.shape[0] != R:
+        raise ValueError(f"gemm_tf32x3_wgrad: incompatible shapes {tuple(A.shape)} {tuple(G.shape)}")
+    A, lda = _gemm_operand(A)
+    G, ldg = _gemm_operand(G)
+    lib = _lib.load()
+    slices = int(lib.eqf_gemm_tf32x3_wgrad_slices(R, K1, N))
+    part = torch.empty((max(slices, 1), K1, N), device=A.device, dtype=torch.float32)
+    with torch.cuda.device(A.device), _kernel("gemm_tf32x3_wgrad", 4 * (A.numel() + G.numel() + 2 * part.numel())):
+        rc = lib.eqf_gemm_tf32x3_wgrad(A.data_ptr(), G.data_ptr(), part.data_ptr(), R, K1, N, lda, ldg, _stream())
+    _lib.check(rc, "eqf_gemm_tf32x3_wgrad")
+    if slices == 1:
+        return part[0]
+    return colsum_raw(part.view(slices, K1 * N)).view(K1, N)
 
 
 def _wgrad_sliced(lib, ws, A, B, lda, ldb, M, N, K):

@@ -151,6 +151,12 @@ int eqf_ln_silu_bwd(const float* x, const float* gamma, const float* beta, const
  * forward (Bt = W^T) and data-gradient (Bt = W) products. */
 int eqf_gemm_tf32x3(const float* A, const float* Bt, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
                     int64_t ldb, int64_t ldc, float* split, void* stream);
+/* Weight gradient of the same linears, W[K1, N] = A[R, K1]^T G[R, N] (what autograd derives for the 'uvw' einsum of
+ * LinearRS): the R rows are cut into eqf_gemm_tf32x3_wgrad_slices(R, K1, N) slices, every CTA reduces one slice into a
+ * TMEM accumulator and writes partial[slice][K1][N]; the caller sums the partials over slices (eqf_colsum). */
+int64_t eqf_gemm_tf32x3_wgrad_slices(int64_t R, int64_t K1, int64_t N);
+int eqf_gemm_tf32x3_wgrad(const float* A, const float* G, float* partial, int64_t R, int64_t K1, int64_t N, int64_t lda,
+                          int64_t ldg, void* stream);
 /* debugging aid: device buffer of 4*1024 int64 receiving CTA 0's clock64 timeline on later launches (NULL = off) */
 void eqf_gemm_tf32x3_set_timeline(long long* device_buffer);
 

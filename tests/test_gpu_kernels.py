@@ -205,6 +205,27 @@ def test_tf32x3_tcgen05_gemm(cuda_device, M, N, K):
     assert torch.equal(ops.gemm_tf32x3_raw(d(Ai), d(Bi)).cpu(), Ai @ Bi.t())
 
 
+@pytest.mark.parametrize("R,K1,N", [(100, 32, 32), (1000, 64, 48), (3001, 100, 72), (36000, 224, 224), (36000, 224, 352),
+                                    (36000, 64, 960), (2324, 128, 128), (11620, 32, 32), (108000, 384, 64), (17, 260, 40)])
+def test_tf32x3_tcgen05_weight_gradient(cuda_device, R, K1, N):
+    """Hand-written tcgen05 3xTF32 weight gradient W = A^T G (MN-major operands, per-slice TMEM accumulators, column
+    sum over slices) vs fp64.  The TMEM accumulation truncates, so the error grows with the rows per slice (~1e-5 at
+    2 000 rows); single-pass TF32 would be 1e-3."""
+    from equiformer_b200 import ops
+    g = torch.Generator().manual_seed(R + K1 + N)
+    A = torch.randn(R, K1, generator=g)
+    G = torch.randn(R, N, generator=g)
+    d = lambda t: t.to(cuda_device)
+    out = ops.gemm_tf32x3_wgrad_raw(d(A), d(G))
+    assert out.shape == (K1, N) and rel_err(out, A.double().t() @ G.double()) < 4e-5
+    wide = torch.randn(R, K1 + 8, generator=g)
+    out = ops.gemm_tf32x3_wgrad_raw(d(wide)[:, 4:4 + K1], d(G))
+    assert rel_err(out, wide[:, 4:4 + K1].double().t() @ G.double()) < 4e-5
+    Ai = torch.randint(-4, 5, (R, K1), generator=g).float()
+    Gi = torch.randint(-4, 5, (R, N), generator=g).float()
+    assert torch.equal(ops.gemm_tf32x3_wgrad_raw(d(Ai), d(Gi)).cpu(), Ai.t() @ Gi)
+
+
 def test_gemm_autograd_closure(cuda_device):
     from equiformer_b200 import ops
     g = torch.Generator().manual_seed(0)

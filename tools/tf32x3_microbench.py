@@ -11,13 +11,25 @@ from equiformer_b200 import ops  # noqa: E402
 
 
 def timeit(fn, iters=20):
+    """GPU time per call: the calls are captured into a CUDA graph and replayed, so host launch overhead (tensor-map
+    encodes, Python) is out of the measurement - as it is in the benchmark's graph-replayed step."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
-    for _ in range(iters):
-        fn()
+    g.replay()
     e.record()
     torch.cuda.synchronize()
     return s.elapsed_time(e) * 1e3 / iters
