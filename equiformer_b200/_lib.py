@@ -110,21 +110,23 @@ SIGNATURES = {
     "eqf_attn_edge_scale": (c_int32, [POINTER(EqfHeadLayout), c_void_p, POINTER(c_void_p), c_void_p, c_int64,
                                       POINTER(c_void_p), c_void_p]),
     "eqf_pointwise_rows": (c_int32, [c_int64]),
-    "eqf_ln_silu_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_float, c_int64, c_int32, c_void_p, c_void_p, c_void_p,
-                                  c_void_p]),
-    "eqf_ln_silu_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p,
+    "eqf_ln_silu_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int64, c_int32, c_void_p, c_void_p,
+                                  c_void_p, c_void_p]),
+    "eqf_ln_silu_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                   c_void_p, c_void_p, c_void_p]),
     "eqf_gemm_tf32x3": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,
                                   c_void_p]),
     "eqf_gemm_tf32x3_set_timeline": (None, [c_void_p]),
     "eqf_gemm_tf32x3_wgrad_slices": (c_int64, [c_int64, c_int64, c_int64]),
     "eqf_gemm_tf32x3_wgrad": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
+    "eqf_gemm_tf32x3_wgrad_accumulate": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
+                                                   c_void_p]),
     "eqf_colsum_scratch_floats": (c_int64, [c_int64, c_int64]),
     "eqf_colsum": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "eqf_eln_rows": (c_int32, [c_int64]),
     "eqf_eln_fwd": (c_int32, [POINTER(EqfNormLayout), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "eqf_eln_bwd": (c_int32, [POINTER(EqfNormLayout), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
-                              c_void_p, c_void_p]),
+                              c_void_p]),
     "eqf_gate_logits_fwd": (c_int32, [POINTER(EqfGateLayout), c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_int64,
                                       c_void_p, c_void_p, POINTER(c_void_p), c_void_p]),
     "eqf_gate_logits_bwd": (c_int32, [POINTER(EqfGateLayout), c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p,

@@ -428,6 +428,7 @@ constexpr int kMBlocks = BM / 32;             // 4 boxes for the 128 output rows
 struct WParams {
   long long R, rows_per_slice;
   int n_tile, n_tiles;                        // output columns per CTA (multiple of 32), number of column tiles
+  int reduce;                                 // 1: TMA reduce-add into W[K1, N] (map_p is 2-D); 0: store partial[slice]
 };
 
 template <int BN>
@@ -593,9 +594,15 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
-        asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
-                     ::"l"(reinterpret_cast<uint64_t>(&map_p)), "r"(nt * p.n_tile + c), "r"(mt * BM + warp * 32),
-                       "r"((int)blockIdx.y), "r"(buf) : "memory");
+        if (p.reduce) {   // element-wise fp32 add in L2: the slices' contributions meet in W itself, no partial buffer
+          asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%1, %2}], [%3];"
+                       ::"l"(reinterpret_cast<uint64_t>(&map_p)), "r"(nt * p.n_tile + c), "r"(mt * BM + warp * 32), "r"(buf)
+                       : "memory");
+        } else {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                       ::"l"(reinterpret_cast<uint64_t>(&map_p)), "r"(nt * p.n_tile + c), "r"(mt * BM + warp * 32),
+                         "r"((int)blockIdx.y), "r"(buf) : "memory");
+        }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
@@ -720,29 +727,47 @@ extern "C" int64_t eqf_gemm_tf32x3_wgrad_slices(int64_t R, int64_t K1, int64_t N
   return eqf::tf32x3::wg::plan(R, K1, N).slices;
 }
 
-// partial[s] = A[rows of slice s, :K1]^T G[rows of slice s, :N]  for every slice s; the weight gradient is the sum over s.
-// A [R, K1] (lda), G [R, N] (ldg) row-major fp32, 16-byte aligned, K1, N, lda, ldg multiples of 4.
-extern "C" int eqf_gemm_tf32x3_wgrad(const float* A, const float* G, float* partial, int64_t R, int64_t K1, int64_t N,
-                                     int64_t lda, int64_t ldg, void* stream) {
+static int wgrad_impl(const float* A, const float* G, float* out, bool reduce, int64_t R, int64_t K1, int64_t N,
+                      int64_t lda, int64_t ldg, void* stream, const char* who) {
   using namespace eqf::tf32x3;
   if (R <= 0 || K1 <= 0 || N <= 0) return EQF_OK;
-  if (!A || !G || !partial) { set_error("eqf_gemm_tf32x3_wgrad: null pointer"); return EQF_ERR_INVALID; }
-  if ((((uintptr_t)A | (uintptr_t)G | (uintptr_t)partial) & 15) || ((K1 | N | lda | ldg) & 3) || lda < K1 || ldg < N) {
-    set_error("eqf_gemm_tf32x3_wgrad: operands must be 16-byte aligned, dimensions multiples of 4");
+  if (!A || !G || !out) { set_error(std::string(who) + ": null pointer"); return EQF_ERR_INVALID; }
+  if ((((uintptr_t)A | (uintptr_t)G | (uintptr_t)out) & 15) || ((K1 | N | lda | ldg) & 3) || lda < K1 || ldg < N) {
+    set_error(std::string(who) + ": operands must be 16-byte aligned, dimensions multiples of 4");
     return EQF_ERR_INVALID;
   }
-  if (R > 0x7fffffffLL) { set_error("eqf_gemm_tf32x3_wgrad: too many rows"); return EQF_ERR_UNSUPPORTED; }
+  if (R > 0x7fffffffLL) { set_error(std::string(who) + ": too many rows"); return EQF_ERR_UNSUPPORTED; }
   const wg::Shape sh = wg::plan(R, K1, N);
   wg::WParams p;
-  p.R = R; p.rows_per_slice = sh.rows_per_slice; p.n_tile = sh.n_tile; p.n_tiles = sh.n_tiles;
+  p.R = R; p.rows_per_slice = sh.rows_per_slice; p.n_tile = sh.n_tile; p.n_tiles = sh.n_tiles; p.reduce = reduce ? 1 : 0;
   CUtensorMap ma, mg, mp;
   int rc;
   if ((rc = make_map(&ma, A, R, K1, lda, wg::BKR, 32, true)) != EQF_OK) return rc;
   if ((rc = make_map(&mg, G, R, N, ldg, wg::BKR, 32, true)) != EQF_OK) return rc;
-  if ((rc = wg::make_map3(&mp, partial, sh.slices, K1, N)) != EQF_OK) return rc;
   cudaStream_t s = (cudaStream_t)stream;
+  if (reduce) {
+    if ((rc = check_cuda(cudaMemsetAsync(out, 0, (size_t)K1 * N * sizeof(float), s), "wgrad memset")) != EQF_OK) return rc;
+    if ((rc = make_map(&mp, out, K1, N, N, 32, kStoreCols)) != EQF_OK) return rc;
+  } else {
+    if ((rc = wg::make_map3(&mp, out, sh.slices, K1, N)) != EQF_OK) return rc;
+  }
   if (sh.n_tile <= 32) return wg::launch<32>(ma, mg, mp, p, sh, s);
   if (sh.n_tile <= 64) return wg::launch<64>(ma, mg, mp, p, sh, s);
   if (sh.n_tile <= 128) return wg::launch<128>(ma, mg, mp, p, sh, s);
   return wg::launch<256>(ma, mg, mp, p, sh, s);
+}
+
+// partial[s] = A[rows of slice s, :K1]^T G[rows of slice s, :N]  for every slice s; the weight gradient is the sum over s
+// (deterministic with eqf_colsum).  A [R, K1] (lda), G [R, N] (ldg) row-major fp32, 16-byte aligned, dims multiples of 4.
+extern "C" int eqf_gemm_tf32x3_wgrad(const float* A, const float* G, float* partial, int64_t R, int64_t K1, int64_t N,
+                                     int64_t lda, int64_t ldg, void* stream) {
+  return wgrad_impl(A, G, partial, false, R, K1, N, lda, ldg, stream, "eqf_gemm_tf32x3_wgrad");
+}
+
+// W[K1, N] (packed) = A^T G directly: W is zeroed and every slice's CTA adds its contribution with a TMA reduce-add
+// (fp32 adds in L2; the order of the slices' additions is not fixed, so the last bits may differ between runs - like
+// the atomic scatter of the reference).  One launch + one memset instead of partials + column sum.
+extern "C" int eqf_gemm_tf32x3_wgrad_accumulate(const float* A, const float* G, float* W, int64_t R, int64_t K1, int64_t N,
+                                                int64_t lda, int64_t ldg, void* stream) {
+  return wgrad_impl(A, G, W, true, R, K1, N, lda, ldg, stream, "eqf_gemm_tf32x3_wgrad_accumulate");
 }

@@ -23,7 +23,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 // y = silu(z), z = (x - mean) * rstd * gamma + beta ; C <= 32 * kMaxPerLane, one warp per row
 constexpr int kMaxPerLane = 8;
 
-__global__ void __launch_bounds__(256) ln_silu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+__global__ void __launch_bounds__(256) ln_silu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ bias,
+                                                          const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float eps, long long R, int C,
                                                           float* __restrict__ y, float* __restrict__ mean,
                                                           float* __restrict__ rstd) {
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(256) ln_silu_fwd_kernel(const float* __restric
 #pragma unroll
     for (int q = 0; q < kMaxPerLane; ++q) {
       const int c = lane + 32 * q;
-      v[q] = (c < C) ? __ldg(x + r * C + c) : 0.f;
+      v[q] = (c < C) ? __ldg(x + r * C + c) + (bias ? __ldg(bias + c) : 0.f) : 0.f;   // bias of the preceding Linear
       s += v[q];
     }
     const float m = wsum(s) / C;
@@ -59,20 +60,21 @@ __global__ void __launch_bounds__(256) ln_silu_fwd_kernel(const float* __restric
   }
 }
 
-// gx, and per-CTA partial sums of dgamma / dbeta (rows = gridDim.x)
-__global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+// gx, and per-CTA partial sums [gridDim.x][3C] = d gamma | d beta | d bias (= column sums of gx)
+__global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ bias,
+                                                          const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, const float* __restrict__ mean,
                                                           const float* __restrict__ rstd, const float* __restrict__ gy,
                                                           long long R, int C, float* __restrict__ gx,
-                                                          float* __restrict__ dgamma_part, float* __restrict__ dbeta_part) {
-  __shared__ float sg[32 * kMaxPerLane], sb[32 * kMaxPerLane];
-  for (int i = threadIdx.x; i < 32 * kMaxPerLane; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }
+                                                          float* __restrict__ part) {
+  __shared__ float sg[32 * kMaxPerLane], sb[32 * kMaxPerLane], sx[32 * kMaxPerLane];
+  for (int i = threadIdx.x; i < 32 * kMaxPerLane; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; sx[i] = 0.f; }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 8;
-  float ag[kMaxPerLane], ab[kMaxPerLane];
+  float ag[kMaxPerLane], ab[kMaxPerLane], ax[kMaxPerLane];
 #pragma unroll
-  for (int q = 0; q < kMaxPerLane; ++q) { ag[q] = 0.f; ab[q] = 0.f; }
+  for (int q = 0; q < kMaxPerLane; ++q) { ag[q] = 0.f; ab[q] = 0.f; ax[q] = 0.f; }
   for (long long r = warp; r < R; r += n_warps) {
     const float m = __ldg(mean + r), rs = __ldg(rstd + r);
     float xh[kMaxPerLane], gz[kMaxPerLane];
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restric
       xh[q] = 0.f; gz[q] = 0.f;
       if (c < C) {
         const float g = __ldg(gamma + c);
-        xh[q] = (__ldg(x + r * C + c) - m) * rs;
+        xh[q] = (__ldg(x + r * C + c) + (bias ? __ldg(bias + c) : 0.f) - m) * rs;
         const float z = xh[q] * g + __ldg(beta + c);
         const float sg_ = sigmoidf_(z);
         const float dz = __ldg(gy + r * C + c) * (sg_ * (1.f + z * (1.f - sg_)));   // d silu / dz
@@ -99,18 +101,24 @@ __global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restric
 #pragma unroll
     for (int q = 0; q < kMaxPerLane; ++q) {
       const int c = lane + 32 * q;
-      if (c < C) gx[r * C + c] = rs * (gz[q] - s1 - xh[q] * s2);
+      if (c < C) {
+        const float v = rs * (gz[q] - s1 - xh[q] * s2);
+        gx[r * C + c] = v;
+        ax[q] += v;
+      }
     }
   }
 #pragma unroll
   for (int q = 0; q < kMaxPerLane; ++q) {
     const int c = lane + 32 * q;
-    if (c < C) { atomicAdd(&sg[c], ag[q]); atomicAdd(&sb[c], ab[q]); }
+    if (c < C) { atomicAdd(&sg[c], ag[q]); atomicAdd(&sb[c], ab[q]); atomicAdd(&sx[c], ax[q]); }
   }
   __syncthreads();
+  float* row = part + (long long)blockIdx.x * 3 * C;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    dgamma_part[(long long)blockIdx.x * C + c] = sg[c];
-    dbeta_part[(long long)blockIdx.x * C + c] = sb[c];
+    row[c] = sg[c];
+    row[C + c] = sb[c];
+    row[2 * C + c] = sx[c];
   }
 }
 
@@ -568,8 +576,8 @@ __global__ void __launch_bounds__(256) eln_bwd_kernel(ELNArgs a) {
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < a.n_w; i += blockDim.x) a.dw_part[(long long)blockIdx.x * a.n_w + i] = sacc[i];
-  for (int i = threadIdx.x; i < a.n_b; i += blockDim.x) a.db_part[(long long)blockIdx.x * a.n_b + i] = sacc[a.n_w + i];
+  // one partial row per CTA: [d weight (n_w) | d bias (n_b)]
+  for (int i = threadIdx.x; i < a.n_w + a.n_b; i += blockDim.x) a.dw_part[(long long)blockIdx.x * (a.n_w + a.n_b) + i] = sacc[i];
 }
 
 static int eln_grid(long long rows) {
@@ -606,25 +614,25 @@ using namespace eqf;
 
 extern "C" int eqf_pointwise_rows(int64_t rows) { return pointwise_grid(rows); }
 
-extern "C" int eqf_ln_silu_fwd(const float* x, const float* gamma, const float* beta, float eps, int64_t R, int32_t C,
-                               float* y, float* mean, float* rstd, void* stream) {
+extern "C" int eqf_ln_silu_fwd(const float* x, const float* bias, const float* gamma, const float* beta, float eps,
+                               int64_t R, int32_t C, float* y, float* mean, float* rstd, void* stream) {
   if (R == 0) return EQF_OK;
   if (!x || !gamma || !beta || !y || !mean || !rstd) { set_error("eqf_ln_silu_fwd: null pointer"); return EQF_ERR_INVALID; }
   if (C < 1 || C > 32 * kMaxPerLane) { set_error("eqf_ln_silu: C must be in 1..256"); return EQF_ERR_UNSUPPORTED; }
-  ln_silu_fwd_kernel<<<pointwise_grid(R), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, eps, R, C, y, mean, rstd);
+  ln_silu_fwd_kernel<<<pointwise_grid(R), 256, 0, (cudaStream_t)stream>>>(x, bias, gamma, beta, eps, R, C, y, mean, rstd);
   return check_cuda(cudaGetLastError(), "ln_silu_fwd_kernel launch");
 }
 
-extern "C" int eqf_ln_silu_bwd(const float* x, const float* gamma, const float* beta, const float* mean, const float* rstd,
-                               const float* gy, int64_t R, int32_t C, float* gx, float* dgamma_part, float* dbeta_part,
+extern "C" int eqf_ln_silu_bwd(const float* x, const float* bias, const float* gamma, const float* beta, const float* mean,
+                               const float* rstd, const float* gy, int64_t R, int32_t C, float* gx, float* part,
                                void* stream) {
   if (R == 0) return EQF_OK;
-  if (!x || !gamma || !beta || !mean || !rstd || !gy || !gx || !dgamma_part || !dbeta_part) {
+  if (!x || !gamma || !beta || !mean || !rstd || !gy || !gx || !part) {
     set_error("eqf_ln_silu_bwd: null pointer"); return EQF_ERR_INVALID;
   }
   if (C < 1 || C > 32 * kMaxPerLane) { set_error("eqf_ln_silu: C must be in 1..256"); return EQF_ERR_UNSUPPORTED; }
-  ln_silu_bwd_kernel<<<pointwise_grid(R), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, mean, rstd, gy, R, C, gx,
-                                                                          dgamma_part, dbeta_part);
+  ln_silu_bwd_kernel<<<pointwise_grid(R), 256, 0, (cudaStream_t)stream>>>(x, bias, gamma, beta, mean, rstd, gy, R, C, gx,
+                                                                          part);
   return check_cuda(cudaGetLastError(), "ln_silu_bwd_kernel launch");
 }
 
@@ -690,12 +698,12 @@ extern "C" int eqf_eln_fwd(const EqfNormLayout* lay, const float* x, const float
 }
 
 extern "C" int eqf_eln_bwd(const EqfNormLayout* lay, const float* x, const float* w, const float* rstd, const float* gy,
-                           int64_t N, float* gx, float* dw_part, float* db_part, void* stream) {
+                           int64_t N, float* gx, float* part, void* stream) {
   ELNArgs a;
   int rc = fill_eln(lay, a);
   if (rc != EQF_OK || N == 0) return rc;
-  if (!x || !w || !rstd || !gy || !gx || !dw_part || (a.n_b > 0 && !db_part)) { set_error("eqf_eln_bwd: null pointer"); return EQF_ERR_INVALID; }
-  a.x = x; a.w = w; a.b = nullptr; a.rstd = const_cast<float*>(rstd); a.gy = gy; a.gx = gx; a.dw_part = dw_part; a.db_part = db_part; a.N = N;
+  if (!x || !w || !rstd || !gy || !gx || !part) { set_error("eqf_eln_bwd: null pointer"); return EQF_ERR_INVALID; }
+  a.x = x; a.w = w; a.b = nullptr; a.rstd = const_cast<float*>(rstd); a.gy = gy; a.gx = gx; a.dw_part = part; a.db_part = nullptr; a.N = N;
   eln_bwd_kernel<<<eln_grid(N), 256, (a.n_w + a.n_b) * sizeof(float), (cudaStream_t)stream>>>(a);
   return check_cuda(cudaGetLastError(), "eln_bwd_kernel launch");
 }

@@ -333,10 +333,10 @@ class GraphAttention(torch.nn.Module):
                 lay = self._gate_layout
                 k0 = f[0].shape[2]
                 blocks = {io: (W, c) for _i1, _i2, io, W, c in sa.lin.tp.linear_weight_blocks()}
-                w_cat = torch.cat([self.sep_alpha.tp.weight.view(k0, -1), blocks[0][0][:, 0, :]], dim=1)
+                w_cat = torch.cat([self.sep_alpha.tp.weight.view(k0, -1), blocks[0][0].reshape(k0, -1)], dim=1)
                 t0 = ops.matmul_f32(f[0].reshape(E, k0), w_cat)
                 bias = torch.cat([self.sep_alpha.bias[0], sa.lin.bias[0]])
-                gated = [ops.matmul_f32(f[g].reshape(E * f[g].shape[1], f[g].shape[2]), blocks[g][0][:, 0, :])
+                gated = [ops.matmul_f32(f[g].reshape(E * f[g].shape[1], f[g].shape[2]), blocks[g][0].reshape(f[g].shape[2], -1))
                          .view(E, f[g].shape[1], -1) for g in range(1, len(f))]
                 logits, v0, *vs = ops.GateLogits.apply(lay, t0, bias, self.alpha_dot.view(H, A), *gated)
                 value = _reblock([v0.view(E, 1, -1), *vs], sa.gate.irreps_out, self.sep_value.irreps_node_input)

@@ -41,11 +41,19 @@ class RadialProfile(nn.Module):
         i = 0
         while i < len(mods):
             m = mods[i]
-            if isinstance(m, nn.Linear):
+            nxt = mods[i + 1] if i + 1 < len(mods) else None
+            nxt2 = mods[i + 2] if i + 2 < len(mods) else None
+            fuse_ln = (isinstance(nxt, nn.LayerNorm) and isinstance(nxt2, nn.SiLU) and nxt.elementwise_affine
+                       and len(nxt.normalized_shape) == 1)
+            if isinstance(m, nn.Linear) and fuse_ln:
+                # Linear -> LayerNorm -> SiLU: GEMM without bias, then ONE kernel for bias + LayerNorm + SiLU
+                out = ops.ln_silu(ops.linear_f32(out, m.weight, None), nxt.weight, nxt.bias, nxt.eps, bias=m.bias)
+                i += 3
+            elif isinstance(m, nn.Linear):
                 out = ops.linear_f32(out, m.weight, m.bias)
                 i += 1
-            elif isinstance(m, nn.LayerNorm) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.SiLU) \
-                    and m.elementwise_affine and len(m.normalized_shape) == 1:
+            elif isinstance(m, nn.LayerNorm) and isinstance(nxt, nn.SiLU) and m.elementwise_affine \
+                    and len(m.normalized_shape) == 1:
                 out = ops.ln_silu(out, m.weight, m.bias, m.eps)      # LayerNorm + SiLU in one pass
                 i += 2
             else:

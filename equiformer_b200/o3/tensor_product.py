@@ -214,10 +214,10 @@ class TensorProduct(torch.nn.Module):
             if y is None:
                 if m2 != 1:
                     raise ValueError("second operand required")
-                Weff = W[:, 0, :]
+                Weff = W.reshape(W.shape[0], W.shape[2])    # a view: `W[:, 0, :]` costs a zero-fill + copy in its backward
                 t = ops.matmul_f32(x.reshape(R * d, -1), Weff).view(R, d, -1)
             elif m2 == 1:
-                t = ops.matmul_f32(x.reshape(R * d, -1), W[:, 0, :]).view(R, d, -1)
+                t = ops.matmul_f32(x.reshape(R * d, -1), W.reshape(W.shape[0], W.shape[2])).view(R, d, -1)
                 t = t * y[:, in2_off[i2]].view(R, 1, 1)
             else:
                 yy = y[:, in2_off[i2]:in2_off[i2] + m2]

@@ -897,6 +897,9 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
 
 
 _TF32X3 = os.environ.get("EQF_GEMM_TF32X3", "1") != "0"
+# EQF_DETERMINISTIC=1: weight gradients through per-slice partials + a fixed-order column sum (bitwise reproducible)
+# instead of TMA reduce-adds whose summation order varies between runs
+_DETERMINISTIC = os.environ.get("EQF_DETERMINISTIC", "0") == "1"
 _TF32X3_SPLIT = {}
 
 
@@ -935,6 +938,12 @@ def gemm_tf32x3_wgrad_raw(A: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
     A, lda = _gemm_operand(A)
     G, ldg = _gemm_operand(G)
     lib = _lib.load()
+    if not _DETERMINISTIC:      # slices add into W through TMA reduce-adds: one launch, no partial buffer / column sum
+        W = torch.empty((K1, N), device=A.device, dtype=torch.float32)
+        with torch.cuda.device(A.device), _kernel("gemm_tf32x3_wgrad", 4 * (A.numel() + G.numel() + W.numel())):
+            rc = lib.eqf_gemm_tf32x3_wgrad_accumulate(A.data_ptr(), G.data_ptr(), W.data_ptr(), R, K1, N, lda, ldg, _stream())
+        _lib.check(rc, "eqf_gemm_tf32x3_wgrad_accumulate")
+        return W
     slices = int(lib.eqf_gemm_tf32x3_wgrad_slices(R, K1, N))
     part = torch.empty((max(slices, 1), K1, N), device=A.device, dtype=torch.float32)
     with torch.cuda.device(A.device), _kernel("gemm_tf32x3_wgrad", 4 * (A.numel() + G.numel() + 2 * part.numel())):
@@ -1115,55 +1124,65 @@ def _higher_order_grads(fn, inputs, grad_outputs):
     return [next(it) if (isinstance(t, torch.Tensor) and t.requires_grad) else None for t in inputs]
 
 
-def ln_silu_torch(x, gamma, beta, eps):
+def ln_silu_torch(x, gamma, beta, eps, bias=None):
+    if bias is not None:
+        x = x + bias
     return torch.nn.functional.silu(torch.nn.functional.layer_norm(x, x.shape[-1:], gamma, beta, eps))
 
 
-def ln_silu_fwd_raw(x, gamma, beta, eps):
+def ln_silu_fwd_raw(x, gamma, beta, eps, bias=None):
     x = _require_cuda(x, "ln_silu x")
     R, C = x.shape
     y = torch.empty_like(x)
     mean = torch.empty(R, device=x.device, dtype=torch.float32)
     rstd = torch.empty(R, device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device), _kernel("ln_silu_fwd", 8 * x.numel()):
-        rc = _lib.load().eqf_ln_silu_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), eps, R, C, y.data_ptr(),
-                                         mean.data_ptr(), rstd.data_ptr(), _stream())
+        rc = _lib.load().eqf_ln_silu_fwd(x.data_ptr(), bias.data_ptr() if bias is not None else None, gamma.data_ptr(),
+                                         beta.data_ptr(), eps, R, C, y.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _stream())
     _lib.check(rc, "eqf_ln_silu_fwd")
     return y, mean, rstd
 
 
-def ln_silu_bwd_raw(x, gamma, beta, mean, rstd, gy):
+def ln_silu_bwd_raw(x, gamma, beta, mean, rstd, gy, bias=None):
+    """Returns (gx, dgamma, dbeta, dbias); dbias (= column sums of gx) is None when there is no bias."""
     gy = _require_cuda(gy, "ln_silu gy")
     R, C = x.shape
     rows = _lib.load().eqf_pointwise_rows(R)
     gx = torch.empty_like(x)
-    dg = torch.empty((rows, C), device=x.device, dtype=torch.float32)
-    db = torch.empty((rows, C), device=x.device, dtype=torch.float32)
+    part = torch.empty((rows, 3 * C), device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device), _kernel("ln_silu_bwd", 12 * x.numel()):
-        rc = _lib.load().eqf_ln_silu_bwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                         gy.data_ptr(), R, C, gx.data_ptr(), dg.data_ptr(), db.data_ptr(), _stream())
+        rc = _lib.load().eqf_ln_silu_bwd(x.data_ptr(), bias.data_ptr() if bias is not None else None, gamma.data_ptr(),
+                                         beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gy.data_ptr(), R, C,
+                                         gx.data_ptr(), part.data_ptr(), _stream())
     _lib.check(rc, "eqf_ln_silu_bwd")
-    return gx, colsum_raw(dg), colsum_raw(db)
+    sums = colsum_raw(part)                      # one reduction for the three parameter gradients
+    return gx, sums[:C], sums[C:2 * C], (sums[2 * C:] if bias is not None else None)
 
 
 class LnSilu(torch.autograd.Function):
-    """``silu(layer_norm(x))`` on ``[rows, C]`` (RadialProfile hidden layers, ref radial_func.py:24-35)."""
+    """``silu(layer_norm(x + bias))`` on ``[rows, C]`` (Linear bias + LayerNorm + SiLU of RadialProfile's hidden layers,
+    ref radial_func.py:24-35); ``bias`` may be None."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps: float):
-        y, mean, rstd = ln_silu_fwd_raw(x, gamma, beta, eps)
-        ctx.eps = eps
-        ctx.save_for_backward(x, gamma, beta, mean, rstd)
+    def forward(ctx, x, bias, gamma, beta, eps: float):
+        y, mean, rstd = ln_silu_fwd_raw(x, gamma, beta, eps, bias)
+        ctx.eps, ctx.has_bias = eps, bias is not None
+        ctx.save_for_backward(x, gamma, beta, mean, rstd, *([bias] if bias is not None else []))
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        x, gamma, beta, mean, rstd, *rest = ctx.saved_tensors
+        bias = rest[0] if ctx.has_bias else None
         if torch.is_grad_enabled():
-            gx, gg, gb = _higher_order_grads(lambda a, b, c: ln_silu_torch(a, b, c, ctx.eps), (x, gamma, beta), (gy,))
-            return gx, gg, gb, None
-        gx, gg, gb = ln_silu_bwd_raw(x, gamma, beta, mean, rstd, gy)
-        return gx, gg, gb, None
+            if bias is None:
+                gx, gg, gb = _higher_order_grads(lambda a, b, c: ln_silu_torch(a, b, c, ctx.eps), (x, gamma, beta), (gy,))
+                return gx, None, gg, gb, None
+            gx, gbias, gg, gb = _higher_order_grads(lambda a, p, b, c: ln_silu_torch(a, b, c, ctx.eps, p),
+                                                    (x, bias, gamma, beta), (gy,))
+            return gx, gbias, gg, gb, None
+        gx, gg, gb, gbias = ln_silu_bwd_raw(x, gamma, beta, mean, rstd, gy.contiguous(), bias)
+        return gx, gbias, gg, gb, None
 
 
 FUSED_ON_ANY_DEVICE = False   # tests/_emulation.py flips this so the fused Functions are exercised on CPU stand-ins
@@ -1173,10 +1192,11 @@ def fused_ok(t: torch.Tensor) -> bool:
     return FUSED_ON_ANY_DEVICE or (t.is_cuda and t.dtype == torch.float32)
 
 
-def ln_silu(x, gamma, beta, eps: float = 1e-5):
+def ln_silu(x, gamma, beta, eps: float = 1e-5, bias=None):
+    """``silu(LayerNorm(x + bias))``: the bias of the preceding Linear rides along (no separate add / bias-gradient pass)."""
     if fused_ok(x) and x.dim() == 2 and x.shape[1] <= 256:
-        return LnSilu.apply(x.contiguous(), gamma, beta, eps)
-    return ln_silu_torch(x, gamma, beta, eps)
+        return LnSilu.apply(x.contiguous(), bias, gamma, beta, eps)
+    return ln_silu_torch(x, gamma, beta, eps, bias)
 
 
 class NormLayout:
@@ -1232,13 +1252,13 @@ def eln_bwd_raw(lay: NormLayout, x, w, rstd, gy):
     N = x.shape[0]
     rows = _lib.load().eqf_eln_rows(N)
     gx = torch.empty_like(x)
-    dw = torch.empty((rows, lay.n_w), device=x.device, dtype=torch.float32)
-    db = torch.empty((rows, max(lay.n_b, 1)), device=x.device, dtype=torch.float32)
+    part = torch.empty((rows, lay.n_w + lay.n_b), device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device), _kernel("eln_bwd", 12 * x.numel()):
         rc = _lib.load().eqf_eln_bwd(ctypes.byref(lay.c), x.data_ptr(), w.data_ptr(), rstd.data_ptr(), gy.data_ptr(), N,
-                                     gx.data_ptr(), dw.data_ptr(), db.data_ptr(), _stream())
+                                     gx.data_ptr(), part.data_ptr(), _stream())
     _lib.check(rc, "eqf_eln_bwd")
-    return gx, colsum_raw(dw), colsum_raw(db)[:lay.n_b]
+    sums = colsum_raw(part)
+    return gx, sums[:lay.n_w], sums[lay.n_w:]
 
 
 class EquivLayerNorm(torch.autograd.Function):

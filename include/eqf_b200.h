@@ -136,14 +136,14 @@ int eqf_attn_edge_scale(const EqfHeadLayout* lay, const float* alpha, const floa
                         const int64_t* dst, int64_t n_edges, float* const* out, void* stream);
 
 /* ---- fused pointwise kernels around the GEMMs -------------------------------------------------------------------
- * y = silu(LayerNorm(x)) on [R, C] rows (C <= 256): the hidden layers of RadialProfile (nets/radial_func.py:24-35).
- * The backward returns per-CTA partial sums of d gamma / d beta in [eqf_pointwise_rows(R), C] buffers.            */
+ * y = silu(LayerNorm(x + bias)) on [R, C] rows (C <= 256): Linear bias + LayerNorm + SiLU of the hidden layers of
+ * RadialProfile (nets/radial_func.py:24-35); bias may be NULL.  The backward writes gx (= gradient of x and of the
+ * broadcast bias) and per-CTA partial sums part[eqf_pointwise_rows(R)][3C] = d gamma | d beta | d bias.          */
 int eqf_pointwise_rows(int64_t rows);
-int eqf_ln_silu_fwd(const float* x, const float* gamma, const float* beta, float eps, int64_t R, int32_t C,
-                    float* y, float* mean, float* rstd, void* stream);
-int eqf_ln_silu_bwd(const float* x, const float* gamma, const float* beta, const float* mean, const float* rstd,
-                    const float* gy, int64_t R, int32_t C, float* gx, float* dgamma_part, float* dbeta_part,
-                    void* stream);
+int eqf_ln_silu_fwd(const float* x, const float* bias, const float* gamma, const float* beta, float eps, int64_t R,
+                    int32_t C, float* y, float* mean, float* rstd, void* stream);
+int eqf_ln_silu_bwd(const float* x, const float* bias, const float* gamma, const float* beta, const float* mean,
+                    const float* rstd, const float* gy, int64_t R, int32_t C, float* gx, float* part, void* stream);
 
 /* Hand-written tcgen05 GEMM (3xTF32, fp32-level accuracy) for the tall per-degree linears:
  * C[M, N] = A[M, K] x Bt[N, K]^T, all row-major fp32; `split` = device scratch of 2*N*K floats (hi / lo planes of Bt).
@@ -157,6 +157,10 @@ int eqf_gemm_tf32x3(const float* A, const float* Bt, float* C, int64_t M, int64_
 int64_t eqf_gemm_tf32x3_wgrad_slices(int64_t R, int64_t K1, int64_t N);
 int eqf_gemm_tf32x3_wgrad(const float* A, const float* G, float* partial, int64_t R, int64_t K1, int64_t N, int64_t lda,
                           int64_t ldg, void* stream);
+/* same product written straight into W[K1, N]: W is zeroed, the slices add into it with TMA reduce-adds (fp32 adds in
+ * L2, order not fixed - last-bit differences between runs, like the reference's atomic scatter) */
+int eqf_gemm_tf32x3_wgrad_accumulate(const float* A, const float* G, float* W, int64_t R, int64_t K1, int64_t N,
+                                     int64_t lda, int64_t ldg, void* stream);
 /* debugging aid: device buffer of 4*1024 int64 receiving CTA 0's clock64 timeline on later launches (NULL = off) */
 void eqf_gemm_tf32x3_set_timeline(long long* device_buffer);
 
@@ -169,7 +173,8 @@ int eqf_colsum(const float* x, int64_t rows, int64_t cols, int64_t ld, float* ou
                void* stream);
 
 /* EquivariantLayerNormV2 ('component' normalisation, affine; nets/layer_norm.py:89-152) on e3nn-layout rows:
- * one fused kernel forward, one backward (per-CTA partial sums of the affine gradients in [eqf_eln_rows(N), .]). */
+ * one fused kernel forward, one backward (per-CTA partial sums of the affine gradients:
+ * part[eqf_eln_rows(N)][n_weight + n_bias] = d weight | d bias). */
 typedef struct {
   int32_t n_entries;
   int32_t mul[EQF_MAX_BLOCKS];
@@ -181,7 +186,7 @@ int eqf_eln_rows(int64_t rows);
 int eqf_eln_fwd(const EqfNormLayout* lay, const float* x, const float* w, const float* b, int64_t N, float* y,
                 float* rstd, void* stream);
 int eqf_eln_bwd(const EqfNormLayout* lay, const float* x, const float* w, const float* rstd, const float* gy,
-                int64_t N, float* gx, float* dw_part, float* db_part, void* stream);
+                int64_t N, float* gx, float* part, void* stream);
 
 /* Gate + attention logits of GraphAttention.forward (graph_attention_transformer.py:492-495, 506-507) in one pass:
  *   t0[e] = [alpha | scalars | gates] pre-activations (+ optional bias), gated[b] planar blocks [E, d, C];

@@ -139,10 +139,11 @@ def gemm_raw(mode, A, B):
     return A @ B.t() if mode == 1 else A.t() @ B
 
 
-def ln_silu_fwd_raw(x, gamma, beta, eps):
-    mean = x.mean(-1)
-    rstd = (x.var(-1, unbiased=False) + eps).rsqrt()
-    return ops.ln_silu_torch(x, gamma, beta, eps), mean, rstd
+def ln_silu_fwd_raw(x, gamma, beta, eps, bias=None):
+    xb = x if bias is None else x + bias
+    mean = xb.mean(-1)
+    rstd = (xb.var(-1, unbiased=False) + eps).rsqrt()
+    return ops.ln_silu_torch(x, gamma, beta, eps, bias), mean, rstd
 
 
 def colsum_raw(x):
@@ -165,11 +166,12 @@ def b_like(lay, x):
     return torch.zeros(lay.n_b, dtype=x.dtype)
 
 
-def ln_silu_bwd_raw(x, gamma, beta, mean, rstd, gy):
+def ln_silu_bwd_raw(x, gamma, beta, mean, rstd, gy, bias=None):
     with torch.enable_grad():
         xs = [t.detach().requires_grad_(True) for t in (x, gamma, beta)]
-        y = torch.nn.functional.silu(torch.nn.functional.layer_norm(xs[0], xs[0].shape[-1:], xs[1], xs[2], 1e-5))
-        return torch.autograd.grad(y, xs, gy)
+        y = ops.ln_silu_torch(xs[0], xs[1], xs[2], 1e-5, bias)
+        gx, gg, gb = torch.autograd.grad(y, xs, gy)
+    return gx, gg, gb, (gx.sum(0) if bias is not None else None)
 
 
 def gate_logits_fwd_raw(lay, t0, bias, alpha_dot, gated):

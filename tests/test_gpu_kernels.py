@@ -207,7 +207,7 @@ def test_tf32x3_tcgen05_gemm(cuda_device, M, N, K):
 
 @pytest.mark.parametrize("R,K1,N", [(100, 32, 32), (1000, 64, 48), (3001, 100, 72), (36000, 224, 224), (36000, 224, 352),
                                     (36000, 64, 960), (2324, 128, 128), (11620, 32, 32), (108000, 384, 64), (17, 260, 40)])
-def test_tf32x3_tcgen05_weight_gradient(cuda_device, R, K1, N):
+def test_tf32x3_tcgen05_weight_gradient(cuda_device, R, K1, N, monkeypatch):
     """Hand-written tcgen05 3xTF32 weight gradient W = A^T G (MN-major operands, per-slice TMEM accumulators, column
     sum over slices) vs fp64.  The TMEM accumulation truncates, so the error grows with the rows per slice (~1e-5 at
     2 000 rows); single-pass TF32 would be 1e-3."""
@@ -223,6 +223,11 @@ def test_tf32x3_tcgen05_weight_gradient(cuda_device, R, K1, N):
     assert rel_err(out, wide[:, 4:4 + K1].double().t() @ G.double()) < 4e-5
     Ai = torch.randint(-4, 5, (R, K1), generator=g).float()
     Gi = torch.randint(-4, 5, (R, N), generator=g).float()
+    assert torch.equal(ops.gemm_tf32x3_wgrad_raw(d(Ai), d(Gi)).cpu(), Ai.t() @ Gi)
+    # the other reduction route (TMA reduce-adds <-> per-slice partials + fixed-order column sum)
+    monkeypatch.setattr(ops, "_DETERMINISTIC", not ops._DETERMINISTIC)
+    out2 = ops.gemm_tf32x3_wgrad_raw(d(A), d(G))
+    assert rel_err(out2, A.double().t() @ G.double()) < 4e-5
     assert torch.equal(ops.gemm_tf32x3_wgrad_raw(d(Ai), d(Gi)).cpu(), Ai.t() @ Gi)
 
 
@@ -308,22 +313,36 @@ def test_dtp_weight_offset_fused(cuda_device, cfg):
     assert rel_err(grads[0], gw_ref) < TOL and rel_err(grads[1], gw_ref.sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize("with_bias", [False, True])
 @pytest.mark.parametrize("R,C", [(1, 64), (1000, 64), (4097, 96), (33, 256)])
-def test_ln_silu_fused(cuda_device, R, C):
-    """silu(LayerNorm(x)) forward and (gx, dgamma, dbeta) backward vs fp64 torch (RadialProfile hidden layers)."""
+def test_ln_silu_fused(cuda_device, R, C, with_bias):
+    """silu(LayerNorm(x + bias)) forward and (gx, dgamma, dbeta, dbias) backward vs fp64 torch (RadialProfile hidden
+    layers: the Linear's bias rides along in the LayerNorm kernel)."""
     from equiformer_b200 import ops
     g = torch.Generator().manual_seed(R + C)
     x = torch.randn(R, C, generator=g) * 2 + 0.3
     gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+    bias = torch.randn(C, generator=g) if with_bias else None
     gy = torch.randn(R, C, generator=g)
     d = lambda t: t.to(cuda_device)
-    y, mean, rstd = ops.ln_silu_fwd_raw(d(x), d(gamma), d(beta), 1e-5)
+    db = d(bias) if with_bias else None
+    y, mean, rstd = ops.ln_silu_fwd_raw(d(x), d(gamma), d(beta), 1e-5, db)
     xs = [t.double().requires_grad_(True) for t in (x, gamma, beta)]
-    ref = ops.ln_silu_torch(xs[0], xs[1], xs[2], 1e-5)
+    b64 = bias.double().requires_grad_(True) if with_bias else None
+    ref = ops.ln_silu_torch(xs[0], xs[1], xs[2], 1e-5, b64)
     assert rel_err(y, ref) < TOL
-    gx, gg, gb = ops.ln_silu_bwd_raw(d(x), d(gamma), d(beta), mean, rstd, d(gy))
-    rx, rg, rb = torch.autograd.grad(ref, xs, gy.double())
+    gx, gg, gb, gbias = ops.ln_silu_bwd_raw(d(x), d(gamma), d(beta), mean, rstd, d(gy), db)
+    rx, rg, rb, *rest = torch.autograd.grad(ref, xs + ([b64] if with_bias else []), gy.double())
     assert rel_err(gx, rx) < 5e-5 and rel_err(gg, rg) < 5e-5 and rel_err(gb, rb) < 5e-5
+    if with_bias:
+        assert rel_err(gbias, rest[0]) < 5e-5
+        # autograd wrapper
+        leaves = [d(t).requires_grad_(True) for t in (x, bias, gamma, beta)]
+        out = ops.ln_silu(leaves[0], leaves[2], leaves[3], 1e-5, bias=leaves[1])
+        ax, abias, ag, ab = torch.autograd.grad(out, leaves, d(gy))
+        assert rel_err(ax, rx) < 5e-5 and rel_err(abias, rest[0]) < 5e-5 and rel_err(ag, rg) < 5e-5 and rel_err(ab, rb) < 5e-5
+    else:
+        assert gbias is None
 
 
 @pytest.mark.parametrize("rows,cols", [(1, 1), (7, 3), (32560, 64), (32560, 352), (32560, 960), (1184, 64), (197, 24576),
