@@ -25,6 +25,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -347,6 +348,244 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 }
 
+// ================================================================================================ narrow outputs: A from TMEM
+// For N <= 128 the loop above is bound by shared-memory traffic per k-tile (TMA writes, the transform's read + two
+// writes of the A tile, and every MMA re-reading its 128-row A operand), not by the tensor pipe or HBM.  This variant
+// keeps the split A operand in TMEM: the transform warps read the TMA-written A tile once (one thread = one row),
+// split it in registers and tcgen05.st the hi / lo parts into TMEM columns; the MMAs take A from TMEM and only the small
+// weight tiles from shared memory.  TMEM: 2 accumulators x BN columns + kStages x 2 x BK columns of A.
+namespace ts {
+
+constexpr int BKT = 32;                      // k-tile of this variant: 128-byte rows (SWIZZLE_128B) - with 64-byte rows the
+constexpr int kRowBytesT = BKT * 4;          // TMA engine's per-row cost, not HBM, paced the tall-skinny A stream
+
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BN>
+struct TSmem {
+  static constexpr int kABytes = BM * kRowBytesT;                   // raw A tile (TMA)
+  static constexpr int kBBytes = BN * kRowBytesT;
+  static constexpr int kStageBytes = kABytes + 2 * kBBytes;         // A raw | B hi | B lo
+  static constexpr int kStoreBytes = kEpilogueWarps * 2 * 32 * kStoreCols * 4;
+  static constexpr int kBudget = 227 * 1024 - 1024;
+  static constexpr int kStagesSmem = (kBudget - kStoreBytes - 1024) / kStageBytes;
+  static constexpr int kStagesTmem = (512 - 2 * BN) / (2 * BKT);
+  static constexpr int kStagesMin = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
+  static constexpr int kStages = kStagesMin > 8 ? 8 : kStagesMin;
+  static_assert(kStages >= 2, "tile does not fit");
+  static constexpr int kTotal = kStages * kStageBytes + kStoreBytes + 1024 + 1024;
+};
+
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]),
+        "f"(v[9]), "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]),
+        "f"(v[18]), "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]),
+        "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31]) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                      const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c, Params p) {
+  using S = TSmem<BN>;
+  constexpr int kStages = S::kStages;
+  constexpr int kTmemCols = 512;
+  constexpr int kACol0 = 2 * BN;                       // first TMEM column of the A staging area
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* store_base = smem + kStages * S::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(store_base + S::kStoreBytes);
+  uint64_t* full = bars;
+  uint64_t* a_ready = bars + kStages;          // A hi / lo of the stage are in TMEM
+  uint64_t* empty = bars + 2 * kStages;
+  uint64_t* tmem_full = bars + 3 * kStages;
+  uint64_t* tmem_empty = bars + 3 * kStages + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long k_tiles = (p.K + BKT - 1) / BKT;
+  const long long n_tiles_total = p.m_blocks * p.n_blocks;
+
+  if (warp == kProducerWarp && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_bhi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_blo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_c)) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&a_ready[s], kTransformWarps);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], kEpilogueWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      const uint32_t tx = (uint32_t)(S::kABytes + 2 * p.n_tile * kRowBytesT);
+      for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        const long long mb = tile / p.n_blocks;
+        const int nb = (int)(tile % p.n_blocks);
+        for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = stage_base + (size_t)s * S::kStageBytes;
+          mbar_expect_tx(&full[s], tx);
+          tma_load_2d(st, &map_a, (int)(kt * BKT), (int)(mb * BM), &full[s]);
+          tma_load_2d(st + S::kABytes, &map_bhi, (int)(kt * BKT), nb * p.n_tile, &full[s]);
+          tma_load_2d(st + S::kABytes + S::kBBytes, &map_blo, (int)(kt * BKT), nb * p.n_tile, &full[s]);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(p.n_tile);
+      uint32_t it = 0, acc_it = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
+        const int a = acc_it & 1;
+        const uint32_t aph = (acc_it >> 1) & 1;
+        mbar_wait(&tmem_empty[a], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+        for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&full[s], ph);          // the weight tiles (and the raw A tile) have landed
+          mbar_wait(&a_ready[s], ph);       // A hi / lo are in TMEM
+          tc_fence_after();
+          const uint32_t st = smem_u32(stage_base + (size_t)s * S::kStageBytes);
+          const uint64_t b_hi = smem_desc_sw128(st + S::kABytes), b_lo = smem_desc_sw128(st + S::kABytes + S::kBBytes);
+          const uint32_t a_hi = tmem_base + (uint32_t)(kACol0 + s * 2 * BKT), a_lo = a_hi + BKT;
+#pragma unroll
+          for (int kb = 0; kb < BKT / UMMA_K; ++kb) {
+            const uint64_t adv = (uint64_t)((kb * UMMA_K * 4) >> 4);
+            const uint32_t acol = (uint32_t)(kb * UMMA_K);
+            umma_tf32_ts(d_tmem, a_lo + acol, b_hi + adv, idesc, (kt > 0 || kb > 0) ? 1u : 0u);
+            umma_tf32_ts(d_tmem, a_hi + acol, b_lo + adv, idesc, 1u);
+            umma_tf32_ts(d_tmem, a_hi + acol, b_hi + adv, idesc, 1u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[a]);
+      }
+    }
+  } else if (warp >= kTransformWarp0) {
+    // one thread = one row of the A tile (TMEM lane = 32 * (warp % 4) + lane); the row's eight 16-byte chunks sit at
+    // SWIZZLE_128B positions chunk ^ (row & 7)
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+      for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full[s], ph);
+        const uint32_t rbase = smem_u32(stage_base + (size_t)s * S::kStageBytes) + (uint32_t)row * (uint32_t)kRowBytesT;
+        float hi[BKT], lo[BKT];
+        float4 v[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) v[c] = lds128(rbase + (uint32_t)((c ^ (row & 7)) << 4));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float x[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            hi[4 * c + q] = tf32_rn(x[q]);
+            lo[4 * c + q] = x[q] - hi[4 * c + q];
+          }
+        }
+        const uint32_t acol = tmem_base + lane_field + (uint32_t)(kACol0 + s * 2 * BKT);
+        tmem_st32(acol, hi);
+        tmem_st32(acol + BKT, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[s]);
+      }
+    }
+  } else {
+    uint32_t acc_it = 0, chunk_it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
+      const long long mb = tile / p.n_blocks;
+      const int nb = (int)(tile % p.n_blocks);
+      const int a = acc_it & 1;
+      const uint32_t aph = (acc_it >> 1) & 1;
+      mbar_wait(&tmem_full[a], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * BN);
+      const int row0 = (int)(mb * BM) + warp * 32;
+      const int col0 = nb * p.n_tile;
+      uint8_t* wbuf = store_base + warp * (2 * 32 * kStoreCols * 4);
+      for (int c = 0; c < p.n_tile; c += kStoreCols, ++chunk_it) {
+        const uint32_t buf = smem_u32(wbuf + (chunk_it & 1) * (32 * kStoreCols * 4));
+        uint32_t v[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr + (uint32_t)c));
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = buf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+          sts128(dst, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                  __uint_as_float(v[4 * j + 3])));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                       ::"l"(reinterpret_cast<uint64_t>(&map_c)), "r"(col0 + c), "r"(row0), "r"(buf) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[a]);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace ts
+
 // hi / lo planes of the (small) weight operand: hi = w rounded to tf32, lo = w - hi
 __global__ void split_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -421,7 +660,10 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMa
 // 3xTF32 split as the forward kernel; here the transform warps split both operand tiles.
 namespace wg {
 
-constexpr int BKR = 16;                       // reduction rows per stage = two k-blocks of 8
+#ifndef EQF_WGRAD_BKR
+#define EQF_WGRAD_BKR 32
+#endif
+constexpr int BKR = EQF_WGRAD_BKR;            // reduction rows per stage (k-blocks of 8)
 constexpr int kBlockBytes = BKR * 128;        // one [BKR x 32] box
 constexpr int kMBlocks = BM / 32;             // 4 boxes for the 128 output rows
 
@@ -667,6 +909,24 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mg, const CUtensorMa
 }
 
 }  // namespace wg
+template <int BN>
+static int launch_ts(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mc,
+                     const Params& p, cudaStream_t s) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(ts::gemm_tf32x3_ts_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::TSmem<BN>::kTotal);
+  });
+  if (attr_err != cudaSuccess) return check_cuda(attr_err, "gemm_tf32x3_ts smem attribute");
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long tiles = p.m_blocks * p.n_blocks;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  ts::gemm_tf32x3_ts_kernel<BN><<<grid, kThreads, ts::TSmem<BN>::kTotal, s>>>(ma, mh, ml, mc, p);
+  return check_cuda(cudaGetLastError(), "gemm_tf32x3_ts_kernel launch");
+}
+
 }  // namespace tf32x3
 }  // namespace eqf
 
@@ -715,6 +975,16 @@ extern "C" int eqf_gemm_tf32x3(const float* A, const float* Bt, float* C, int64_
   if ((rc = make_map(&mh, hi, N, K, K, n_tile, BK)) != EQF_OK) return rc;
   if ((rc = make_map(&ml, lo, N, K, K, n_tile, BK)) != EQF_OK) return rc;
   if ((rc = make_map(&mc, C, M, N, ldc, 32, kStoreCols)) != EQF_OK) return rc;
+  // narrow outputs: A operand from TMEM, 128-byte k-tiles (EQF_TF32X3_TS=0 selects the shared-memory variant everywhere)
+  static const bool use_ts = [] { const char* e = std::getenv("EQF_TF32X3_TS"); return e == nullptr || e[0] != '0'; }();
+  if (use_ts && n_tile <= 128) {
+    if ((rc = make_map(&ma, A, M, K, lda, BM, ts::BKT)) != EQF_OK) return rc;
+    if ((rc = make_map(&mh, hi, N, K, K, n_tile, ts::BKT)) != EQF_OK) return rc;
+    if ((rc = make_map(&ml, lo, N, K, K, n_tile, ts::BKT)) != EQF_OK) return rc;
+    if (n_tile <= 32) return launch_ts<32>(ma, mh, ml, mc, p, s);
+    if (n_tile <= 64) return launch_ts<64>(ma, mh, ml, mc, p, s);
+    return launch_ts<128>(ma, mh, ml, mc, p, s);
+  }
   if (n_tile <= 64) return launch<64>(ma, mh, ml, mc, p, s);
   if (n_tile <= 128) return launch<128>(ma, mh, ml, mc, p, s);
   return launch<256>(ma, mh, ml, mc, p, s);

@@ -870,13 +870,14 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
         if mode == 0:
             return A @ B
         return A @ B.t() if mode == 1 else A.t() @ B
-    # forward / data-gradient products with a wide output run on the hand-written 3xTF32 tcgen05 kernel (1.2-1.6x the
-    # CUTLASS collective there, profiles/r1_tf32x3_microbench.jsonl); narrow outputs stay on the CUTLASS kernel
-    if mode != 2 and _TF32X3 and N >= 128 and M >= 16384 and not gemm_backend_forced():
+    # forward / data-gradient products of the edge-level linears run on the hand-written 3xTF32 tcgen05 kernels (A from
+    # shared memory for wide outputs, from TMEM for N <= 128): 1.1-1.7x the CUTLASS collective on every layer shape
+    # (profiles/r1_tf32x3_microbench.jsonl)
+    if mode != 2 and _TF32X3 and M >= 16384 and not gemm_backend_forced():
         return gemm_tf32x3_raw(A, B if mode == 1 else B.t().contiguous())
-    # weight gradient: the hand-written kernel (one TMEM accumulator per row slice) wins for wide outputs and for the
-    # short node-level reductions; long reductions into narrow outputs stay on the sliced CUTLASS launch
-    if mode == 2 and _TF32X3 and (N >= 128 or K < 16384) and not gemm_backend_forced():
+    # weight gradient: the hand-written kernel (one TMEM accumulator per row slice, 32-row TMA boxes) is ahead of the
+    # sliced CUTLASS launch on every layer shape (profiles/r1_tf32x3_wgrad_microbench.jsonl)
+    if mode == 2 and _TF32X3 and not gemm_backend_forced():
         return gemm_tf32x3_wgrad_raw(A, B)
     A, lda = _gemm_operand(A)
     B, ldb = _gemm_operand(B)
@@ -889,11 +890,19 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
         return _wgrad_sliced(lib, ws, A, B, lda, ldb, M, N, K)
     C = torch.empty((M, N), device=A.device, dtype=torch.float32)
     flops_bytes = 4 * (A.numel() + B.numel() + C.numel())
-    with torch.cuda.device(A.device), _kernel("gemm_fast_f32", flops_bytes):
+    with torch.cuda.device(A.device), _kernel(_gemm_name("gemm_fast_f32", mode, M, N, K), flops_bytes):
         rc = lib.eqf_gemm_f32(mode, A.data_ptr(), B.data_ptr(), C.data_ptr(), M, N, K, lda, ldb, N, 0.0,
                               ws.data_ptr(), ws.numel(), _stream())
     _lib.check_gemm(rc, "eqf_gemm_f32")
     return C
+
+
+_GEMM_SHAPE_NAMES = os.environ.get("EQF_PROFILE_GEMM_SHAPES", "0") == "1"
+
+
+def _gemm_name(base: str, mode: int, M: int, N: int, K: int) -> str:
+    """Kernel name for the bench's per-kernel table; with EQF_PROFILE_GEMM_SHAPES=1 one row per (mode, shape)."""
+    return f"{base}[m{mode} {M}x{N}x{K}]" if _GEMM_SHAPE_NAMES else base
 
 
 _TF32X3 = os.environ.get("EQF_GEMM_TF32X3", "1") != "0"
@@ -920,7 +929,7 @@ def gemm_tf32x3_raw(A: torch.Tensor, Bt: torch.Tensor) -> torch.Tensor:
     if split is None or split.numel() < need:
         split = torch.empty(max(need, 1 << 20), device=A.device, dtype=torch.float32)
         _TF32X3_SPLIT[A.device] = split
-    with torch.cuda.device(A.device), _kernel("gemm_tf32x3", 4 * (A.numel() + Bt.numel() + C.numel())):
+    with torch.cuda.device(A.device), _kernel(_gemm_name("gemm_tf32x3", 1, M, N, K), 4 * (A.numel() + Bt.numel() + C.numel())):
         rc = _lib.load().eqf_gemm_tf32x3(A.data_ptr(), Bt.data_ptr(), C.data_ptr(), M, N, K, lda, K, N, split.data_ptr(),
                                          _stream())
     _lib.check(rc, "eqf_gemm_tf32x3")
@@ -940,7 +949,7 @@ def gemm_tf32x3_wgrad_raw(A: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     if not _DETERMINISTIC:      # slices add into W through TMA reduce-adds: one launch, no partial buffer / column sum
         W = torch.empty((K1, N), device=A.device, dtype=torch.float32)
-        with torch.cuda.device(A.device), _kernel("gemm_tf32x3_wgrad", 4 * (A.numel() + G.numel() + W.numel())):
+        with torch.cuda.device(A.device), _kernel(_gemm_name("gemm_tf32x3_wgrad", 2, K1, N, R), 4 * (A.numel() + G.numel() + W.numel())):
             rc = lib.eqf_gemm_tf32x3_wgrad_accumulate(A.data_ptr(), G.data_ptr(), W.data_ptr(), R, K1, N, lda, ldg, _stream())
         _lib.check(rc, "eqf_gemm_tf32x3_wgrad_accumulate")
         return W
@@ -976,7 +985,7 @@ def _wgrad_sliced(lib, ws, A, B, lda, ldb, M, N, K):
     tail = K - slices * chunk
     part = torch.empty((slices + (1 if tail else 0), M, N), device=A.device, dtype=torch.float32)
     nbytes = 4 * (A.numel() + B.numel() + 2 * part.numel())
-    with torch.cuda.device(A.device), _kernel("gemm_fast_f32_wgrad", nbytes):
+    with torch.cuda.device(A.device), _kernel(_gemm_name("gemm_fast_f32_wgrad", 2, M, N, K), nbytes):
         rc = lib.eqf_gemm_f32_wgrad_sliced(A.data_ptr(), B.data_ptr(), part.data_ptr(), M, N, chunk, slices, lda, ldb,
                                            ws.data_ptr(), ws.numel(), _stream())
         _lib.check_gemm(rc, "eqf_gemm_f32_wgrad_sliced")
