@@ -114,8 +114,8 @@ SIGNATURES = {
                                   c_void_p, c_void_p]),
     "eqf_ln_silu_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32,
                                   c_void_p, c_void_p, c_void_p]),
-    "eqf_gemm_tf32x3": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p,
-                                  c_void_p]),
+    "eqf_gemm_tf32x3": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, c_int32,
+                                  c_void_p, c_void_p]),
     "eqf_gemm_tf32x3_set_timeline": (None, [c_void_p]),
     "eqf_gemm_tf32x3_wgrad_slices": (c_int64, [c_int64, c_int64, c_int64]),
     "eqf_gemm_tf32x3_wgrad": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),

@@ -596,6 +596,19 @@ __global__ void split_kernel(const float* __restrict__ w, float* __restrict__ hi
   }
 }
 
+// the same split for a weight stored [K, N] (forward product C = A W): the hi / lo planes come out transposed, [N, K]
+__global__ void split_transpose_kernel(const float* __restrict__ w, long long ldw, float* __restrict__ hi,
+                                       float* __restrict__ lo, long long N, long long K) {
+  const long long n_el = N * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / K, k = i - n * K;
+    const float v = w[k * ldw + n];
+    const float h = tf32_rn(v);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -936,16 +949,17 @@ static long long* g_tf32x3_dbg = nullptr;
 // debugging aid: device buffer of 4 * 1024 int64 that receives CTA 0's clock64 timeline on the next launches (NULL = off)
 extern "C" void eqf_gemm_tf32x3_set_timeline(long long* device_buffer) { g_tf32x3_dbg = device_buffer; }
 
-// C[M, N] = A[M, K] (row-major, lda) x Bt[N, K]^T (row-major, ldb), 3xTF32 on tcgen05.  `split` is device scratch of
-// 2 * N * K floats for the hi / lo planes of Bt.  All pointers 16-byte aligned, K, lda, ldb, ldc multiples of 4.
+// C[M, N] = A[M, K] (row-major, lda) x W, 3xTF32 on tcgen05.  The weight operand is either Bt[N, K] (b_is_kn = 0, row
+// stride ldb >= K: data gradient, W = Bt^T) or B[K, N] (b_is_kn = 1, row stride ldb >= N: forward, W = B).  `split` is
+// device scratch of 2 * N * K floats for its hi / lo planes.  Pointers 16-byte aligned, K, lda, ldc multiples of 4.
 extern "C" int eqf_gemm_tf32x3(const float* A, const float* Bt, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
-                               int64_t ldb, int64_t ldc, float* split, void* stream) {
+                               int64_t ldb, int64_t ldc, int32_t b_is_kn, float* split, void* stream) {
   using namespace eqf::tf32x3;
   if (M <= 0 || N <= 0) return EQF_OK;
   if (!A || !Bt || !C || !split) { set_error("eqf_gemm_tf32x3: null pointer"); return EQF_ERR_INVALID; }
   if (K <= 0) { set_error("eqf_gemm_tf32x3: K must be positive"); return EQF_ERR_INVALID; }
-  if ((((uintptr_t)A | (uintptr_t)Bt | (uintptr_t)C | (uintptr_t)split) & 15) || ((K | lda | ldb | ldc) & 3) || lda < K ||
-      ldb < K || ldc < N) {
+  if ((((uintptr_t)A | (uintptr_t)C | (uintptr_t)split) & 15) || ((K | lda | ldc) & 3) || lda < K || ldc < N ||
+      ldb < (b_is_kn ? N : K)) {
     set_error("eqf_gemm_tf32x3: operands must be 16-byte aligned, K and leading dimensions multiples of 4");
     return EQF_ERR_INVALID;
   }
@@ -957,7 +971,8 @@ extern "C" int eqf_gemm_tf32x3(const float* A, const float* Bt, float* C, int64_
   {
     const long long n = N * K;
     const unsigned blocks = (unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
-    if (ldb == K) split_kernel<<<blocks, 256, 0, s>>>(Bt, hi, lo, n);
+    if (b_is_kn) split_transpose_kernel<<<blocks, 256, 0, s>>>(Bt, ldb, hi, lo, N, K);
+    else if (ldb == K) split_kernel<<<blocks, 256, 0, s>>>(Bt, hi, lo, n);
     else { set_error("eqf_gemm_tf32x3: Bt must be packed (ldb == K)"); return EQF_ERR_UNSUPPORTED; }
   }
   int rc = check_cuda(cudaGetLastError(), "split_kernel launch");

@@ -20,9 +20,12 @@ __device__ __forceinline__ float wsum(float v) {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm + SiLU
-// y = silu(z), z = (x - mean) * rstd * gamma + beta ; C <= 32 * kMaxPerLane, one warp per row
+// y = silu(z), z = (x - mean) * rstd * gamma + beta ; C <= 32 * kMaxPerLane, one warp per row.  The kernels are
+// instantiated for 2 / 4 / 8 columns per lane: at C = 64 (the radial MLP) the 8-column version carried 102 registers
+// for six live arrays it did not need - 2 CTAs per SM and a latency-bound 42 us per call (profiles launch list).
 constexpr int kMaxPerLane = 8;
 
+template <int PER>
 __global__ void __launch_bounds__(256) ln_silu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ bias,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, float eps, long long R, int C,
@@ -31,10 +34,10 @@ __global__ void __launch_bounds__(256) ln_silu_fwd_kernel(const float* __restric
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 8;
   for (long long r = warp; r < R; r += n_warps) {
-    float v[kMaxPerLane];
+    float v[PER];
     float s = 0.f;
 #pragma unroll
-    for (int q = 0; q < kMaxPerLane; ++q) {
+    for (int q = 0; q < PER; ++q) {
       const int c = lane + 32 * q;
       v[q] = (c < C) ? __ldg(x + r * C + c) + (bias ? __ldg(bias + c) : 0.f) : 0.f;   // bias of the preceding Linear
       s += v[q];
@@ -42,14 +45,14 @@ __global__ void __launch_bounds__(256) ln_silu_fwd_kernel(const float* __restric
     const float m = wsum(s) / C;
     float ss = 0.f;
 #pragma unroll
-    for (int q = 0; q < kMaxPerLane; ++q) {
+    for (int q = 0; q < PER; ++q) {
       const int c = lane + 32 * q;
       const float d = (c < C) ? v[q] - m : 0.f;
       ss += d * d;
     }
     const float rs = rsqrtf(wsum(ss) / C + eps);
 #pragma unroll
-    for (int q = 0; q < kMaxPerLane; ++q) {
+    for (int q = 0; q < PER; ++q) {
       const int c = lane + 32 * q;
       if (c < C) {
         const float z = (v[q] - m) * rs * __ldg(gamma + c) + __ldg(beta + c);
@@ -61,26 +64,27 @@ __global__ void __launch_bounds__(256) ln_silu_fwd_kernel(const float* __restric
 }
 
 // gx, and per-CTA partial sums [gridDim.x][3C] = d gamma | d beta | d bias (= column sums of gx)
+template <int PER>
 __global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restrict__ x, const float* __restrict__ bias,
                                                           const float* __restrict__ gamma,
                                                           const float* __restrict__ beta, const float* __restrict__ mean,
                                                           const float* __restrict__ rstd, const float* __restrict__ gy,
                                                           long long R, int C, float* __restrict__ gx,
                                                           float* __restrict__ part) {
-  __shared__ float sg[32 * kMaxPerLane], sb[32 * kMaxPerLane], sx[32 * kMaxPerLane];
-  for (int i = threadIdx.x; i < 32 * kMaxPerLane; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; sx[i] = 0.f; }
+  __shared__ float sg[32 * PER], sb[32 * PER], sx[32 * PER];
+  for (int i = threadIdx.x; i < 32 * PER; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; sx[i] = 0.f; }
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 8;
-  float ag[kMaxPerLane], ab[kMaxPerLane], ax[kMaxPerLane];
+  float ag[PER], ab[PER], ax[PER];
 #pragma unroll
-  for (int q = 0; q < kMaxPerLane; ++q) { ag[q] = 0.f; ab[q] = 0.f; ax[q] = 0.f; }
+  for (int q = 0; q < PER; ++q) { ag[q] = 0.f; ab[q] = 0.f; ax[q] = 0.f; }
   for (long long r = warp; r < R; r += n_warps) {
     const float m = __ldg(mean + r), rs = __ldg(rstd + r);
-    float xh[kMaxPerLane], gz[kMaxPerLane];
+    float xh[PER], gz[PER];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int q = 0; q < kMaxPerLane; ++q) {
+    for (int q = 0; q < PER; ++q) {
       const int c = lane + 32 * q;
       xh[q] = 0.f; gz[q] = 0.f;
       if (c < C) {
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restric
     s1 = wsum(s1) / C;
     s2 = wsum(s2) / C;
 #pragma unroll
-    for (int q = 0; q < kMaxPerLane; ++q) {
+    for (int q = 0; q < PER; ++q) {
       const int c = lane + 32 * q;
       if (c < C) {
         const float v = rs * (gz[q] - s1 - xh[q] * s2);
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restric
     }
   }
 #pragma unroll
-  for (int q = 0; q < kMaxPerLane; ++q) {
+  for (int q = 0; q < PER; ++q) {
     const int c = lane + 32 * q;
     if (c < C) { atomicAdd(&sg[c], ag[q]); atomicAdd(&sb[c], ab[q]); atomicAdd(&sx[c], ax[q]); }
   }
@@ -619,7 +623,10 @@ extern "C" int eqf_ln_silu_fwd(const float* x, const float* bias, const float* g
   if (R == 0) return EQF_OK;
   if (!x || !gamma || !beta || !y || !mean || !rstd) { set_error("eqf_ln_silu_fwd: null pointer"); return EQF_ERR_INVALID; }
   if (C < 1 || C > 32 * kMaxPerLane) { set_error("eqf_ln_silu: C must be in 1..256"); return EQF_ERR_UNSUPPORTED; }
-  ln_silu_fwd_kernel<<<pointwise_grid(R), 256, 0, (cudaStream_t)stream>>>(x, bias, gamma, beta, eps, R, C, y, mean, rstd);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 64) ln_silu_fwd_kernel<2><<<pointwise_grid(R), 256, 0, st>>>(x, bias, gamma, beta, eps, R, C, y, mean, rstd);
+  else if (C <= 128) ln_silu_fwd_kernel<4><<<pointwise_grid(R), 256, 0, st>>>(x, bias, gamma, beta, eps, R, C, y, mean, rstd);
+  else ln_silu_fwd_kernel<8><<<pointwise_grid(R), 256, 0, st>>>(x, bias, gamma, beta, eps, R, C, y, mean, rstd);
   return check_cuda(cudaGetLastError(), "ln_silu_fwd_kernel launch");
 }
 
@@ -631,8 +638,10 @@ extern "C" int eqf_ln_silu_bwd(const float* x, const float* bias, const float* g
     set_error("eqf_ln_silu_bwd: null pointer"); return EQF_ERR_INVALID;
   }
   if (C < 1 || C > 32 * kMaxPerLane) { set_error("eqf_ln_silu: C must be in 1..256"); return EQF_ERR_UNSUPPORTED; }
-  ln_silu_bwd_kernel<<<pointwise_grid(R), 256, 0, (cudaStream_t)stream>>>(x, bias, gamma, beta, mean, rstd, gy, R, C, gx,
-                                                                          part);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 64) ln_silu_bwd_kernel<2><<<pointwise_grid(R), 256, 0, st>>>(x, bias, gamma, beta, mean, rstd, gy, R, C, gx, part);
+  else if (C <= 128) ln_silu_bwd_kernel<4><<<pointwise_grid(R), 256, 0, st>>>(x, bias, gamma, beta, mean, rstd, gy, R, C, gx, part);
+  else ln_silu_bwd_kernel<8><<<pointwise_grid(R), 256, 0, st>>>(x, bias, gamma, beta, mean, rstd, gy, R, C, gx, part);
   return check_cuda(cudaGetLastError(), "ln_silu_bwd_kernel launch");
 }
 

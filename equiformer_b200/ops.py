@@ -874,7 +874,7 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     # shared memory for wide outputs, from TMEM for N <= 128): 1.1-1.7x the CUTLASS collective on every layer shape
     # (profiles/r1_tf32x3_microbench.jsonl)
     if mode != 2 and _TF32X3 and M >= 16384 and not gemm_backend_forced():
-        return gemm_tf32x3_raw(A, B if mode == 1 else B.t().contiguous())
+        return gemm_tf32x3_raw(A, B, b_is_kn=(mode == 0))
     # weight gradient: the hand-written kernel (one TMEM accumulator per row slice, 32-row TMA boxes) is ahead of the
     # sliced CUTLASS launch on every layer shape (profiles/r1_tf32x3_wgrad_microbench.jsonl)
     if mode == 2 and _TF32X3 and not gemm_backend_forced():
@@ -912,17 +912,18 @@ _DETERMINISTIC = os.environ.get("EQF_DETERMINISTIC", "0") == "1"
 _TF32X3_SPLIT = {}
 
 
-def gemm_tf32x3_raw(A: torch.Tensor, Bt: torch.Tensor) -> torch.Tensor:
-    """``A[M, K] @ Bt[N, K]^T`` through the hand-written tcgen05 3xTF32 kernel (``eqf_gemm_tf32x3``)."""
+def gemm_tf32x3_raw(A: torch.Tensor, Bt: torch.Tensor, b_is_kn: bool = False) -> torch.Tensor:
+    """``A[M, K] @ Bt[N, K]^T`` - or ``A @ B`` with ``B[K, N]`` when ``b_is_kn`` - through the hand-written tcgen05
+    3xTF32 kernels (``eqf_gemm_tf32x3``)."""
     A = _require_cuda(A, "gemm A")
-    Bt = _require_cuda(Bt, "gemm Bt")
-    (M, K), N = A.shape, Bt.shape[0]
-    if Bt.shape[1] != K:
+    Bt = _require_cuda(Bt, "gemm B")
+    M, K = A.shape
+    N = Bt.shape[1] if b_is_kn else Bt.shape[0]
+    if (Bt.shape[0] if b_is_kn else Bt.shape[1]) != K:
         raise ValueError(f"gemm_tf32x3: incompatible shapes {tuple(A.shape)} {tuple(Bt.shape)}")
     A, lda = _gemm_operand(A)
-    Bt = Bt.contiguous()
-    if Bt.data_ptr() % 16:
-        Bt = Bt.clone()
+    if Bt.stride(1) != 1 or (not b_is_kn and Bt.stride(0) != K):
+        Bt = Bt.contiguous()
     C = torch.empty((M, N), device=A.device, dtype=torch.float32)
     need = 2 * N * K
     split = _TF32X3_SPLIT.get(A.device)
@@ -930,8 +931,8 @@ def gemm_tf32x3_raw(A: torch.Tensor, Bt: torch.Tensor) -> torch.Tensor:
         split = torch.empty(max(need, 1 << 20), device=A.device, dtype=torch.float32)
         _TF32X3_SPLIT[A.device] = split
     with torch.cuda.device(A.device), _kernel(_gemm_name("gemm_tf32x3", 1, M, N, K), 4 * (A.numel() + Bt.numel() + C.numel())):
-        rc = _lib.load().eqf_gemm_tf32x3(A.data_ptr(), Bt.data_ptr(), C.data_ptr(), M, N, K, lda, K, N, split.data_ptr(),
-                                         _stream())
+        rc = _lib.load().eqf_gemm_tf32x3(A.data_ptr(), Bt.data_ptr(), C.data_ptr(), M, N, K, lda, Bt.stride(0), N,
+                                         1 if b_is_kn else 0, split.data_ptr(), _stream())
     _lib.check(rc, "eqf_gemm_tf32x3")
     return C
 

@@ -145,12 +145,13 @@ int eqf_ln_silu_fwd(const float* x, const float* bias, const float* gamma, const
 int eqf_ln_silu_bwd(const float* x, const float* bias, const float* gamma, const float* beta, const float* mean,
                     const float* rstd, const float* gy, int64_t R, int32_t C, float* gx, float* part, void* stream);
 
-/* Hand-written tcgen05 GEMM (3xTF32, fp32-level accuracy) for the tall per-degree linears:
- * C[M, N] = A[M, K] x Bt[N, K]^T, all row-major fp32; `split` = device scratch of 2*N*K floats (hi / lo planes of Bt).
- * Replaces the e3nn 'uvw' einsum -> cuBLAS SGEMM of LinearRS (nets/tensor_product_rescale.py:165-174) on the
- * forward (Bt = W^T) and data-gradient (Bt = W) products. */
+/* Hand-written tcgen05 GEMM (3xTF32, fp32-level accuracy) for the tall per-degree linears: C[M, N] = A[M, K] x W, all
+ * row-major fp32.  W is given as Bt[N, K] (b_is_kn = 0, data gradient: W = Bt^T) or as B[K, N] (b_is_kn = 1, forward);
+ * `split` = device scratch of 2*N*K floats (hi / lo planes of the weights).  Replaces the e3nn 'uvw' einsum -> cuBLAS
+ * SGEMM of LinearRS (nets/tensor_product_rescale.py:165-174).  Outputs wider than 128 columns: split A tile in shared
+ * memory; N <= 128: A operand from TMEM. */
 int eqf_gemm_tf32x3(const float* A, const float* Bt, float* C, int64_t M, int64_t N, int64_t K, int64_t lda,
-                    int64_t ldb, int64_t ldc, float* split, void* stream);
+                    int64_t ldb, int64_t ldc, int32_t b_is_kn, float* split, void* stream);
 /* Weight gradient of the same linears, W[K1, N] = A[R, K1]^T G[R, N] (what autograd derives for the 'uvw' einsum of
  * LinearRS): the R rows are cut into eqf_gemm_tf32x3_wgrad_slices(R, K1, N) slices, every CTA reduces one slice into a
  * TMEM accumulator and writes partial[slice][K1][N]; the caller sums the partials over slices (eqf_colsum). */

@@ -203,6 +203,8 @@ def test_tf32x3_tcgen05_gemm(cuda_device, M, N, K):
     Ai = torch.randint(-8, 9, (M, K), generator=g).float()
     Bi = torch.randint(-8, 9, (N, K), generator=g).float()
     assert torch.equal(ops.gemm_tf32x3_raw(d(Ai), d(Bi)).cpu(), Ai @ Bi.t())
+    # weight given as B[K, N] (forward layout): transposed while it is split
+    assert rel_err(ops.gemm_tf32x3_raw(d(A), d(Bt).t().contiguous(), b_is_kn=True), ref) < tol
 
 
 @pytest.mark.parametrize("R,K1,N", [(100, 32, 32), (1000, 64, 48), (3001, 100, 72), (36000, 224, 224), (36000, 224, 352),
