@@ -304,7 +304,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const int row0 = (int)(mb * BM) + warp * 32;
       const int col0 = nb * p.n_tile;
       uint8_t* wbuf = store_base + warp * (2 * 32 * kStoreCols * 4);
-      for (int c = 0; c < p.n_tile; c += kStoreCols, ++chunk_it) {
+      const int n_valid = (p.N - col0) < p.n_tile ? (int)(p.N - col0) : p.n_tile;   // columns of this tile that exist
+      for (int c = 0; c < n_valid; c += kStoreCols, ++chunk_it) {
         const uint32_t buf = smem_u32(wbuf + (chunk_it & 1) * (32 * kStoreCols * 4));
         uint32_t v[32];
         asm volatile(
@@ -542,7 +543,8 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       const int row0 = (int)(mb * BM) + warp * 32;
       const int col0 = nb * p.n_tile;
       uint8_t* wbuf = store_base + warp * (2 * 32 * kStoreCols * 4);
-      for (int c = 0; c < p.n_tile; c += kStoreCols, ++chunk_it) {
+      const int n_valid = (p.N - col0) < p.n_tile ? (int)(p.N - col0) : p.n_tile;   // columns of this tile that exist
+      for (int c = 0; c < n_valid; c += kStoreCols, ++chunk_it) {
         const uint32_t buf = smem_u32(wbuf + (chunk_it & 1) * (32 * kStoreCols * 4));
         uint32_t v[32];
         asm volatile(
@@ -977,12 +979,13 @@ extern "C" int eqf_gemm_tf32x3(const float* A, const float* Bt, float* C, int64_
   }
   int rc = check_cuda(cudaGetLastError(), "split_kernel launch");
   if (rc != EQF_OK) return rc;
-  // column tiles: one tile of round_up(N, 16) columns when N <= 256, else tiles of 256 (the last one narrower: its
-  // out-of-range weight rows load as zeros and its out-of-range columns are clipped by the TMA store)
+  // column tiles: one tile of round_up(N, 16) columns when N <= 256 (out-of-range weight rows load as zeros,
+  // out-of-range columns are clipped by the TMA store), else
   const int n_blocks = (int)((N + 255) / 256);
-  const int n_tile = n_blocks == 1 ? (int)((N + 15) & ~15LL) : 256;
+  // several column tiles: as even as possible in multiples of 32 (the store chunk), e.g. 384 -> 192 + 192, 352 -> 192 + 160
+  const int n_tile = n_blocks == 1 ? (int)((N + 15) & ~15LL) : (int)((((N + n_blocks - 1) / n_blocks) + 31) & ~31LL);
   Params p;
-  p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.n_tile = n_tile; p.n_blocks = n_blocks;
+  p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.n_tile = n_tile; p.n_blocks = (int)((N + n_tile - 1) / n_tile);
   p.m_blocks = (M + BM - 1) / BM;
   p.dbg = g_tf32x3_dbg;
   CUtensorMap ma, mh, ml, mc;
