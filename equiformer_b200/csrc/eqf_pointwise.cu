@@ -502,17 +502,28 @@ struct ELNArgs {
   int n_entries, dim, n_w, n_b;
   int mul[EQF_MAX_BLOCKS], d[EQF_MAX_BLOCKS], scalar[EQF_MAX_BLOCKS], off[EQF_MAX_BLOCKS], woff[EQF_MAX_BLOCKS], boff[EQF_MAX_BLOCKS];
   float eps; long long N;
+  // planar variant: one packed [N, d, mul] buffer per entry (channel innermost) instead of e3nn-layout rows
+  int planar;
+  const float* xp[EQF_MAX_BLOCKS]; float* yp[EQF_MAX_BLOCKS]; const float* gyp[EQF_MAX_BLOCKS]; float* gxp[EQF_MAX_BLOCKS];
 };
+
+// entry t of row r: base pointer of its mul*d values, and the channel of the i-th value
+__device__ __forceinline__ const float* eln_in(const ELNArgs& a, const float* rows, const float* const* blocks, long long r, int t) {
+  return a.planar ? blocks[t] + r * (a.mul[t] * a.d[t]) : rows + r * a.dim + a.off[t];
+}
+__device__ __forceinline__ float* eln_out(const ELNArgs& a, float* rows, float* const* blocks, long long r, int t) {
+  return a.planar ? blocks[t] + r * (a.mul[t] * a.d[t]) : rows + r * a.dim + a.off[t];
+}
+__device__ __forceinline__ int eln_chan(const ELNArgs& a, int t, int i) { return a.planar ? i % a.mul[t] : i / a.d[t]; }
 
 __global__ void __launch_bounds__(256) eln_fwd_kernel(ELNArgs a) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 8;
   for (long long r = warp; r < a.N; r += n_warps) {
-    const float* x = a.x + r * a.dim;
-    float* y = a.y + r * a.dim;
     for (int t = 0; t < a.n_entries; ++t) {
       const int mul = a.mul[t], d = a.d[t], n = mul * d;
-      const float* xe = x + a.off[t];
+      const float* xe = eln_in(a, a.x, a.xp, r, t);
+      float* ye = eln_out(a, a.y, a.yp, r, t);
       float mean = 0.f;
       if (a.scalar[t]) {
         float s = 0.f;
@@ -523,10 +534,10 @@ __global__ void __launch_bounds__(256) eln_fwd_kernel(ELNArgs a) {
       for (int i = lane; i < n; i += 32) { const float f = __ldg(xe + i) - mean; ss += f * f; }
       const float rs = rsqrtf(wsum(ss) / n + a.eps);
       for (int i = lane; i < n; i += 32) {
-        const int c = i / d;
+        const int c = eln_chan(a, t, i);
         float v = (__ldg(xe + i) - mean) * rs * __ldg(a.w + a.woff[t] + c);
         if (a.scalar[t]) v += __ldg(a.b + a.boff[t] + c);
-        y[a.off[t] + i] = v;
+        ye[i] = v;
       }
       if (lane == 0) a.rstd[r * a.n_entries + t] = rs;
     }
@@ -540,13 +551,11 @@ __global__ void __launch_bounds__(256) eln_bwd_kernel(ELNArgs a) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 8;
   for (long long r = warp; r < a.N; r += n_warps) {
-    const float* x = a.x + r * a.dim;
-    const float* gy = a.gy + r * a.dim;
-    float* gx = a.gx + r * a.dim;
     for (int t = 0; t < a.n_entries; ++t) {
       const int mul = a.mul[t], d = a.d[t], n = mul * d;
-      const float* xe = x + a.off[t];
-      const float* ge = gy + a.off[t];
+      const float* xe = eln_in(a, a.x, a.xp, r, t);
+      const float* ge = eln_in(a, a.gy, a.gyp, r, t);
+      float* gxe = eln_out(a, a.gx, a.gxp, r, t);
       const float rs = __ldg(a.rstd + r * a.n_entries + t);
       float mean = 0.f;
       if (a.scalar[t]) {
@@ -557,7 +566,7 @@ __global__ void __launch_bounds__(256) eln_bwd_kernel(ELNArgs a) {
       // s1 = sum g*w*f
       float s1 = 0.f;
       for (int i = lane; i < n; i += 32) {
-        const int c = i / d;
+        const int c = eln_chan(a, t, i);
         const float f = __ldg(xe + i) - mean, g = __ldg(ge + i);
         s1 += g * __ldg(a.w + a.woff[t] + c) * f;
         atomicAdd(&sacc[a.woff[t] + c], g * f * rs);
@@ -567,15 +576,15 @@ __global__ void __launch_bounds__(256) eln_bwd_kernel(ELNArgs a) {
       const float k = -s1 * rs * rs * rs / n;           // dL/dn * 2/n with dL/dn = -1/2 r^3 s1
       float gsum = 0.f;
       for (int i = lane; i < n; i += 32) {
-        const int c = i / d;
+        const int c = eln_chan(a, t, i);
         const float f = __ldg(xe + i) - mean;
         const float gf = __ldg(ge + i) * rs * __ldg(a.w + a.woff[t] + c) + f * k;
-        gx[a.off[t] + i] = gf;
+        gxe[i] = gf;
         gsum += gf;
       }
       if (a.scalar[t]) {                                  // centring: g_x = g_f - mean(g_f)
         const float gm = wsum(gsum) / n;
-        for (int i = lane; i < n; i += 32) gx[a.off[t] + i] -= gm;
+        for (int i = lane; i < n; i += 32) gxe[i] -= gm;
       }
     }
   }
@@ -602,6 +611,7 @@ static int fill_eln(const EqfNormLayout* lay, ELNArgs& a) {
     if (lay->is_scalar[t]) boff += lay->mul[t];
   }
   a.dim = off; a.n_w = woff; a.n_b = boff;
+  a.planar = 0;
   return EQF_OK;
 }
 
@@ -744,4 +754,39 @@ extern "C" int eqf_colsum(const float* x, int64_t rows, int64_t cols, int64_t ld
   if (vec) colsum_kernel<4><<<grid, block, 0, s>>>(x, rows, cols, ld, out, part, counters);
   else colsum_kernel<1><<<grid, block, 0, s>>>(x, rows, cols, ld, out, part, counters);
   return check_cuda(cudaGetLastError(), "colsum_kernel launch");
+}
+
+
+// planar variants: entry t of the node features is a packed [N, d_t, mul_t] buffer (channel innermost), as the GEMM /
+// tensor-product kernels keep them - the transformer blocks then never leave the planar layout
+extern "C" int eqf_eln_fwd_planar(const EqfNormLayout* lay, const float* const* x_blocks, const float* w, const float* b,
+                                  int64_t N, float* const* y_blocks, float* rstd, void* stream) {
+  ELNArgs a;
+  int rc = fill_eln(lay, a);
+  if (rc != EQF_OK || N == 0) return rc;
+  if (!x_blocks || !y_blocks || !w || !rstd || (a.n_b > 0 && !b)) { set_error("eqf_eln_fwd_planar: null pointer"); return EQF_ERR_INVALID; }
+  a.planar = 1; a.x = nullptr; a.y = nullptr; a.w = w; a.b = b; a.rstd = rstd; a.N = N;
+  for (int t = 0; t < a.n_entries; ++t) {
+    if (!x_blocks[t] || !y_blocks[t]) { set_error("eqf_eln_fwd_planar: null block"); return EQF_ERR_INVALID; }
+    a.xp[t] = x_blocks[t]; a.yp[t] = y_blocks[t];
+  }
+  eln_fwd_kernel<<<eln_grid(N), 256, 0, (cudaStream_t)stream>>>(a);
+  return check_cuda(cudaGetLastError(), "eln_fwd_kernel (planar) launch");
+}
+
+extern "C" int eqf_eln_bwd_planar(const EqfNormLayout* lay, const float* const* x_blocks, const float* w, const float* rstd,
+                                  const float* const* gy_blocks, int64_t N, float* const* gx_blocks, float* part,
+                                  void* stream) {
+  ELNArgs a;
+  int rc = fill_eln(lay, a);
+  if (rc != EQF_OK || N == 0) return rc;
+  if (!x_blocks || !gy_blocks || !gx_blocks || !w || !rstd || !part) { set_error("eqf_eln_bwd_planar: null pointer"); return EQF_ERR_INVALID; }
+  a.planar = 1; a.x = nullptr; a.gy = nullptr; a.gx = nullptr; a.w = w; a.b = nullptr; a.rstd = const_cast<float*>(rstd);
+  a.dw_part = part; a.db_part = nullptr; a.N = N;
+  for (int t = 0; t < a.n_entries; ++t) {
+    if (!x_blocks[t] || !gy_blocks[t] || !gx_blocks[t]) { set_error("eqf_eln_bwd_planar: null block"); return EQF_ERR_INVALID; }
+    a.xp[t] = x_blocks[t]; a.gyp[t] = gy_blocks[t]; a.gxp[t] = gx_blocks[t];
+  }
+  eln_bwd_kernel<<<eln_grid(N), 256, (a.n_w + a.n_b) * sizeof(float), (cudaStream_t)stream>>>(a);
+  return check_cuda(cudaGetLastError(), "eln_bwd_kernel (planar) launch");
 }

@@ -307,15 +307,29 @@ class GraphAttention(torch.nn.Module):
                                            [mul for mul, _ in irreps_attn_heads], num_heads)
 
     # ---------------------------------------------------------------------------------------------
+    @property
+    def supports_planar(self) -> bool:
+        """True when the block can stay in the planar layout (no output dropout to apply on e3nn-layout features)."""
+        return self.proj_drop is None or not self.training or getattr(self.proj_drop, "drop_prob", 1.0) == 0.0
+
     def forward(self, node_input, node_attr, edge_src, edge_dst, edge_attr, edge_scalars, batch, **kwargs):
-        n_nodes = node_input.shape[0]
+        xs = ops.to_planar(node_input, self.irreps_node_input)
+        node = self.forward_planar(xs, node_attr, edge_src, edge_dst, edge_attr, edge_scalars, batch, **kwargs)
+        node_output = ops.from_planar(node)                                               # [ref :522]
+        if self.proj_drop is not None:
+            node_output = self.proj_drop(node_output)
+        return node_output
+
+    def forward_planar(self, xs, node_attr, edge_src, edge_dst, edge_attr, edge_scalars, batch, **kwargs):
+        """The layer on planar node blocks (one ``[N, 2l+1, mul]`` tensor per input entry) -> planar output blocks,
+        before the output dropout."""
+        n_nodes = xs[0].shape[0]
         graph = _graph_for(edge_src, edge_dst, n_nodes, kwargs)
         edge_attr = graph.sort_edges(edge_attr).contiguous()
         edge_scalars = graph.sort_edges(edge_scalars)
         E, H, A = graph.n_edges, self.num_heads, self.mul_alpha_head
 
         # merge (node level, per-degree GEMMs) then gather + add along the edge list      [ref :485-487]
-        xs = ops.to_planar(node_input, self.irreps_node_input)
         m_src = self.merge_src.planar(xs)
         m_dst = self.merge_dst.planar(xs)
         # the gather + add of ref :487 happens inside the DTP kernel's operand load (node tables stay L2-resident)
@@ -379,12 +393,9 @@ class GraphAttention(torch.nn.Module):
         node = ops.attention_aggregate(self._head_layout, graph, attn.contiguous(), [v.contiguous() for v in value])
 
         if self.rescale_degree:                                                           # [ref :516-520]
-            degree = (graph.row_ptr[1:] - graph.row_ptr[:-1]).to(node_input.dtype).view(-1, 1, 1)
+            degree = (graph.row_ptr[1:] - graph.row_ptr[:-1]).to(node[0].dtype).view(-1, 1, 1)
             node = [t * degree for t in node]
-        node_output = ops.from_planar(self.proj.planar(node))                             # [ref :522]
-        if self.proj_drop is not None:
-            node_output = self.proj_drop(node_output)
-        return node_output
+        return self.proj.planar(node)
 
     def extra_repr(self) -> str:
         return f"rescale_degree={self.rescale_degree}, "
@@ -413,9 +424,18 @@ class FeedForwardNetwork(torch.nn.Module):
             lay = ops.gate_only_layout(gate, f1.irreps_out)
             self._gate_layout = lay if (lay is not None and f1.bias[0].numel() == lay.width) else None
 
+    @property
+    def supports_planar(self) -> bool:
+        return self.proj_drop is None or not self.training or getattr(self.proj_drop, "drop_prob", 1.0) == 0.0
+
     def forward(self, node_input, node_attr, **kwargs):
+        node_output = ops.from_planar(self.forward_planar(ops.to_planar(node_input, self.irreps_node_input), node_attr))
+        if self.proj_drop is not None:
+            node_output = self.proj_drop(node_output)
+        return node_output
+
+    def forward_planar(self, xs, node_attr, **kwargs):
         # planar end to end: entries of fctp_1's gate input -> gate -> fctp_2
-        xs = ops.to_planar(node_input, self.irreps_node_input)
         # the models feed the constant scalar 1 as node_attr (ref :869): the multiply by it is skipped when marked so
         y = None if (getattr(node_attr, "_eqf_all_ones", False) and self.irreps_node_attr.dim == 1) else node_attr
         gate = self.fctp_1.gate
@@ -430,10 +450,7 @@ class FeedForwardNetwork(torch.nn.Module):
                 h = _reblock(gate.planar(h), gate.irreps_out, self.fctp_2.irreps_in1)
             else:
                 h = [gate(t) for t in h]
-        node_output = ops.from_planar(self.fctp_2.planar(h, y))
-        if self.proj_drop is not None:
-            node_output = self.proj_drop(node_output)
-        return node_output
+        return self.fctp_2.planar(h, y)
 
 
 class TransBlock(torch.nn.Module):
@@ -484,6 +501,24 @@ class TransBlock(torch.nn.Module):
         if self.drop_path is not None:
             features = self.drop_path(features, batch)
         return node_output + features
+
+    @property
+    def supports_planar(self) -> bool:
+        """The whole block can run on planar node blocks: fused LayerNorms, no shortcut projection, no stochastic depth
+        or output dropout in effect."""
+        return (getattr(self.norm_1, "supports_planar", False) and getattr(self.norm_2, "supports_planar", False)
+                and self.ffn_shortcut is None and (self.drop_path is None or not self.training)
+                and self.ga.supports_planar and self.ffn.supports_planar
+                and self.irreps_node_input == self.irreps_node_output)
+
+    def forward_planar(self, xs, node_attr, edge_src, edge_dst, edge_attr, edge_scalars, batch, **kwargs):
+        """``forward`` on planar node blocks -> planar node blocks: the features never pass through the e3nn layout
+        (saves the layout copies at every sub-layer boundary, ~24 small launches per block and step)."""
+        f = self.ga.forward_planar(self.norm_1.planar(xs), node_attr, edge_src, edge_dst, edge_attr, edge_scalars, batch,
+                                   **kwargs)
+        xs = [a + b for a, b in zip(xs, f)]
+        f = self.ffn.forward_planar(self.norm_2.planar(xs), node_attr)
+        return [a + b for a, b in zip(xs, f)]
 
 
 class NodeEmbeddingNetwork(torch.nn.Module):
@@ -654,9 +689,8 @@ class GraphAttentionTransformer(torch.nn.Module):
         node_features = atom_embedding + edge_degree_embedding
         node_attr = torch.ones_like(node_features.narrow(1, 0, 1))
         node_attr._eqf_all_ones = True          # lets the node-level FCTPs skip the multiply by the constant 1
-        for blk in self.blocks:
-            node_features = blk(node_input=node_features, node_attr=node_attr, edge_src=edge_src, edge_dst=edge_dst,
-                                edge_attr=edge_sh, edge_scalars=edge_length_embedding, batch=batch, graph=graph)
+        node_features = _run_blocks(self.blocks, node_features, self.irreps_node_embedding, node_attr, edge_src, edge_dst,
+                                    edge_sh, edge_length_embedding, batch, graph)
         node_features = self.norm(node_features, batch=batch)
         if self.out_dropout is not None:
             node_features = self.out_dropout(node_features)
@@ -665,6 +699,23 @@ class GraphAttentionTransformer(torch.nn.Module):
         if self.scale is not None:
             outputs = self.scale * outputs
         return outputs
+
+
+def _run_blocks(blocks, node_features, irreps, node_attr, edge_src, edge_dst, edge_sh, edge_scalars, batch, graph):
+    """The transformer blocks; consecutive blocks that support it keep the node features in planar blocks."""
+    planar = None
+    for blk in blocks:
+        kw = dict(node_attr=node_attr, edge_src=edge_src, edge_dst=edge_dst, edge_attr=edge_sh, edge_scalars=edge_scalars,
+                  batch=batch, graph=graph)
+        if getattr(blk, "supports_planar", False) and ops.fused_ok(node_features if planar is None else planar[0]):
+            if planar is None:
+                planar = ops.to_planar(node_features, Irreps(irreps))
+            planar = blk.forward_planar(planar, **kw)
+        else:
+            if planar is not None:
+                node_features, planar = ops.from_planar(planar), None
+            node_features = blk(node_input=node_features, **kw)
+    return ops.from_planar(planar) if planar is not None else node_features
 
 
 def _qm9(irreps_in, radius, num_basis, atomref, task_mean, task_std, **over):

@@ -14,7 +14,7 @@ from .drop import EquivariantDropout
 from .expnorm_rbf import ExpNormalSmearing
 from .fast_activation import Activation
 from .gaussian_rbf import GaussianRadialBasisLayer
-from .graph_attention_transformer import (EdgeDegreeEmbeddingNetwork, GraphAttention, NodeEmbeddingNetwork,
+from .graph_attention_transformer import (_run_blocks, EdgeDegreeEmbeddingNetwork, GraphAttention, NodeEmbeddingNetwork,
                                           ScaledScatter, TransBlock, get_norm_layer)
 from .layer_norm import EquivariantLayerNormV2
 from .registry import register_model
@@ -129,9 +129,8 @@ class GraphAttentionTransformerMD17(torch.nn.Module):
         node_features = atom_embedding + edge_degree_embedding
         node_attr = torch.ones_like(node_features.narrow(1, 0, 1))
         node_attr._eqf_all_ones = True
-        for blk in self.blocks:
-            node_features = blk(node_input=node_features, node_attr=node_attr, edge_src=edge_src, edge_dst=edge_dst,
-                                edge_attr=edge_sh, edge_scalars=edge_length_embedding, batch=batch, graph=graph)
+        node_features = _run_blocks(self.blocks, node_features, self.irreps_node_embedding, node_attr, edge_src, edge_dst,
+                                    edge_sh, edge_length_embedding, batch, graph)
         node_features = self.norm(node_features, batch=batch)
         if self.out_dropout is not None:
             node_features = self.out_dropout(node_features)

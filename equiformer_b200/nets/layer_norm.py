@@ -38,6 +38,16 @@ class EquivariantLayerNormV2(nn.Module):
     def __repr__(self) -> str:
         return f"{self.__class__.__name__}({self.irreps}, eps={self.eps})"
 
+    @property
+    def supports_planar(self) -> bool:
+        return self._layout is not None
+
+    def planar(self, xs):
+        """The same normalisation on planar blocks (one ``[N, 2l+1, mul]`` tensor per irreps entry)."""
+        if self._layout is None:
+            raise NotImplementedError("planar LayerNorm needs the affine 'component' configuration")
+        return ops.equivariant_layer_norm_planar(self._layout, xs, self.affine_weight, self.affine_bias)
+
     def forward(self, node_input, **kwargs):
         x = node_input.float() if node_input.dtype in (torch.float16, torch.bfloat16) else node_input
         if x.shape[-1] != self.irreps.dim:

@@ -1297,6 +1297,72 @@ def equivariant_layer_norm(lay: NormLayout, x, w, b):
     return eln_torch(lay, x, w, b)
 
 
+def _planar_dims(lay: NormLayout):
+    return tuple((m, d) for m, d, _ in lay.entries)
+
+
+def eln_planar_torch(lay: NormLayout, xs, w, b):
+    """Torch statement of the planar LayerNorm: through the e3nn-layout one (higher-order path, CPU stand-in)."""
+    dims = _planar_dims(lay)
+    return list(_to_planar_impl(eln_torch(lay, _from_planar_impl(xs), w, b), dims))
+
+
+def eln_planar_fwd_raw(lay: NormLayout, xs, w, b):
+    xs = [_require_cuda(x, "eln block").contiguous() for x in xs]
+    N = xs[0].shape[0]
+    ys = [torch.empty_like(x) for x in xs]
+    rstd = torch.empty((N, len(lay.entries)), device=xs[0].device, dtype=torch.float32)
+    with torch.cuda.device(xs[0].device), _kernel("eln_fwd", 8 * sum(x.numel() for x in xs)):
+        rc = _lib.load().eqf_eln_fwd_planar(ctypes.byref(lay.c), _ptr_array(xs), w.data_ptr(), b.data_ptr(), N,
+                                            _ptr_array(ys), rstd.data_ptr(), _stream())
+    _lib.check(rc, "eqf_eln_fwd_planar")
+    return ys, rstd
+
+
+def eln_planar_bwd_raw(lay: NormLayout, xs, w, rstd, gys):
+    gys = [_require_cuda(g, "eln gy block").contiguous() for g in gys]
+    N = xs[0].shape[0]
+    rows = _lib.load().eqf_eln_rows(N)
+    gxs = [torch.empty_like(x) for x in xs]
+    part = torch.empty((rows, lay.n_w + lay.n_b), device=xs[0].device, dtype=torch.float32)
+    with torch.cuda.device(xs[0].device), _kernel("eln_bwd", 12 * sum(x.numel() for x in xs)):
+        rc = _lib.load().eqf_eln_bwd_planar(ctypes.byref(lay.c), _ptr_array(xs), w.data_ptr(), rstd.data_ptr(),
+                                            _ptr_array(gys), N, _ptr_array(gxs), part.data_ptr(), _stream())
+    _lib.check(rc, "eqf_eln_bwd_planar")
+    sums = colsum_raw(part)
+    return gxs, sums[:lay.n_w], sums[lay.n_w:]
+
+
+class EquivLayerNormPlanar(torch.autograd.Function):
+    """``EquivariantLayerNormV2`` on planar blocks (one packed ``[N, 2l+1, mul]`` tensor per entry) - the transformer
+    blocks keep the node features in the layout the GEMM and tensor-product kernels read.  apply(lay, w, b, *xs)."""
+
+    @staticmethod
+    def forward(ctx, lay: NormLayout, w, b, *xs):
+        xs = [x.contiguous() for x in xs]
+        ys, rstd = eln_planar_fwd_raw(lay, xs, w, b)
+        ctx.lay = lay
+        ctx.save_for_backward(w, b, rstd, *xs)
+        return tuple(ys)
+
+    @staticmethod
+    def backward(ctx, *gys):
+        w, b, rstd, *xs = ctx.saved_tensors
+        gys = [g if g is not None else torch.zeros_like(x) for g, x in zip(gys, xs)]
+        if torch.is_grad_enabled():
+            fn = lambda ww, bb, *blocks: tuple(eln_planar_torch(ctx.lay, list(blocks), ww, bb))
+            grads = _higher_order_grads(fn, (w, b, *xs), gys)
+            return (None, *grads)
+        gxs, gw, gb = eln_planar_bwd_raw(ctx.lay, xs, w, rstd, gys)
+        return (None, gw, gb, *gxs)
+
+
+def equivariant_layer_norm_planar(lay: NormLayout, xs, w, b):
+    if fused_ok(xs[0]) and xs[0].shape[0] > 0:
+        return list(EquivLayerNormPlanar.apply(lay, w, b, *xs))
+    return eln_planar_torch(lay, list(xs), w, b)
+
+
 class GateLayout:
     """Static description of the fused gate + logits op (see ``eqf_gate_logits_fwd`` in include/eqf_b200.h)."""
 

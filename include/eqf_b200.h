@@ -189,6 +189,12 @@ int eqf_eln_fwd(const EqfNormLayout* lay, const float* x, const float* w, const 
 int eqf_eln_bwd(const EqfNormLayout* lay, const float* x, const float* w, const float* rstd, const float* gy,
                 int64_t N, float* gx, float* part, void* stream);
 
+/* the same on planar node features: entry t is a packed [N, d_t, mul_t] buffer (host arrays of device pointers) */
+int eqf_eln_fwd_planar(const EqfNormLayout* lay, const float* const* x_blocks, const float* w, const float* b, int64_t N,
+                       float* const* y_blocks, float* rstd, void* stream);
+int eqf_eln_bwd_planar(const EqfNormLayout* lay, const float* const* x_blocks, const float* w, const float* rstd,
+                       const float* const* gy_blocks, int64_t N, float* const* gx_blocks, float* part, void* stream);
+
 /* Gate + attention logits of GraphAttention.forward (graph_attention_transformer.py:492-495, 506-507) in one pass:
  *   t0[e] = [alpha | scalars | gates] pre-activations (+ optional bias), gated[b] planar blocks [E, d, C];
  *   z[e,h] = sum_k c_slr * SmoothLeakyReLU(alpha[e,h,k]) * alpha_dot[h,k];  v0 = c_silu * silu(scalars);

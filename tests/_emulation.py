@@ -162,6 +162,18 @@ def eln_bwd_raw(lay, x, w, rstd, gy):
     return gx, gw, gb if gb is not None else torch.zeros(lay.n_b)
 
 
+def eln_planar_fwd_raw(lay, xs, w, b):
+    return ops.eln_planar_torch(lay, list(xs), w, b), torch.zeros(xs[0].shape[0], len(lay.entries))
+
+
+def eln_planar_bwd_raw(lay, xs, w, rstd, gys):
+    ins = [t.detach().requires_grad_(True) for t in (w, b_like(lay, xs[0]), *xs)]
+    with torch.enable_grad():
+        ys = ops.eln_planar_torch(lay, ins[2:], ins[0], ins[1])
+    g = torch.autograd.grad(ys, ins, list(gys), allow_unused=True)
+    return list(g[2:]), g[0], (g[1] if g[1] is not None else torch.zeros(lay.n_b))
+
+
 def b_like(lay, x):
     return torch.zeros(lay.n_b, dtype=x.dtype)
 
@@ -190,7 +202,7 @@ def gate_logits_bwd_raw(lay, t0, bias, alpha_dot, gated, gz, gv0, gvout):
     return grads[0], list(grads[2:]), (grads[1].reshape(-1) if lay.n_alpha > 0 else None)
 
 
-_PATCHED = ["colsum_raw", "eln_fwd_raw", "eln_bwd_raw", "ln_silu_fwd_raw", "ln_silu_bwd_raw", "gate_logits_fwd_raw", "gate_logits_bwd_raw", "gemm_raw", "dtp_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
+_PATCHED = ["colsum_raw", "eln_fwd_raw", "eln_bwd_raw", "eln_planar_fwd_raw", "eln_planar_bwd_raw", "ln_silu_fwd_raw", "ln_silu_bwd_raw", "gate_logits_fwd_raw", "gate_logits_bwd_raw", "gemm_raw", "dtp_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
             "seg_softmax_raw", "attn_aggregate_raw", "attn_edge_dot_raw", "attn_edge_scale_raw"]
 
 

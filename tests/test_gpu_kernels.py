@@ -411,6 +411,29 @@ def test_equivariant_layer_norm_fused(cuda_device, entries, N):
     assert rel_err(ax, rx) < 5e-5 and rel_err(aw, rw) < 5e-5 and rel_err(ab, rb) < 5e-5
 
 
+@pytest.mark.parametrize("entries", [[(128, 1, True), (64, 3, False), (32, 5, False)], [(8, 1, True), (8, 1, False), (5, 3, False)]])
+@pytest.mark.parametrize("N", [1, 2324])
+def test_equivariant_layer_norm_planar(cuda_device, entries, N):
+    """The planar variant (one packed [N, 2l+1, mul] block per entry) agrees with the e3nn-layout statement in fp64."""
+    from equiformer_b200 import ops
+    lay = ops.NormLayout(entries, 1e-5)
+    g = torch.Generator().manual_seed(N + len(entries))
+    xs = [torch.randn(N, d, m, generator=g) * 1.5 + 0.2 for m, d, _ in entries]
+    gys = [torch.randn(N, d, m, generator=g) for m, d, _ in entries]
+    w, b = torch.randn(lay.n_w, generator=g), torch.randn(lay.n_b, generator=g)
+    d_ = lambda t: t.to(cuda_device)
+    leaves64 = [t.double().requires_grad_(True) for t in (w, b, *xs)]
+    ref = ops.eln_planar_torch(lay, leaves64[2:], leaves64[0], leaves64[1])
+    rgrads = torch.autograd.grad(ref, leaves64, [t.double() for t in gys])
+    leaves = [d_(t).requires_grad_(True) for t in (w, b, *xs)]
+    out = ops.equivariant_layer_norm_planar(lay, leaves[2:], leaves[0], leaves[1])
+    for a, r in zip(out, ref):
+        assert rel_err(a, r) < TOL
+    grads = torch.autograd.grad(out, leaves, [d_(t) for t in gys])
+    for a, r in zip(grads, rgrads):
+        assert rel_err(a, r) < 5e-5
+
+
 @pytest.mark.parametrize("cfg", [dict(A0=128, S=128, H=4, ds=(3, 5), Cs=(64, 32)), dict(A0=256, S=256, H=8, ds=(3,), Cs=(128,)),
                                  dict(A0=128, S=128, H=4, ds=(3, 5, 7), Cs=(64, 64, 32)),
                                  dict(A0=16, S=16, H=4, ds=(3, 5), Cs=(8, 4)),       # tiny heads: one lane per head
