@@ -448,6 +448,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   if (warp == kProducerWarp) {
     if (lane == 0) {
       uint32_t it = 0;
+      int n_stamp = 0;
       const uint32_t tx = (uint32_t)(S::kABytes + 2 * p.n_tile * kRowBytesT);
       for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
         const long long mb = tile / p.n_blocks;
@@ -456,6 +457,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
+          stamp(p, 0, n_stamp);
           uint8_t* st = stage_base + (size_t)s * S::kStageBytes;
           mbar_expect_tx(&full[s], tx);
           tma_load_2d(st, &map_a, (int)(kt * BKT), (int)(mb * BM), &full[s]);
@@ -468,6 +470,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     if (lane == 0) {
       const uint32_t idesc = instr_desc(p.n_tile);
       uint32_t it = 0, acc_it = 0;
+      int n_stamp = 0;
       for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
         const int a = acc_it & 1;
         const uint32_t aph = (acc_it >> 1) & 1;
@@ -478,7 +481,9 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&full[s], ph);          // the weight tiles (and the raw A tile) have landed
+          stamp(p, 1, n_stamp);
           mbar_wait(&a_ready[s], ph);       // A hi / lo are in TMEM
+          stamp(p, 1, n_stamp);
           tc_fence_after();
           const uint32_t st = smem_u32(stage_base + (size_t)s * S::kStageBytes);
           const uint64_t b_hi = smem_desc_sw128(st + S::kABytes), b_lo = smem_desc_sw128(st + S::kABytes + S::kBBytes);
@@ -492,6 +497,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             umma_tf32_ts(d_tmem, a_hi + acol, b_hi + adv, idesc, 1u);
           }
           umma_commit(&empty[s]);
+          stamp(p, 1, n_stamp);
         }
         umma_commit(&tmem_full[a]);
       }
@@ -502,11 +508,14 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t it = 0;
+    int n_stamp = 0;
+    const bool stamper = (threadIdx.x == kTransformWarp0 * 32);
     for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
       for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(&full[s], ph);
+        if (stamper) stamp(p, 2, n_stamp);
         const uint32_t rbase = smem_u32(stage_base + (size_t)s * S::kStageBytes) + (uint32_t)row * (uint32_t)kRowBytesT;
         float hi[BKT], lo[BKT];
         float4 v[8];
@@ -528,16 +537,19 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready[s]);
+        if (stamper) stamp(p, 2, n_stamp);
       }
     }
   } else {
     uint32_t acc_it = 0, chunk_it = 0;
+    int n_stamp = 0;
     for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
       const long long mb = tile / p.n_blocks;
       const int nb = (int)(tile % p.n_blocks);
       const int a = acc_it & 1;
       const uint32_t aph = (acc_it >> 1) & 1;
       mbar_wait(&tmem_full[a], aph);
+      if (threadIdx.x == 0) stamp(p, 3, n_stamp);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * BN);
       const int row0 = (int)(mb * BM) + warp * 32;
@@ -575,6 +587,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[a]);
+      if (threadIdx.x == 0) stamp(p, 3, n_stamp);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
