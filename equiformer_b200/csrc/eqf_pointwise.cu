@@ -381,11 +381,13 @@ __global__ void __launch_bounds__(256) gate_logits_bwd_vec_kernel(GateArgs a) {
 }
 
 static bool gate_vec_ok(const GateArgs& a) {
-  if (a.A0 % 4 || a.S % 4 || (a.A0 / a.H) % 4) return false;
+  if (a.S % 4) return false;
+  for (int b = 0; b < a.n_gated; ++b) if (a.C[b] % 4) return false;
+  if (a.A0 == 0) return true;                           // gate-only use (FFN): the logits loops do not run at all
+  if (a.A0 % 4 || (a.A0 / a.H) % 4) return false;
   const int lph = a.A0 / a.H / 4;
   if (lph < 1 || lph > 32 || (lph & (lph - 1))) return false;
   if (lph > 1 && (a.A0 / 4) % 32 != 0) return false;   // head sums use full-warp shuffles: every lane must take part
-  for (int b = 0; b < a.n_gated; ++b) if (a.C[b] % 4) return false;
   return true;
 }
 

@@ -463,3 +463,27 @@ def test_gate_logits_fused(cuda_device, cfg):
     assert rel_err(gdot.view_as(ad), rg[2]) < 5e-5
     for a, b in zip(ggated, rg[3:]):
         assert rel_err(a, b) < 5e-5
+
+
+@pytest.mark.parametrize("cfg", [dict(S=384, ds=(3, 5), Cs=(192, 96)), dict(S=20, ds=(3,), Cs=(6,))])   # vec / scalar kernels
+def test_gate_only_fused(cuda_device, cfg):
+    """Gate-only use of the fused kernel (FFN: bias + SiLU on scalars + sigmoid gates on the rest, ref :128-154)."""
+    from equiformer_b200 import ops
+    lay = ops.GateLayout(0, cfg["S"], 1, cfg["ds"], cfg["Cs"], 1.6791767923989418, 1.8467055342154763, 1.0, 0.2)
+    N = 2324
+    g = torch.Generator().manual_seed(2)
+    t0 = torch.randn(N, lay.width, generator=g)
+    bias = torch.randn(lay.width, generator=g) * 0.3
+    gated = [torch.randn(N, d_, c, generator=g) for d_, c in zip(cfg["ds"], cfg["Cs"])]
+    gouts = [torch.randn(N, cfg["S"], generator=g)] + [torch.randn_like(t) for t in gated]
+    d = lambda t: t.to(cuda_device)
+    leaves = [d(t).requires_grad_(True) for t in (t0, bias, *gated)]
+    outs = ops.gate_fused(lay, leaves[0], leaves[1], leaves[2:])
+    ins = [t.double().requires_grad_(True) for t in (t0, bias, *gated)]
+    _z, *ref = ops.gate_logits_torch(lay, ins[0], ins[1], None, *ins[2:])
+    for a, b in zip(outs, ref):
+        assert rel_err(a, b) < TOL
+    grads = torch.autograd.grad(outs, leaves, [d(t) for t in gouts])
+    rgrads = torch.autograd.grad(ref, ins, [t.double() for t in gouts])
+    for a, b in zip(grads, rgrads):
+        assert rel_err(a, b) < 5e-5
