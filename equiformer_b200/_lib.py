@@ -123,7 +123,7 @@ SIGNATURES = {
                                                    c_void_p]),
     "eqf_colsum_scratch_floats": (c_int64, [c_int64, c_int64]),
     "eqf_colsum": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "eqf_eln_rows": (c_int32, [c_int64]),
+    "eqf_eln_rows": (c_int32, [POINTER(EqfNormLayout), c_int64]),
     "eqf_eln_fwd": (c_int32, [POINTER(EqfNormLayout), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "eqf_eln_bwd": (c_int32, [POINTER(EqfNormLayout), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                               c_void_p]),

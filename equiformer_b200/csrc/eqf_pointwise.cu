@@ -126,6 +126,88 @@ __global__ void __launch_bounds__(256) ln_silu_bwd_kernel(const float* __restric
   }
 }
 
+// C == 64 (the radial MLP): half a warp per row, one float4 per lane - two rows in flight per warp, a quarter of the
+// memory instructions and 4-step reductions; the generic kernels above spent 18-23 us per call on latency.
+__device__ __forceinline__ float hsum16(float v) {
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256) ln_silu_fwd64_kernel(const float* __restrict__ x, const float* __restrict__ bias,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            float eps, long long R, float* __restrict__ y,
+                                                            float* __restrict__ mean, float* __restrict__ rstd) {
+  const int lane = threadIdx.x & 31, sub = lane & 15;
+  const long long pair = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_pairs = (long long)gridDim.x * 8;
+  const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + sub), b4 = __ldg(reinterpret_cast<const float4*>(beta) + sub);
+  const float4 p4 = bias ? __ldg(reinterpret_cast<const float4*>(bias) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long r = pair * 2 + (lane >> 4); r < R + (lane >> 4); r += n_pairs * 2) {   // both halves iterate together
+    const bool ok = r < R;
+    float4 v = ok ? __ldg(reinterpret_cast<const float4*>(x + r * 64) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x += p4.x; v.y += p4.y; v.z += p4.z; v.w += p4.w;
+    const float m = hsum16(v.x + v.y + v.z + v.w) * (1.f / 64.f);
+    const float dx = v.x - m, dy = v.y - m, dz = v.z - m, dw = v.w - m;
+    const float rs = rsqrtf(hsum16(dx * dx + dy * dy + dz * dz + dw * dw) * (1.f / 64.f) + eps);
+    if (ok) {
+      const float zx = dx * rs * g4.x + b4.x, zy = dy * rs * g4.y + b4.y, zz = dz * rs * g4.z + b4.z, zw = dw * rs * g4.w + b4.w;
+      reinterpret_cast<float4*>(y + r * 64)[sub] = make_float4(zx * sigmoidf_(zx), zy * sigmoidf_(zy), zz * sigmoidf_(zz), zw * sigmoidf_(zw));
+      if (sub == 0) { mean[r] = m; rstd[r] = rs; }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) ln_silu_bwd64_kernel(const float* __restrict__ x, const float* __restrict__ bias,
+                                                            const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                            const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                            const float* __restrict__ gy, long long R, float* __restrict__ gx,
+                                                            float* __restrict__ part) {
+  __shared__ float sacc[3 * 64];
+  for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, sub = lane & 15;
+  const long long pair = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_pairs = (long long)gridDim.x * 8;
+  const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma) + sub), b4 = __ldg(reinterpret_cast<const float4*>(beta) + sub);
+  const float4 p4 = bias ? __ldg(reinterpret_cast<const float4*>(bias) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f}, ax[4] = {0.f, 0.f, 0.f, 0.f};
+  for (long long r = pair * 2 + (lane >> 4); r < R + (lane >> 4); r += n_pairs * 2) {
+    const bool ok = r < R;
+    const float m = ok ? __ldg(mean + r) : 0.f, rs = ok ? __ldg(rstd + r) : 0.f;
+    const float4 xv = ok ? __ldg(reinterpret_cast<const float4*>(x + r * 64) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 gv = ok ? __ldg(reinterpret_cast<const float4*>(gy + r * 64) + sub) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float xs[4] = {xv.x + p4.x, xv.y + p4.y, xv.z + p4.z, xv.w + p4.w};
+    const float gs[4] = {gv.x, gv.y, gv.z, gv.w};
+    const float gm[4] = {g4.x, g4.y, g4.z, g4.w}, bt[4] = {b4.x, b4.y, b4.z, b4.w};
+    float xh[4], gz[4], s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      xh[q] = (xs[q] - m) * rs;
+      const float z = xh[q] * gm[q] + bt[q];
+      const float sg_ = sigmoidf_(z);
+      const float dz = gs[q] * (sg_ * (1.f + z * (1.f - sg_)));
+      ag[q] += dz * xh[q];
+      ab[q] += dz;
+      gz[q] = dz * gm[q];
+      s1 += gz[q];
+      s2 += gz[q] * xh[q];
+    }
+    s1 = hsum16(s1) * (1.f / 64.f);
+    s2 = hsum16(s2) * (1.f / 64.f);
+    float o[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { o[q] = rs * (gz[q] - s1 - xh[q] * s2); ax[q] += o[q]; }
+    if (ok) reinterpret_cast<float4*>(gx + r * 64)[sub] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    atomicAdd(&sacc[4 * sub + q], ag[q]);
+    atomicAdd(&sacc[64 + 4 * sub + q], ab[q]);
+    atomicAdd(&sacc[128 + 4 * sub + q], ax[q]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) part[(long long)blockIdx.x * 192 + i] = sacc[i];
+}
+
 // ------------------------------------------------------------------------------------------------ gate + logits
 // Inputs (planar): t0 [E, A0 + S + Gt]  = [alpha pre-activations | scalars | gates]   (biases already added)
 //                  gated blocks g_b [E, d_b, C_b] (b < n_gated), sum_b C_b == Gt, gates consumed in block order
@@ -521,8 +603,11 @@ __device__ __forceinline__ int eln_chan(const ELNArgs& a, int t, int i) { return
 __global__ void __launch_bounds__(256) eln_fwd_kernel(ELNArgs a) {
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 8;
-  for (long long r = warp; r < a.N; r += n_warps) {
-    for (int t = 0; t < a.n_entries; ++t) {
+  // one warp per (row, irreps entry): three times the parallelism of a warp per row on these latency-bound node tensors
+  for (long long task = warp; task < a.N * a.n_entries; task += n_warps) {
+    const long long r = task / a.n_entries;
+    {
+      const int t = (int)(task - r * a.n_entries);
       const int mul = a.mul[t], d = a.d[t], n = mul * d;
       const float* xe = eln_in(a, a.x, a.xp, r, t);
       float* ye = eln_out(a, a.y, a.yp, r, t);
@@ -552,8 +637,10 @@ __global__ void __launch_bounds__(256) eln_bwd_kernel(ELNArgs a) {
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 8;
-  for (long long r = warp; r < a.N; r += n_warps) {
-    for (int t = 0; t < a.n_entries; ++t) {
+  for (long long task = warp; task < a.N * a.n_entries; task += n_warps) {
+    const long long r = task / a.n_entries;
+    {
+      const int t = (int)(task - r * a.n_entries);
       const int mul = a.mul[t], d = a.d[t], n = mul * d;
       const float* xe = eln_in(a, a.x, a.xp, r, t);
       const float* ge = eln_in(a, a.gy, a.gyp, r, t);
@@ -595,9 +682,9 @@ __global__ void __launch_bounds__(256) eln_bwd_kernel(ELNArgs a) {
   for (int i = threadIdx.x; i < a.n_w + a.n_b; i += blockDim.x) a.dw_part[(long long)blockIdx.x * (a.n_w + a.n_b) + i] = sacc[i];
 }
 
-static int eln_grid(long long rows) {
-  long long blocks = (rows + 7) / 8;
-  if (blocks > 148LL * 2) blocks = 148LL * 2;
+static int eln_grid(long long rows, int n_entries = 1) {
+  long long blocks = (rows * n_entries + 7) / 8;
+  if (blocks > 148LL * 4) blocks = 148LL * 4;
   return (int)(blocks < 1 ? 1 : blocks);
 }
 
@@ -636,7 +723,9 @@ extern "C" int eqf_ln_silu_fwd(const float* x, const float* bias, const float* g
   if (!x || !gamma || !beta || !y || !mean || !rstd) { set_error("eqf_ln_silu_fwd: null pointer"); return EQF_ERR_INVALID; }
   if (C < 1 || C > 32 * kMaxPerLane) { set_error("eqf_ln_silu: C must be in 1..256"); return EQF_ERR_UNSUPPORTED; }
   cudaStream_t st = (cudaStream_t)stream;
-  if (C <= 64) ln_silu_fwd_kernel<2><<<pointwise_grid(R), 256, 0, st>>>(x, bias, gamma, beta, eps, R, C, y, mean, rstd);
+  const bool al16 = ((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)bias) & 15) == 0);
+  if (C == 64 && al16) ln_silu_fwd64_kernel<<<pointwise_grid((R + 1) / 2), 256, 0, st>>>(x, bias, gamma, beta, eps, R, y, mean, rstd);
+  else if (C <= 64) ln_silu_fwd_kernel<2><<<pointwise_grid(R), 256, 0, st>>>(x, bias, gamma, beta, eps, R, C, y, mean, rstd);
   else if (C <= 128) ln_silu_fwd_kernel<4><<<pointwise_grid(R), 256, 0, st>>>(x, bias, gamma, beta, eps, R, C, y, mean, rstd);
   else ln_silu_fwd_kernel<8><<<pointwise_grid(R), 256, 0, st>>>(x, bias, gamma, beta, eps, R, C, y, mean, rstd);
   return check_cuda(cudaGetLastError(), "ln_silu_fwd_kernel launch");
@@ -651,7 +740,10 @@ extern "C" int eqf_ln_silu_bwd(const float* x, const float* bias, const float* g
   }
   if (C < 1 || C > 32 * kMaxPerLane) { set_error("eqf_ln_silu: C must be in 1..256"); return EQF_ERR_UNSUPPORTED; }
   cudaStream_t st = (cudaStream_t)stream;
-  if (C <= 64) ln_silu_bwd_kernel<2><<<pointwise_grid(R), 256, 0, st>>>(x, bias, gamma, beta, mean, rstd, gy, R, C, gx, part);
+  const bool al16 = ((((uintptr_t)x | (uintptr_t)gx | (uintptr_t)gy | (uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)bias) & 15) == 0);
+  // NB: the partial buffer always has eqf_pointwise_rows(R) rows; the 64-wide kernel launches that many CTAs as well
+  if (C == 64 && al16) ln_silu_bwd64_kernel<<<pointwise_grid(R), 256, 0, st>>>(x, bias, gamma, beta, mean, rstd, gy, R, gx, part);
+  else if (C <= 64) ln_silu_bwd_kernel<2><<<pointwise_grid(R), 256, 0, st>>>(x, bias, gamma, beta, mean, rstd, gy, R, C, gx, part);
   else if (C <= 128) ln_silu_bwd_kernel<4><<<pointwise_grid(R), 256, 0, st>>>(x, bias, gamma, beta, mean, rstd, gy, R, C, gx, part);
   else ln_silu_bwd_kernel<8><<<pointwise_grid(R), 256, 0, st>>>(x, bias, gamma, beta, mean, rstd, gy, R, C, gx, part);
   return check_cuda(cudaGetLastError(), "ln_silu_bwd_kernel launch");
@@ -705,7 +797,7 @@ extern "C" int eqf_gate_logits_bwd(const EqfGateLayout* lay, const float* t0, co
 }
 
 
-extern "C" int eqf_eln_rows(int64_t rows) { return eln_grid(rows); }
+extern "C" int eqf_eln_rows(const EqfNormLayout* lay, int64_t rows) { return eln_grid(rows, lay ? lay->n_entries : 1); }
 
 extern "C" int eqf_eln_fwd(const EqfNormLayout* lay, const float* x, const float* w, const float* b, int64_t N, float* y,
                            float* rstd, void* stream) {
@@ -714,7 +806,7 @@ extern "C" int eqf_eln_fwd(const EqfNormLayout* lay, const float* x, const float
   if (rc != EQF_OK || N == 0) return rc;
   if (!x || !w || !y || !rstd || (a.n_b > 0 && !b)) { set_error("eqf_eln_fwd: null pointer"); return EQF_ERR_INVALID; }
   a.x = x; a.w = w; a.b = b; a.y = y; a.rstd = rstd; a.N = N;
-  eln_fwd_kernel<<<eln_grid(N), 256, 0, (cudaStream_t)stream>>>(a);
+  eln_fwd_kernel<<<eln_grid(N, a.n_entries), 256, 0, (cudaStream_t)stream>>>(a);
   return check_cuda(cudaGetLastError(), "eln_fwd_kernel launch");
 }
 
@@ -725,7 +817,7 @@ extern "C" int eqf_eln_bwd(const EqfNormLayout* lay, const float* x, const float
   if (rc != EQF_OK || N == 0) return rc;
   if (!x || !w || !rstd || !gy || !gx || !part) { set_error("eqf_eln_bwd: null pointer"); return EQF_ERR_INVALID; }
   a.x = x; a.w = w; a.b = nullptr; a.rstd = const_cast<float*>(rstd); a.gy = gy; a.gx = gx; a.dw_part = part; a.db_part = nullptr; a.N = N;
-  eln_bwd_kernel<<<eln_grid(N), 256, (a.n_w + a.n_b) * sizeof(float), (cudaStream_t)stream>>>(a);
+  eln_bwd_kernel<<<eln_grid(N, a.n_entries), 256, (a.n_w + a.n_b) * sizeof(float), (cudaStream_t)stream>>>(a);
   return check_cuda(cudaGetLastError(), "eln_bwd_kernel launch");
 }
 
@@ -772,7 +864,7 @@ extern "C" int eqf_eln_fwd_planar(const EqfNormLayout* lay, const float* const* 
     if (!x_blocks[t] || !y_blocks[t]) { set_error("eqf_eln_fwd_planar: null block"); return EQF_ERR_INVALID; }
     a.xp[t] = x_blocks[t]; a.yp[t] = y_blocks[t];
   }
-  eln_fwd_kernel<<<eln_grid(N), 256, 0, (cudaStream_t)stream>>>(a);
+  eln_fwd_kernel<<<eln_grid(N, a.n_entries), 256, 0, (cudaStream_t)stream>>>(a);
   return check_cuda(cudaGetLastError(), "eln_fwd_kernel (planar) launch");
 }
 
@@ -789,6 +881,6 @@ extern "C" int eqf_eln_bwd_planar(const EqfNormLayout* lay, const float* const* 
     if (!x_blocks[t] || !gy_blocks[t] || !gx_blocks[t]) { set_error("eqf_eln_bwd_planar: null block"); return EQF_ERR_INVALID; }
     a.xp[t] = x_blocks[t]; a.gyp[t] = gy_blocks[t]; a.gxp[t] = gx_blocks[t];
   }
-  eln_bwd_kernel<<<eln_grid(N), 256, (a.n_w + a.n_b) * sizeof(float), (cudaStream_t)stream>>>(a);
+  eln_bwd_kernel<<<eln_grid(N, a.n_entries), 256, (a.n_w + a.n_b) * sizeof(float), (cudaStream_t)stream>>>(a);
   return check_cuda(cudaGetLastError(), "eln_bwd_kernel (planar) launch");
 }

@@ -1260,7 +1260,7 @@ def eln_fwd_raw(lay: NormLayout, x, w, b):
 def eln_bwd_raw(lay: NormLayout, x, w, rstd, gy):
     gy = _require_cuda(gy, "eln gy")
     N = x.shape[0]
-    rows = _lib.load().eqf_eln_rows(N)
+    rows = _lib.load().eqf_eln_rows(ctypes.byref(lay.c), N)
     gx = torch.empty_like(x)
     part = torch.empty((rows, lay.n_w + lay.n_b), device=x.device, dtype=torch.float32)
     with torch.cuda.device(x.device), _kernel("eln_bwd", 12 * x.numel()):
@@ -1322,7 +1322,7 @@ def eln_planar_fwd_raw(lay: NormLayout, xs, w, b):
 def eln_planar_bwd_raw(lay: NormLayout, xs, w, rstd, gys):
     gys = [_require_cuda(g, "eln gy block").contiguous() for g in gys]
     N = xs[0].shape[0]
-    rows = _lib.load().eqf_eln_rows(N)
+    rows = _lib.load().eqf_eln_rows(ctypes.byref(lay.c), N)
     gxs = [torch.empty_like(x) for x in xs]
     part = torch.empty((rows, lay.n_w + lay.n_b), device=xs[0].device, dtype=torch.float32)
     with torch.cuda.device(xs[0].device), _kernel("eln_bwd", 12 * sum(x.numel() for x in xs)):

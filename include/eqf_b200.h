@@ -183,7 +183,7 @@ typedef struct {
   int32_t is_scalar[EQF_MAX_BLOCKS];   /* 0e entries: mean-centred, carry the affine bias */
   float eps;
 } EqfNormLayout;
-int eqf_eln_rows(int64_t rows);
+int eqf_eln_rows(const EqfNormLayout* lay, int64_t rows);   /* CTAs of a backward launch = rows of `part` */
 int eqf_eln_fwd(const EqfNormLayout* lay, const float* x, const float* w, const float* b, int64_t N, float* y,
                 float* rstd, void* stream);
 int eqf_eln_bwd(const EqfNormLayout* lay, const float* x, const float* w, const float* rstd, const float* gy,
