@@ -128,6 +128,8 @@ struct Params {
   int n_blocks;      // ceil(N / n_tile)
   long long m_blocks;
   long long* dbg;    // optional timeline of CTA 0 (clock64 stamps), see tools/tf32x3_timeline.py
+  int dbg_skip;      // measurement aid (EQF_TF32X3_DBG_SKIP): bit 0 skips the transform math, bit 1 the MMAs - results are
+                     // garbage then; what remains is the load / synchronisation skeleton
 };
 
 // dbg layout: role r in {0 producer, 1 mma, 2 transform, 3 epilogue}: dbg[r * 1024 + n] = n-th stamp of that role
@@ -364,15 +366,21 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
   return (uint64_t)((addr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int BN>
+// STACK (n_tile == BN <= 64): the hi and lo weight tiles are adjacent in shared memory, so ONE MMA with N' = 2 BN
+// computes a_hi*b_hi and a_hi*b_lo side by side (accumulator columns [0, BN) and [BN, 2 BN)), a second one adds a_lo*b_hi
+// to the first half; the epilogue adds the halves.  Two MMAs per k-block instead of three: with outputs this narrow the
+// tensor pipe is bound by the number of MMA instructions, not by their size (skipping the MMAs: 68 -> 44 us on
+// [162 800, 352] -> 32, while skipping the transform only gains 8 us).
+template <int BN, bool STACK>
 struct TSmem {
+  static constexpr int kAccCols = STACK ? 2 * BN : BN;              // TMEM columns per accumulator buffer
   static constexpr int kABytes = BM * kRowBytesT;                   // raw A tile (TMA)
   static constexpr int kBBytes = BN * kRowBytesT;
   static constexpr int kStageBytes = kABytes + 2 * kBBytes;         // A raw | B hi | B lo
   static constexpr int kStoreBytes = kEpilogueWarps * 2 * 32 * kStoreCols * 4;
   static constexpr int kBudget = 227 * 1024 - 1024;
   static constexpr int kStagesSmem = (kBudget - kStoreBytes - 1024) / kStageBytes;
-  static constexpr int kStagesTmem = (512 - 2 * BN) / (2 * BKT);
+  static constexpr int kStagesTmem = (512 - 2 * kAccCols) / (2 * BKT);
   static constexpr int kStagesMin = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
   static constexpr int kStages = kStagesMin > 8 ? 8 : kStagesMin;
   static_assert(kStages >= 2, "tile does not fit");
@@ -396,14 +404,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
         "f"(v[27]), "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31]) : "memory");
 }
 
-template <int BN>
+template <int BN, bool STACK>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                       const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_c, Params p) {
-  using S = TSmem<BN>;
+  using S = TSmem<BN, STACK>;
   constexpr int kStages = S::kStages;
   constexpr int kTmemCols = 512;
-  constexpr int kACol0 = 2 * BN;                       // first TMEM column of the A staging area
+  constexpr int kAcc = S::kAccCols;
+  constexpr int kACol0 = 2 * kAcc;                       // first TMEM column of the A staging area
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
@@ -469,6 +478,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
   } else if (warp == kMmaWarp) {
     if (lane == 0) {
       const uint32_t idesc = instr_desc(p.n_tile);
+      const uint32_t idesc2 = instr_desc(2 * p.n_tile);          // STACK: [b_hi | b_lo] as one operand
       uint32_t it = 0, acc_it = 0;
       int n_stamp = 0;
       for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
@@ -476,7 +486,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const uint32_t aph = (acc_it >> 1) & 1;
         mbar_wait(&tmem_empty[a], aph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * kAcc);
         for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
@@ -490,11 +500,17 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
           const uint32_t a_hi = tmem_base + (uint32_t)(kACol0 + s * 2 * BKT), a_lo = a_hi + BKT;
 #pragma unroll
           for (int kb = 0; kb < BKT / UMMA_K; ++kb) {
+            if (p.dbg_skip & 2) break;
             const uint64_t adv = (uint64_t)((kb * UMMA_K * 4) >> 4);
             const uint32_t acol = (uint32_t)(kb * UMMA_K);
-            umma_tf32_ts(d_tmem, a_lo + acol, b_hi + adv, idesc, (kt > 0 || kb > 0) ? 1u : 0u);
-            umma_tf32_ts(d_tmem, a_hi + acol, b_lo + adv, idesc, 1u);
-            umma_tf32_ts(d_tmem, a_hi + acol, b_hi + adv, idesc, 1u);
+            if constexpr (STACK) {
+              umma_tf32_ts(d_tmem, a_hi + acol, b_hi + adv, idesc2, (kt > 0 || kb > 0) ? 1u : 0u);   // hi*hi | hi*lo
+              umma_tf32_ts(d_tmem, a_lo + acol, b_hi + adv, idesc, 1u);                               // + lo*hi
+            } else {
+              umma_tf32_ts(d_tmem, a_lo + acol, b_hi + adv, idesc, (kt > 0 || kb > 0) ? 1u : 0u);
+              umma_tf32_ts(d_tmem, a_hi + acol, b_lo + adv, idesc, 1u);
+              umma_tf32_ts(d_tmem, a_hi + acol, b_hi + adv, idesc, 1u);
+            }
           }
           umma_commit(&empty[s]);
           stamp(p, 1, n_stamp);
@@ -516,6 +532,12 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(&full[s], ph);
         if (stamper) stamp(p, 2, n_stamp);
+        if (p.dbg_skip & 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_ready[s]);
+          continue;
+        }
         const uint32_t rbase = smem_u32(stage_base + (size_t)s * S::kStageBytes) + (uint32_t)row * (uint32_t)kRowBytesT;
         float hi[BKT], lo[BKT];
         float4 v[8];
@@ -551,7 +573,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       mbar_wait(&tmem_full[a], aph);
       if (threadIdx.x == 0) stamp(p, 3, n_stamp);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kAcc);
       const int row0 = (int)(mb * BM) + warp * 32;
       const int col0 = nb * p.n_tile;
       uint8_t* wbuf = store_base + warp * (2 * 32 * kStoreCols * 4);
@@ -567,9 +589,24 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
               "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
               "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr + (uint32_t)c));
+        uint32_t v2[32];
+        if constexpr (STACK) {     // the hi*lo half of the stacked accumulator
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(v2[0]), "=r"(v2[1]), "=r"(v2[2]), "=r"(v2[3]), "=r"(v2[4]), "=r"(v2[5]), "=r"(v2[6]), "=r"(v2[7]),
+                "=r"(v2[8]), "=r"(v2[9]), "=r"(v2[10]), "=r"(v2[11]), "=r"(v2[12]), "=r"(v2[13]), "=r"(v2[14]), "=r"(v2[15]),
+                "=r"(v2[16]), "=r"(v2[17]), "=r"(v2[18]), "=r"(v2[19]), "=r"(v2[20]), "=r"(v2[21]), "=r"(v2[22]), "=r"(v2[23]),
+                "=r"(v2[24]), "=r"(v2[25]), "=r"(v2[26]), "=r"(v2[27]), "=r"(v2[28]), "=r"(v2[29]), "=r"(v2[30]), "=r"(v2[31])
+              : "r"(taddr + (uint32_t)(BN + c)));
+        }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if constexpr (STACK) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint32_t dst = buf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
@@ -937,13 +974,14 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mg, const CUtensorMa
 }
 
 }  // namespace wg
-template <int BN>
+template <int BN, bool STACK>
 static int launch_ts(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mc,
                      const Params& p, cudaStream_t s) {
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(ts::gemm_tf32x3_ts_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, ts::TSmem<BN>::kTotal);
+    attr_err = cudaFuncSetAttribute(ts::gemm_tf32x3_ts_kernel<BN, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    ts::TSmem<BN, STACK>::kTotal);
   });
   if (attr_err != cudaSuccess) return check_cuda(attr_err, "gemm_tf32x3_ts smem attribute");
   int sms = 148, dev = 0;
@@ -951,7 +989,7 @@ static int launch_ts(const CUtensorMap& ma, const CUtensorMap& mh, const CUtenso
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long long tiles = p.m_blocks * p.n_blocks;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  ts::gemm_tf32x3_ts_kernel<BN><<<grid, kThreads, ts::TSmem<BN>::kTotal, s>>>(ma, mh, ml, mc, p);
+  ts::gemm_tf32x3_ts_kernel<BN, STACK><<<grid, kThreads, ts::TSmem<BN, STACK>::kTotal, s>>>(ma, mh, ml, mc, p);
   return check_cuda(cudaGetLastError(), "gemm_tf32x3_ts_kernel launch");
 }
 
@@ -1001,6 +1039,7 @@ extern "C" int eqf_gemm_tf32x3(const float* A, const float* Bt, float* C, int64_
   p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.n_tile = n_tile; p.n_blocks = (int)((N + n_tile - 1) / n_tile);
   p.m_blocks = (M + BM - 1) / BM;
   p.dbg = g_tf32x3_dbg;
+  { const char* e = std::getenv("EQF_TF32X3_DBG_SKIP"); p.dbg_skip = e ? std::atoi(e) : 0; }
   CUtensorMap ma, mh, ml, mc;
   if ((rc = make_map(&ma, A, M, K, lda, BM, BK)) != EQF_OK) return rc;
   if ((rc = make_map(&mh, hi, N, K, K, n_tile, BK)) != EQF_OK) return rc;
@@ -1012,9 +1051,12 @@ extern "C" int eqf_gemm_tf32x3(const float* A, const float* Bt, float* C, int64_
     if ((rc = make_map(&ma, A, M, K, lda, BM, ts::BKT)) != EQF_OK) return rc;
     if ((rc = make_map(&mh, hi, N, K, K, n_tile, ts::BKT)) != EQF_OK) return rc;
     if ((rc = make_map(&ml, lo, N, K, K, n_tile, ts::BKT)) != EQF_OK) return rc;
-    if (n_tile <= 32) return launch_ts<32>(ma, mh, ml, mc, p, s);
-    if (n_tile <= 64) return launch_ts<64>(ma, mh, ml, mc, p, s);
-    return launch_ts<128>(ma, mh, ml, mc, p, s);
+    static const bool stack = [] { const char* e = std::getenv("EQF_TF32X3_STACK"); return e == nullptr || e[0] != '0'; }();
+    if (stack && n_tile == 32) return launch_ts<32, true>(ma, mh, ml, mc, p, s);
+    if (stack && n_tile == 64) return launch_ts<64, true>(ma, mh, ml, mc, p, s);
+    if (n_tile <= 32) return launch_ts<32, false>(ma, mh, ml, mc, p, s);
+    if (n_tile <= 64) return launch_ts<64, false>(ma, mh, ml, mc, p, s);
+    return launch_ts<128, false>(ma, mh, ml, mc, p, s);
   }
   if (n_tile <= 64) return launch<64>(ma, mh, ml, mc, p, s);
   if (n_tile <= 128) return launch<128>(ma, mh, ml, mc, p, s);
