@@ -736,6 +736,7 @@ struct WParams {
   long long R, rows_per_slice;
   int n_tile, n_tiles;                        // output columns per CTA (multiple of 32), number of column tiles
   int reduce;                                 // 1: TMA reduce-add into W[K1, N] (map_p is 2-D); 0: store partial[slice]
+  int dbg_skip;                               // measurement aid: bit 0 skips the transform, bit 1 the MMAs (garbage results)
 };
 
 template <int BN>
@@ -835,6 +836,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const uint32_t st = smem_u32(stage_base_of(smem, s, S::kStageBytes));
 #pragma unroll
         for (int kb = 0; kb < BKR / UMMA_K; ++kb) {
+          if (p.dbg_skip & 2) break;
           const uint32_t off = (uint32_t)kb * 1024u;              // next 8-row group inside every 32-column block
           const uint64_t a_hi = smem_desc_mn(st + off), g_hi = smem_desc_mn(st + S::kABytes + off);
           const uint64_t a_lo = smem_desc_mn(st + S::kRaw + off), g_lo = smem_desc_mn(st + S::kRaw + S::kABytes + off);
@@ -854,7 +856,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const uint32_t ph = (kt / kStages) & 1;
       mbar_wait(&full[s], ph);
       const uint32_t st = smem_u32(stage_base_of(smem, s, S::kStageBytes));
-      for (int base = 0; base < n_piece; base += 4 * kTransformThreads) {
+      for (int base = (p.dbg_skip & 1) ? n_piece : 0; base < n_piece; base += 4 * kTransformThreads) {
         float4 v[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -1083,6 +1085,7 @@ static int wgrad_impl(const float* A, const float* G, float* out, bool reduce, i
   const wg::Shape sh = wg::plan(R, K1, N);
   wg::WParams p;
   p.R = R; p.rows_per_slice = sh.rows_per_slice; p.n_tile = sh.n_tile; p.n_tiles = sh.n_tiles; p.reduce = reduce ? 1 : 0;
+  { const char* e = std::getenv("EQF_TF32X3_DBG_SKIP"); p.dbg_skip = e ? std::atoi(e) : 0; }
   CUtensorMap ma, mg, mp;
   int rc;
   if ((rc = make_map(&ma, A, R, K1, lda, wg::BKR, 32, true)) != EQF_OK) return rc;
