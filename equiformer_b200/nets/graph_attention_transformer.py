@@ -574,8 +574,8 @@ class EdgeDegreeEmbeddingNetwork(torch.nn.Module):
         edge_scalars = graph.sort_edges(edge_scalars)
         ones = torch.ones((n_nodes, 1, 1), dtype=node_input.dtype, device=node_input.device)
         node_feats = self.exp.planar([ones])
-        weight = self.rad(edge_scalars)
-        edge_feats = self.dw.tp.planar_depthwise_gathered(graph, node_feats, None, edge_attr, weight)
+        weight = self.rad(edge_scalars, add_offset=False)        # the radial offset is added inside the DTP kernel
+        edge_feats = self.dw.tp.planar_depthwise_gathered(graph, node_feats, None, edge_attr, weight, self.rad.offset)
         edge_feats = self.proj.planar(edge_feats)
         summed = ops.attention_aggregate(self._sum_layout, graph, None, [t.contiguous() for t in edge_feats])
         return ops.from_planar(summed).div(self.scale_scatter.avg_aggregate_num ** 0.5)
