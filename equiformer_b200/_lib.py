@@ -19,7 +19,7 @@ PKG_DIR = Path(__file__).resolve().parent
 CSRC_DIR = PKG_DIR / "csrc"
 INCLUDE_DIR = PKG_DIR.parent / "include"
 LIB_PATH = PKG_DIR / "libeqf_b200.so"
-SOURCES = ("eqf_abi.cu", "eqf_dtp.cu", "eqf_dtp_vec.cu", "eqf_dtp_v3.cu", "eqf_attn.cu", "eqf_pointwise.cu", "eqf_gemm_tf32x3.cu")
+SOURCES = ("eqf_abi.cu", "eqf_dtp.cu", "eqf_dtp_vec.cu", "eqf_dtp_v3.cu", "eqf_attn.cu", "eqf_pointwise.cu", "eqf_gemm_tf32x3.cu", "eqf_graph.cu")
 GEMM_LIB_PATH = PKG_DIR / "libeqf_gemm.so"
 GEMM_SOURCES = ("eqf_gemm.cu",)
 
@@ -121,6 +121,9 @@ SIGNATURES = {
     "eqf_gemm_tf32x3_wgrad": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "eqf_gemm_tf32x3_wgrad_accumulate": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                                                    c_void_p]),
+    "eqf_radius_graph_count": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_int32, c_int64, c_void_p, c_void_p]),
+    "eqf_radius_graph_fill": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
+                                        c_void_p]),
     "eqf_colsum_scratch_floats": (c_int64, [c_int64, c_int64]),
     "eqf_colsum": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "eqf_eln_rows": (c_int32, [POINTER(EqfNormLayout), c_int64]),

@@ -1,9 +1,10 @@
-"""Neighbour-list construction for synthetic inputs (stand-in for ``torch_cluster.radius_graph``).
+"""Neighbour-list construction (stand-in for ``torch_cluster.radius_graph``).
 
-Out of the kernel scope for this round: a plain torch brute force over same-graph pairs that
-reproduces the ordering contract the hot path relies on - ``edge_index[1]`` (the centre atom, ``edge_dst``)
-ascending, neighbours in index order, no self loops, ``d < r`` - as used at
-``nets/graph_attention_transformer.py:866-867``.
+The ordering contract the hot path relies on - ``edge_index[1]`` (the centre atom, ``edge_dst``) ascending, neighbours
+in index order, no self loops, ``d < r``, at most ``max_num_neighbors`` per centre - as used at
+``nets/graph_attention_transformer.py:866-867``.  On CUDA fp32 inputs two small kernels (count, fill) around one
+prefix sum do it (``eqf_radius_graph_count / _fill``); the torch brute force below is the statement they are tested
+against and the path for CPU tensors (host-side tests, oracle inputs).
 """
 from __future__ import annotations
 
@@ -15,6 +16,54 @@ import torch
 def radius_graph(pos: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None,
                  max_num_neighbors: int = 32, loop: bool = False, chunk: int = 4096) -> torch.Tensor:
     """Return ``edge_index [2, E]`` with row 0 = neighbour (source) and row 1 = centre (destination, ascending)."""
+    n = pos.shape[0]
+    if pos.is_cuda and pos.dtype == torch.float32 and n > 0 and (batch is None or batch.dtype == torch.long):
+        return _radius_graph_cuda(pos, r, batch, max_num_neighbors, loop)
+    return radius_graph_torch(pos, r, batch, max_num_neighbors, loop, chunk)
+
+
+def radius_graph_csr(pos: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None, max_num_neighbors: int = 32,
+                     loop: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``(edge_index [2, E], row_ptr [N + 1])``: the neighbour list and the CSR offsets of its (sorted) centres."""
+    n = pos.shape[0]
+    if pos.is_cuda and pos.dtype == torch.float32 and n > 0 and (batch is None or batch.dtype == torch.long):
+        return _radius_graph_cuda(pos, r, batch, max_num_neighbors, loop, with_row_ptr=True)
+    edge = radius_graph_torch(pos, r, batch, max_num_neighbors, loop)
+    row_ptr = torch.zeros(n + 1, dtype=torch.int64, device=pos.device)
+    torch.cumsum(torch.bincount(edge[1], minlength=n), 0, out=row_ptr[1:])
+    return edge, row_ptr
+
+
+def _radius_graph_cuda(pos, r, batch, max_num_neighbors, loop, with_row_ptr: bool = False):
+    import ctypes
+
+    from . import _lib
+    lib = _lib.load()
+    n = pos.shape[0]
+    p = pos.detach().contiguous()
+    b = batch.contiguous() if batch is not None else None
+    cap = int(max_num_neighbors) if max_num_neighbors is not None else n
+    stream = ctypes.c_void_p(torch.cuda.current_stream(pos.device).cuda_stream)
+    row_ptr = torch.zeros(n + 1, dtype=torch.int64, device=pos.device)
+    deg = torch.empty(n, dtype=torch.int64, device=pos.device)
+    with torch.cuda.device(pos.device):
+        rc = lib.eqf_radius_graph_count(p.data_ptr(), b.data_ptr() if b is not None else None, n, float(r) * float(r),
+                                        1 if loop else 0, cap, deg.data_ptr(), stream)
+        _lib.check(rc, "eqf_radius_graph_count")
+        torch.cumsum(deg, 0, out=row_ptr[1:])
+        n_edges = int(row_ptr[-1].item())          # the one host synchronisation of the neighbour search
+        edge = torch.empty((2, n_edges), dtype=torch.int64, device=pos.device)
+        if n_edges > 0:
+            rc = lib.eqf_radius_graph_fill(p.data_ptr(), b.data_ptr() if b is not None else None, n, float(r) * float(r),
+                                           1 if loop else 0, cap, row_ptr.data_ptr(), edge[0].data_ptr(), edge[1].data_ptr(),
+                                           stream)
+            _lib.check(rc, "eqf_radius_graph_fill")
+    return (edge, row_ptr) if with_row_ptr else edge
+
+
+def radius_graph_torch(pos: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None,
+                       max_num_neighbors: int = 32, loop: bool = False, chunk: int = 4096) -> torch.Tensor:
+    """The plain torch brute force over same-graph pairs (reference statement of the contract above)."""
     n = pos.shape[0]
     if batch is None:
         batch = torch.zeros(n, dtype=torch.long, device=pos.device)

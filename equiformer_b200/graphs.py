@@ -15,7 +15,7 @@ from typing import Callable, Dict, Tuple
 import torch
 
 from . import ops
-from .graph import radius_graph
+from .graph import radius_graph_csr
 
 
 class _Captured:
@@ -62,11 +62,8 @@ class GraphedForwardBackward:
 
     def __call__(self, pos, batch, z, target) -> torch.Tensor:
         """Neighbour search (eager) + replay of the captured forward/backward; returns the (static) loss tensor."""
-        edge = radius_graph(pos, self.max_radius, batch, max_num_neighbors=1000)
+        edge, row_ptr = radius_graph_csr(pos, self.max_radius, batch, max_num_neighbors=1000)
         src, dst = edge[0], edge[1]
-        counts = torch.bincount(dst, minlength=pos.shape[0])
-        row_ptr = torch.zeros(pos.shape[0] + 1, dtype=torch.int64, device=pos.device)
-        torch.cumsum(counts, 0, out=row_ptr[1:])
         src_perm = torch.sort(src, stable=True).indices          # CSC view for the transpose of the source gather
         src_row_ptr = torch.zeros(pos.shape[0] + 1, dtype=torch.int64, device=pos.device)
         torch.cumsum(torch.bincount(src, minlength=pos.shape[0]), 0, out=src_row_ptr[1:])

@@ -165,6 +165,15 @@ int eqf_gemm_tf32x3_wgrad_accumulate(const float* A, const float* G, float* W, i
 /* debugging aid: device buffer of 4*1024 int64 receiving CTA 0's clock64 timeline on later launches (NULL = off) */
 void eqf_gemm_tf32x3_set_timeline(long long* device_buffer);
 
+/* Neighbour list of the batched molecules: edge (j -> i) iff same graph, j != i (unless loop), |pos_j - pos_i| < r, at
+ * most max_neighbors per centre (the first ones in index order); sorted by centre, neighbours ascending - what
+ * torch_cluster.radius_graph(pos, r, batch, max_num_neighbors) returns at nets/graph_attention_transformer.py:866-867.
+ * count -> caller scans deg into row_ptr[n + 1] -> fill. */
+int eqf_radius_graph_count(const float* pos, const int64_t* batch, int64_t n, float r_squared, int32_t loop,
+                           int64_t max_neighbors, int64_t* deg, void* stream);
+int eqf_radius_graph_fill(const float* pos, const int64_t* batch, int64_t n, float r_squared, int32_t loop,
+                          int64_t max_neighbors, const int64_t* row_ptr, int64_t* src, int64_t* dst, void* stream);
+
 /* Column sums out[c] = sum_r x[r, c] (row stride ld): the bias / radial-offset gradients the reference gets from
  * autograd's broadcast reduction (nets/tensor_product_rescale.py:120-134, radial_func.py:45-49), and the final
  * reduction of per-CTA partial rows.  Deterministic (fixed summation order). */

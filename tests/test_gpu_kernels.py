@@ -487,3 +487,24 @@ def test_gate_only_fused(cuda_device, cfg):
     rgrads = torch.autograd.grad(ref, ins, [t.double() for t in gouts])
     for a, b in zip(grads, rgrads):
         assert rel_err(a, b) < 5e-5
+
+
+@pytest.mark.parametrize("n_graphs,cap,loop", [(1, 1000, False), (7, 1000, False), (7, 5, False), (3, 1000, True), (40, 12, False)])
+def test_radius_graph_kernels_match_torch_statement(cuda_device, n_graphs, cap, loop):
+    """Neighbour list (count / fill kernels) == the torch brute force, bit for bit: same edges, same order, same CSR."""
+    from equiformer_b200.graph import radius_graph, radius_graph_csr, radius_graph_torch
+    g = torch.Generator().manual_seed(n_graphs * 31 + cap)
+    sizes = torch.randint(1, 30, (n_graphs,), generator=g)
+    batch = torch.repeat_interleave(torch.arange(n_graphs), sizes)
+    pos = torch.rand(int(sizes.sum()), 3, generator=g) * 4.0
+    pos[0] = pos[-1] if n_graphs == 1 else pos[0]            # a coincident pair (d = 0) when both are in one graph
+    p, b = pos.to(cuda_device), batch.to(cuda_device)
+    for bb in (b, None):
+        ref = radius_graph_torch(p, 2.5, bb, max_num_neighbors=cap, loop=loop)
+        out, row_ptr = radius_graph_csr(p, 2.5, bb, max_num_neighbors=cap, loop=loop)
+        assert torch.equal(out, ref)
+        assert torch.equal(radius_graph(p, 2.5, bb, max_num_neighbors=cap, loop=loop), ref)
+        counts = torch.bincount(ref[1], minlength=p.shape[0])
+        assert torch.equal(row_ptr[1:], torch.cumsum(counts, 0)) and int(row_ptr[0]) == 0
+    empty = radius_graph(p[:1], 2.5, None, max_num_neighbors=cap, loop=False)
+    assert empty.shape == (2, 0)
