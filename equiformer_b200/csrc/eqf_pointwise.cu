@@ -208,6 +208,83 @@ __global__ void __launch_bounds__(256) ln_silu_bwd64_kernel(const float* __restr
   for (int i = threadIdx.x; i < 3 * 64; i += blockDim.x) part[(long long)blockIdx.x * 192 + i] = sacc[i];
 }
 
+// ------------------------------------------------------------------------------------------------ Gaussian radial basis
+// rbf[e, k] = exp(-z^2 / 2) / (a s_k),  z = (w d_e / cutoff + b - mean_k) / s_k,  s_k = |std_k| + 1e-5,  a = sqrt(2 * 3.14159)
+// (GaussianRadialBasisLayer, nets/gaussian_rbf.py:5-40; the truncated pi is the reference's).  One warp per edge, K = 128
+// basis functions as one float4 per lane; the eager version is ~5 elementwise launches forward and ~15 backward (four of
+// them [E, 128] column reductions) on the same [E, 128] tensor.
+constexpr float kRbfA = 2.5066272160f;   // sqrt(2 * 3.14159): the reference truncates pi
+
+__global__ void __launch_bounds__(256) rbf_fwd_kernel(const float* __restrict__ dist, const float* __restrict__ mean,
+                                                      const float* __restrict__ std, const float* __restrict__ wp,
+                                                      const float* __restrict__ bp, float inv_cut,
+                                                      long long E, float* __restrict__ out) {
+  const float w = __ldg(wp), b = __ldg(bp);       // [1, 1] parameters: read on the device (no host synchronisation)
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 8;
+  const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean) + lane);
+  float4 s4 = __ldg(reinterpret_cast<const float4*>(std) + lane);
+  s4 = make_float4(fabsf(s4.x) + 1e-5f, fabsf(s4.y) + 1e-5f, fabsf(s4.z) + 1e-5f, fabsf(s4.w) + 1e-5f);
+  for (long long e = warp; e < E; e += n_warps) {
+    const float x = w * (__ldg(dist + e) * inv_cut) + b;
+    const float zx = (x - m4.x) / s4.x, zy = (x - m4.y) / s4.y, zz = (x - m4.z) / s4.z, zw = (x - m4.w) / s4.w;
+    reinterpret_cast<float4*>(out + e * 128)[lane] =
+        make_float4(expf(-0.5f * zx * zx) / (kRbfA * s4.x), expf(-0.5f * zy * zy) / (kRbfA * s4.y),
+                    expf(-0.5f * zz * zz) / (kRbfA * s4.z), expf(-0.5f * zw * zw) / (kRbfA * s4.w));
+  }
+}
+
+// g_dist[e] and per-CTA partial rows part[grid][258] = d mean (128) | d std (128) | d w | d b
+__global__ void __launch_bounds__(256) rbf_bwd_kernel(const float* __restrict__ dist, const float* __restrict__ mean,
+                                                      const float* __restrict__ std, const float* __restrict__ wp,
+                                                      const float* __restrict__ bp, float inv_cut,
+                                                      const float* __restrict__ g, long long E, float* __restrict__ g_dist,
+                                                      float* __restrict__ part) {
+  const float w = __ldg(wp), b = __ldg(bp);
+  __shared__ float sacc[258];
+  for (int i = threadIdx.x; i < 258; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long warp = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * 8;
+  const float4 m4 = __ldg(reinterpret_cast<const float4*>(mean) + lane);
+  const float4 r4 = __ldg(reinterpret_cast<const float4*>(std) + lane);
+  const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+  const float raw[4] = {r4.x, r4.y, r4.z, r4.w};
+  float ss[4], am[4] = {0.f, 0.f, 0.f, 0.f}, as[4] = {0.f, 0.f, 0.f, 0.f}, aw = 0.f, ab = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) ss[q] = fabsf(raw[q]) + 1e-5f;
+  for (long long e = warp; e < E; e += n_warps) {
+    const float d = __ldg(dist + e) * inv_cut;
+    const float x = w * d + b;
+    const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + e * 128) + lane);
+    const float gg[4] = {g4.x, g4.y, g4.z, g4.w};
+    float gx = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float z = (x - mm[q]) / ss[q];
+      const float o = expf(-0.5f * z * z) / (kRbfA * ss[q]);
+      const float t = gg[q] * o / ss[q];          // g * out / s
+      gx -= t * z;                                 // d out / d x = -z out / s
+      am[q] += t * z;                              // d out / d mean = +z out / s
+      as[q] += t * (z * z - 1.f);                  // d out / d s = out (z^2 - 1) / s
+    }
+    gx = wsum(gx);
+    if (lane == 0) {
+      g_dist[e] = gx * w * inv_cut;
+      aw += gx * d;
+      ab += gx;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    atomicAdd(&sacc[4 * lane + q], am[q]);
+    atomicAdd(&sacc[128 + 4 * lane + q], as[q] * (raw[q] < 0.f ? -1.f : 1.f));     // d|std| / d std
+  }
+  if (lane == 0) { atomicAdd(&sacc[256], aw); atomicAdd(&sacc[257], ab); }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 258; i += blockDim.x) part[(long long)blockIdx.x * 258 + i] = sacc[i];
+}
+
 // ------------------------------------------------------------------------------------------------ gate + logits
 // Inputs (planar): t0 [E, A0 + S + Gt]  = [alpha pre-activations | scalars | gates]   (biases already added)
 //                  gated blocks g_b [E, d_b, C_b] (b < n_gated), sum_b C_b == Gt, gates consumed in block order
@@ -883,4 +960,24 @@ extern "C" int eqf_eln_bwd_planar(const EqfNormLayout* lay, const float* const* 
   }
   eln_bwd_kernel<<<eln_grid(N, a.n_entries), 256, (a.n_w + a.n_b) * sizeof(float), (cudaStream_t)stream>>>(a);
   return check_cuda(cudaGetLastError(), "eln_bwd_kernel (planar) launch");
+}
+
+
+// Gaussian radial basis with K = 128 functions (gaussian_rbf.py:5-40): out [E, 128]
+extern "C" int eqf_rbf_fwd(const float* dist, const float* mean, const float* std, const float* weight, const float* bias,
+                           float cutoff, int64_t n_edges, float* out, void* stream) {
+  if (n_edges == 0) return EQF_OK;
+  if (!dist || !mean || !std || !weight || !bias || !out || cutoff == 0.f) { set_error("eqf_rbf_fwd: bad arguments"); return EQF_ERR_INVALID; }
+  rbf_fwd_kernel<<<pointwise_grid(n_edges), 256, 0, (cudaStream_t)stream>>>(dist, mean, std, weight, bias, 1.f / cutoff, n_edges, out);
+  return check_cuda(cudaGetLastError(), "rbf_fwd_kernel launch");
+}
+
+// g_dist [E] and partial rows part[eqf_pointwise_rows(E)][258] = d mean | d std | d weight | d bias
+extern "C" int eqf_rbf_bwd(const float* dist, const float* mean, const float* std, const float* weight, const float* bias,
+                           float cutoff, const float* g, int64_t n_edges, float* g_dist, float* part, void* stream) {
+  if (n_edges == 0) return EQF_OK;
+  if (!dist || !mean || !std || !weight || !bias || !g || !g_dist || !part || cutoff == 0.f) { set_error("eqf_rbf_bwd: bad arguments"); return EQF_ERR_INVALID; }
+  rbf_bwd_kernel<<<pointwise_grid(n_edges), 256, 0, (cudaStream_t)stream>>>(dist, mean, std, weight, bias, 1.f / cutoff, g, n_edges,
+                                                                             g_dist, part);
+  return check_cuda(cudaGetLastError(), "rbf_bwd_kernel launch");
 }

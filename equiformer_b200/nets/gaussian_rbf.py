@@ -3,6 +3,8 @@ from __future__ import annotations
 
 import torch
 
+from .. import ops
+
 _PI = 3.14159  # the reference truncates pi (gaussian_rbf.py:6); kept for parity
 
 
@@ -23,11 +25,8 @@ class GaussianRadialBasisLayer(torch.nn.Module):
         torch.nn.init.constant_(self.bias, 0)
 
     def forward(self, dist, node_atom=None, edge_src=None, edge_dst=None):
-        x = (dist / self.cutoff).unsqueeze(-1)
-        x = self.weight * x + self.bias
-        std = self.std.abs() + 1e-5
-        z = (x - self.mean) / std
-        return torch.exp(-0.5 * z * z) / (((2 * _PI) ** 0.5) * std)
+        # one fused kernel each way on CUDA fp32 with 128 basis functions, the torch statement otherwise
+        return ops.gaussian_rbf(dist, self.mean, self.std, self.weight, self.bias, self.cutoff)
 
     def extra_repr(self) -> str:
         return (f"mean_init_max={self.mean_init_max}, mean_init_min={self.mean_init_min}, "

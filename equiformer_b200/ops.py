@@ -1363,6 +1363,65 @@ def equivariant_layer_norm_planar(lay: NormLayout, xs, w, b):
     return eln_planar_torch(lay, list(xs), w, b)
 
 
+def gaussian_rbf_torch(dist, mean, std, weight, bias, cutoff: float):
+    """Torch statement of GaussianRadialBasisLayer.forward (ref nets/gaussian_rbf.py:5-40, truncated pi included)."""
+    x = weight * (dist / cutoff).unsqueeze(-1) + bias
+    s = std.abs() + 1e-5
+    z = (x - mean) / s
+    return torch.exp(-0.5 * z * z) / (((2 * 3.14159) ** 0.5) * s)
+
+
+def rbf_fwd_raw(dist, mean, std, weight, bias, cutoff: float):
+    dist = _require_cuda(dist, "rbf dist").contiguous()
+    E = dist.shape[0]
+    out = torch.empty((E, 128), device=dist.device, dtype=torch.float32)
+    with torch.cuda.device(dist.device), _kernel("rbf_fwd", 4 * (E + out.numel())):
+        rc = _lib.load().eqf_rbf_fwd(dist.data_ptr(), mean.data_ptr(), std.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                                     float(cutoff), E, out.data_ptr(), _stream())
+    _lib.check(rc, "eqf_rbf_fwd")
+    return out
+
+
+def rbf_bwd_raw(dist, mean, std, weight, bias, cutoff: float, g):
+    g = _require_cuda(g, "rbf g").contiguous()
+    E = dist.shape[0]
+    rows = _lib.load().eqf_pointwise_rows(E)
+    g_dist = torch.empty(E, device=dist.device, dtype=torch.float32)
+    part = torch.empty((rows, 258), device=dist.device, dtype=torch.float32)
+    with torch.cuda.device(dist.device), _kernel("rbf_bwd", 4 * (2 * E + g.numel())):
+        rc = _lib.load().eqf_rbf_bwd(dist.data_ptr(), mean.data_ptr(), std.data_ptr(), weight.data_ptr(), bias.data_ptr(),
+                                     float(cutoff), g.data_ptr(), E, g_dist.data_ptr(), part.data_ptr(), _stream())
+    _lib.check(rc, "eqf_rbf_bwd")
+    sums = colsum_raw(part)
+    return g_dist, sums[:128], sums[128:256], sums[256:257], sums[257:258]
+
+
+class GaussianRbf(torch.autograd.Function):
+    """Fused Gaussian radial basis (forward one kernel, backward one kernel + one column sum)."""
+
+    @staticmethod
+    def forward(ctx, dist, mean, std, weight, bias, cutoff: float):
+        ctx.cutoff = cutoff
+        ctx.save_for_backward(dist, mean, std, weight, bias)
+        return rbf_fwd_raw(dist, mean, std, weight, bias, cutoff)
+
+    @staticmethod
+    def backward(ctx, g):
+        dist, mean, std, weight, bias = ctx.saved_tensors
+        if torch.is_grad_enabled():
+            fn = lambda d, m, s, w, b: gaussian_rbf_torch(d, m, s, w, b, ctx.cutoff)
+            grads = _higher_order_grads(fn, (dist, mean, std, weight, bias), (g,))
+            return (*grads, None)
+        gd, gm, gs, gw, gb = rbf_bwd_raw(dist, mean, std, weight, bias, ctx.cutoff, g)
+        return gd, gm.view_as(mean), gs.view_as(std), gw.view_as(weight), gb.view_as(bias), None
+
+
+def gaussian_rbf(dist, mean, std, weight, bias, cutoff: float):
+    if fused_ok(dist) and dist.dim() == 1 and mean.numel() == 128 and dist.shape[0] > 0:
+        return GaussianRbf.apply(dist.contiguous(), mean, std, weight, bias, float(cutoff))
+    return gaussian_rbf_torch(dist, mean, std, weight, bias, cutoff)
+
+
 class GateLayout:
     """Static description of the fused gate + logits op (see ``eqf_gate_logits_fwd`` in include/eqf_b200.h)."""
 

@@ -174,6 +174,15 @@ int eqf_radius_graph_count(const float* pos, const int64_t* batch, int64_t n, fl
 int eqf_radius_graph_fill(const float* pos, const int64_t* batch, int64_t n, float r_squared, int32_t loop,
                           int64_t max_neighbors, const int64_t* row_ptr, int64_t* src, int64_t* dst, void* stream);
 
+/* GaussianRadialBasisLayer with 128 basis functions (nets/gaussian_rbf.py:5-40): out[e, k] = exp(-z^2/2) / (a s_k),
+ * z = (weight * dist_e / cutoff + bias - mean_k) / s_k, s_k = |std_k| + 1e-5, a = sqrt(2 * 3.14159); weight and bias
+ * are one-element device tensors.  The backward
+ * returns g_dist[E] and per-CTA partial sums part[eqf_pointwise_rows(E)][258] = d mean | d std | d weight | d bias. */
+int eqf_rbf_fwd(const float* dist, const float* mean, const float* std, const float* weight, const float* bias,
+                float cutoff, int64_t n_edges, float* out, void* stream);
+int eqf_rbf_bwd(const float* dist, const float* mean, const float* std, const float* weight, const float* bias,
+                float cutoff, const float* g, int64_t n_edges, float* g_dist, float* part, void* stream);
+
 /* Column sums out[c] = sum_r x[r, c] (row stride ld): the bias / radial-offset gradients the reference gets from
  * autograd's broadcast reduction (nets/tensor_product_rescale.py:120-134, radial_func.py:45-49), and the final
  * reduction of per-CTA partial rows.  Deterministic (fixed summation order). */

@@ -146,6 +146,18 @@ def ln_silu_fwd_raw(x, gamma, beta, eps, bias=None):
     return ops.ln_silu_torch(x, gamma, beta, eps, bias), mean, rstd
 
 
+def rbf_fwd_raw(dist, mean, std, weight, bias, cutoff):
+    return ops.gaussian_rbf_torch(dist, mean, std, weight, bias, cutoff)
+
+
+def rbf_bwd_raw(dist, mean, std, weight, bias, cutoff, g):
+    ins = [t.detach().requires_grad_(True) for t in (dist, mean, std, weight, bias)]
+    with torch.enable_grad():
+        out = ops.gaussian_rbf_torch(*ins, cutoff)
+    gd, gm, gs, gw, gb = torch.autograd.grad(out, ins, g)
+    return gd, gm.reshape(-1), gs.reshape(-1), gw.reshape(-1), gb.reshape(-1)
+
+
 def colsum_raw(x):
     return x.sum(0)
 
@@ -202,7 +214,7 @@ def gate_logits_bwd_raw(lay, t0, bias, alpha_dot, gated, gz, gv0, gvout):
     return grads[0], list(grads[2:]), (grads[1].reshape(-1) if lay.n_alpha > 0 else None)
 
 
-_PATCHED = ["colsum_raw", "eln_fwd_raw", "eln_bwd_raw", "eln_planar_fwd_raw", "eln_planar_bwd_raw", "ln_silu_fwd_raw", "ln_silu_bwd_raw", "gate_logits_fwd_raw", "gate_logits_bwd_raw", "gemm_raw", "dtp_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
+_PATCHED = ["rbf_fwd_raw", "rbf_bwd_raw", "colsum_raw", "eln_fwd_raw", "eln_bwd_raw", "eln_planar_fwd_raw", "eln_planar_bwd_raw", "ln_silu_fwd_raw", "ln_silu_bwd_raw", "gate_logits_fwd_raw", "gate_logits_bwd_raw", "gemm_raw", "dtp_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
             "seg_softmax_raw", "attn_aggregate_raw", "attn_edge_dot_raw", "attn_edge_scale_raw"]
 
 

@@ -508,3 +508,25 @@ def test_radius_graph_kernels_match_torch_statement(cuda_device, n_graphs, cap, 
         assert torch.equal(row_ptr[1:], torch.cumsum(counts, 0)) and int(row_ptr[0]) == 0
     empty = radius_graph(p[:1], 2.5, None, max_num_neighbors=cap, loop=False)
     assert empty.shape == (2, 0)
+
+
+@pytest.mark.parametrize("E", [1, 777, 32560])
+def test_gaussian_rbf_fused(cuda_device, E):
+    """GaussianRadialBasisLayer (ref nets/gaussian_rbf.py:5-40) fused forward / backward vs the fp64 torch statement."""
+    from equiformer_b200 import ops
+    g = torch.Generator().manual_seed(E)
+    dist = torch.rand(E, generator=g) * 5.0
+    mean = torch.rand(1, 128, generator=g)
+    std = (torch.rand(1, 128, generator=g) * 0.99 + 0.01) * torch.where(torch.rand(1, 128, generator=g) < 0.1, -1.0, 1.0)
+    weight, bias = torch.tensor([[1.3]]), torch.tensor([[-0.05]])
+    gout = torch.randn(E, 128, generator=g)
+    d = lambda t: t.to(cuda_device)
+    leaves = [d(t).requires_grad_(True) for t in (dist, mean, std, weight, bias)]
+    out = ops.gaussian_rbf(*leaves, 5.0)
+    ins = [t.double().requires_grad_(True) for t in (dist, mean, std, weight, bias)]
+    ref = ops.gaussian_rbf_torch(*ins, 5.0)
+    assert rel_err(out, ref) < 2e-6
+    grads = torch.autograd.grad(out, leaves, d(gout))
+    rgrads = torch.autograd.grad(ref, ins, gout.double())
+    for a, b in zip(grads, rgrads):
+        assert rel_err(a, b) < 5e-5
