@@ -58,6 +58,26 @@ __global__ void __launch_bounds__(256) seg_softmax_kernel(const float* __restric
   }
 }
 
+// backward of the segment softmax: gz_e = alpha_e (ga_e - sum_{f in seg(e)} alpha_f ga_f); one warp per destination node
+// (the eager version is a multiply, an index_add into [N, H], a gather back to [E, H], a multiply and a subtract)
+__global__ void __launch_bounds__(256) seg_softmax_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ ga,
+                                                              const long long* __restrict__ row_ptr, long long n_nodes, int H,
+                                                              float* __restrict__ gz) {
+  const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= n_nodes) return;
+  const int lane = threadIdx.x & 31;
+  const long long r0 = row_ptr[t], r1 = row_ptr[t + 1];
+  for (int h = 0; h < H; ++h) {
+    float s = 0.f;
+    for (long long e = r0 + lane; e < r1; e += 32) s += __ldg(alpha + e * H + h) * __ldg(ga + e * H + h);
+    s = warp_add(s);
+    for (long long e = r0 + lane; e < r1; e += 32) {
+      const float a = __ldg(alpha + e * H + h);
+      gz[e * H + h] = a * (__ldg(ga + e * H + h) - s);
+    }
+  }
+}
+
 __device__ __forceinline__ int find_group(const HeadArgs& a, int chunk) {
   int g = 0;
   while (g + 1 < a.n_groups && chunk >= a.chunk_start[g + 1]) ++g;
@@ -296,6 +316,17 @@ extern "C" int eqf_seg_softmax(const float* z, const int64_t* row_ptr, int64_t n
   seg_softmax_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(
       z, reinterpret_cast<const long long*>(row_ptr), n_nodes, n_heads, alpha);
   return check_cuda(cudaGetLastError(), "seg_softmax_kernel launch");
+}
+
+extern "C" int eqf_seg_softmax_bwd(const float* alpha, const float* ga, const int64_t* row_ptr, int64_t n_nodes,
+                                   int32_t n_heads, float* gz, void* stream) {
+  if (n_nodes == 0) return EQF_OK;
+  if (!alpha || !ga || !row_ptr || !gz || n_heads < 1) { set_error("eqf_seg_softmax_bwd: bad arguments"); return EQF_ERR_INVALID; }
+  const int wpb = 8;
+  const long long blocks = (n_nodes + wpb - 1) / wpb;
+  seg_softmax_bwd_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(
+      alpha, ga, reinterpret_cast<const long long*>(row_ptr), n_nodes, n_heads, gz);
+  return check_cuda(cudaGetLastError(), "seg_softmax_bwd_kernel launch");
 }
 
 extern "C" int eqf_attn_aggregate(const EqfHeadLayout* lay, const float* alpha, const float* const* V,

@@ -647,6 +647,16 @@ def seg_softmax_raw(z: torch.Tensor, graph: Graph) -> torch.Tensor:
     return alpha
 
 
+def seg_softmax_bwd_raw(alpha: torch.Tensor, ga: torch.Tensor, graph: Graph) -> torch.Tensor:
+    ga = _require_cuda(ga, "softmax cotangent").contiguous()
+    gz = torch.empty_like(alpha)
+    with torch.cuda.device(alpha.device), _kernel("seg_softmax_bwd", 12 * alpha.numel()):
+        rc = _lib.load().eqf_seg_softmax_bwd(alpha.data_ptr(), ga.data_ptr(), graph.row_ptr.data_ptr(), graph.n_nodes,
+                                             alpha.shape[1], gz.data_ptr(), _stream())
+    _lib.check(rc, "eqf_seg_softmax_bwd")
+    return gz
+
+
 def attn_aggregate_raw(lay: HeadLayout, alpha, Vs, graph: Graph, by_src: bool = False) -> List[torch.Tensor]:
     """Segment reduction over destination segments (default) or, with ``by_src``, over source segments via the CSC."""
     Vs = lay.check(Vs, graph.n_edges, "aggregate V")
@@ -709,7 +719,10 @@ class SegSoftmax(torch.autograd.Function):
         (alpha,) = ctx.saved_tensors
         g = ctx.graph
         # d alpha_e / d z_f = alpha_e (delta_ef - alpha_f) inside a segment (the 1e-16 is below fp32 resolution
-        # of any non-empty segment sum, which is >= 1); small [E, H] tensors -> differentiable torch ops.
+        # of any non-empty segment sum, which is >= 1).  First order: one kernel; under create_graph the small [E, H]
+        # tensors go through differentiable torch ops.
+        if not torch.is_grad_enabled() and fused_ok(alpha):
+            return seg_softmax_bwd_raw(alpha, ga, g), None
         t = alpha * ga
         s = torch.zeros((g.n_nodes, alpha.shape[1]), device=alpha.device, dtype=alpha.dtype).index_add(0, g.dst, t)
         return t - alpha * s.index_select(0, g.dst), None

@@ -119,6 +119,9 @@ typedef struct {
  * at graph_attention_transformer.py:508 (PyG 2.0.3 semantics).  row_ptr is the CSR of edge_dst.   */
 int eqf_seg_softmax(const float* z, const int64_t* row_ptr, int64_t n_nodes, int32_t n_heads,
                     float* alpha, void* stream);
+/* its backward: gz[e,h] = alpha[e,h] (ga[e,h] - sum_{f -> dst(e)} alpha[f,h] ga[f,h]) */
+int eqf_seg_softmax_bwd(const float* alpha, const float* ga, const int64_t* row_ptr, int64_t n_nodes, int32_t n_heads,
+                        float* gz, void* stream);
 
 /* out[g][t,j] = sum_{e in seg(t)} alpha[e,head(j)] * V[g][e,j]   (alpha NULL: plain segment sum)
  * == value*alpha followed by torch_scatter.scatter(..., edge_dst) (:512-513).

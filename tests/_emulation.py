@@ -87,6 +87,12 @@ def dtp_grad_xw_raw(plan, xs, y, w, gs, gather=None, w_offset=None):
     return dtp_grad_x_raw(plan, gs, y, w), dtp_grad_w_raw(plan, xs, y, gs, w.dim() == 1)
 
 
+def seg_softmax_bwd_raw(alpha, ga, graph):
+    t = alpha * ga
+    s = torch.zeros((graph.n_nodes, alpha.shape[1]), dtype=alpha.dtype).index_add(0, graph.dst, t)
+    return t - alpha * s.index_select(0, graph.dst)
+
+
 def _head_of(lay, g):
     C = lay.Cs[g]
     return torch.arange(C) // (C // lay.n_heads)
@@ -215,7 +221,7 @@ def gate_logits_bwd_raw(lay, t0, bias, alpha_dot, gated, gz, gv0, gvout):
 
 
 _PATCHED = ["rbf_fwd_raw", "rbf_bwd_raw", "colsum_raw", "eln_fwd_raw", "eln_bwd_raw", "eln_planar_fwd_raw", "eln_planar_bwd_raw", "ln_silu_fwd_raw", "ln_silu_bwd_raw", "gate_logits_fwd_raw", "gate_logits_bwd_raw", "gemm_raw", "dtp_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
-            "seg_softmax_raw", "attn_aggregate_raw", "attn_edge_dot_raw", "attn_edge_scale_raw"]
+            "seg_softmax_raw", "seg_softmax_bwd_raw", "attn_aggregate_raw", "attn_edge_dot_raw", "attn_edge_scale_raw"]
 
 
 @contextlib.contextmanager

@@ -530,3 +530,24 @@ def test_gaussian_rbf_fused(cuda_device, E):
     rgrads = torch.autograd.grad(ref, ins, gout.double())
     for a, b in zip(grads, rgrads):
         assert rel_err(a, b) < 5e-5
+
+
+def test_segment_softmax_backward_fused(cuda_device):
+    """First-order backward of the segment softmax (one kernel) vs autograd through an fp64 per-segment softmax."""
+    from equiformer_b200 import ops
+    n_nodes, E, H = 37, 500, 4
+    graph, src, dst = _graph(n_nodes, E, 21, cuda_device)
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(E, H, generator=g)
+    ga = torch.randn(E, H, generator=g)
+    zd = z.to(cuda_device).requires_grad_(True)
+    alpha = ops.segment_softmax(zd, graph)
+    (gz,) = torch.autograd.grad(alpha, zd, ga.to(cuda_device))
+    z64 = z.double().requires_grad_(True)
+    out = torch.zeros(E, H, dtype=torch.float64)
+    for t in range(n_nodes):
+        m = dst == t
+        if m.any():
+            out = out + torch.zeros(E, H, dtype=torch.float64).masked_scatter(m[:, None].expand(E, H), torch.softmax(z64[m], dim=0))
+    (ref,) = torch.autograd.grad(out, z64, ga.double())
+    assert rel_err(alpha, out) < TOL and rel_err(gz, ref) < 5e-5
