@@ -134,10 +134,9 @@ SIGNATURES = {
     "eqf_eln_fwd": (c_int32, [POINTER(EqfNormLayout), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "eqf_eln_bwd": (c_int32, [POINTER(EqfNormLayout), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
                               c_void_p]),
-    "eqf_eln_fwd_planar": (c_int32, [POINTER(EqfNormLayout), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
-                                     c_void_p, c_void_p]),
-    "eqf_eln_bwd_planar": (c_int32, [POINTER(EqfNormLayout), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p,
-                                     c_void_p, c_void_p]),
+    "eqf_eln_fwd_planar": (c_int32, [POINTER(EqfNormLayout), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "eqf_eln_bwd_planar": (c_int32, [POINTER(EqfNormLayout), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                     c_void_p]),
     "eqf_gate_logits_fwd": (c_int32, [POINTER(EqfGateLayout), c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_int64,
                                       c_void_p, c_void_p, POINTER(c_void_p), c_void_p]),
     "eqf_gate_logits_bwd": (c_int32, [POINTER(EqfGateLayout), c_void_p, c_void_p, POINTER(c_void_p), c_void_p, c_void_p,

@@ -666,9 +666,6 @@ struct ELNArgs {
   // planar variant: one packed [N, d, mul] buffer per entry (channel innermost) instead of e3nn-layout rows
   int planar;
   const float* xp[EQF_MAX_BLOCKS]; float* yp[EQF_MAX_BLOCKS]; const float* gyp[EQF_MAX_BLOCKS]; float* gxp[EQF_MAX_BLOCKS];
-  // planar + residual: forward normalises s = x + r and also writes s; backward adds the cotangent of s to gx
-  const float* rp[EQF_MAX_BLOCKS]; float* sp[EQF_MAX_BLOCKS]; const float* gsp[EQF_MAX_BLOCKS];
-  int with_res, with_gs;
 };
 
 // entry t of row r: base pointer of its mul*d values, and the channel of the i-th value
@@ -691,25 +688,18 @@ __global__ void __launch_bounds__(256) eln_fwd_kernel(ELNArgs a) {
       const int mul = a.mul[t], d = a.d[t], n = mul * d;
       const float* xe = eln_in(a, a.x, a.xp, r, t);
       float* ye = eln_out(a, a.y, a.yp, r, t);
-      if (a.with_res) {          // s = x + residual: written once, normalised below
-        const float* re = a.rp[t] + r * n;
-        float* se = a.sp[t] + r * n;
-        for (int i = lane; i < n; i += 32) se[i] = __ldg(xe + i) + __ldg(re + i);
-        __syncwarp();
-        xe = se;
-      }
       float mean = 0.f;
       if (a.scalar[t]) {
         float s = 0.f;
-        for (int i = lane; i < n; i += 32) s += xe[i];
+        for (int i = lane; i < n; i += 32) s += __ldg(xe + i);
         mean = wsum(s) / n;
       }
       float ss = 0.f;
-      for (int i = lane; i < n; i += 32) { const float f = xe[i] - mean; ss += f * f; }
+      for (int i = lane; i < n; i += 32) { const float f = __ldg(xe + i) - mean; ss += f * f; }
       const float rs = rsqrtf(wsum(ss) / n + a.eps);
       for (int i = lane; i < n; i += 32) {
         const int c = eln_chan(a, t, i);
-        float v = (xe[i] - mean) * rs * __ldg(a.w + a.woff[t] + c);
+        float v = (__ldg(xe + i) - mean) * rs * __ldg(a.w + a.woff[t] + c);
         if (a.scalar[t]) v += __ldg(a.b + a.boff[t] + c);
         ye[i] = v;
       }
@@ -762,10 +752,6 @@ __global__ void __launch_bounds__(256) eln_bwd_kernel(ELNArgs a) {
         const float gm = wsum(gsum) / n;
         for (int i = lane; i < n; i += 32) gxe[i] -= gm;
       }
-      if (a.with_gs) {                                    // the residual stream's own cotangent passes straight through
-        const float* gse = a.gsp[t] + r * n;
-        for (int i = lane; i < n; i += 32) gxe[i] += __ldg(gse + i);
-      }
     }
   }
   __syncthreads();
@@ -791,7 +777,7 @@ static int fill_eln(const EqfNormLayout* lay, ELNArgs& a) {
     if (lay->is_scalar[t]) boff += lay->mul[t];
   }
   a.dim = off; a.n_w = woff; a.n_b = boff;
-  a.planar = 0; a.with_res = 0; a.with_gs = 0;
+  a.planar = 0;
   return EQF_OK;
 }
 
@@ -944,9 +930,8 @@ extern "C" int eqf_colsum(const float* x, int64_t rows, int64_t cols, int64_t ld
 
 // planar variants: entry t of the node features is a packed [N, d_t, mul_t] buffer (channel innermost), as the GEMM /
 // tensor-product kernels keep them - the transformer blocks then never leave the planar layout
-extern "C" int eqf_eln_fwd_planar(const EqfNormLayout* lay, const float* const* x_blocks, const float* const* res_blocks,
-                                  float* const* sum_blocks, const float* w, const float* b, int64_t N,
-                                  float* const* y_blocks, float* rstd, void* stream) {
+extern "C" int eqf_eln_fwd_planar(const EqfNormLayout* lay, const float* const* x_blocks, const float* w, const float* b,
+                                  int64_t N, float* const* y_blocks, float* rstd, void* stream) {
   ELNArgs a;
   int rc = fill_eln(lay, a);
   if (rc != EQF_OK || N == 0) return rc;
@@ -956,21 +941,13 @@ extern "C" int eqf_eln_fwd_planar(const EqfNormLayout* lay, const float* const* 
     if (!x_blocks[t] || !y_blocks[t]) { set_error("eqf_eln_fwd_planar: null block"); return EQF_ERR_INVALID; }
     a.xp[t] = x_blocks[t]; a.yp[t] = y_blocks[t];
   }
-  if (res_blocks != nullptr) {       // y = LN(x + res), sum_blocks receives x + res (the new residual stream)
-    if (sum_blocks == nullptr) { set_error("eqf_eln_fwd_planar: residual without sum output"); return EQF_ERR_INVALID; }
-    for (int t = 0; t < a.n_entries; ++t) {
-      if (!res_blocks[t] || !sum_blocks[t]) { set_error("eqf_eln_fwd_planar: null residual block"); return EQF_ERR_INVALID; }
-      a.rp[t] = res_blocks[t]; a.sp[t] = sum_blocks[t];
-    }
-    a.with_res = 1;
-  }
   eln_fwd_kernel<<<eln_grid(N, a.n_entries), 256, 0, (cudaStream_t)stream>>>(a);
   return check_cuda(cudaGetLastError(), "eln_fwd_kernel (planar) launch");
 }
 
 extern "C" int eqf_eln_bwd_planar(const EqfNormLayout* lay, const float* const* x_blocks, const float* w, const float* rstd,
-                                  const float* const* gy_blocks, const float* const* gsum_blocks, int64_t N,
-                                  float* const* gx_blocks, float* part, void* stream) {
+                                  const float* const* gy_blocks, int64_t N, float* const* gx_blocks, float* part,
+                                  void* stream) {
   ELNArgs a;
   int rc = fill_eln(lay, a);
   if (rc != EQF_OK || N == 0) return rc;
@@ -980,13 +957,6 @@ extern "C" int eqf_eln_bwd_planar(const EqfNormLayout* lay, const float* const* 
   for (int t = 0; t < a.n_entries; ++t) {
     if (!x_blocks[t] || !gy_blocks[t] || !gx_blocks[t]) { set_error("eqf_eln_bwd_planar: null block"); return EQF_ERR_INVALID; }
     a.xp[t] = x_blocks[t]; a.gyp[t] = gy_blocks[t]; a.gxp[t] = gx_blocks[t];
-  }
-  if (gsum_blocks != nullptr) {      // x_blocks are the normalised sums; their own cotangent is added to gx
-    for (int t = 0; t < a.n_entries; ++t) {
-      if (!gsum_blocks[t]) { set_error("eqf_eln_bwd_planar: null gsum block"); return EQF_ERR_INVALID; }
-      a.gsp[t] = gsum_blocks[t];
-    }
-    a.with_gs = 1;
   }
   eln_bwd_kernel<<<eln_grid(N, a.n_entries), 256, (a.n_w + a.n_b) * sizeof(float), (cudaStream_t)stream>>>(a);
   return check_cuda(cudaGetLastError(), "eln_bwd_kernel (planar) launch");

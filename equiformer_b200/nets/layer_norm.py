@@ -42,12 +42,11 @@ class EquivariantLayerNormV2(nn.Module):
     def supports_planar(self) -> bool:
         return self._layout is not None
 
-    def planar(self, xs, residual=None):
-        """The same normalisation on planar blocks (one ``[N, 2l+1, mul]`` tensor per irreps entry).  With ``residual``
-        (blocks of the same shapes) returns ``(LN(xs + residual), xs + residual)`` from one kernel."""
+    def planar(self, xs):
+        """The same normalisation on planar blocks (one ``[N, 2l+1, mul]`` tensor per irreps entry)."""
         if self._layout is None:
             raise NotImplementedError("planar LayerNorm needs the affine 'component' configuration")
-        return ops.equivariant_layer_norm_planar(self._layout, xs, self.affine_weight, self.affine_bias, residual)
+        return ops.equivariant_layer_norm_planar(self._layout, xs, self.affine_weight, self.affine_bias)
 
     def forward(self, node_input, **kwargs):
         x = node_input.float() if node_input.dtype in (torch.float16, torch.bfloat16) else node_input

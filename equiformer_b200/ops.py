@@ -1314,48 +1314,33 @@ def _planar_dims(lay: NormLayout):
     return tuple((m, d) for m, d, _ in lay.entries)
 
 
-def eln_planar_torch(lay: NormLayout, xs, w, b, res=None):
-    """Torch statement of the planar LayerNorm: through the e3nn-layout one (higher-order path, CPU stand-in).
-    With ``res`` returns ``(LN(x + res) blocks, x + res blocks)``."""
+def eln_planar_torch(lay: NormLayout, xs, w, b):
+    """Torch statement of the planar LayerNorm: through the e3nn-layout one (higher-order path, CPU stand-in)."""
     dims = _planar_dims(lay)
-    if res is not None:
-        ss = [x + r for x, r in zip(xs, res)]
-        return list(_to_planar_impl(eln_torch(lay, _from_planar_impl(ss), w, b), dims)), ss
     return list(_to_planar_impl(eln_torch(lay, _from_planar_impl(xs), w, b), dims))
 
 
-def eln_planar_fwd_raw(lay: NormLayout, xs, w, b, res=None):
-    """``ys, rstd`` - or ``ys, sums, rstd`` with ``res`` (sums = x + res is what the kernel normalises)."""
+def eln_planar_fwd_raw(lay: NormLayout, xs, w, b):
     xs = [_require_cuda(x, "eln block").contiguous() for x in xs]
     N = xs[0].shape[0]
     ys = [torch.empty_like(x) for x in xs]
     rstd = torch.empty((N, len(lay.entries)), device=xs[0].device, dtype=torch.float32)
-    ss = None
-    if res is not None:
-        res = [_require_cuda(r, "eln residual block").contiguous() for r in res]
-        ss = [torch.empty_like(x) for x in xs]
     with torch.cuda.device(xs[0].device), _kernel("eln_fwd", 8 * sum(x.numel() for x in xs)):
-        rc = _lib.load().eqf_eln_fwd_planar(ctypes.byref(lay.c), _ptr_array(xs), _ptr_array(res) if res is not None else None,
-                                            _ptr_array(ss) if ss is not None else None, w.data_ptr(), b.data_ptr(), N,
+        rc = _lib.load().eqf_eln_fwd_planar(ctypes.byref(lay.c), _ptr_array(xs), w.data_ptr(), b.data_ptr(), N,
                                             _ptr_array(ys), rstd.data_ptr(), _stream())
     _lib.check(rc, "eqf_eln_fwd_planar")
-    return (ys, ss, rstd) if res is not None else (ys, rstd)
+    return ys, rstd
 
 
-def eln_planar_bwd_raw(lay: NormLayout, xs, w, rstd, gys, gss=None):
-    """``xs`` are the tensors that were normalised (the sums when a residual was fused); ``gss`` the cotangents of the
-    residual stream, added to the returned input gradients."""
+def eln_planar_bwd_raw(lay: NormLayout, xs, w, rstd, gys):
     gys = [_require_cuda(g, "eln gy block").contiguous() for g in gys]
-    if gss is not None:
-        gss = [_require_cuda(g, "eln gs block").contiguous() for g in gss]
     N = xs[0].shape[0]
     rows = _lib.load().eqf_eln_rows(ctypes.byref(lay.c), N)
     gxs = [torch.empty_like(x) for x in xs]
     part = torch.empty((rows, lay.n_w + lay.n_b), device=xs[0].device, dtype=torch.float32)
     with torch.cuda.device(xs[0].device), _kernel("eln_bwd", 12 * sum(x.numel() for x in xs)):
         rc = _lib.load().eqf_eln_bwd_planar(ctypes.byref(lay.c), _ptr_array(xs), w.data_ptr(), rstd.data_ptr(),
-                                            _ptr_array(gys), _ptr_array(gss) if gss is not None else None, N,
-                                            _ptr_array(gxs), part.data_ptr(), _stream())
+                                            _ptr_array(gys), N, _ptr_array(gxs), part.data_ptr(), _stream())
     _lib.check(rc, "eqf_eln_bwd_planar")
     sums = colsum_raw(part)
     return gxs, sums[:lay.n_w], sums[lay.n_w:]
@@ -1363,51 +1348,32 @@ def eln_planar_bwd_raw(lay: NormLayout, xs, w, rstd, gys, gss=None):
 
 class EquivLayerNormPlanar(torch.autograd.Function):
     """``EquivariantLayerNormV2`` on planar blocks (one packed ``[N, 2l+1, mul]`` tensor per entry) - the transformer
-    blocks keep the node features in the layout the GEMM and tensor-product kernels read.
-    apply(lay, w, b, has_res, *xs[, *res]) -> (*ys[, *sums]): with ``has_res`` the pre-norm residual add is fused
-    (``sums = x + res`` is the new residual stream, ``ys = LN(sums)``)."""
+    blocks keep the node features in the layout the GEMM and tensor-product kernels read.  apply(lay, w, b, *xs)."""
 
     @staticmethod
-    def forward(ctx, lay: NormLayout, w, b, has_res: bool, *blocks):
-        n = len(lay.entries)
-        xs = [x.contiguous() for x in blocks[:n]]
-        ctx.lay, ctx.has_res = lay, has_res
-        if has_res:
-            ys, ss, rstd = eln_planar_fwd_raw(lay, xs, w, b, res=list(blocks[n:]))
-            ctx.save_for_backward(w, b, rstd, *ss)
-            return (*ys, *ss)
+    def forward(ctx, lay: NormLayout, w, b, *xs):
+        xs = [x.contiguous() for x in xs]
         ys, rstd = eln_planar_fwd_raw(lay, xs, w, b)
+        ctx.lay = lay
         ctx.save_for_backward(w, b, rstd, *xs)
         return tuple(ys)
 
     @staticmethod
-    def backward(ctx, *gs):
-        w, b, rstd, *xs = ctx.saved_tensors          # xs: what was normalised (the sums when a residual was fused)
-        n = len(xs)
-        gys = [g if g is not None else torch.zeros_like(x) for g, x in zip(gs[:n], xs)]
-        gss = None
-        if ctx.has_res and any(g is not None for g in gs[n:]):
-            gss = [g if g is not None else torch.zeros_like(x) for g, x in zip(gs[n:], xs)]
+    def backward(ctx, *gys):
+        w, b, rstd, *xs = ctx.saved_tensors
+        gys = [g if g is not None else torch.zeros_like(x) for g, x in zip(gys, xs)]
         if torch.is_grad_enabled():
-            # through the torch statement, as a function of the normalised tensors (d sum / d x = d sum / d res = 1)
-            fn = lambda ww, bb, *blk: tuple(eln_planar_torch(ctx.lay, list(blk), ww, bb))
-            gw, gb, *gx = _higher_order_grads(fn, (w, b, *xs), gys)
-            if gss is not None:
-                gx = [a + c for a, c in zip(gx, gss)]
-        else:
-            gx, gw, gb = eln_planar_bwd_raw(ctx.lay, xs, w, rstd, gys, gss)
-        return (None, gw, gb, None, *gx, *(gx if ctx.has_res else ()))
+            fn = lambda ww, bb, *blocks: tuple(eln_planar_torch(ctx.lay, list(blocks), ww, bb))
+            grads = _higher_order_grads(fn, (w, b, *xs), gys)
+            return (None, *grads)
+        gxs, gw, gb = eln_planar_bwd_raw(ctx.lay, xs, w, rstd, gys)
+        return (None, gw, gb, *gxs)
 
 
-def equivariant_layer_norm_planar(lay: NormLayout, xs, w, b, res=None):
-    """``LN(xs)`` blocks, or with ``res``: ``(LN(xs + res) blocks, xs + res blocks)``."""
-    n = len(lay.entries)
+def equivariant_layer_norm_planar(lay: NormLayout, xs, w, b):
     if fused_ok(xs[0]) and xs[0].shape[0] > 0:
-        if res is not None:
-            out = EquivLayerNormPlanar.apply(lay, w, b, True, *xs, *res)
-            return list(out[:n]), list(out[n:])
-        return list(EquivLayerNormPlanar.apply(lay, w, b, False, *xs))
-    return eln_planar_torch(lay, list(xs), w, b, res)
+        return list(EquivLayerNormPlanar.apply(lay, w, b, *xs))
+    return eln_planar_torch(lay, list(xs), w, b)
 
 
 def gaussian_rbf_torch(dist, mean, std, weight, bias, cutoff: float):

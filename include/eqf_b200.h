@@ -210,16 +210,11 @@ int eqf_eln_fwd(const EqfNormLayout* lay, const float* x, const float* w, const 
 int eqf_eln_bwd(const EqfNormLayout* lay, const float* x, const float* w, const float* rstd, const float* gy,
                 int64_t N, float* gx, float* part, void* stream);
 
-/* the same on planar node features: entry t is a packed [N, d_t, mul_t] buffer (host arrays of device pointers).
- * With res_blocks != NULL the pre-norm residual add of TransBlock.forward (graph_attention_transformer.py:645-655) is
- * fused in: sum_blocks = x + res (the new residual stream) and y = LayerNorm(sum); the backward then takes the sums as
- * x_blocks and adds gsum_blocks (cotangent of the residual stream) to gx, which is the gradient of x and of res. */
-int eqf_eln_fwd_planar(const EqfNormLayout* lay, const float* const* x_blocks, const float* const* res_blocks,
-                       float* const* sum_blocks, const float* w, const float* b, int64_t N, float* const* y_blocks,
-                       float* rstd, void* stream);
+/* the same on planar node features: entry t is a packed [N, d_t, mul_t] buffer (host arrays of device pointers) */
+int eqf_eln_fwd_planar(const EqfNormLayout* lay, const float* const* x_blocks, const float* w, const float* b, int64_t N,
+                       float* const* y_blocks, float* rstd, void* stream);
 int eqf_eln_bwd_planar(const EqfNormLayout* lay, const float* const* x_blocks, const float* w, const float* rstd,
-                       const float* const* gy_blocks, const float* const* gsum_blocks, int64_t N,
-                       float* const* gx_blocks, float* part, void* stream);
+                       const float* const* gy_blocks, int64_t N, float* const* gx_blocks, float* part, void* stream);
 
 /* Gate + attention logits of GraphAttention.forward (graph_attention_transformer.py:492-495, 506-507) in one pass:
  *   t0[e] = [alpha | scalars | gates] pre-activations (+ optional bias), gated[b] planar blocks [E, d, C];

@@ -180,23 +180,16 @@ def eln_bwd_raw(lay, x, w, rstd, gy):
     return gx, gw, gb if gb is not None else torch.zeros(lay.n_b)
 
 
-def eln_planar_fwd_raw(lay, xs, w, b, res=None):
-    rstd = torch.zeros(xs[0].shape[0], len(lay.entries))
-    if res is not None:
-        ys, ss = ops.eln_planar_torch(lay, list(xs), w, b, list(res))
-        return ys, ss, rstd
-    return ops.eln_planar_torch(lay, list(xs), w, b), rstd
+def eln_planar_fwd_raw(lay, xs, w, b):
+    return ops.eln_planar_torch(lay, list(xs), w, b), torch.zeros(xs[0].shape[0], len(lay.entries))
 
 
-def eln_planar_bwd_raw(lay, xs, w, rstd, gys, gss=None):
+def eln_planar_bwd_raw(lay, xs, w, rstd, gys):
     ins = [t.detach().requires_grad_(True) for t in (w, b_like(lay, xs[0]), *xs)]
     with torch.enable_grad():
         ys = ops.eln_planar_torch(lay, ins[2:], ins[0], ins[1])
     g = torch.autograd.grad(ys, ins, list(gys), allow_unused=True)
-    gxs = list(g[2:])
-    if gss is not None:
-        gxs = [a + c for a, c in zip(gxs, gss)]
-    return gxs, g[0], (g[1] if g[1] is not None else torch.zeros(lay.n_b))
+    return list(g[2:]), g[0], (g[1] if g[1] is not None else torch.zeros(lay.n_b))
 
 
 def b_like(lay, x):
