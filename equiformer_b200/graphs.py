@@ -19,7 +19,7 @@ from .graph import radius_graph_csr
 
 
 class _Captured:
-    __slots__ = ("graph", "pos", "batch", "z", "target", "src", "dst", "row_ptr", "src_perm", "src_row_ptr", "csr", "loss")
+    __slots__ = ("graph", "pos", "batch", "z", "target", "src", "dst", "row_ptr", "csr", "loss")
 
 
 class GraphedForwardBackward:
@@ -31,6 +31,9 @@ class GraphedForwardBackward:
         self.captures = 0
 
     def _fwd_bwd(self, c: _Captured) -> torch.Tensor:
+        # the source-sorted (CSC) view of the edge list is rebuilt inside the captured region from the static `src`
+        # buffer (sort + scatter-add + scan, no host synchronisation): nothing of it is left on the host's critical path
+        c.csr._src_perm = c.csr._src_row_ptr = None
         out = self.model.forward_edges(c.pos, c.batch, c.z, c.src, c.dst, graph=c.csr, n_graphs=c.target.shape[0])
         loss = self.loss_fn(out, c.target)
         # gradients as a list + one multi-tensor copy into the flat bucket (autograd's per-parameter accumulation into
@@ -38,15 +41,14 @@ class GraphedForwardBackward:
         self.bucket.store(torch.autograd.grad(loss, self.bucket.params, allow_unused=True))
         return loss.detach()
 
-    def _capture(self, pos, batch, z, target, src, dst, row_ptr, src_perm, src_row_ptr) -> _Captured:
+    def _capture(self, pos, batch, z, target, src, dst, row_ptr) -> _Captured:
         c = _Captured()
         c.pos, c.batch, c.z, c.target = pos.clone(), batch.clone(), z.clone(), target.clone()
         c.src, c.dst, c.row_ptr = src.clone(), dst.clone(), row_ptr.clone()
-        c.src_perm, c.src_row_ptr = src_perm.clone(), src_row_ptr.clone()
         csr = ops.Graph.__new__(ops.Graph)
         csr.n_nodes, csr.n_edges, csr.perm = int(pos.shape[0]), int(src.numel()), None
         csr.src, csr.dst, csr.row_ptr = c.src, c.dst, c.row_ptr
-        csr._src_perm, csr._src_row_ptr = c.src_perm, c.src_row_ptr
+        csr._src_perm = csr._src_row_ptr = None
         c.csr = csr
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -64,24 +66,15 @@ class GraphedForwardBackward:
         """Neighbour search (eager) + replay of the captured forward/backward; returns the (static) loss tensor."""
         edge, row_ptr = radius_graph_csr(pos, self.max_radius, batch, max_num_neighbors=1000)
         src, dst = edge[0], edge[1]
-        src_perm = torch.sort(src, stable=True).indices          # CSC view for the transpose of the source gather
-        src_row_ptr = torch.zeros(pos.shape[0] + 1, dtype=torch.int64, device=pos.device)
-        torch.cumsum(torch.bincount(src, minlength=pos.shape[0]), 0, out=src_row_ptr[1:])
         key = (int(pos.shape[0]), int(src.numel()), int(target.shape[0]))
         c = self._cache.get(key)
         if c is None:
             if len(self._cache) >= self.max_cached:
                 self._cache.pop(next(iter(self._cache)))
-            c = self._capture(pos, batch, z, target, src, dst, row_ptr, src_perm, src_row_ptr)
+            c = self._capture(pos, batch, z, target, src, dst, row_ptr)
             self._cache[key] = c
-        c.pos.copy_(pos, non_blocking=True)
-        c.batch.copy_(batch, non_blocking=True)
-        c.z.copy_(z, non_blocking=True)
-        c.target.copy_(target, non_blocking=True)
-        c.src.copy_(src)
-        c.dst.copy_(dst)
-        c.row_ptr.copy_(row_ptr)
-        c.src_perm.copy_(src_perm)
-        c.src_row_ptr.copy_(src_row_ptr)
+        # inputs -> static buffers: one multi-tensor copy per dtype instead of seven small launches
+        torch._foreach_copy_([c.pos, c.target], [pos, target])
+        torch._foreach_copy_([c.batch, c.z, c.src, c.dst, c.row_ptr], [batch, z, src, dst, row_ptr])
         c.graph.replay()
         return c.loss

@@ -618,7 +618,9 @@ class Graph:
     def build_csc(self) -> None:
         """Source-sorted view of the same edge list: ``src_perm`` (segment position -> edge id) and ``src_row_ptr``."""
         self._src_perm = torch.sort(self.src, stable=True).indices
-        counts = torch.bincount(self.src, minlength=self.n_nodes)
+        # counts by scatter-add (torch.bincount synchronises with the host; this has to be capturable in a CUDA graph)
+        counts = torch.zeros(self.n_nodes, dtype=torch.int64, device=self.src.device)
+        counts.index_add_(0, self.src, torch.ones_like(self.src))
         self._src_row_ptr = torch.zeros(self.n_nodes + 1, dtype=torch.int64, device=self.src.device)
         torch.cumsum(counts, 0, out=self._src_row_ptr[1:])
 
