@@ -97,3 +97,67 @@ def test_product_refuses_cpu_tensors():
     x, y, w = torch.randn(5, 20), torch.randn(5, 4), torch.randn(5, dtp.tp.weight_numel)
     with pytest.raises(_lib.EqfError):
         dtp(x, y, w)
+
+
+def test_planar_resident_blocks_match_the_e3nn_layout_path():
+    """The transformer blocks run on planar node blocks when every sub-layer supports it and fall back to the stock
+    e3nn-layout `TransBlock.forward` otherwise (e.g. stochastic depth in training): both routes give the same model."""
+    from equiformer_b200.nets import graph_attention_transformer as G
+    model = _build("graph_attention_transformer_nonlinear_l2")
+    pos, batch, z = molecules([5, 8], seed=4, dtype=torch.float64)
+    assert all(blk.supports_planar for blk in model.blocks[:-1])          # the last block projects to irreps_feature
+    calls = {"planar": 0, "stock": 0}
+    orig_planar, orig_forward = G.TransBlock.forward_planar, G.TransBlock.forward
+
+    def spy_planar(self, *a, **k):
+        calls["planar"] += 1
+        return orig_planar(self, *a, **k)
+
+    def spy_forward(self, *a, **k):
+        calls["stock"] += 1
+        return orig_forward(self, *a, **k)
+
+    G.TransBlock.forward_planar, G.TransBlock.forward = spy_planar, spy_forward
+    try:
+        with emulated_kernels():
+            out_planar = model(f_in=None, pos=pos, batch=batch, node_atom=z)
+            n_planar = dict(calls)
+            class _KeepAll(torch.nn.Module):                              # a drop path that drops nothing
+                def forward(self, x, batch):
+                    return x
+
+            for blk in model.blocks:                                      # force the fallback route
+                blk.drop_path = _KeepAll()
+            model.train()
+            for m in model.modules():
+                if isinstance(m, torch.nn.Dropout):
+                    m.p = 0.0
+            calls.update(planar=0, stock=0)
+            out_stock = model(f_in=None, pos=pos, batch=batch, node_atom=z)
+    finally:
+        G.TransBlock.forward_planar, G.TransBlock.forward = orig_planar, orig_forward
+    assert n_planar["planar"] == len(model.blocks) - 1 and n_planar["stock"] == 1
+    assert calls["planar"] == 0 and calls["stock"] == len(model.blocks)
+    assert rel_err(out_stock, out_planar) < 1e-10
+
+
+def test_radius_graph_statement_contract():
+    """The torch statement of the neighbour list: centres ascending, neighbours ascending inside a centre, no self
+    loops, same graph only, d < r, at most `max_num_neighbors` (the first ones) per centre."""
+    from equiformer_b200.graph import radius_graph, radius_graph_csr
+    g = torch.Generator().manual_seed(0)
+    pos = torch.rand(40, 3, generator=g) * 3.0
+    batch = torch.repeat_interleave(torch.arange(4), 10)
+    edge = radius_graph(pos, 1.5, batch, max_num_neighbors=1000)
+    src, dst = edge
+    assert bool((dst[1:] >= dst[:-1]).all()) and bool((src != dst).all()) and bool((batch[src] == batch[dst]).all())
+    same = dst[1:] == dst[:-1]
+    assert bool((src[1:][same] > src[:-1][same]).all())
+    d = (pos[src] - pos[dst]).norm(dim=1)
+    assert bool((d < 1.5).all())
+    full = ((pos[:, None] - pos[None]).norm(dim=-1) < 1.5) & (batch[:, None] == batch[None]) & ~torch.eye(40, dtype=torch.bool)
+    assert int(full.sum()) == edge.shape[1]
+    capped, row_ptr = radius_graph_csr(pos, 1.5, batch, max_num_neighbors=2)
+    assert int(torch.bincount(capped[1], minlength=40).max()) <= 2 and int(row_ptr[-1]) == capped.shape[1]
+    kept = {(int(a), int(b)) for a, b in zip(*capped)}
+    assert kept <= {(int(a), int(b)) for a, b in zip(src, dst)}
