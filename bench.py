@@ -294,7 +294,7 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    # `ncu --profile-from-start off` (tools/gpu_round10.sh) lists exactly the launches of the headline region
+    # `ncu --profile-from-start off` (tools/rounds/gpu_round10.sh) lists exactly the launches of the headline region
     mark = os.environ.get("EQF_BENCH_CUDA_PROFILER") == "1"
     if mark:
         torch.cuda.cudart().cudaProfilerStart()
