@@ -191,16 +191,36 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise EqfError("nvcc not found: cannot build libeqf_b200.so")
-    tmp = LIB_PATH.with_suffix(".so.tmp%d" % os.getpid())
-    cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE_DIR), "-o", str(tmp), *[str(s) for s in sources()]]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise EqfError("nvcc failed:\n" + proc.stdout + proc.stderr)
-    if verbose:
-        print(proc.stderr)
-    os.replace(tmp, LIB_PATH)
+    # one nvcc per source file, in parallel (the plan-specialised and the tcgen05 files take a minute each), then one
+    # link step; objects live in a scratch directory next to the library
+    from concurrent.futures import ThreadPoolExecutor
+    obj_dir = PKG_DIR / "build" / ("obj%d" % os.getpid())
+    obj_dir.mkdir(parents=True, exist_ok=True)
+    compile_flags = [f for f in NVCC_FLAGS if f != "--shared"]
+
+    def compile_one(src: Path):
+        obj = obj_dir / (src.stem + ".o")
+        cmd = [nvcc, *compile_flags, "-I", str(INCLUDE_DIR), "-c", "-o", str(obj), str(src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        return obj, subprocess.run(cmd, capture_output=True, text=True)
+
+    try:
+        with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+            results = list(pool.map(compile_one, sources()))
+        for _obj, proc in results:
+            if proc.returncode != 0:
+                raise EqfError("nvcc failed:\n" + proc.stdout + proc.stderr)
+            if verbose:
+                print(proc.stderr)
+        tmp = LIB_PATH.with_suffix(".so.tmp%d" % os.getpid())
+        link = subprocess.run([nvcc, "--shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
+                               "-o", str(tmp), *[str(o) for o, _ in results]], capture_output=True, text=True)
+        if link.returncode != 0:
+            raise EqfError("nvcc link failed:\n" + link.stdout + link.stderr)
+        os.replace(tmp, LIB_PATH)
+    finally:
+        shutil.rmtree(obj_dir, ignore_errors=True)
     return LIB_PATH
 
 
