@@ -248,6 +248,34 @@ def test_gemm_autograd_closure(cuda_device):
     assert rel_err(A.grad, A2.grad) < 1e-5 and rel_err(B.grad, B2.grad) < 1e-5
 
 
+def test_aggregate_hub_degrees(cuda_device):
+    """Segment sums with in-/out-degrees 0, 1, 31, 32, 33 and 70, with and without weights and through the CSC
+    permutation: pins the unrolled edge loop of the aggregation kernel at its even / odd / long-segment cases."""
+    from equiformer_b200 import ops
+    degrees = [0, 1, 31, 32, 33, 70, 3, 0, 5]
+    n_nodes, H = len(degrees), 4
+    dst = torch.repeat_interleave(torch.arange(n_nodes), torch.tensor(degrees))
+    E = dst.numel()
+    g = torch.Generator().manual_seed(5)
+    hub_src = torch.repeat_interleave(torch.arange(n_nodes), torch.tensor(degrees[::-1]))[torch.randperm(E, generator=g)]
+    dims, chans = (1, 3, 5), (128, 64, 32)
+    lay = ops.HeadLayout(dims, chans, H)
+    graph = ops.Graph(hub_src.to(cuda_device), dst.to(cuda_device), n_nodes)
+    cpu_graph = type("G", (), {"dst": dst, "n_nodes": n_nodes, "n_edges": E})
+    Vs = [torch.randn(E, d, c, generator=g) for d, c in zip(dims, chans)]
+    alpha = torch.rand(E, H, generator=g)
+    dev = lambda t: t.to(cuda_device)
+    for al in (alpha, None):
+        out = ops.attn_aggregate_raw(lay, None if al is None else dev(al), [dev(v) for v in Vs], graph)
+        ref = emu.attn_aggregate_raw(lay, None if al is None else al.double(), [v.double() for v in Vs], cpu_graph)
+        for a, b in zip(out, ref):
+            assert rel_err(a, b) < TOL
+    by_src = ops.attn_aggregate_raw(lay, None, [dev(v) for v in Vs], graph, by_src=True)     # through the CSC permutation
+    for a, v in zip(by_src, Vs):
+        exp = torch.zeros(n_nodes, *v.shape[1:], dtype=torch.float64).index_add_(0, hub_src, v.double())
+        assert rel_err(a, exp) < TOL
+
+
 @pytest.mark.parametrize("with_b", [True, False])
 def test_dtp_gather_fused_and_csc_aggregate(cuda_device, with_b):
     """x = A[src] (+ B[dst]) gathered inside the kernels (ref :487 folded into :491) and the CSC segment sum."""

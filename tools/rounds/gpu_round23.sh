@@ -1,16 +1,14 @@
 #!/bin/bash
+# quick validation: GPU tests, smoke, one bench line without the CPU leg
 set -u
-for skip in 0 1 2 3; do
-echo "== skip=$skip"; EQF_TF32X3_DBG_SKIP=$skip timeout 120 python - <<'PY'
-import sys, os, torch
-sys.path.insert(0, '.')
-from equiformer_b200 import ops
-sys.path.insert(0, 'tools')
-from tf32x3_microbench import timeit
-dev = torch.device('cuda:0')
-for (M, K, N) in [(162800, 352, 32), (97680, 384, 64), (32560, 224, 128)]:
-    A = torch.randn(M, K, device=dev); Bt = torch.randn(N, K, device=dev)
-    us = timeit(lambda: ops.gemm_tf32x3_raw(A, Bt))
-    print(f"  {M}x{K}->{N}: {us:.1f} us, A stream {4*M*K/us/1e3:.0f} GB/s")
+TAG=${1:-r3d}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+echo "== pytest gpu (all)"; timeout 900 python -m pytest tests -m gpu -q -x 2>&1 | tail -4
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
+echo "== bench"; timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench.json 2> $OUT/bench.err; echo "rc=$?"; tail -3 $OUT/bench.err; cut -c1-300 $OUT/bench.json
+python - <<PY
+import json
+d = json.load(open("$OUT/bench.json"))
+print({k: round(v["ms_per_step"], 3) for k, v in d["kernels"].items() if k.startswith("attn")})
 PY
-done
