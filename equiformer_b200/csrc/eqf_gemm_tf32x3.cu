@@ -638,6 +638,312 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 
 }  // namespace ts
 
+// ================================================================================================ CTA-pair variant
+// The stacked narrow-output kernel above is bound by the NUMBER of MMA instructions (about 100 cycles each whatever
+// their width).  Here two CTAs of a cluster (one TPC) share each instruction: tcgen05.mma.cta_group::2 with M = 256 -
+// CTA r owns rows [256 t + 128 r, +128) of the tile (its A hi / lo in its own TMEM, its accumulator rows in its own
+// TMEM) and supplies HALF of the weight operand's columns from its own shared memory:
+//   MMA 1  a_hi x [b_hi | b_lo]   N' = 2 BN   CTA 0 holds b_hi (columns [0, BN)), CTA 1 holds b_lo ([BN, 2 BN))   region Y
+//   MMA 2  a_lo x  b_hi           N  = BN     CTA 0 holds b_hi rows [0, BN/2), CTA 1 rows [BN/2, BN)             region X
+// so one instruction pair covers 256 rows instead of 128 and each SM reads half the weight bytes per row.
+// Only the leader (rank 0) issues MMAs; its commits are multicast to both CTAs' `empty` / `tmem_full` barriers; the
+// transform and epilogue warps of both CTAs arrive on the LEADER's `a_ready` / `tmem_empty` barriers (mapa + remote arrive).
+//
+// MEASURED (profiles/r1_tf32x3_cta_pair_*.txt): bit-identical to the single-CTA kernel, and 9-11 % SLOWER
+// ([162 800, 352] -> 32: 70.5 vs 64.7 us; [97 680, 384] -> 64: 56.1 vs 50.3 us), so it stays opt-in (EQF_TF32X3_2SM=1).
+// The timeline shows why: an M = 256 pair instruction occupies the issue slot of the one leader thread for the same
+// ~85 cycles as an M = 128 one, but it is the ONLY issuer for two SMs - instructions per row halve and so do the
+// issuers, nothing is gained - while the shapes' real floor is the A stream (load skeleton alone: 46 of 65 us).  What a
+// pair does save, weight bytes read from shared memory per SM, is not what limits a 32- or 64-column output.
+namespace ts2 {
+
+using ts::BKT;
+using ts::kRowBytesT;
+
+template <int BN>
+struct T2Smem {
+  static constexpr int kAccCols = 2 * BN;
+  static constexpr int kABytes = BM * kRowBytesT;
+  static constexpr int kYBytes = BN * kRowBytesT;
+  static constexpr int kXBytes = (BN / 2) * kRowBytesT;
+  static constexpr int kStageBytes = kABytes + kYBytes + kXBytes;
+  static_assert(kYBytes % 1024 == 0 && kXBytes % 1024 == 0, "operand regions must keep the 1024-byte swizzle alignment");
+  static constexpr int kStoreBytes = kEpilogueWarps * 2 * 32 * kStoreCols * 4;
+  static constexpr int kBudget = 227 * 1024 - 1024;
+  static constexpr int kStagesSmem = (kBudget - kStoreBytes - 1024) / kStageBytes;
+  static constexpr int kStagesTmem = (512 - 2 * kAccCols) / (2 * BKT);
+  static constexpr int kStagesMin = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
+  static constexpr int kStages = kStagesMin > 8 ? 8 : kStagesMin;
+  static_assert(kStages >= 2, "tile does not fit");
+  static constexpr int kTotal = kStages * kStageBytes + kStoreBytes + 1024 + 1024;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_on(uint64_t* bar, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(bar)), "r"(rank));
+  // plain arrive (as cutlass::arch::ClusterBarrier::arrive(cta_id)): with .release.cluster the compiler emits
+  // MEMBAR.ALL.GPU in front of it - ~3 000 cycles per k-tile, which made the first version 2x SLOWER than one CTA.
+  // What the leader's MMA consumes was made visible by other means: the operand tiles by the TMA's own completion on
+  // this CTA's barrier, the tensor-memory stores by tcgen05.wait::st + fence::before_thread_sync.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!done);
+}
+// arrives on `bar` in BOTH CTAs once every MMA issued so far has finished
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// kind::tf32, fp32 accumulate, K-major A and B, M = 256 (the pair), N = n
+__device__ __forceinline__ uint32_t instr_desc_pair(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32x3_ts2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                       const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_bhalf,
+                       const __grid_constant__ CUtensorMap map_c, Params p) {
+  using S = T2Smem<BN>;
+  constexpr int kStages = S::kStages;
+  constexpr int kTmemCols = 512;
+  constexpr int kAcc = S::kAccCols;
+  constexpr int kACol0 = 2 * kAcc;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* store_base = smem + kStages * S::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(store_base + S::kStoreBytes);
+  uint64_t* full = bars;                        // local: this CTA's TMA loads of the stage have landed
+  uint64_t* a_ready = bars + kStages;           // leader's copy counts the transform warps of BOTH CTAs
+  uint64_t* empty = bars + 2 * kStages;         // both copies: multicast commit
+  uint64_t* tmem_full = bars + 3 * kStages;     // both copies: multicast commit
+  uint64_t* tmem_empty = bars + 3 * kStages + 2;   // leader's copy counts the epilogue warps of BOTH CTAs
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const long long k_tiles = (p.K + BKT - 1) / BKT;
+  const long long m2_blocks = (p.M + 2 * BM - 1) / (2 * BM);
+  const long long n_tiles_total = m2_blocks * p.n_blocks;
+  const long long first_tile = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+
+  if (warp == kProducerWarp && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_bhi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_blo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_bhalf)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_c)) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&a_ready[s], 2 * kTransformWarps);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 2 * kEpilogueWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {     // the same warp of both CTAs allocates (and later frees) the pair's tensor memory
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();        // barrier inits and the allocation are visible to the peer before anything arrives remotely
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      int n_stamp = 0;
+      const int half = p.n_tile >> 1;
+      const uint32_t tx = (uint32_t)(S::kABytes + (p.n_tile + half) * kRowBytesT);
+      const CUtensorMap* map_y = rank == 0 ? &map_bhi : &map_blo;
+      for (long long tile = first_tile; tile < n_tiles_total; tile += tile_step) {
+        const long long mb2 = tile / p.n_blocks;
+        const int nb = (int)(tile % p.n_blocks);
+        const int row0 = (int)(mb2 * 2 * BM) + (int)rank * BM;
+        for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          stamp(p, 0, n_stamp);
+          uint8_t* st = stage_base + (size_t)s * S::kStageBytes;
+          mbar_expect_tx(&full[s], tx);
+          tma_load_2d(st, &map_a, (int)(kt * BKT), row0, &full[s]);
+          tma_load_2d(st + S::kABytes, map_y, (int)(kt * BKT), nb * p.n_tile, &full[s]);
+          tma_load_2d(st + S::kABytes + S::kYBytes, &map_bhalf, (int)(kt * BKT), nb * p.n_tile + (int)rank * half, &full[s]);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = instr_desc_pair(p.n_tile);
+      const uint32_t idesc2 = instr_desc_pair(2 * p.n_tile);
+      uint32_t it = 0, acc_it = 0;
+      int n_stamp = 0;
+      for (long long tile = first_tile; tile < n_tiles_total; tile += tile_step, ++acc_it) {
+        const int a = acc_it & 1;
+        const uint32_t aph = (acc_it >> 1) & 1;
+        mbar_wait_cluster(&tmem_empty[a], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(a * kAcc);
+        for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&full[s], ph);
+          stamp(p, 1, n_stamp);
+          mbar_wait_cluster(&a_ready[s], ph);      // both CTAs: operand tiles landed, A hi / lo in tensor memory
+          stamp(p, 1, n_stamp);
+          tc_fence_after();
+          const uint32_t st = smem_u32(stage_base + (size_t)s * S::kStageBytes);
+          const uint64_t b_y = ts::smem_desc_sw128(st + S::kABytes), b_x = ts::smem_desc_sw128(st + S::kABytes + S::kYBytes);
+          const uint32_t a_hi = tmem_base + (uint32_t)(kACol0 + s * 2 * BKT), a_lo = a_hi + BKT;
+#pragma unroll
+          for (int kb = 0; kb < BKT / UMMA_K; ++kb) {
+            if (p.dbg_skip & 2) break;
+            const uint64_t adv = (uint64_t)((kb * UMMA_K * 4) >> 4);
+            const uint32_t acol = (uint32_t)(kb * UMMA_K);
+            umma_tf32_ts_pair(d_tmem, a_hi + acol, b_y + adv, idesc2, (kt > 0 || kb > 0) ? 1u : 0u);   // hi*hi | hi*lo
+            umma_tf32_ts_pair(d_tmem, a_lo + acol, b_x + adv, idesc, 1u);                               // + lo*hi
+          }
+          umma_commit_pair(&empty[s]);
+          stamp(p, 1, n_stamp);
+        }
+        umma_commit_pair(&tmem_full[a]);
+      }
+    }
+  } else if (warp >= kTransformWarp0) {
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t it = 0;
+    int n_stamp = 0;
+    const bool stamper = (threadIdx.x == kTransformWarp0 * 32);
+    for (long long tile = first_tile; tile < n_tiles_total; tile += tile_step) {
+      for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full[s], ph);
+        if (stamper) stamp(p, 2, n_stamp);
+        if (!(p.dbg_skip & 1)) {
+          const uint32_t rbase = smem_u32(stage_base + (size_t)s * S::kStageBytes) + (uint32_t)row * (uint32_t)kRowBytesT;
+          float hi[BKT], lo[BKT];
+          float4 v[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = lds128(rbase + (uint32_t)((c ^ (row & 7)) << 4));
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float x[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              hi[4 * c + q] = tf32_rn(x[q]);
+              lo[4 * c + q] = x[q] - hi[4 * c + q];
+            }
+          }
+          const uint32_t acol = tmem_base + lane_field + (uint32_t)(kACol0 + s * 2 * BKT);
+          ts::tmem_st32(acol, hi);
+          ts::tmem_st32(acol + BKT, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_on(&a_ready[s], 0);
+        if (stamper) stamp(p, 2, n_stamp);
+      }
+    }
+  } else {
+    uint32_t acc_it = 0, chunk_it = 0;
+    int n_stamp = 0;
+    for (long long tile = first_tile; tile < n_tiles_total; tile += tile_step, ++acc_it) {
+      const long long mb2 = tile / p.n_blocks;
+      const int nb = (int)(tile % p.n_blocks);
+      const int a = acc_it & 1;
+      const uint32_t aph = (acc_it >> 1) & 1;
+      mbar_wait(&tmem_full[a], aph);
+      if (threadIdx.x == 0) stamp(p, 3, n_stamp);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kAcc);
+      const long long row0 = mb2 * 2 * BM + (long long)rank * BM + warp * 32;
+      const int col0 = nb * p.n_tile;
+      uint8_t* wbuf = store_base + warp * (2 * 32 * kStoreCols * 4);
+      const int n_valid = (p.N - col0) < p.n_tile ? (int)(p.N - col0) : p.n_tile;
+      for (int c = 0; c < n_valid; c += kStoreCols, ++chunk_it) {
+        const uint32_t buf = smem_u32(wbuf + (chunk_it & 1) * (32 * kStoreCols * 4));
+        uint32_t v[32], v2[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+              "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+              "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+              "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(taddr + (uint32_t)c));
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v2[0]), "=r"(v2[1]), "=r"(v2[2]), "=r"(v2[3]), "=r"(v2[4]), "=r"(v2[5]), "=r"(v2[6]), "=r"(v2[7]),
+              "=r"(v2[8]), "=r"(v2[9]), "=r"(v2[10]), "=r"(v2[11]), "=r"(v2[12]), "=r"(v2[13]), "=r"(v2[14]), "=r"(v2[15]),
+              "=r"(v2[16]), "=r"(v2[17]), "=r"(v2[18]), "=r"(v2[19]), "=r"(v2[20]), "=r"(v2[21]), "=r"(v2[22]), "=r"(v2[23]),
+              "=r"(v2[24]), "=r"(v2[25]), "=r"(v2[26]), "=r"(v2[27]), "=r"(v2[28]), "=r"(v2[29]), "=r"(v2[30]), "=r"(v2[31])
+            : "r"(taddr + (uint32_t)(BN + c)));
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = buf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+          sts128(dst, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                  __uint_as_float(v[4 * j + 3])));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0 && row0 < p.M) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                       ::"l"(reinterpret_cast<uint64_t>(&map_c)), "r"(col0 + c), "r"((int)row0), "r"(buf) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_on(&tmem_empty[a], 0);
+      if (threadIdx.x == 0) stamp(p, 3, n_stamp);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  cluster_sync_all();        // nobody leaves (or frees tensor memory) while the peer can still arrive here
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace ts2
+
 // hi / lo planes of the (small) weight operand: hi = w rounded to tf32, lo = w - hi
 __global__ void split_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -995,6 +1301,38 @@ static int launch_ts(const CUtensorMap& ma, const CUtensorMap& mh, const CUtenso
   return check_cuda(cudaGetLastError(), "gemm_tf32x3_ts_kernel launch");
 }
 
+// CTA-pair launch: clusters of two CTAs, one cluster per TPC
+template <int BN>
+static int launch_ts2(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mhalf,
+                      const CUtensorMap& mc, const Params& p, cudaStream_t s) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(ts2::gemm_tf32x3_ts2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    ts2::T2Smem<BN>::kTotal);
+  });
+  if (attr_err != cudaSuccess) return check_cuda(attr_err, "gemm_tf32x3_ts2 smem attribute");
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long tiles = ((p.M + 2 * BM - 1) / (2 * BM)) * p.n_blocks;
+  const long long pairs = tiles < sms / 2 ? tiles : sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = ts2::T2Smem<BN>::kTotal;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return check_cuda(cudaLaunchKernelEx(&cfg, ts2::gemm_tf32x3_ts2_kernel<BN>, ma, mh, ml, mhalf, mc, p),
+                    "gemm_tf32x3_ts2_kernel launch");
+}
+
 }  // namespace tf32x3
 }  // namespace eqf
 
@@ -1054,6 +1392,13 @@ extern "C" int eqf_gemm_tf32x3(const float* A, const float* Bt, float* C, int64_
     if ((rc = make_map(&mh, hi, N, K, K, n_tile, ts::BKT)) != EQF_OK) return rc;
     if ((rc = make_map(&ml, lo, N, K, K, n_tile, ts::BKT)) != EQF_OK) return rc;
     static const bool stack = [] { const char* e = std::getenv("EQF_TF32X3_STACK"); return e == nullptr || e[0] != '0'; }();
+    // CTA-pair variant (EQF_TF32X3_2SM=1; off by default): one M = 256 instruction pair per 256 rows
+    const char* pair_env = std::getenv("EQF_TF32X3_2SM");
+    if (stack && pair_env != nullptr && pair_env[0] == '1' && (n_tile == 32 || n_tile == 64) && N == n_tile) {
+      CUtensorMap mhalf;
+      if ((rc = make_map(&mhalf, hi, N, K, K, n_tile / 2, ts::BKT)) != EQF_OK) return rc;
+      return n_tile == 32 ? launch_ts2<32>(ma, mh, ml, mhalf, mc, p, s) : launch_ts2<64>(ma, mh, ml, mhalf, mc, p, s);
+    }
     if (stack && n_tile == 32) return launch_ts<32, true>(ma, mh, ml, mc, p, s);
     if (stack && n_tile == 64) return launch_ts<64, true>(ma, mh, ml, mc, p, s);
     if (n_tile <= 32) return launch_ts<32, false>(ma, mh, ml, mc, p, s);

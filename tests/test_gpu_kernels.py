@@ -207,6 +207,24 @@ def test_tf32x3_tcgen05_gemm(cuda_device, M, N, K):
     assert rel_err(ops.gemm_tf32x3_raw(d(A), d(Bt).t().contiguous(), b_is_kn=True), ref) < tol
 
 
+@pytest.mark.parametrize("M,N,K", [(100, 64, 96), (128, 32, 32), (130, 32, 352), (1000, 64, 100), (40000, 32, 96), (97680, 64, 384)])
+def test_tf32x3_cta_pair_kernel_matches_single_cta(cuda_device, M, N, K, monkeypatch):
+    """The opt-in cta_group::2 variant of the narrow-output kernel (EQF_TF32X3_2SM=1; two CTAs share each M = 256
+    instruction) must reproduce the single-CTA kernel bit for bit - same products, same accumulation order - including
+    tiles whose second half lies past the last row."""
+    from equiformer_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(cuda_device)
+    Bt = torch.randn(N, K, generator=g).to(cuda_device)
+    monkeypatch.setenv("EQF_TF32X3_2SM", "0")
+    single = ops.gemm_tf32x3_raw(A, Bt)
+    monkeypatch.setenv("EQF_TF32X3_2SM", "1")
+    pair = ops.gemm_tf32x3_raw(A, Bt)
+    assert torch.equal(single, pair)
+    assert rel_err(pair, A.double().cpu() @ Bt.double().cpu().t()) < 6e-6 * max(1.0, (K / 256) ** 0.5)
+    assert torch.equal(ops.gemm_tf32x3_raw(A, Bt.t().contiguous(), b_is_kn=True), pair)
+
+
 @pytest.mark.parametrize("R,K1,N", [(100, 32, 32), (1000, 64, 48), (3001, 100, 72), (36000, 224, 224), (36000, 224, 352),
                                     (36000, 64, 960), (2324, 128, 128), (11620, 32, 32), (108000, 384, 64), (17, 260, 40)])
 def test_tf32x3_tcgen05_weight_gradient(cuda_device, R, K1, N, monkeypatch):
