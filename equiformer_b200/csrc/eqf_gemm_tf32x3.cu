@@ -985,7 +985,7 @@ static EncodeTiled encode_fn() {
 // 2-D fp32 tensor [rows, cols] with row stride ld (elements), box = [box_rows, box_cols], swizzle span = box row bytes
 // (64 or 128), zero fill out of bounds (loads) / clipping (stores)
 static int make_map(CUtensorMap* map, const float* base, long long rows, long long cols, long long ld, int box_rows,
-                    int box_cols, bool atom_32b = false) {
+                    int box_cols, bool atom_32b = false, bool linear = false) {
   EncodeTiled enc = encode_fn();
   if (enc == nullptr) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return EQF_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -993,7 +993,9 @@ static int make_map(CUtensorMap* map, const float* base, long long rows, long lo
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   // atom_32b: 32-byte chunks swizzled within the 128-byte span - the only layout the MMA accepts for MN-major tf32 operands
-  const CUtensorMapSwizzle sw = atom_32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+  // linear: rows of the box land back to back, unswizzled (read by threads, never by the MMA)
+  const CUtensorMapSwizzle sw = linear ? CU_TENSOR_MAP_SWIZZLE_NONE
+                                : atom_32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
                                 : (box_cols * 4 == 128) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1281,6 +1283,233 @@ static int launch(const CUtensorMap& ma, const CUtensorMap& mg, const CUtensorMa
   return check_cuda(cudaGetLastError(), "wgrad_tf32x3_kernel launch");
 }
 
+
+// ------------------------------------------------------------------------------------------------ narrow outputs
+// N <= 64: the A^T operand goes through TENSOR memory instead of shared memory.  The kernel above splits both tiles in
+// shared memory (20 KB read + 40 KB written per 32-row stage) and every MMA re-reads its A tiles from there - shared-memory
+// bandwidth, not HBM, bounded it.  Here the A tile lands unswizzled ([32 rows][128 columns]); transform thread k1 reads
+// its COLUMN (a warp reads 32 consecutive floats per row: conflict-free), splits it in registers and stores hi / lo as
+// 32 + 32 columns of its tensor-memory lane - the transpose costs nothing, and that is the K-major layout an MMA takes
+// its A operand from.  Only the small G tile is split in shared memory, hi and lo blocks back to back so that
+// [g_hi | g_lo] is ONE MN-major operand of N' = 2 n columns (stacked as in ts::):
+//   MMA 1  a_hi x [g_hi | g_lo]   -> accumulator columns [0, n) and [n, 2n)
+//   MMA 2  a_lo x  g_hi           -> added to [0, n);   the epilogue adds the halves.
+template <int BN>
+struct WTSmem {
+  static constexpr int kABytes = BKR * BM * 4;                     // raw A tile, 512-byte rows
+  static constexpr int kGBytes = (BN / 32) * kBlockBytes;          // G hi; G lo follows
+  static constexpr int kStageBytes = kABytes + 2 * kGBytes;
+  static constexpr int kAcc = 2 * BN;
+  static constexpr int kStoreBytes = kEpilogueWarps * 2 * 32 * kStoreCols * 4;
+  static constexpr int kBudget = 227 * 1024 - 1024;
+  static constexpr int kStagesSmem = (kBudget - kStoreBytes - 1024) / kStageBytes;
+  static constexpr int kStagesTmem = (512 - kAcc) / (2 * BKR);
+  static constexpr int kStagesMin = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
+  static constexpr int kStages = kStagesMin > 8 ? 8 : kStagesMin;
+  static_assert(kStages >= 2, "tile does not fit");
+  static constexpr int kTotal = kStages * kStageBytes + kStoreBytes + 1024 + 1024;
+};
+
+// A from tensor memory (K-major by construction), B MN-major
+__device__ __forceinline__ uint32_t instr_desc_ts_mn(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_g,
+                       const __grid_constant__ CUtensorMap map_p, WParams p) {
+  static_assert(BKR == 32, "one tcgen05.st.x32 per half");
+  using S = WTSmem<BN>;
+  constexpr int kStages = S::kStages;
+  constexpr int kTmemCols = 512;
+  constexpr int kACol0 = S::kAcc;
+  constexpr int g_blocks = BN / 32;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* store_base = smem + kStages * S::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(store_base + S::kStoreBytes);
+  uint64_t* full = bars;
+  uint64_t* a_ready = bars + kStages;
+  uint64_t* empty = bars + 2 * kStages;
+  uint64_t* tmem_full = bars + 3 * kStages;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 3 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mt = blockIdx.x;                  // one column tile (n_tile == BN)
+  const long long r0 = (long long)blockIdx.y * p.rows_per_slice;
+  long long rows = p.R - r0;
+  if (rows > p.rows_per_slice) rows = p.rows_per_slice;
+  const int k_tiles = (int)((rows + BKR - 1) / BKR);
+
+  if (warp == kProducerWarp && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_g)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_p)) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&a_ready[s], kTransformWarps);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == kProducerWarp) {
+    if (lane == 0) {
+      const uint32_t tx = (uint32_t)(S::kABytes + S::kGBytes);
+      for (int kt = 0; kt < k_tiles; ++kt) {
+        const int s = kt % kStages;
+        const uint32_t ph = (kt / kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = stage_base_of(smem, s, S::kStageBytes);
+        mbar_expect_tx(&full[s], tx);
+        const int row = (int)(r0 + (long long)kt * BKR);
+        tma_load_2d(st, &map_a, mt * BM, row, &full[s]);
+        for (int j = 0; j < g_blocks; ++j) tma_load_2d(st + S::kABytes + j * kBlockBytes, &map_g, 32 * j, row, &full[s]);
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc_ts_mn(BN), idesc2 = instr_desc_ts_mn(2 * BN);
+      for (int kt = 0; kt < k_tiles; ++kt) {
+        const int s = kt % kStages;
+        const uint32_t ph = (kt / kStages) & 1;
+        mbar_wait(&a_ready[s], ph);
+        tc_fence_after();
+        const uint32_t st = smem_u32(stage_base_of(smem, s, S::kStageBytes));
+        const uint32_t a_hi = tmem_base + (uint32_t)(kACol0 + s * 2 * BKR), a_lo = a_hi + BKR;
+#pragma unroll
+        for (int kb = 0; kb < BKR / UMMA_K; ++kb) {
+          if (p.dbg_skip & 2) break;
+          const uint64_t g = smem_desc_mn(st + S::kABytes + (uint32_t)kb * 1024u);    // [g_hi | g_lo], next 8-row group
+          const uint32_t acol = (uint32_t)(kb * UMMA_K);
+          ts::umma_tf32_ts(tmem_base, a_hi + acol, g, idesc2, (kt > 0 || kb > 0) ? 1u : 0u);
+          ts::umma_tf32_ts(tmem_base, a_lo + acol, g, idesc, 1u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else if (warp >= kTransformWarp0) {
+    const int t = threadIdx.x - kTransformWarp0 * 32;          // index for the G pieces
+    const int col = (warp & 3) * 32 + lane;                    // column of the A tile = tensor-memory lane (a warp owns
+    const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;   // the lane quarter 32 (warp % 4))
+    constexpr int n_piece = g_blocks * kBlockBytes / 16;
+    for (int kt = 0; kt < k_tiles; ++kt) {
+      const int s = kt % kStages;
+      const uint32_t ph = (kt / kStages) & 1;
+      mbar_wait(&full[s], ph);
+      const uint32_t st = smem_u32(stage_base_of(smem, s, S::kStageBytes));
+      if (!(p.dbg_skip & 1)) {
+        const uint32_t gbase = st + S::kABytes;
+        float4 v[n_piece / kTransformThreads];
+#pragma unroll
+        for (int i = 0; i < n_piece / kTransformThreads; ++i) v[i] = lds128(gbase + (uint32_t)(i * kTransformThreads + t) * 16u);
+#pragma unroll
+        for (int i = 0; i < n_piece / kTransformThreads; ++i)
+          split_store(gbase + (uint32_t)(i * kTransformThreads + t) * 16u, S::kGBytes, v[i]);
+        float hi[BKR], lo[BKR];
+#pragma unroll
+        for (int r = 0; r < BKR; ++r) {
+          float x;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(st + (uint32_t)(r * BM * 4 + col * 4)));
+          hi[r] = tf32_rn(x);
+          lo[r] = x - hi[r];
+        }
+        const uint32_t acol = tmem_base + lane_field + (uint32_t)(kACol0 + s * 2 * BKR);
+        ts::tmem_st32(acol, hi);
+        ts::tmem_st32(acol + BKR, lo);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_ready[s]);
+    }
+  } else {
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint8_t* wbuf = store_base + warp * (2 * 32 * kStoreCols * 4);
+    uint32_t chunk_it = 0;
+    for (int c = 0; c < BN; c += kStoreCols, ++chunk_it) {
+      const uint32_t buf = smem_u32(wbuf + (chunk_it & 1) * (32 * kStoreCols * 4));
+      uint32_t v[32], v2[32];
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr + (uint32_t)c));
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v2[0]), "=r"(v2[1]), "=r"(v2[2]), "=r"(v2[3]), "=r"(v2[4]), "=r"(v2[5]), "=r"(v2[6]), "=r"(v2[7]),
+            "=r"(v2[8]), "=r"(v2[9]), "=r"(v2[10]), "=r"(v2[11]), "=r"(v2[12]), "=r"(v2[13]), "=r"(v2[14]), "=r"(v2[15]),
+            "=r"(v2[16]), "=r"(v2[17]), "=r"(v2[18]), "=r"(v2[19]), "=r"(v2[20]), "=r"(v2[21]), "=r"(v2[22]), "=r"(v2[23]),
+            "=r"(v2[24]), "=r"(v2[25]), "=r"(v2[26]), "=r"(v2[27]), "=r"(v2[28]), "=r"(v2[29]), "=r"(v2[30]), "=r"(v2[31])
+          : "r"(taddr + (uint32_t)(BN + c)));
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t dst = buf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+        sts128(dst, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                __uint_as_float(v[4 * j + 3])));
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        if (p.reduce) {
+          asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%1, %2}], [%3];"
+                       ::"l"(reinterpret_cast<uint64_t>(&map_p)), "r"(c), "r"(mt * BM + warp * 32), "r"(buf) : "memory");
+        } else {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+                       ::"l"(reinterpret_cast<uint64_t>(&map_p)), "r"(c), "r"(mt * BM + warp * 32), "r"((int)blockIdx.y), "r"(buf)
+                       : "memory");
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    tc_fence_before();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+template <int BN>
+static int launch_ts(const CUtensorMap& ma, const CUtensorMap& mg, const CUtensorMap& mp, const WParams& p, const Shape& sh,
+                     cudaStream_t s) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(wgrad_tf32x3_ts_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WTSmem<BN>::kTotal);
+  });
+  if (attr_err != cudaSuccess) return check_cuda(attr_err, "wgrad_tf32x3_ts smem attribute");
+  dim3 grid((unsigned)sh.m_tiles, (unsigned)sh.slices);
+  wgrad_tf32x3_ts_kernel<BN><<<grid, kThreads, WTSmem<BN>::kTotal, s>>>(ma, mg, mp, p);
+  return check_cuda(cudaGetLastError(), "wgrad_tf32x3_ts_kernel launch");
+}
+
 }  // namespace wg
 template <int BN, bool STACK>
 static int launch_ts(const CUtensorMap& ma, const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mc,
@@ -1441,6 +1670,13 @@ static int wgrad_impl(const float* A, const float* G, float* out, bool reduce, i
     if ((rc = make_map(&mp, out, K1, N, N, 32, kStoreCols)) != EQF_OK) return rc;
   } else {
     if ((rc = wg::make_map3(&mp, out, sh.slices, K1, N)) != EQF_OK) return rc;
+  }
+  // narrow outputs: A^T through tensor memory (wg::wgrad_tf32x3_ts_kernel; EQF_TF32X3_WGRAD_TS=0 keeps the
+  // shared-memory kernel): 89.9 -> 60.1 us on [162 800, 352]^T x 32, 63.0 -> 43.5 us on [97 680, 384]^T x 64
+  const char* wts = std::getenv("EQF_TF32X3_WGRAD_TS");
+  if ((wts == nullptr || wts[0] != '0') && sh.n_tiles == 1 && sh.n_tile <= 64) {
+    if ((rc = make_map(&ma, A, R, K1, lda, wg::BKR, BM, false, true)) != EQF_OK) return rc;
+    return sh.n_tile == 32 ? wg::launch_ts<32>(ma, mg, mp, p, sh, s) : wg::launch_ts<64>(ma, mg, mp, p, sh, s);
   }
   if (sh.n_tile <= 32) return wg::launch<32>(ma, mg, mp, p, sh, s);
   if (sh.n_tile <= 64) return wg::launch<64>(ma, mg, mp, p, sh, s);

@@ -227,11 +227,14 @@ def test_tf32x3_cta_pair_kernel_matches_single_cta(cuda_device, M, N, K, monkeyp
 
 @pytest.mark.parametrize("R,K1,N", [(100, 32, 32), (1000, 64, 48), (3001, 100, 72), (36000, 224, 224), (36000, 224, 352),
                                     (36000, 64, 960), (2324, 128, 128), (11620, 32, 32), (108000, 384, 64), (17, 260, 40)])
-def test_tf32x3_tcgen05_weight_gradient(cuda_device, R, K1, N, monkeypatch):
+@pytest.mark.parametrize("a_through_tmem", ["1", "0"])
+def test_tf32x3_tcgen05_weight_gradient(cuda_device, R, K1, N, a_through_tmem, monkeypatch):
     """Hand-written tcgen05 3xTF32 weight gradient W = A^T G (MN-major operands, per-slice TMEM accumulators, column
     sum over slices) vs fp64.  The TMEM accumulation truncates, so the error grows with the rows per slice (~1e-5 at
-    2 000 rows); single-pass TF32 would be 1e-3."""
+    2 000 rows); single-pass TF32 would be 1e-3.  Outputs of <= 64 columns take the A^T operand through tensor memory
+    (the default) or, with EQF_TF32X3_WGRAD_TS=0, through shared memory like the wide ones: both are covered."""
     from equiformer_b200 import ops
+    monkeypatch.setenv("EQF_TF32X3_WGRAD_TS", a_through_tmem)
     g = torch.Generator().manual_seed(R + K1 + N)
     A = torch.randn(R, K1, generator=g)
     G = torch.randn(R, N, generator=g)
