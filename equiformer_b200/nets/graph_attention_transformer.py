@@ -17,7 +17,7 @@ There is no CPU implementation of these two forwards: CPU tensors raise (``equif
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Sequence
+from typing import List, Sequence
 
 import torch
 

@@ -23,7 +23,7 @@ from __future__ import annotations
 
 import collections
 import re
-from typing import Iterable, Iterator, List, Tuple, Union
+from typing import Iterator, List, Tuple, Union
 
 _IRREP_RE = re.compile(r"^\s*(\d+)\s*([eoy])\s*$")
 

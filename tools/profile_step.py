@@ -1,5 +1,4 @@
 """torch.profiler breakdown of one training step of bench.py's workload: GPU-busy time vs wall time, top kernels."""
-import json
 import os
 import sys
 

@@ -1,8 +1,8 @@
-import sys, os, ctypes
+import sys, os
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from equiformer_b200 import ops, _lib
+from equiformer_b200 import _lib
 dev = torch.device("cuda:0")
 lib = _lib.load()
 torch.set_printoptions(linewidth=250, precision=2, sci_mode=False)
