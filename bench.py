@@ -15,7 +15,8 @@ backward (+ gradient all-reduce for N>1) + AdamW update.  Metric: edges processe
 * ``roofline`` - the dominant hand-written kernel by summed device time (CUDA events around every launch of our
                  kernels, on the launching stream, inside the timed region): algorithmic bytes / time vs the measured
                  HBM copy bandwidth in MEASURED_PEAKS.json.
-* ``cpu_baseline`` - the oracle (reference-style op chain, torch CPU) timed on a bounded sample of the same batch.
+* ``cpu_baseline`` - the oracle (reference-style op chain, torch CPU) timed on a bounded sample of the same batch
+                     (N = 1 only; null in multi-GPU runs).
 
 Multi-GPU: one process per GPU (torchrun), independent molecule batch per rank (weak scaling), NCCL all-reduce of
 one flat gradient bucket per step; time = max over ranks, measured with CUDA events between barriers.
@@ -339,7 +340,7 @@ def run_ours(args):
                     "timed_in": "instrumented eager pass of the same step: CUDA events around each launch of our kernels, "
                                 "a GPU-side delay queued before each pair keeps host launch gaps out of the interval"}
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU leg is an N = 1 figure (rank 0's host cores)
             torch.set_num_threads(host_threads())
             params, cfg, cpos, cbatch, cz, ctgt, cgraphs, cedges = cpu_sample(args.ref_graphs)
             oracle_step(params, cfg, cpos, cbatch, cz, ctgt, cgraphs)
