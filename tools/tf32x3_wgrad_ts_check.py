@@ -12,13 +12,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = [  # R, K1, N
     (100, 32, 32), (1000, 64, 48), (3001, 100, 64), (17, 260, 40), (11620, 32, 32), (6972, 64, 64), (2324, 128, 32),
     (162800, 352, 32), (97680, 384, 64), (32560, 224, 64), (162800, 96, 32), (97680, 192, 64),
+    # 65 ... 128 columns: only differ between the variants with EQF_WGRAD_TS_LEVEL=2 (see main)
+    (1000, 64, 72), (2324, 128, 128), (32560, 224, 128), (32560, 672, 128), (36000, 300, 96),
 ]
+LEVEL = os.environ.get("EQF_WGRAD_TS_LEVEL", "1")      # "2": also route 65 ... 128 columns through tensor memory
 
 
 def run_case(R, K1, N, ts):
     import torch
     from equiformer_b200 import ops
-    os.environ["EQF_TF32X3_WGRAD_TS"] = "1" if ts else "0"
+    os.environ["EQF_TF32X3_WGRAD_TS"] = LEVEL if ts else "0"
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(R + 7 * K1 + N)
     A = torch.randn(R, K1, generator=g).to(dev)
