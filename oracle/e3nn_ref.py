@@ -5,6 +5,8 @@ PARITY UNPINNED: ``e3nn==0.4.4`` (``/root/reference/env/env_equiformer.yml:358``
 dependency, absent from this image and not installable (no network); the reference ships no tests or golden vectors
 (SURVEY.md section 4).  This file therefore restates e3nn's *published* algorithms and is anchored on the
 reference's call sites and on mathematical invariants (tests/test_oracle.py), not on outputs of the real library.
+(What IS pinned to the reference's own code - its module and model files executed on top of these restatements - is
+listed in ``oracle/equiformer_ref.py``.)
 
 Call sites restated:
   * ``o3.TensorProduct(..., path_normalization='none')``  - nets/tensor_product_rescale.py:33-37

@@ -1,4 +1,6 @@
-"""CPU: self-consistency of the oracle (PARITY UNPINNED: no reference golden vectors exist - SURVEY.md section 4).
+"""CPU: self-consistency of the oracle's third-party numerics (PARITY UNPINNED for those: e3nn cannot run here and the
+reference ships no golden vectors - SURVEY.md section 4; what IS pinned to the reference's own code lives in
+tests/test_reference_golden.py).
 
 What can be pinned without the absent third-party packages: e3nn's normalize2mom recipe reproduces the constants the
 survey recorded, the tensor product is O(3)-equivariant under Wigner matrices derived independently from the SH,
