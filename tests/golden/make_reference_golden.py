@@ -380,6 +380,26 @@ def main():
     print(f"wrote {path}: {len(small)} arrays, {os.path.getsize(path) / 1024:.0f} KiB; energy {energy.flatten().tolist()}")
     torch.set_default_dtype(torch.float32)
 
+    # ---- every registered configuration that does not need ocpmodels' Bessel basis, at its real size: parameter and
+    # buffer names with shapes, as the reference's constructors create them (no forward; a few KB of JSON)
+    import json
+    table = {}
+    for mod, irreps_in, names in (
+            (gat, "5x0e", ["graph_attention_transformer_l2", "graph_attention_transformer_nonlinear_l2",
+                           "graph_attention_transformer_nonlinear_l2_e3"]),
+            (md, "64x0e", ["graph_attention_transformer_l2_md17", "graph_attention_transformer_nonlinear_l2_md17",
+                           "graph_attention_transformer_nonlinear_l2_e3_md17", "graph_attention_transformer_nonlinear_exp_l2_md17",
+                           "graph_attention_transformer_nonlinear_exp_l3_md17", "graph_attention_transformer_nonlinear_attn_exp_l3_md17",
+                           "graph_attention_transformer_nonlinear_exp_l3_e3_md17"])):
+        for name in names:
+            model = getattr(mod, name)(irreps_in=irreps_in, radius=5.0, num_basis=128)
+            table[name] = {k: list(v.shape) for k, v in model.state_dict().items() if v is not None}
+            print(f"  {name}: {len(table[name])} entries, {sum(p.numel() for p in model.parameters())} parameters")
+    path = os.path.join(HERE, "reference_state_shapes.json")
+    with open(path, "w") as f:
+        json.dump(table, f, indent=0, sort_keys=True)
+    print(f"wrote {path}: {os.path.getsize(path) / 1024:.0f} KiB")
+
 
 if __name__ == "__main__":
     main()
