@@ -380,6 +380,42 @@ def main():
     print(f"wrote {path}: {len(small)} arrays, {os.path.getsize(path) / 1024:.0f} KiB; energy {energy.flatten().tolist()}")
     torch.set_default_dtype(torch.float32)
 
+    # ---- the HEADLINE configuration at its real size (3.53 M parameters).  Large tensors are replaced by a closed form of
+    # (name, shape, mean, std) that the tests rebuild (tests/helpers.closed_form_tensor), small ones are stored verbatim
+    from tests.helpers import closed_form_tensor
+    torch.manual_seed(3)
+    model = gat.graph_attention_transformer_nonlinear_l2(irreps_in="5x0e", radius=5.0, num_basis=128)
+    head = {}
+    with torch.no_grad():
+        for k, v in model.state_dict().items():
+            if v is None or not v.is_floating_point() or v.numel() == 0:
+                continue
+            if v.numel() <= 1024:
+                if v.abs().max() == 0:
+                    v.add_(0.05 * torch.randn(v.shape, generator=gen))
+                head[f"small/{k}"] = v.detach().float().numpy().copy()
+            else:
+                mean, std = float(v.mean()), float(v.std())
+                head[f"stat/{k}"] = np.asarray([mean, std], dtype=np.float64)
+                v.copy_(closed_form_tensor(k, v.shape, mean, std))
+    torch.set_default_dtype(torch.float64)
+    model = model.double().eval()
+    n_atoms = [9, 7]
+    batch = torch.repeat_interleave(torch.arange(2), torch.tensor(n_atoms))
+    pos = _f32(1.9 * torch.randn(sum(n_atoms), 3, generator=gen, dtype=torch.float64))
+    z = torch.tensor([6, 1, 1, 8, 7, 1, 9, 6, 1, 6, 6, 8, 1, 1, 7, 1])
+    taps = {}
+    hook = model.blocks[0].register_forward_hook(lambda m, i, o: taps.__setitem__("blocks.0", o.detach()))
+    with torch.no_grad():
+        energy = model(f_in=None, pos=pos, batch=batch, node_atom=z)
+    hook.remove()
+    torch.set_default_dtype(torch.float32)
+    head.update({"pos": pos.float().numpy(), "batch": batch.numpy(), "z": z.numpy(), "energy": energy.numpy(),
+                 "tap/blocks.0": taps["blocks.0"].numpy()})
+    path = os.path.join(HERE, "reference_model_headline.npz")
+    np.savez_compressed(path, **head)
+    print(f"wrote {path}: {len(head)} arrays, {os.path.getsize(path) / 1024:.0f} KiB; energy {energy.flatten().tolist()}")
+
     # ---- every registered configuration that does not need ocpmodels' Bessel basis, at its real size: parameter and
     # buffer names with shapes, as the reference's constructors create them (no forward; a few KB of JSON)
     import json
