@@ -293,3 +293,38 @@ def test_cuda_headline_model_matches_reference_model_file(cuda_device):
     with torch.no_grad():
         energy = model(f_in=None, pos=pos, batch=batch, node_atom=z)
     assert float((energy.double().cpu() - torch.from_numpy(g["energy"])).abs().max()) < 3e-4
+
+
+# --------------------------------- host logic of the mirrors (kernels emulated in float64 on the CPU) vs the reference
+
+def test_mirror_host_logic_matches_reference_model_files():
+    """The mirrors' own wiring (planar layouts, fused-op call sequence, autograd closure for the forces) with the raw
+    kernel calls swapped for float64 torch walks (tests/_emulation.py), against the three reference-run model fixtures."""
+    from equiformer_b200.nets import model_entrypoint
+    from equiformer_b200.nets.graph_attention_transformer import GraphAttentionTransformer
+    from equiformer_b200.nets.graph_attention_transformer_md17 import GraphAttentionTransformerMD17
+    from tests._emulation import emulated_kernels
+
+    g = np.load(SMALL)
+    model = _mirror_model(g, GraphAttentionTransformer).double()
+    with emulated_kernels(), torch.no_grad():
+        energy = model(f_in=None, pos=torch.from_numpy(g["pos"]).double(), batch=torch.from_numpy(g["batch"]),
+                       node_atom=torch.from_numpy(g["z"]))
+    assert rel_err(energy, torch.from_numpy(g["energy"])) < 1e-10
+
+    g = np.load(os.path.join(os.path.dirname(SMALL), "reference_model_md17_small.npz"))
+    model = _mirror_model(g, GraphAttentionTransformerMD17).double()
+    with emulated_kernels():
+        energy, forces = model(node_atom=torch.from_numpy(g["z"]), pos=torch.from_numpy(g["pos"]).double(),
+                               batch=torch.from_numpy(g["batch"]))
+    assert rel_err(energy.detach(), torch.from_numpy(g["energy"])) < 1e-10
+    assert rel_err(forces.detach(), torch.from_numpy(g["forces"])) < 1e-9
+
+    g, state = _headline_state()
+    model = model_entrypoint("graph_attention_transformer_nonlinear_l2")(irreps_in="5x0e", radius=5.0, num_basis=128)
+    model.load_state_dict(state, strict=False)
+    model = model.eval().double()
+    with emulated_kernels(), torch.no_grad():
+        energy = model(f_in=None, pos=torch.from_numpy(g["pos"]).double(), batch=torch.from_numpy(g["batch"]),
+                       node_atom=torch.from_numpy(g["z"]))
+    assert rel_err(energy, torch.from_numpy(g["energy"])) < 1e-9
