@@ -299,6 +299,22 @@ def main():
     out["activation/y"] = m(x).detach().numpy()
     out["activation/irreps"] = np.asarray("48x0e+16x0o")
 
+    # ---- stochastic depth and equivariant dropout (drop.py:31-106) in TRAINING mode: same torch seed, same draws.
+    # EquivariantDropout multiplies through o3.ElementwiseTensorProduct, which here is the plain per-multiplicity product
+    # (the only thing that product can be for scalar masks in 'component' normalisation)
+    _stub_third_party()
+    drop = _reference_module("drop")
+    node_irreps = sys.modules["e3nn.o3"].Irreps("128x0e+64x1e+32x2e")
+    x = _f32(torch.randn(31, 480, generator=torch.Generator().manual_seed(99), dtype=torch.float64)).float()   # own stream, the cases below keep their draws
+    batch31 = torch.repeat_interleave(torch.arange(5), torch.tensor([7, 6, 6, 5, 7]))
+    out["drop/x"], out["drop/batch"] = x.numpy(), batch31.numpy()
+    for tag, module, args in (("drop_path", drop.DropPath(0.3), (x,)), ("graph_drop_path", drop.GraphDropPath(0.4), (x, batch31)),
+                              ("equivariant_dropout", drop.EquivariantDropout(node_irreps, 0.25), (x,)),
+                              ("scalars_dropout", drop.EquivariantScalarsDropout(node_irreps, 0.25), (x,))):
+        module.train()
+        torch.manual_seed(321)
+        out[f"drop/{tag}"] = module(*args).numpy()
+
     path = os.path.join(HERE, "reference_modules.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB")

@@ -328,3 +328,16 @@ def test_mirror_host_logic_matches_reference_model_files():
         energy = model(f_in=None, pos=torch.from_numpy(g["pos"]).double(), batch=torch.from_numpy(g["batch"]),
                        node_atom=torch.from_numpy(g["z"]))
     assert rel_err(energy, torch.from_numpy(g["energy"])) < 1e-9
+
+
+def test_drop_modules_draw_like_the_reference(gold):
+    """DropPath / GraphDropPath / EquivariantDropout / EquivariantScalarsDropout in training mode (drop.py:31-106): with
+    the same torch seed the mirrors must make the same draws in the same order and scale the same way - bit for bit."""
+    from equiformer_b200.nets import drop
+    x, batch = _t(gold, "drop/x", torch.float32), torch.from_numpy(gold["drop/batch"])
+    for tag, module, args in (("drop_path", drop.DropPath(0.3), (x,)), ("graph_drop_path", drop.GraphDropPath(0.4), (x, batch)),
+                              ("equivariant_dropout", drop.EquivariantDropout("128x0e+64x1e+32x2e", 0.25), (x,)),
+                              ("scalars_dropout", drop.EquivariantScalarsDropout("128x0e+64x1e+32x2e", 0.25), (x,))):
+        module.train()
+        torch.manual_seed(321)
+        assert torch.equal(module(*args), _t(gold, f"drop/{tag}", torch.float32)), tag
