@@ -360,8 +360,11 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "edges_per_step": edges_total, "atoms_per_rank": int(pos.shape[0]),
                        "parallelism": f"dp{world}", "l2": f"inputs larger than L2: {mem_gb:.2f} GB of activations per step",
-                       "gemm": ("tcgen05, fp32-accurate: hand-written 3xTF32 kernels (wide forward/dgrad, wide and node-level "
-                                "wgrad) + CUTLASS 3xBF16 collective (narrow outputs, long narrow wgrad)"
+                       "dropout": "attention-weight dropout p = 0 (configuration default 0.2, an [E, 4] mask): the only "
+                                  "stochastic op of the step, off so that the run is comparable with the parity tests",
+                       "gemm": ("tcgen05, fp32-accurate: hand-written 3xTF32 kernels (edge-level forward / dgrad / wgrad, "
+                                "node-level wgrad; A through TMEM for outputs of <= 128 / <= 64 columns) + cuBLAS for the "
+                                "node-level forward products"
                                 if ops.gemm_backend() == "cutlass" else "cuBLAS SGEMM fp32 (allow_tf32=False)"),
                        "launch": ("CUDA-graph replay of forward+loss+backward per (atoms, edges) signature; neighbour "
                                   "search, all-reduce and AdamW eager") if args.graph else "eager",
