@@ -364,7 +364,7 @@ def run_ours(args):
                                   "stochastic op of the step, off so that the run is comparable with the parity tests",
                        "gemm": ("tcgen05, fp32-accurate: hand-written 3xTF32 kernels (edge-level forward / dgrad / wgrad, "
                                 "node-level wgrad; A through TMEM for outputs of <= 128 / <= 64 columns) + cuBLAS for the "
-                                "node-level forward products"
+                                "node-level forward and data-gradient products"
                                 if ops.gemm_backend() == "cutlass" else "cuBLAS SGEMM fp32 (allow_tf32=False)"),
                        "launch": ("CUDA-graph replay of forward+loss+backward per (atoms, edges) signature; neighbour "
                                   "search, all-reduce and AdamW eager") if args.graph else "eager",
