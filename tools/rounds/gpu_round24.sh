@@ -1,14 +1,14 @@
 #!/bin/bash
+# first call of the next round: everything that was written after the round-1 GPU budget ended
+#   - the full GPU suite (includes tests/test_reference_golden.py::test_cuda_headline_model_matches_reference_model_file, never run on a B200)
+#   - the 128-column tensor-memory weight gradient (EQF_TF32X3_WGRAD_TS=2): parity + timing against the shared-memory kernel
+#   - one bench line with and without it
 set -u
-TAG=${1:-r2o}
+TAG=${1:-r4a}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
-echo "== pytest tf32x3"; timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "tf32x3" 2>&1 | tail -5
-echo "== fwd microbench"; timeout 240 python tools/tf32x3_microbench.py > $OUT/tf32x3.jsonl 2> $OUT/tf32x3.err; tail -2 $OUT/tf32x3.err
-grep '"us"' $OUT/tf32x3.jsonl | python -c "
-import sys,json
-print(' '.join(f\"{json.loads(l)['shape']}={json.loads(l)['us']:.1f}({json.loads(l)['rel_err']:.0e})\" for l in sys.stdin))"
-echo "== wgrad microbench"; timeout 240 python tools/tf32x3_wgrad_microbench.py > $OUT/wgrad.jsonl 2> $OUT/wgrad.err; tail -2 $OUT/wgrad.err
-grep '"us"' $OUT/wgrad.jsonl | python -c "
-import sys,json
-print(' '.join(f\"{json.loads(l)['shape']}={json.loads(l)['us']:.1f}({json.loads(l)['rel_err']:.0e})\" for l in sys.stdin))"
+echo "== pytest gpu (all)"; timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -6
+echo "== wgrad through tensor memory, 65 ... 128 columns"
+EQF_WGRAD_TS_LEVEL=2 timeout 400 python tools/tf32x3_wgrad_ts_check.py $OUT/wgrad_ts_level2.jsonl | tail -40
+echo "== bench (default)"; timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench.json 2> $OUT/bench.err; echo "rc=$?"; cut -c1-260 $OUT/bench.json
+echo "== bench (EQF_TF32X3_WGRAD_TS=2)"; EQF_TF32X3_WGRAD_TS=2 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_ts2.json 2> $OUT/bench_ts2.err; echo "rc=$?"; cut -c1-260 $OUT/bench_ts2.json
