@@ -32,6 +32,7 @@ Run in the build container only (``python tests/golden/make_reference_golden.py`
 from __future__ import annotations
 
 import importlib
+import json
 import os
 import sys
 import types
@@ -432,9 +433,55 @@ def main():
     np.savez_compressed(path, **head)
     print(f"wrote {path}: {len(head)} arrays, {os.path.getsize(path) / 1024:.0f} KiB; energy {energy.flatten().tolist()}")
 
+    # ---- one transformer block at the OC20 IS2RE `l1_256_nonlinear` sizes (oc20/configs/is2re/all/graph_attention_transformer/
+    # l1_256_nonlinear_g@2_local.yml: 256x0e+128x1e, 8 heads of 32x0e+16x1e, mlp 768x0e+384x1e, Lmax = 1).  The OC20 model
+    # file itself needs ocpmodels; its blocks are the TransBlock class of graph_attention_transformer.py, run here.
+    torch.manual_seed(5)
+    kw = dict(irreps_node_input="256x0e+128x1e", irreps_node_attr="1x0e", irreps_edge_attr="1x0e+1x1e",
+              irreps_node_output="256x0e+128x1e", fc_neurons=[128, 64, 64], irreps_head="32x0e+16x1e", num_heads=8,
+              irreps_pre_attn="256x0e+128x1e", rescale_degree=False, nonlinear_message=True, alpha_drop=0.0, proj_drop=0.0,
+              drop_path_rate=0.0, irreps_mlp_mid="768x0e+384x1e", norm_layer="layer")
+    blk = gat.TransBlock(**kw)
+    oc = {}
+    with torch.no_grad():
+        for k, v in blk.state_dict().items():
+            if v is None or not v.is_floating_point() or v.numel() == 0:
+                continue
+            if v.numel() <= 1024:
+                if v.abs().max() == 0:
+                    v.add_(0.05 * torch.randn(v.shape, generator=gen))
+                oc[f"small/{k}"] = v.detach().float().numpy().copy()
+            else:
+                mean, std = float(v.mean()), float(v.std())
+                oc[f"stat/{k}"] = np.asarray([mean, std], dtype=np.float64)
+                v.copy_(closed_form_tensor(k, v.shape, mean, std))
+    oc["shapes"] = np.asarray(json.dumps({k: list(v.shape) for k, v in blk.state_dict().items() if v is not None}))
+    torch.set_default_dtype(torch.float64)
+    blk = blk.double().eval()
+    n_nodes = 14
+    g2 = torch.Generator().manual_seed(77)
+    pos = 2.0 * torch.randn(n_nodes, 3, generator=g2, dtype=torch.float64)
+    batch = torch.zeros(n_nodes, dtype=torch.long)
+    edge_src, edge_dst = sys.modules["torch_cluster"].radius_graph(pos, 5.0, batch)
+    edge_sh = sys.modules["e3nn.o3"].spherical_harmonics("1x0e+1x1e", pos[edge_src] - pos[edge_dst], True, "component")
+    edge_scalars = _f32(torch.rand(edge_src.shape[0], 128, generator=g2, dtype=torch.float64))
+    x = _f32(torch.randn(n_nodes, 640, generator=g2, dtype=torch.float64))
+    edge_sh = _f32(edge_sh)
+    with torch.no_grad():
+        y = blk(node_input=x, node_attr=torch.ones(n_nodes, 1), edge_src=edge_src, edge_dst=edge_dst, edge_attr=edge_sh,
+                edge_scalars=edge_scalars, batch=batch)
+    torch.set_default_dtype(torch.float32)
+    oc.update({"x": x.float().numpy(), "edge_src": edge_src.numpy(), "edge_dst": edge_dst.numpy(), "edge_sh": edge_sh.float().numpy(),
+               "edge_scalars": edge_scalars.float().numpy(), "y": y.numpy()})
+    for k, v in kw.items():
+        if v is not None:
+            oc[f"cfg/{k}"] = np.asarray(v)
+    path = os.path.join(HERE, "reference_block_oc20_l1.npz")
+    np.savez_compressed(path, **oc)
+    print(f"wrote {path}: {len(oc)} arrays, {os.path.getsize(path) / 1024:.0f} KiB; E = {edge_src.shape[0]}, max|y| = {float(y.abs().max()):.3f}")
+
     # ---- every registered configuration that does not need ocpmodels' Bessel basis, at its real size: parameter and
     # buffer names with shapes, as the reference's constructors create them (no forward; a few KB of JSON)
-    import json
     table = {}
     for mod, irreps_in, names in (
             (gat, "5x0e", ["graph_attention_transformer_l2", "graph_attention_transformer_nonlinear_l2",

@@ -341,3 +341,78 @@ def test_drop_modules_draw_like_the_reference(gold):
         module.train()
         torch.manual_seed(321)
         assert torch.equal(module(*args), _t(gold, f"drop/{tag}", torch.float32)), tag
+
+
+# ------------------------------------------------------------ one block at the OC20 IS2RE l1_256_nonlinear sizes
+
+OC20_BLOCK = os.path.join(os.path.dirname(SMALL), "reference_block_oc20_l1.npz")
+
+
+def _oc20_block():
+    import json
+    from tests.helpers import closed_form_tensor
+    g = np.load(OC20_BLOCK)
+    state = {}
+    for k, shape in json.loads(str(g["shapes"])).items():
+        if f"small/{k}" in g.files:
+            state[k] = torch.from_numpy(g[f"small/{k}"])
+        elif f"stat/{k}" in g.files:
+            mean, std = (float(v) for v in g[f"stat/{k}"])
+            state[k] = closed_form_tensor(k, shape, mean, std)
+        else:
+            state[k] = torch.zeros(shape)
+            assert state[k].numel() == 0, k
+    kw = {k[len("cfg/"):]: (str(g[k]) if g[k].dtype.kind in "US" else bool(g[k]) if g[k].dtype.kind == "b" else
+                            [int(c) for c in g[k]] if g[k].ndim == 1 else int(g[k]) if g[k].dtype.kind == "i" else float(g[k]))
+          for k in g.files if k.startswith("cfg/")}
+    inputs = {k: torch.from_numpy(g[k]) for k in ("x", "edge_src", "edge_dst", "edge_sh", "edge_scalars")}
+    return g, state, kw, inputs
+
+
+def test_oracle_block_matches_reference_at_oc20_sizes():
+    """``TransBlock`` (graph_attention_transformer.py:575-667) at the channel counts of the OC20 ``l1_256_nonlinear``
+    configuration (256x0e+128x1e, 8 heads, Lmax = 1), run by the reference's code, vs ``oracle.trans_block``."""
+    g, state, kw, t = _oc20_block()
+    cfg = R.Config(irreps_node_embedding=kw["irreps_node_input"], irreps_sh=kw["irreps_edge_attr"], irreps_head=kw["irreps_head"],
+                   irreps_mlp_mid=kw["irreps_mlp_mid"], num_heads=kw["num_heads"], nonlinear_message=kw["nonlinear_message"])
+    params = {f"b.{k}": v for k, v in R.cast_params(state, torch.float64).items()}
+    irreps = e3.parse_irreps(kw["irreps_node_input"])
+    x = t["x"].double()
+    out = R.trans_block(params, "b", cfg, irreps, irreps, x, torch.ones_like(x[:, :1]), t["edge_src"], t["edge_dst"],
+                        t["edge_sh"].double(), t["edge_scalars"].double())
+    assert rel_err(out, torch.from_numpy(g["y"])) < 1e-10
+
+
+def test_mirror_block_host_logic_matches_reference_at_oc20_sizes():
+    from equiformer_b200.nets.graph_attention_transformer import TransBlock
+    from tests._emulation import emulated_kernels
+    g, state, kw, t = _oc20_block()
+    blk = TransBlock(**kw)
+    res = blk.load_state_dict(state, strict=False)
+    assert not res.unexpected_keys and all(k.endswith("tp.output_mask") for k in res.missing_keys)
+    blk = blk.eval().double()
+    x = t["x"].double()
+    with emulated_kernels(), torch.no_grad():
+        out = blk(node_input=x, node_attr=torch.ones_like(x[:, :1]), edge_src=t["edge_src"], edge_dst=t["edge_dst"],
+                  edge_attr=t["edge_sh"].double(), edge_scalars=t["edge_scalars"].double(),
+                  batch=torch.zeros(x.shape[0], dtype=torch.long))
+    assert rel_err(out, torch.from_numpy(g["y"])) < 1e-10
+
+
+@pytest.mark.gpu
+def test_cuda_block_matches_reference_at_oc20_sizes(cuda_device):
+    """The CUDA path of one transformer block at the OC20 ``l1_256_nonlinear`` sizes (generated ``oc20_l1`` kernels,
+    8 heads) against the reference-run fixture; float32 vs float64, same bound as the layer-level oracle test
+    (tests/test_gpu_model.py::test_oc20_l1_layer_vs_oracle).  Written after the round-1 GPU budget ended."""
+    from equiformer_b200.nets.graph_attention_transformer import TransBlock
+    g, state, kw, t = _oc20_block()
+    blk = TransBlock(**kw)
+    blk.load_state_dict(state, strict=False)
+    blk = blk.eval().to(cuda_device)
+    d = lambda v: v.to(cuda_device)
+    x = d(t["x"])
+    with torch.no_grad():
+        out = blk(node_input=x, node_attr=torch.ones_like(x[:, :1]), edge_src=d(t["edge_src"]), edge_dst=d(t["edge_dst"]),
+                  edge_attr=d(t["edge_sh"]), edge_scalars=d(t["edge_scalars"]),
+                  batch=torch.zeros(x.shape[0], dtype=torch.long, device=cuda_device))
+    assert rel_err(out, torch.from_numpy(g["y"])) < 1e-4
