@@ -24,7 +24,14 @@ channel counts.  There the third-party calls the file makes - ``o3.TensorProduct
 ``torch_cluster.radius_graph`` - are served by stubs built on the ORACLE's restatements of those libraries
 (``oracle/e3nn_ref.py``), so this fixture pins the oracle's restatement of the reference's own files (instruction lists,
 irreps sorting, rescale / bias handling, head reshapes, attention wiring, residuals, scale factors), not the third-party
-numerics underneath, which stay "parity unpinned".
+numerics underneath, which stay "parity unpinned".  With the same stubs the script also writes
+  * ``reference_model_md17_small.npz``  - the MD17 model file (Lmax = 3, exp-normal basis, forces by autograd),
+  * ``reference_model_headline.npz``    - the headline configuration at full size (3.53 M parameters; large tensors are a
+                                          closed form of (name, shape, mean, std), see tests/helpers.closed_form_tensor),
+  * ``reference_block_oc20_l1.npz``     - one TransBlock at the OC20 IS2RE l1_256_nonlinear sizes,
+  * ``reference_state_shapes.json``     - parameter / buffer names and shapes of every registered configuration that does
+                                          not need ocpmodels' Bessel basis, from the reference's constructors,
+and, inside ``reference_modules.npz``, training-mode outputs of the dropout / stochastic-depth modules of ``drop.py``.
 
 Run in the build container only (``python tests/golden/make_reference_golden.py``); the GPU box has no
 ``/root/reference`` and only ever reads the committed ``.npz`` files.  No reference source is copied anywhere.
