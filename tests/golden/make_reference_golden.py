@@ -355,8 +355,12 @@ def main():
         energy = model(f_in=None, pos=pos, batch=batch, node_atom=z)
     for h in hooks:
         h.remove()
+    model.zero_grad()
+    (model(f_in=None, pos=pos, batch=batch, node_atom=z) ** 2).sum().backward()        # d(sum E^2) / d(parameters)
+    grads = {f"grad/{k}": p.grad.detach().numpy() for k, p in model.named_parameters() if p.grad is not None}
     small = {f"state/{k}": v.detach().float().numpy() if v.is_floating_point() else v.numpy()
              for k, v in model.state_dict().items() if v is not None}
+    small.update(grads)
     for k, v in model.state_dict().items():
         if v is not None and v.is_floating_point():
             assert torch.equal(v.float().double(), v), k
@@ -389,8 +393,12 @@ def main():
     batch = torch.zeros(9, dtype=torch.long)
     pos = _f32(1.8 * torch.randn(9, 3, generator=gen, dtype=torch.float64))
     energy, forces = model(node_atom=z, pos=pos.clone(), batch=batch)
+    model.zero_grad()
+    (energy.sum() + (forces ** 2).sum()).backward()            # energy + force loss: a second derivative through the forward
+    grads = {f"grad/{k}": p.grad.detach().numpy() for k, p in model.named_parameters() if p.grad is not None}
     small = {f"state/{k}": v.detach().float().numpy() if v.is_floating_point() else v.numpy()
              for k, v in model.state_dict().items() if v is not None}
+    small.update(grads)
     for k, v in model.state_dict().items():
         if v is not None and v.is_floating_point():
             assert torch.equal(v.float().double(), v), k

@@ -416,3 +416,60 @@ def test_cuda_block_matches_reference_at_oc20_sizes(cuda_device):
                   edge_attr=d(t["edge_sh"]), edge_scalars=d(t["edge_scalars"]),
                   batch=torch.zeros(x.shape[0], dtype=torch.long, device=cuda_device))
     assert rel_err(out, torch.from_numpy(g["y"])) < 1e-4
+
+
+# --------------------------------------------------------------- backward: parameter gradients of the reference's models
+
+def _worst_grad(got: dict, g, n_min: int):
+    keys = [k[len("grad/"):] for k in g.files if k.startswith("grad/")]
+    assert len(keys) >= n_min
+    worst = 0.0
+    for k in keys:
+        ref = torch.from_numpy(g[f"grad/{k}"])
+        assert got[k] is not None, k
+        worst = max(worst, float((got[k].detach().double() - ref).abs().max() / ref.abs().max().clamp_min(1e-12)))
+    return worst
+
+
+def test_parameter_gradients_match_reference_qm9_small():
+    """d(sum E^2)/d(parameters) from the reference's own backward through its own forward, vs autograd through the
+    oracle and through the mirror (closed autograd families, kernels emulated)."""
+    from equiformer_b200.nets.graph_attention_transformer import GraphAttentionTransformer
+    from tests._emulation import emulated_kernels
+    g, state, cfg = _small_case()
+    pos, batch, z = torch.from_numpy(g["pos"]).double(), torch.from_numpy(g["batch"]), torch.from_numpy(g["z"])
+    params = {k: v.requires_grad_(v.is_floating_point()) for k, v in R.cast_params(state, torch.float64).items()}
+    (R.model_forward(params, cfg, pos, batch, z, n_graphs=2) ** 2).sum().backward()
+    assert _worst_grad({k: v.grad for k, v in params.items()}, g, 80) < 1e-8
+    model = _mirror_model(g, GraphAttentionTransformer).double()
+    with emulated_kernels():
+        (model(f_in=None, pos=pos, batch=batch, node_atom=z) ** 2).sum().backward()
+    assert _worst_grad({k: p.grad for k, p in model.named_parameters()}, g, 80) < 1e-7
+
+
+def test_parameter_gradients_match_reference_md17_small():
+    """The energy + force loss of MD17 training (a second derivative through the forward): parameter gradients from the
+    reference's model file vs the oracle and the mirror."""
+    from equiformer_b200.nets.graph_attention_transformer_md17 import GraphAttentionTransformerMD17
+    from tests._emulation import emulated_kernels
+    g = np.load(os.path.join(os.path.dirname(SMALL), "reference_model_md17_small.npz"))
+    state = {k[len("state/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state/")}
+    cfg = R.Config(irreps_node_embedding=str(g["cfg/irreps_node_embedding"]), irreps_sh=str(g["cfg/irreps_sh"]),
+                   irreps_head=str(g["cfg/irreps_head"]), irreps_mlp_mid=str(g["cfg/irreps_mlp_mid"]),
+                   irreps_feature=str(g["cfg/irreps_feature"]), num_heads=int(g["cfg/num_heads"]),
+                   num_layers=int(g["cfg/num_layers"]), max_radius=float(g["cfg/max_radius"]),
+                   number_of_basis=int(g["cfg/number_of_basis"]), basis_type="exp",
+                   nonlinear_message=bool(g["cfg/nonlinear_message"]), max_atom_type=64, qm9_atom_remap=False)
+    pos, batch, z = torch.from_numpy(g["pos"]).double(), torch.from_numpy(g["batch"]), torch.from_numpy(g["z"])
+    params = {k: v.requires_grad_(v.is_floating_point()) for k, v in R.cast_params(state, torch.float64).items()}
+    e, f = R.energy_and_forces(params, cfg, pos, batch, z, 1, create_graph=True)
+    (e.sum() + (f ** 2).sum()).backward()
+    assert _worst_grad({k: v.grad for k, v in params.items()}, g, 80) < 1e-8
+    model = _mirror_model(g, GraphAttentionTransformerMD17).double().train()
+    for m in model.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    with emulated_kernels():
+        e, f = model(node_atom=z, pos=pos.clone(), batch=batch)
+        (e.sum() + (f ** 2).sum()).backward()
+    assert _worst_grad({k: p.grad for k, p in model.named_parameters()}, g, 80) < 1e-6
