@@ -1,8 +1,9 @@
 """Drop-in mirror of the reference's ``nets`` package for the graph-attention hot path."""
-from . import graph_attention_transformer, graph_attention_transformer_md17  # noqa: F401  (register models)
+from . import dp_attention_transformer, graph_attention_transformer, graph_attention_transformer_md17  # noqa: F401  (register models)
 from .registry import list_models, model_entrypoint, register_model  # noqa: F401
 from .graph_attention_transformer import (  # noqa: F401
     DepthwiseTensorProduct, EdgeDegreeEmbeddingNetwork, FeedForwardNetwork, GraphAttention,
     GraphAttentionTransformer, SeparableFCTP, TransBlock)
+from .dp_attention_transformer import DotProductAttention, DotProductAttentionTransformer, DPTransBlock  # noqa: F401
 from .tensor_product_rescale import (  # noqa: F401
     FullyConnectedTensorProductRescale, LinearRS, TensorProductRescale)

@@ -472,11 +472,8 @@ class TransBlock(torch.nn.Module):
         self.irreps_mlp_mid = Irreps(irreps_mlp_mid) if irreps_mlp_mid is not None else self.irreps_node_input
 
         self.norm_1 = get_norm_layer(norm_layer)(self.irreps_node_input)
-        self.ga = GraphAttention(irreps_node_input=self.irreps_node_input, irreps_node_attr=self.irreps_node_attr,
-                                 irreps_edge_attr=self.irreps_edge_attr, irreps_node_output=self.irreps_node_input,
-                                 fc_neurons=fc_neurons, irreps_head=self.irreps_head, num_heads=self.num_heads,
-                                 irreps_pre_attn=self.irreps_pre_attn, rescale_degree=self.rescale_degree,
-                                 nonlinear_message=self.nonlinear_message, alpha_drop=alpha_drop, proj_drop=proj_drop)
+        # the attention sub-layer registers under the reference's attribute name ("ga"; "dpa" in DPTransBlock)
+        setattr(self, self._attn_name, self._make_attention(fc_neurons, alpha_drop, proj_drop))
         self.drop_path = GraphDropPath(drop_path_rate) if drop_path_rate > 0.0 else None
         self.norm_2 = get_norm_layer(norm_layer)(self.irreps_node_input)
         self.ffn = FeedForwardNetwork(irreps_node_input=self.irreps_node_input, irreps_node_attr=self.irreps_node_attr,
@@ -487,10 +484,23 @@ class TransBlock(torch.nn.Module):
             self.ffn_shortcut = FullyConnectedTensorProductRescale(
                 self.irreps_node_input, self.irreps_node_attr, self.irreps_node_output, bias=True, rescale=_RESCALE)
 
+    _attn_name = "ga"
+
+    def _make_attention(self, fc_neurons, alpha_drop, proj_drop):
+        return GraphAttention(irreps_node_input=self.irreps_node_input, irreps_node_attr=self.irreps_node_attr,
+                              irreps_edge_attr=self.irreps_edge_attr, irreps_node_output=self.irreps_node_input,
+                              fc_neurons=fc_neurons, irreps_head=self.irreps_head, num_heads=self.num_heads,
+                              irreps_pre_attn=self.irreps_pre_attn, rescale_degree=self.rescale_degree,
+                              nonlinear_message=self.nonlinear_message, alpha_drop=alpha_drop, proj_drop=proj_drop)
+
+    @property
+    def attention(self):
+        return getattr(self, self._attn_name)
+
     def forward(self, node_input, node_attr, edge_src, edge_dst, edge_attr, edge_scalars, batch, **kwargs):
         features = self.norm_1(node_input, batch=batch)
-        features = self.ga(node_input=features, node_attr=node_attr, edge_src=edge_src, edge_dst=edge_dst,
-                           edge_attr=edge_attr, edge_scalars=edge_scalars, batch=batch, **kwargs)
+        features = self.attention(node_input=features, node_attr=node_attr, edge_src=edge_src, edge_dst=edge_dst,
+                                  edge_attr=edge_attr, edge_scalars=edge_scalars, batch=batch, **kwargs)
         if self.drop_path is not None:
             features = self.drop_path(features, batch)
         node_output = node_input + features
@@ -508,14 +518,14 @@ class TransBlock(torch.nn.Module):
         or output dropout in effect."""
         return (getattr(self.norm_1, "supports_planar", False) and getattr(self.norm_2, "supports_planar", False)
                 and self.ffn_shortcut is None and (self.drop_path is None or not self.training)
-                and self.ga.supports_planar and self.ffn.supports_planar
+                and self.attention.supports_planar and self.ffn.supports_planar
                 and self.irreps_node_input == self.irreps_node_output)
 
     def forward_planar(self, xs, node_attr, edge_src, edge_dst, edge_attr, edge_scalars, batch, **kwargs):
         """``forward`` on planar node blocks -> planar node blocks: the features never pass through the e3nn layout
         (saves the layout copies at every sub-layer boundary, ~24 small launches per block and step)."""
-        f = self.ga.forward_planar(self.norm_1.planar(xs), node_attr, edge_src, edge_dst, edge_attr, edge_scalars, batch,
-                                   **kwargs)
+        f = self.attention.forward_planar(self.norm_1.planar(xs), node_attr, edge_src, edge_dst, edge_attr, edge_scalars,
+                                          batch, **kwargs)
         xs = [a + b for a, b in zip(xs, f)]
         f = self.ffn.forward_planar(self.norm_2.planar(xs), node_attr)
         return [a + b for a, b in zip(xs, f)]
@@ -637,10 +647,12 @@ class GraphAttentionTransformer(torch.nn.Module):
         self.register_buffer("_atom_remap", torch.tensor([-1, 0, -1, -1, -1, -1, 1, 2, 3, 4]), persistent=False)
         self.apply(self._init_weights)
 
+    _block_cls = TransBlock
+
     def build_blocks(self):
         for i in range(self.num_layers):
             out = self.irreps_node_embedding if i != self.num_layers - 1 else self.irreps_feature
-            self.blocks.append(TransBlock(
+            self.blocks.append(self._block_cls(
                 irreps_node_input=self.irreps_node_embedding, irreps_node_attr=self.irreps_node_attr,
                 irreps_edge_attr=self.irreps_edge_attr, irreps_node_output=out, fc_neurons=self.fc_neurons,
                 irreps_head=self.irreps_head, num_heads=self.num_heads, irreps_pre_attn=self.irreps_pre_attn,

@@ -203,6 +203,7 @@ class Config:
     qm9_atom_remap: bool = True
     avg_degree: float = 15.57930850982666
     avg_num_nodes: float = 18.03065905448718
+    attention: str = "graph"          # "graph": GraphAttention / TransBlock; "dot_product": nets/dp_attention_transformer.py
 
 
 def graph_attention(params: Params, prefix: str, irreps_in, irreps_edge, irreps_head, num_heads, irreps_node_output,
@@ -253,6 +254,36 @@ def graph_attention(params: Params, prefix: str, irreps_in, irreps_edge, irreps_
     return linear_rs(params, f"{prefix}.proj", heads_all, irreps_node_output, attn)             # :522
 
 
+def dot_product_attention(params: Params, prefix: str, irreps_in, irreps_edge, irreps_head, num_heads, irreps_node_output,
+                          x, edge_src, edge_dst, edge_sh, edge_scalars):
+    """DotProductAttention.forward - nets/dp_attention_transformer.py:128-162 (eval mode, rescale_degree=False)"""
+    n = x.shape[0]
+    pre = irreps_in
+    heads_q, _ = sort_irreps_even_first([(m, l, p) for _ in range(num_heads) for m, l, p in irreps_head])
+    heads_q = e3.simplify(heads_q)                                                              # :93-96
+    heads_kv, _ = sort_irreps_even_first([(m, l, p) for _ in range(2 * num_heads) for m, l, p in irreps_head])
+    heads_kv = e3.simplify(heads_kv)                                                            # :98-100
+    q = linear_rs(params, f"{prefix}.query", irreps_in, heads_q, x)                             # :131
+    q = vec2heads(q, irreps_head, num_heads)                                                    # :132
+    norm = 1.0 / math.sqrt(sum(m for m, _, _ in irreps_head))                                   # ScaleFactor :49-66
+    q = torch.cat([q[..., sl] * (norm / math.sqrt(2 * l + 1))
+                   for sl, (_, l, _) in zip(e3.irreps_slices(irreps_head), irreps_head)], dim=-1)
+    msg_src = linear_rs(params, f"{prefix}.merge_src", irreps_in, pre, x)                       # :135
+    msg_dst = linear_rs(params, f"{prefix}.merge_dst", irreps_in, pre, x, bias=False)           # :136
+    kv = msg_src.index_select(0, edge_src) + msg_dst.index_select(0, edge_dst)                  # :137
+    s_out, s_ins = dtp_instructions(pre, irreps_edge, heads_kv)                                 # SeparableFCTP, no activation
+    weight = radial_profile(params, f"{prefix}.key_value.dtp_rad", edge_scalars)
+    kv = e3.tensor_product(kv, edge_sh, weight, pre, irreps_edge, s_out, s_ins, False)          # :138
+    kv = linear_rs(params, f"{prefix}.key_value.lin", e3.simplify(s_out), heads_kv, kv)
+    kv = vec2heads(kv, irreps_head, 2 * num_heads)                                              # :139
+    k, v = kv[:, :num_heads], kv[:, num_heads:]                                                 # :141-142
+    alpha = torch.einsum("bik,bik->bi", q.index_select(0, edge_dst), k)                         # :145
+    alpha = pyg_softmax(alpha, edge_dst, n).unsqueeze(-1)                                       # :146-147
+    attn = scatter_sum(v * alpha, edge_dst, n)                                                  # :150-151
+    attn = heads2vec(attn, irreps_head)                                                         # :152
+    return linear_rs(params, f"{prefix}.proj", heads_q, irreps_node_output, attn)               # :160
+
+
 def feed_forward(params: Params, prefix: str, irreps_in, irreps_mid, irreps_out, x, node_attr):
     """FeedForwardNetwork.forward - :566-571"""
     scalars, gates, gated = irreps2gate(irreps_mid)
@@ -269,8 +300,12 @@ def trans_block(params: Params, prefix: str, cfg: Config, irreps_in, irreps_out,
     """TransBlock.forward - :639-667 (drop_path = 0)"""
     irreps_edge = e3.parse_irreps(cfg.irreps_sh)
     h = layer_norm_v2(params, f"{prefix}.norm_1", irreps_in, x)
-    h = graph_attention(params, f"{prefix}.ga", irreps_in, irreps_edge, e3.parse_irreps(cfg.irreps_head),
-                        cfg.num_heads, irreps_in, cfg.nonlinear_message, h, edge_src, edge_dst, edge_sh, edge_scalars)
+    if cfg.attention == "dot_product":      # DPTransBlock.forward - nets/dp_attention_transformer.py:228-255, same skeleton
+        h = dot_product_attention(params, f"{prefix}.dpa", irreps_in, irreps_edge, e3.parse_irreps(cfg.irreps_head),
+                                  cfg.num_heads, irreps_in, h, edge_src, edge_dst, edge_sh, edge_scalars)
+    else:
+        h = graph_attention(params, f"{prefix}.ga", irreps_in, irreps_edge, e3.parse_irreps(cfg.irreps_head),
+                            cfg.num_heads, irreps_in, cfg.nonlinear_message, h, edge_src, edge_dst, edge_sh, edge_scalars)
     y = x + h
     h = layer_norm_v2(params, f"{prefix}.norm_2", irreps_in, y)
     h = feed_forward(params, f"{prefix}.ffn", irreps_in, e3.parse_irreps(cfg.irreps_mlp_mid), irreps_out, h, node_attr)

@@ -473,3 +473,58 @@ def test_parameter_gradients_match_reference_md17_small():
         e, f = model(node_atom=z, pos=pos.clone(), batch=batch)
         (e.sum() + (f ** 2).sum()).backward()
     assert _worst_grad({k: p.grad for k, p in model.named_parameters()}, g, 80) < 1e-6
+
+
+# ------------------------------------------------------------------ dot-product attention variant
+
+DP_SMALL = os.path.join(os.path.dirname(SMALL), "reference_model_dp_small.npz")
+
+
+def _dp_case():
+    g = np.load(DP_SMALL)
+    state = {k[len("state/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state/")}
+    cfg = R.Config(irreps_node_embedding=str(g["cfg/irreps_node_embedding"]), irreps_sh=str(g["cfg/irreps_sh"]),
+                   irreps_head=str(g["cfg/irreps_head"]), irreps_mlp_mid=str(g["cfg/irreps_mlp_mid"]),
+                   irreps_feature=str(g["cfg/irreps_feature"]), num_heads=int(g["cfg/num_heads"]),
+                   num_layers=int(g["cfg/num_layers"]), max_radius=float(g["cfg/max_radius"]),
+                   number_of_basis=int(g["cfg/number_of_basis"]), basis_type="gaussian", nonlinear_message=False,
+                   attention="dot_product")
+    pos, batch, z = torch.from_numpy(g["pos"]).double(), torch.from_numpy(g["batch"]), torch.from_numpy(g["z"])
+    return g, state, cfg, pos, batch, z
+
+
+def test_oracle_dot_product_attention_model_matches_reference_model_file():
+    """``nets/dp_attention_transformer.py`` (DotProductAttention / DPTransBlock / DotProductAttentionTransformer) run by
+    the reference's code vs the oracle's restatement: energies and parameter gradients of sum E^2."""
+    g, state, cfg, pos, batch, z = _dp_case()
+    params = {k: v.requires_grad_(v.is_floating_point()) for k, v in R.cast_params(state, torch.float64).items()}
+    energy = R.model_forward(params, cfg, pos, batch, z, n_graphs=2)
+    assert rel_err(energy.detach(), torch.from_numpy(g["energy"])) < 1e-11
+    (energy ** 2).sum().backward()
+    assert _worst_grad({k: v.grad for k, v in params.items()}, g, 70) < 1e-8
+
+
+def test_mirror_dot_product_attention_matches_reference_model_file():
+    """The mirror of the dot-product variant (``ops.EdgeDot`` logits on the existing kernels; emulated here in float64)
+    loaded with the reference's ``state_dict``: energies and parameter gradients against the reference-run fixture."""
+    from equiformer_b200.nets.dp_attention_transformer import DotProductAttentionTransformer
+    from tests._emulation import emulated_kernels
+    g, _state, _cfg, pos, batch, z = _dp_case()
+    model = _mirror_model(g, DotProductAttentionTransformer).double()
+    with emulated_kernels():
+        energy = model(f_in=None, pos=pos, batch=batch, node_atom=z)
+        (energy ** 2).sum().backward()
+    assert rel_err(energy.detach(), torch.from_numpy(g["energy"])) < 1e-10
+    assert _worst_grad({k: p.grad for k, p in model.named_parameters()}, g, 70) < 1e-7
+
+
+@pytest.mark.gpu
+def test_cuda_dot_product_attention_matches_reference_model_file(cuda_device):
+    """The dot-product variant on the CUDA kernels (float32) against the reference-run energies.  Written after the
+    round-1 GPU budget ended."""
+    from equiformer_b200.nets.dp_attention_transformer import DotProductAttentionTransformer
+    g, _state, _cfg, pos, batch, z = _dp_case()
+    model = _mirror_model(g, DotProductAttentionTransformer).to(cuda_device)
+    with torch.no_grad():
+        energy = model(f_in=None, pos=pos.float().to(cuda_device), batch=batch.to(cuda_device), node_atom=z.to(cuda_device))
+    assert rel_err(energy, torch.from_numpy(g["energy"])) < 5e-5

@@ -1,6 +1,7 @@
 #!/bin/bash
 # first call of the next round: everything that was written after the round-1 GPU budget ended
-#   - the full GPU suite (includes test_cuda_headline_model_matches_reference_model_file and test_cuda_block_matches_reference_at_oc20_sizes of tests/test_reference_golden.py, never run on a B200)
+#   - the full GPU suite (includes test_cuda_headline_model_matches_reference_model_file, test_cuda_block_matches_reference_at_oc20_sizes and
+#     test_cuda_dot_product_attention_matches_reference_model_file of tests/test_reference_golden.py, never run on a B200)
 #   - the 128-column tensor-memory weight gradient (EQF_TF32X3_WGRAD_TS=2): parity + timing against the shared-memory kernel
 #   - one bench line with and without it
 set -u
