@@ -4,6 +4,7 @@ from .registry import list_models, model_entrypoint, register_model  # noqa: F40
 from .graph_attention_transformer import (  # noqa: F401
     DepthwiseTensorProduct, EdgeDegreeEmbeddingNetwork, FeedForwardNetwork, GraphAttention,
     GraphAttentionTransformer, SeparableFCTP, TransBlock)
-from .dp_attention_transformer import DotProductAttention, DotProductAttentionTransformer, DPTransBlock  # noqa: F401
+from .dp_attention_transformer import (  # noqa: F401
+    DotProductAttention, DotProductAttentionTransformer, DotProductAttentionTransformerMD17, DPTransBlock)
 from .tensor_product_rescale import (  # noqa: F401
     FullyConnectedTensorProductRescale, LinearRS, TensorProductRescale)

@@ -19,6 +19,7 @@ from ..o3 import Irreps
 from .drop import EquivariantDropout
 from .graph_attention_transformer import (_RESCALE, AttnHeads2Vec, GraphAttentionTransformer, SeparableFCTP, TransBlock,
                                           Vec2AttnHeads, _graph_for, _is_sorted_simplified)
+from .graph_attention_transformer_md17 import GraphAttentionTransformerMD17
 from .registry import register_model
 from .tensor_product_rescale import LinearRS, sort_irreps_even_first
 
@@ -164,3 +165,48 @@ def dot_product_attention_transformer_l2(irreps_in, radius, num_basis=128, atomr
         irreps_feature="512x0e", irreps_head="32x0e+16x1e+8x2e", num_heads=4, irreps_pre_attn=None, rescale_degree=False,
         nonlinear_message=False, irreps_mlp_mid="384x0e+192x1e+96x2e", norm_layer="layer", alpha_drop=0.2, proj_drop=0.0,
         out_drop=0.0, drop_path_rate=0.0, mean=task_mean, std=task_std, scale=None, atomref=atomref)
+
+
+class DotProductAttentionTransformerMD17(GraphAttentionTransformerMD17):
+    """The MD17 energy + force model with ``DPTransBlock`` s (drop-in for ``nets/dp_attention_transformer_md17.py`` :57-236)."""
+
+    _block_cls = DPTransBlock
+
+    def __init__(self, irreps_in="64x0e", irreps_node_embedding="128x0e+64x1e+32x2e", num_layers=6, irreps_node_attr="1x0e",
+                 irreps_sh="1x0e+1x1e+1x2e", max_radius=5.0, number_of_basis=128, basis_type="gaussian", fc_neurons=[64, 64],
+                 irreps_feature="512x0e", irreps_head="32x0e+16x1o+8x2e", num_heads=4, irreps_pre_attn=None,
+                 rescale_degree=False, nonlinear_message=False, irreps_mlp_mid="128x0e+64x1e+32x2e", norm_layer="layer",
+                 alpha_drop=0.2, proj_drop=0.0, out_drop=0.0, drop_path_rate=0.0, mean=None, std=None, scale=None,
+                 atomref=None):
+        super().__init__(irreps_in=irreps_in, irreps_node_embedding=irreps_node_embedding, num_layers=num_layers,
+                         irreps_node_attr=irreps_node_attr, irreps_sh=irreps_sh, max_radius=max_radius,
+                         number_of_basis=number_of_basis, basis_type=basis_type, fc_neurons=fc_neurons,
+                         irreps_feature=irreps_feature, irreps_head=irreps_head, num_heads=num_heads,
+                         irreps_pre_attn=irreps_pre_attn, rescale_degree=rescale_degree, nonlinear_message=nonlinear_message,
+                         irreps_mlp_mid=irreps_mlp_mid, use_attn_head=False, norm_layer=norm_layer, alpha_drop=alpha_drop,
+                         proj_drop=proj_drop, out_drop=out_drop, drop_path_rate=drop_path_rate, mean=mean, std=std,
+                         scale=scale, atomref=atomref)
+
+
+def _dp_md17(irreps_in, radius, num_basis, atomref, task_mean, task_std, **family):
+    return DotProductAttentionTransformerMD17(
+        irreps_in=irreps_in, num_layers=6, irreps_node_attr="1x0e", max_radius=radius, number_of_basis=num_basis,
+        fc_neurons=[64, 64], basis_type="exp", irreps_feature="512x0e", num_heads=4, irreps_pre_attn=None,
+        rescale_degree=False, nonlinear_message=False, norm_layer="layer", alpha_drop=0.0, proj_drop=0.0, out_drop=0.0,
+        drop_path_rate=0.0, mean=task_mean, std=task_std, scale=None, atomref=atomref, **family)
+
+
+@register_model
+def dot_product_attention_transformer_exp_l2_md17(irreps_in, radius, num_basis=128, atomref=None, task_mean=None,
+                                                  task_std=None, **kwargs):
+    return _dp_md17(irreps_in, radius, num_basis, atomref, task_mean, task_std,
+                    irreps_node_embedding="128x0e+64x1e+32x2e", irreps_sh="1x0e+1x1e+1x2e",
+                    irreps_head="32x0e+16x1e+8x2e", irreps_mlp_mid="384x0e+192x1e+96x2e")
+
+
+@register_model
+def dot_product_attention_transformer_exp_l3_md17(irreps_in, radius, num_basis=128, atomref=None, task_mean=None,
+                                                  task_std=None, **kwargs):
+    return _dp_md17(irreps_in, radius, num_basis, atomref, task_mean, task_std,
+                    irreps_node_embedding="128x0e+64x1e+64x2e+32x3e", irreps_sh="1x0e+1x1e+1x2e+1x3e",
+                    irreps_head="32x0e+16x1e+16x2e+8x3e", irreps_mlp_mid="384x0e+192x1e+192x2e+96x3e")

@@ -30,6 +30,8 @@ _AVG_DEGREE = 15.57930850982666
 
 
 class GraphAttentionTransformerMD17(torch.nn.Module):
+    _block_cls = TransBlock      # DPTransBlock in the dot-product variant (nets/dp_attention_transformer.py)
+
     def __init__(self, irreps_in="64x0e", irreps_node_embedding="128x0e+64x1e+32x2e", num_layers=6,
                  irreps_node_attr="1x0e", irreps_sh="1x0e+1x1e+1x2e", max_radius=5.0, number_of_basis=128,
                  basis_type="gaussian", fc_neurons=[64, 64], irreps_feature="512x0e",
@@ -73,7 +75,7 @@ class GraphAttentionTransformerMD17(torch.nn.Module):
         self.blocks = torch.nn.ModuleList()
         for i in range(num_layers):
             out = self.irreps_node_embedding if i != num_layers - 1 else self.irreps_feature
-            self.blocks.append(TransBlock(
+            self.blocks.append(self._block_cls(
                 irreps_node_input=self.irreps_node_embedding, irreps_node_attr=self.irreps_node_attr,
                 irreps_edge_attr=self.irreps_edge_attr, irreps_node_output=out, fc_neurons=self.fc_neurons,
                 irreps_head=self.irreps_head, num_heads=num_heads, irreps_pre_attn=irreps_pre_attn,

@@ -487,6 +487,44 @@ def main():
     np.savez_compressed(path, **small)
     print(f"wrote {path}: {len(small)} arrays, {os.path.getsize(path) / 1024:.0f} KiB; energy {energy.flatten().tolist()}")
 
+    # ---- the dot-product variant of the MD17 model (nets/dp_attention_transformer_md17.py): energy, forces, gradients
+    dpm = _reference_module("dp_attention_transformer_md17")
+    cfg = dict(irreps_in="64x0e", irreps_node_embedding="16x0e+8x1e+4x2e+4x3e", num_layers=2, irreps_node_attr="1x0e",
+               irreps_sh="1x0e+1x1e+1x2e+1x3e", max_radius=5.0, number_of_basis=16, basis_type="exp", fc_neurons=[16, 16],
+               irreps_feature="32x0e", irreps_head="8x0e+4x1e+2x2e+2x3e", num_heads=2, irreps_pre_attn=None,
+               rescale_degree=False, nonlinear_message=False, irreps_mlp_mid="24x0e+12x1e+6x2e+6x3e", norm_layer="layer",
+               alpha_drop=0.0, proj_drop=0.0, out_drop=0.0, drop_path_rate=0.0)
+    torch.manual_seed(17)
+    model = dpm.DotProductAttentionTransformerMD17(**cfg)
+    g4 = torch.Generator().manual_seed(8765)
+    with torch.no_grad():
+        for name, prm in model.named_parameters():
+            if prm.abs().max() == 0 or "bias" in name or "offset" in name:
+                prm.add_(0.1 * torch.randn(prm.shape, generator=g4))
+    torch.set_default_dtype(torch.float64)
+    model = model.double().eval()
+    z = torch.tensor([6, 8, 1, 1, 6, 1, 8, 1])
+    batch = torch.zeros(8, dtype=torch.long)
+    pos = _f32(1.7 * torch.randn(8, 3, generator=g4, dtype=torch.float64))
+    energy, forces = model(node_atom=z, pos=pos.clone(), batch=batch)
+    model.zero_grad()
+    (energy.sum() + (forces ** 2).sum()).backward()
+    torch.set_default_dtype(torch.float32)
+    small = {f"state/{k}": v.detach().float().numpy() if v.is_floating_point() else v.numpy()
+             for k, v in model.state_dict().items() if v is not None}
+    for k, v in model.state_dict().items():
+        if v is not None and v.is_floating_point():
+            assert torch.equal(v.float().double(), v), k
+    small.update({f"grad/{k}": p.grad.detach().numpy() for k, p in model.named_parameters() if p.grad is not None})
+    small.update({"pos": pos.float().numpy(), "batch": batch.numpy(), "z": z.numpy(), "energy": energy.detach().numpy(),
+                  "forces": forces.detach().numpy()})
+    for k, v in cfg.items():
+        if v is not None:
+            small[f"cfg/{k}"] = np.asarray(v)
+    path = os.path.join(HERE, "reference_model_dp_md17_small.npz")
+    np.savez_compressed(path, **small)
+    print(f"wrote {path}: {len(small)} arrays, {os.path.getsize(path) / 1024:.0f} KiB; energy {energy.flatten().tolist()}")
+
     # ---- one transformer block at the OC20 IS2RE `l1_256_nonlinear` sizes (oc20/configs/is2re/all/graph_attention_transformer/
     # l1_256_nonlinear_g@2_local.yml: 256x0e+128x1e, 8 heads of 32x0e+16x1e, mlp 768x0e+384x1e, Lmax = 1).  The OC20 model
     # file itself needs ocpmodels; its blocks are the TransBlock class of graph_attention_transformer.py, run here.
@@ -544,7 +582,8 @@ def main():
                            "graph_attention_transformer_nonlinear_l2_e3_md17", "graph_attention_transformer_nonlinear_exp_l2_md17",
                            "graph_attention_transformer_nonlinear_exp_l3_md17", "graph_attention_transformer_nonlinear_attn_exp_l3_md17",
                            "graph_attention_transformer_nonlinear_exp_l3_e3_md17"]),
-            (dp, "5x0e", ["dot_product_attention_transformer_l2"])):
+            (dp, "5x0e", ["dot_product_attention_transformer_l2"]),
+            (dpm, "64x0e", ["dot_product_attention_transformer_exp_l2_md17", "dot_product_attention_transformer_exp_l3_md17"])):
         for name in names:
             model = getattr(mod, name)(irreps_in=irreps_in, radius=5.0, num_basis=128)
             table[name] = {k: list(v.shape) for k, v in model.state_dict().items() if v is not None}

@@ -528,3 +528,33 @@ def test_cuda_dot_product_attention_matches_reference_model_file(cuda_device):
     with torch.no_grad():
         energy = model(f_in=None, pos=pos.float().to(cuda_device), batch=batch.to(cuda_device), node_atom=z.to(cuda_device))
     assert rel_err(energy, torch.from_numpy(g["energy"])) < 5e-5
+
+
+def test_dot_product_md17_variant_matches_reference_model_file():
+    """``nets/dp_attention_transformer_md17.py`` (Lmax = 3, exp-normal basis, forces by autograd) run by the reference's
+    code: the oracle and the mirror (emulated kernels) against energy, forces and the gradients of the energy + force loss."""
+    from equiformer_b200.nets.dp_attention_transformer import DotProductAttentionTransformerMD17
+    from tests._emulation import emulated_kernels
+    g = np.load(os.path.join(os.path.dirname(SMALL), "reference_model_dp_md17_small.npz"))
+    state = {k[len("state/"):]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state/")}
+    cfg = R.Config(irreps_node_embedding=str(g["cfg/irreps_node_embedding"]), irreps_sh=str(g["cfg/irreps_sh"]),
+                   irreps_head=str(g["cfg/irreps_head"]), irreps_mlp_mid=str(g["cfg/irreps_mlp_mid"]),
+                   irreps_feature=str(g["cfg/irreps_feature"]), num_heads=int(g["cfg/num_heads"]),
+                   num_layers=int(g["cfg/num_layers"]), max_radius=float(g["cfg/max_radius"]),
+                   number_of_basis=int(g["cfg/number_of_basis"]), basis_type="exp", nonlinear_message=False,
+                   max_atom_type=64, qm9_atom_remap=False, attention="dot_product")
+    pos, batch, z = torch.from_numpy(g["pos"]).double(), torch.from_numpy(g["batch"]), torch.from_numpy(g["z"])
+    params = {k: v.requires_grad_(v.is_floating_point()) for k, v in R.cast_params(state, torch.float64).items()}
+    e, f = R.energy_and_forces(params, cfg, pos, batch, z, 1, create_graph=True)
+    (e.sum() + (f ** 2).sum()).backward()
+    assert rel_err(e.detach(), torch.from_numpy(g["energy"])) < 1e-11
+    assert rel_err(f.detach(), torch.from_numpy(g["forces"])) < 1e-10
+    assert _worst_grad({k: v.grad for k, v in params.items()}, g, 70) < 1e-8
+
+    model = _mirror_model(g, DotProductAttentionTransformerMD17).double().train()
+    with emulated_kernels():
+        e, f = model(node_atom=z, pos=pos.clone(), batch=batch)
+        (e.sum() + (f ** 2).sum()).backward()
+    assert rel_err(e.detach(), torch.from_numpy(g["energy"])) < 1e-10
+    assert rel_err(f.detach(), torch.from_numpy(g["forces"])) < 1e-9
+    assert _worst_grad({k: p.grad for k, p in model.named_parameters()}, g, 70) < 1e-6
