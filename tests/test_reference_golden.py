@@ -72,7 +72,6 @@ def test_oracle_layer_norm_matches_reference(gold, tag):
 # ------------------------------------------------------------------------------------ host-side mirrors (CPU, fp64)
 
 def _mirror(kind, gold, tag=None):
-    from equiformer_b200 import nets
     from equiformer_b200.nets import expnorm_rbf, gaussian_rbf, layer_norm, radial_func
     if kind == "gaussian_rbf":
         m, prefix = gaussian_rbf.GaussianRadialBasisLayer(int(gold["gaussian_rbf/num_basis"]), float(gold["gaussian_rbf/cutoff"])), kind
@@ -84,7 +83,6 @@ def _mirror(kind, gold, tag=None):
     else:
         prefix = f"layer_norm_{tag}"
         m = layer_norm.EquivariantLayerNormV2(str(gold[f"{prefix}/irreps"]), eps=float(gold[f"{prefix}/eps"]))
-    assert nets is not None
     missing = m.load_state_dict(_state(gold, prefix, torch.float32), strict=True)      # the reference's own keys and shapes
     assert not missing.missing_keys and not missing.unexpected_keys
     return m, prefix
