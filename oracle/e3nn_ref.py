@@ -5,6 +5,8 @@ PARITY UNPINNED: ``e3nn==0.4.4`` (``/root/reference/env/env_equiformer.yml:358``
 dependency, absent from this image and not installable (no network); the reference ships no tests or golden vectors
 (SURVEY.md section 4).  This file therefore restates e3nn's *published* algorithms and is anchored on the
 reference's call sites and on mathematical invariants (tests/test_oracle.py), not on outputs of the real library.
+Third-party anchors that do exist (tests/test_o3.py): the spherical harmonics against scipy's, the SU(2) coefficients against
+sympy's, the real Wigner 3j against the Gaunt tensors of the harmonics (all components, up to one sign per triple).
 (What IS pinned to the reference's own code - its module and model files executed on top of these restatements - is
 listed in ``oracle/equiformer_ref.py``.)
 

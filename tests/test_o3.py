@@ -94,3 +94,55 @@ def test_sh_is_twice_differentiable():
     f = lambda t: o3.spherical_harmonics("1x0e+1x1e+1x2e+1x3e", t, True, "component")
     assert torch.autograd.gradcheck(f, (v,), atol=1e-7)
     assert torch.autograd.gradgradcheck(f, (v,), atol=1e-6)
+
+
+def test_spherical_harmonics_against_scipy():
+    """Third-party anchor for the SH numerics: 'component'-normalised e3nn harmonics = sqrt(4 pi) x the standard real
+    spherical harmonics (sqrt(2) (-1)^m Re / Im of scipy's complex Y_l^m, no extra phase) evaluated in the frame whose
+    polar axis is e3nn's y:  (x', y', z') = (z, x, y).  Every (l, m) up to l = 3, oracle and product."""
+    sp = pytest.importorskip("scipy.special")
+    import numpy as np
+    g = torch.Generator().manual_seed(0)
+    v = torch.randn(300, 3, generator=g, dtype=torch.float64)
+    v = v / v.norm(dim=1, keepdim=True)
+    x, y, z = (v[:, i].numpy() for i in range(3))
+    polar, azimuth = np.arccos(np.clip(y, -1, 1)), np.arctan2(x, z)
+
+    def complex_sh(l, m):
+        return sp.sph_harm_y(l, m, polar, azimuth) if hasattr(sp, "sph_harm_y") else sp.sph_harm(m, l, azimuth, polar)
+
+    cols = []
+    for l in range(4):
+        for m in range(-l, l + 1):
+            c = complex_sh(l, abs(m))
+            real = c.real if m == 0 else math.sqrt(2) * (-1) ** m * (c.real if m > 0 else c.imag)
+            cols.append(math.sqrt(4 * math.pi) * real)
+    ref = torch.from_numpy(np.stack(cols, axis=1))
+    assert (e3.spherical_harmonics([0, 1, 2, 3], v, True, "component") - ref).abs().max() < 1e-12
+    assert (o3.spherical_harmonics("1x0e+1x1e+1x2e+1x3e", v, True, "component") - ref).abs().max() < 1e-12
+
+
+def test_wigner_3j_equals_gaunt_tensor_of_the_harmonics():
+    """Third-party anchor for the real Wigner 3j: for every even l1 + l2 + l3 (up to 3), the sphere average of
+    Y^{l1}_a Y^{l2}_b Y^{l3}_c - harmonics pinned to scipy above, Gauss-Legendre x uniform quadrature, exact at this
+    degree - equals  s sqrt((2l1+1)(2l2+1)(2l3+1)) (l1 l2 l3; 0 0 0) C_abc  with sympy's 3j symbol and ONE sign s = +-1
+    per triple.  That fixes every component of the real-basis tensor; only that global sign per (l1, l2, l3) remains an
+    e3nn convention that cannot be checked without e3nn (odd sums vanish here; (1,1,1) is anchored on epsilon / sqrt 6)."""
+    sympy_wigner = pytest.importorskip("sympy.physics.wigner")
+    ct, wt = np.polynomial.legendre.leggauss(16)
+    phi = 2 * np.pi * np.arange(33) / 33
+    CT, PH = np.meshgrid(ct, phi, indexing="ij")
+    st = np.sqrt(1 - CT ** 2)
+    pts = torch.from_numpy(np.stack([st * np.cos(PH), st * np.sin(PH), CT], -1).reshape(-1, 3))
+    w = torch.from_numpy((wt[:, None] * np.full((1, 33), 2 * np.pi / 33)).reshape(-1)) / (4 * np.pi)
+    Y = e3.spherical_harmonics([0, 1, 2, 3], pts, True, "component")
+    sl = [slice(0, 1), slice(1, 4), slice(4, 9), slice(9, 16)]
+    for l1, l2, l3 in TRIPLES:
+        if (l1 + l2 + l3) % 2:
+            continue
+        gaunt = torch.einsum("n,na,nb,nc->abc", w, Y[:, sl[l1]], Y[:, sl[l2]], Y[:, sl[l3]])
+        pref = math.sqrt((2 * l1 + 1) * (2 * l2 + 1) * (2 * l3 + 1)) * float(sympy_wigner.wigner_3j(l1, l2, l3, 0, 0, 0))
+        for C in (e3.wigner_3j(l1, l2, l3), torch.from_numpy(wigner_3j_np(l1, l2, l3))):
+            s = float((gaunt * C).sum() / (C * C).sum()) / pref
+            assert abs(abs(s) - 1.0) < 1e-12, (l1, l2, l3, s)
+            assert (gaunt - s * pref * C).abs().max() < 1e-12, (l1, l2, l3)
