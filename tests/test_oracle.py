@@ -126,3 +126,22 @@ def test_forces_are_minus_energy_gradient():
             e2 = R.model_forward(params, cfg, p2, batch, z, 1)
         fd = -(e1 - e2).item() / (2 * h)
         assert abs(fd - f[atom, axis].item()) < 1e-6 * max(1.0, abs(fd)), (atom, axis, fd, f[atom, axis].item())
+
+
+def test_normalize2mom_constants_against_exact_second_moments():
+    """The one e3nn number that is a Monte-Carlo estimate (1e6 samples, seed 0): how far can it be from what e3nn itself
+    computed?  At most as far as it is from the exact value (adaptive quadrature of f(z)^2 against the normal density) -
+    0.16 % for SiLU, 0.03 % for the sigmoid, 0.15 % for the smooth leaky ReLU - which bounds the one remaining
+    scale ambiguity of the activations."""
+    integrate = pytest.importorskip("scipy.integrate")
+
+    def exact(f):
+        val, _ = integrate.quad(lambda z: f(z) ** 2 * math.exp(-z * z / 2) / math.sqrt(2 * math.pi), -12, 12,
+                                epsabs=1e-14, epsrel=1e-14)
+        return val ** -0.5
+
+    sig = lambda z: 1 / (1 + math.exp(-z))  # noqa: E731
+    fs = {"silu": lambda z: z * sig(z), "sigmoid": sig,
+          "smooth_leaky_relu_0.2": lambda z: 0.6 * z + 0.4 * z * (2 * sig(z) - 1)}
+    for name, f in fs.items():
+        assert abs(e3.NORMALIZE2MOM[name] - exact(f)) / exact(f) < 2e-3, name
