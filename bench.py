@@ -44,7 +44,7 @@ WORKLOAD = "QM9 synthetic batch: 128 molecules x ~18 atoms, radius 5 A, Lmax=2 (
 
 
 def synthetic_batch(seed: int):
-    from tests.helpers import qm9_like_batch
+    from equiformer_b200.synthetic import qm9_like_batch
     pos, batch, z = qm9_like_batch(N_GRAPHS, seed=seed)
     g = torch.Generator().manual_seed(seed + 1000)
     target = torch.randn(N_GRAPHS, 1, generator=g)

@@ -17,11 +17,11 @@ import torch
 from .. import ops
 from ..o3 import Irreps
 from .drop import EquivariantDropout
-from .graph_attention_transformer import (_RESCALE, AttnHeads2Vec, GraphAttentionTransformer, SeparableFCTP, TransBlock,
+from .graph_attention_transformer import (_AVG_DEGREE, _RESCALE, AttnHeads2Vec, GraphAttentionTransformer, SeparableFCTP, TransBlock,
                                           Vec2AttnHeads, _graph_for, _is_sorted_simplified)
 from .graph_attention_transformer_md17 import GraphAttentionTransformerMD17
 from .registry import register_model
-from .tensor_product_rescale import LinearRS, sort_irreps_even_first
+from .tensor_product_rescale import LinearRS
 
 assert _RESCALE
 
@@ -60,10 +60,16 @@ class DotProductAttention(torch.nn.Module):
         self.num_heads = num_heads
         self.rescale_degree = rescale_degree
 
-        irreps_attn_heads, _, _ = sort_irreps_even_first(self.irreps_head * num_heads)
+        # the reference uses e3nn's plain ``Irreps.sort()`` here (odd before even; ref :90-97), not the even-first sort of
+        # GraphAttention; the planar kernels need one entry per irrep in (l ascending, even first) order, so head irreps
+        # that mix parities (where the two sorts differ) are refused rather than laid out differently from the reference
+        if any(ir.p != 1 for _, ir in self.irreps_head):
+            raise NotImplementedError("DotProductAttention with odd-parity head irreps: the reference's Irreps.sort() "
+                                      "layout (odd before even) is not supported by the planar kernels")
+        irreps_attn_heads, _, _ = (self.irreps_head * num_heads).sort()
         irreps_attn_heads = irreps_attn_heads.simplify()
         self.query = LinearRS(self.irreps_node_input, irreps_attn_heads)
-        irreps_kv_heads, _, _ = sort_irreps_even_first(self.irreps_head * num_heads * 2)
+        irreps_kv_heads, _, _ = (self.irreps_head * num_heads * 2).sort()
         irreps_kv_heads = irreps_kv_heads.simplify()
         self.merge_src = LinearRS(self.irreps_node_input, self.irreps_pre_attn, bias=True)
         self.merge_dst = LinearRS(self.irreps_node_input, self.irreps_pre_attn, bias=False)
@@ -116,7 +122,7 @@ class DotProductAttention(torch.nn.Module):
         node = ops.attention_aggregate(self._head_layout, graph, attn.contiguous(), v)           # [ref :149-152]
         if self.rescale_degree:                                                                  # [ref :154-158]
             degree = (graph.row_ptr[1:] - graph.row_ptr[:-1]).to(node[0].dtype).view(-1, 1, 1)
-            node = [t * degree for t in node]
+            node = [t * (degree / _AVG_DEGREE) for t in node]                                    # [ref :152] DP variant only
         return self.proj.planar(node)                                                            # [ref :160]
 
     def extra_repr(self) -> str:

@@ -684,18 +684,31 @@ class GraphAttentionTransformer(torch.nn.Module):
 
     def forward(self, f_in, pos, batch, node_atom, **kwargs) -> torch.Tensor:
         edge_src, edge_dst = radius_graph(pos, r=self.max_radius, batch=batch, max_num_neighbors=1000)
-        return self.forward_edges(pos, batch, node_atom, edge_src, edge_dst, n_graphs=kwargs.get("n_graphs"))
+        # radius_graph emits the edge list sorted by destination: skip the (host-synchronising) sortedness check
+        return self.forward_edges(pos, batch, node_atom, edge_src, edge_dst, n_graphs=kwargs.get("n_graphs"),
+                                  edges_sorted=True)
 
-    def forward_edges(self, pos, batch, node_atom, edge_src, edge_dst, graph=None, n_graphs=None) -> torch.Tensor:
+    def forward_edges(self, pos, batch, node_atom, edge_src, edge_dst, graph=None, n_graphs=None,
+                      edges_sorted: bool = False) -> torch.Tensor:
         """Everything after neighbour search (ref :868-899); free of host synchronisation when ``graph`` (the CSR of
-        the destination-sorted edge list) and ``n_graphs`` are supplied, so it can be captured in a CUDA graph."""
+        the destination-sorted edge list) and ``n_graphs`` are supplied, so it can be captured in a CUDA graph.
+        Contract: the kernels need the edge list sorted by destination.  A caller-supplied ``graph`` carries its own
+        order; otherwise the list is checked (one host synchronisation) and, when unsorted, everything per-edge is
+        permuted - unless the caller vouches for the order with ``edges_sorted=True``."""
         edge_vec = pos.index_select(0, edge_src) - pos.index_select(0, edge_dst)
         edge_sh = o3.spherical_harmonics(l=self.irreps_edge_attr, x=edge_vec, normalize=True, normalization="component")
         edge_length = edge_vec.norm(dim=1)
         atom_embedding, _attr, _onehot = self.atom_embed(self._atom_remap[node_atom])
         edge_length_embedding = self.rbf(edge_length)
         if graph is None:
-            graph = ops.Graph(edge_src, edge_dst, pos.shape[0], check_sorted=False)
+            graph = ops.Graph(edge_src, edge_dst, pos.shape[0], check_sorted=not edges_sorted)
+            if graph.perm is not None:      # unsorted input: work on the sorted copy (per-edge tensors are derived below)
+                edge_src, edge_dst = graph.src, graph.dst
+                edge_vec = pos.index_select(0, edge_src) - pos.index_select(0, edge_dst)
+                edge_sh = o3.spherical_harmonics(l=self.irreps_edge_attr, x=edge_vec, normalize=True,
+                                                 normalization="component")
+                edge_length_embedding = self.rbf(edge_vec.norm(dim=1))
+                graph.perm = None
         edge_degree_embedding = self.edge_deg_embed(atom_embedding, edge_sh, edge_length_embedding, edge_src, edge_dst,
                                                     batch, graph=graph)
         node_features = atom_embedding + edge_degree_embedding

@@ -832,19 +832,26 @@ _GEMM_MODE = None
 
 
 def gemm_backend() -> str:
-    """'cutlass' (tcgen05 fast-fp32, libeqf_gemm.so) or 'torch' (cuBLAS SGEMM); env EQF_GEMM overrides."""
+    """Which kernel carries the fp32-accurate edge-level products:
+
+    * ``'tf32x3'`` (default) - the hand-written tcgen05 3xTF32 kernels of ``libeqf_b200.so`` (``eqf_gemm_tf32x3*``);
+    * ``'cutlass'`` - the CUTLASS fast-fp32 instantiation of ``libeqf_gemm.so`` (cross-check / fallback; the library is
+      optional and only needed when this is selected with ``EQF_GEMM=cutlass`` or ``EQF_GEMM_TF32X3=0``);
+    * ``'torch'`` - cuBLAS SGEMM everywhere (``EQF_GEMM=torch``)."""
     global _GEMM_MODE
     if _GEMM_MODE is None:
-        import os
-        want = os.environ.get("EQF_GEMM", "cutlass")
-        if want == "cutlass" and not _lib.GEMM_LIB_PATH.exists():
-            raise _lib.EqfError(f"{_lib.GEMM_LIB_PATH} is missing: run __graft_entry__.build() (or set EQF_GEMM=torch)")
+        want = os.environ.get("EQF_GEMM", "tf32x3")
+        if want == "cutlass" or (want == "tf32x3" and not _TF32X3):
+            want = "cutlass"
+            if not _lib.GEMM_LIB_PATH.exists():
+                raise _lib.EqfError(f"{_lib.GEMM_LIB_PATH} is missing: build it with equiformer_b200._lib.build_gemm() "
+                                    "(it is optional: the default EQF_GEMM=tf32x3 does not need it)")
         _GEMM_MODE = want
     return _GEMM_MODE
 
 
 def gemm_backend_forced() -> bool:
-    import os
+    """EQF_GEMM_FORCE=1: every aligned product goes to the CUTLASS library kernel (tests / micro-benchmarks)."""
     return os.environ.get("EQF_GEMM_FORCE", "0") == "1"
 
 
@@ -860,6 +867,9 @@ def _gemm_operand(t: torch.Tensor):
 # reduction length from which the weight gradient runs as the sliced tcgen05 launch; node-level products (2 324 atoms x
 # (2l+1) rows) included: 24.6 -> 22.9 ms/step against cuBLAS's single-wave SIMT kernel there (gpurun r1n)
 _WGRAD_MIN_K = int(os.environ.get("EQF_WGRAD_MIN_K", "2048"))
+# rows from which forward / data-gradient products leave cuBLAS for the tcgen05 kernels; EQF_GEMM_MIN_M=1 sends the small
+# reference-run fixtures (tests/golden/reference_model_*.npz) through the hand-written kernels as well
+_GEMM_MIN_M = int(os.environ.get("EQF_GEMM_MIN_M", "16384"))
 
 
 def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
@@ -876,24 +886,26 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     if not ok:
         raise ValueError(f"gemm mode {mode}: incompatible shapes {tuple(A.shape)} {tuple(B.shape)}")
     aligned = all(v % 4 == 0 for v in (A.shape[1], B.shape[1], N)) and min(M, N, K) > 0
-    # measured policy (profiles/r1_gemm_microbench.jsonl): the tcgen05 fast-fp32 kernel wins on the tall edge-level
-    # products (forward / data gradient, 1.3-1.6x over cuBLAS SGEMM); the weight gradient (tiny output, reduction over
-    # all rows) and node-level products are faster in cuBLAS.
-    use_cutlass = (A.is_cuda and A.dtype == torch.float32 and aligned and gemm_backend() == "cutlass"
-                   and (gemm_backend_forced() or (mode != 2 and M >= 16384) or (mode == 2 and K >= _WGRAD_MIN_K)))
+    fast = A.is_cuda and A.dtype == torch.float32 and aligned
+    backend = gemm_backend() if fast else "torch"
+    forced = fast and gemm_backend_forced()
+    # measured policy (profiles/r1_gemm_microbench.jsonl): the tensor-core kernels win on the tall edge-level products
+    # (forward / data gradient from _GEMM_MIN_M rows, weight gradient from _WGRAD_MIN_K reduction rows); below that cuBLAS.
+    # forward / data-gradient products of the edge-level linears run on the hand-written 3xTF32 tcgen05 kernels (A from
+    # shared memory for wide outputs, from TMEM for N <= 128): 1.1-1.7x the CUTLASS collective on every layer shape
+    # (profiles/r1_tf32x3_microbench.jsonl); the weight gradient (one TMEM accumulator per row slice, 32-row TMA boxes)
+    # is ahead of the sliced CUTLASS launch on every layer shape (profiles/r1_tf32x3_wgrad_microbench.jsonl)
+    if backend == "tf32x3" and not forced:
+        if mode != 2 and M >= _GEMM_MIN_M:
+            return gemm_tf32x3_raw(A, B, b_is_kn=(mode == 0))
+        if mode == 2 and K >= _WGRAD_MIN_K:
+            return gemm_tf32x3_wgrad_raw(A, B)
+    use_cutlass = fast and (forced or (backend == "cutlass" and ((mode != 2 and M >= _GEMM_MIN_M)
+                                                                  or (mode == 2 and K >= _WGRAD_MIN_K))))
     if not use_cutlass:
         if mode == 0:
             return A @ B
         return A @ B.t() if mode == 1 else A.t() @ B
-    # forward / data-gradient products of the edge-level linears run on the hand-written 3xTF32 tcgen05 kernels (A from
-    # shared memory for wide outputs, from TMEM for N <= 128): 1.1-1.7x the CUTLASS collective on every layer shape
-    # (profiles/r1_tf32x3_microbench.jsonl)
-    if mode != 2 and _TF32X3 and M >= 16384 and not gemm_backend_forced():
-        return gemm_tf32x3_raw(A, B, b_is_kn=(mode == 0))
-    # weight gradient: the hand-written kernel (one TMEM accumulator per row slice, 32-row TMA boxes) is ahead of the
-    # sliced CUTLASS launch on every layer shape (profiles/r1_tf32x3_wgrad_microbench.jsonl)
-    if mode == 2 and _TF32X3 and not gemm_backend_forced():
-        return gemm_tf32x3_wgrad_raw(A, B)
     A, lda = _gemm_operand(A)
     B, ldb = _gemm_operand(B)
     lib = _lib.load_gemm()

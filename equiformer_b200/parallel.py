@@ -96,13 +96,22 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
             dist.broadcast(t.data, src)
 
 
+def is_no_decay(name: str, skip_list=()) -> bool:
+    """The reference's weight-decay exemption rule (``optim_factory.py:33-36``): by parameter name only."""
+    return (name.endswith(".bias") or name.endswith(".affine_weight") or name.endswith(".affine_bias")
+            or name.endswith(".mean_shift") or "bias." in name or name in skip_list)
+
+
 class FlatAdamW:
     """AdamW over ONE flat parameter buffer (decoupled weight decay, bias correction as torch.optim.AdamW).
 
     The model has ~290 small parameter tensors; a multi-tensor optimiser step costs more GPU time in launch slots
     than the 14 MB of state deserve.  Parameters are re-pointed to views of one flat buffer (gradients already are,
-    see :class:`FlatGradAllReduce`), so a step is six element-wise kernels on 3.5 M floats.  ``no_decay`` is a set of
-    parameter names exempt from weight decay (the reference's ``no_weight_decay()`` list, ``optim_factory.py:27-42``).
+    see :class:`FlatGradAllReduce`), so a step is six element-wise kernels on 3.5 M floats.  Weight decay follows the
+    reference's ``add_weight_decay`` (``optim_factory.py:27-42``) by NAME, not by shape - e3nn keeps every
+    ``tp.weight`` as a flat 1-D tensor and those are decayed: exempt are ``*.bias``, ``*.affine_weight``,
+    ``*.affine_bias``, ``*.mean_shift``, names containing ``bias.`` (the ``ParameterList`` biases) and ``no_decay``
+    (the model's ``no_weight_decay()`` skip list).
     """
 
     def __init__(self, named_params, bucket: FlatGradAllReduce, lr=5e-4, betas=(0.9, 0.999), eps=1e-8,
@@ -118,7 +127,7 @@ class FlatAdamW:
                 n = p.numel()
                 flat[off:off + n].copy_(p.reshape(-1))
                 p.data = flat[off:off + n].view_as(p)
-                decay[off:off + n] = 0.0 if (name in no_decay or p.dim() <= 1) else weight_decay
+                decay[off:off + n] = 0.0 if is_no_decay(name, no_decay) else weight_decay
         self.flat, self.decay = flat, decay
         self.m = torch.zeros_like(flat)
         self.v = torch.zeros_like(flat)

@@ -255,8 +255,9 @@ def graph_attention(params: Params, prefix: str, irreps_in, irreps_edge, irreps_
 
 
 def dot_product_attention(params: Params, prefix: str, irreps_in, irreps_edge, irreps_head, num_heads, irreps_node_output,
-                          x, edge_src, edge_dst, edge_sh, edge_scalars):
-    """DotProductAttention.forward - nets/dp_attention_transformer.py:128-162 (eval mode, rescale_degree=False)"""
+                          x, edge_src, edge_dst, edge_sh, edge_scalars, rescale_degree: bool = False):
+    """DotProductAttention.forward - nets/dp_attention_transformer.py:128-162 (eval mode; ``rescale_degree`` multiplies
+    by degree / _AVG_DEGREE, :148-152 - the division belongs to this variant only)"""
     n = x.shape[0]
     pre = irreps_in
     heads_q, _ = sort_irreps_even_first([(m, l, p) for _ in range(num_heads) for m, l, p in irreps_head])
@@ -280,8 +281,11 @@ def dot_product_attention(params: Params, prefix: str, irreps_in, irreps_edge, i
     alpha = torch.einsum("bik,bik->bi", q.index_select(0, edge_dst), k)                         # :145
     alpha = pyg_softmax(alpha, edge_dst, n).unsqueeze(-1)                                       # :146-147
     attn = scatter_sum(v * alpha, edge_dst, n)                                                  # :150-151
-    attn = heads2vec(attn, irreps_head)                                                         # :152
-    return linear_rs(params, f"{prefix}.proj", heads_q, irreps_node_output, attn)               # :160
+    attn = heads2vec(attn, irreps_head)                                                         # :146
+    if rescale_degree:                                                                          # :148-152
+        degree = torch.zeros(n, dtype=x.dtype).index_add_(0, edge_dst, torch.ones(edge_dst.numel(), dtype=x.dtype))
+        attn = attn * degree.view(-1, 1) / 15.57930850982666
+    return linear_rs(params, f"{prefix}.proj", heads_q, irreps_node_output, attn)               # :154
 
 
 def feed_forward(params: Params, prefix: str, irreps_in, irreps_mid, irreps_out, x, node_attr):

@@ -161,3 +161,30 @@ def test_radius_graph_statement_contract():
     assert int(torch.bincount(capped[1], minlength=40).max()) <= 2 and int(row_ptr[-1]) == capped.shape[1]
     kept = {(int(a), int(b)) for a, b in zip(*capped)}
     assert kept <= {(int(a), int(b)) for a, b in zip(src, dst)}
+
+
+def test_dot_product_attention_rescale_degree_divides_by_the_average_degree():
+    """ref nets/dp_attention_transformer.py:148-152: ``attn * degree / _AVG_DEGREE`` (the mirror multiplied by
+    the degree only)."""
+    from oracle import e3nn_ref as e3
+    from oracle import equiformer_ref as R
+    from equiformer_b200 import o3
+    from equiformer_b200.graph import radius_graph
+    from equiformer_b200.nets.dp_attention_transformer import DotProductAttention
+    torch.manual_seed(0)
+    irreps, sh, head = "16x0e+8x1e", "1x0e+1x1e", "4x0e+2x1e"
+    dpa = DotProductAttention(irreps, "1x0e", sh, irreps, [8, 8, 8], head, 4, rescale_degree=True, alpha_drop=0.0,
+                              proj_drop=0.0).double().eval()
+    pos, batch, _ = molecules([6, 9], seed=3, dtype=torch.float64)
+    src, dst = radius_graph(pos, 5.0, batch, max_num_neighbors=1000)
+    sh_e = o3.spherical_harmonics(sh, pos[src] - pos[dst], True, "component")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(pos.shape[0], 40, generator=g, dtype=torch.float64)
+    rbf = torch.randn(src.numel(), 8, generator=g, dtype=torch.float64)
+    with emulated_kernels():
+        out = dpa(x, None, src, dst, sh_e, rbf, batch)
+    params = {"dpa." + k: v for k, v in R.cast_params(dpa.state_dict(), torch.float64).items()}
+    ir = e3.parse_irreps(irreps)
+    ref = R.dot_product_attention(params, "dpa", ir, e3.parse_irreps(sh), e3.parse_irreps(head), 4, ir, x, src, dst, sh_e,
+                                  rbf, rescale_degree=True)
+    assert rel_err(out, ref) < 1e-10

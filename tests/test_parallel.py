@@ -64,16 +64,35 @@ def test_bench_reference_arm_ranks_other_than_zero_exit_quietly(monkeypatch, cap
 
 
 def test_flat_adamw_matches_torch_adamw():
-    """FlatAdamW (one flat buffer, six element-wise kernels) == torch.optim.AdamW with the same decay groups."""
-    from equiformer_b200.parallel import FlatAdamW, FlatGradAllReduce
+    """FlatAdamW (one flat buffer, six element-wise kernels) == torch.optim.AdamW with the decay groups of the
+    reference's ``add_weight_decay`` (optim_factory.py:27-42): exemption by NAME - a flat 1-D ``tp.weight`` is decayed."""
+    from equiformer_b200.nets.tensor_product_rescale import LinearRS
+    from equiformer_b200.parallel import FlatAdamW, FlatGradAllReduce, is_no_decay
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = LinearRS("6x0e", "5x0e", bias=True)          # lin.tp.weight is 1-D (30), lin.bias.0 exempt
+            self.fc = torch.nn.Linear(5, 3)
+            self.norm = torch.nn.Module()
+            self.norm.affine_weight = torch.nn.Parameter(torch.ones(3))   # '*.affine_weight' is exempt
+            self.scale = torch.nn.Parameter(torch.ones(3))           # 1-D, NOT exempt under the reference rule
+
+        def forward(self, x):
+            return self.fc(torch.nn.functional.silu(self.lin(x))) * self.scale * self.norm.affine_weight
+
     torch.manual_seed(0)
-    make = lambda: torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.SiLU(), torch.nn.Linear(5, 3)).double()
-    a, b = make(), make()
+    a, b = Net().double(), Net().double()
     b.load_state_dict(a.state_dict())
+    assert a.lin.tp.weight.dim() == 1
     bucket = FlatGradAllReduce(a.parameters())
-    opt_a = FlatAdamW(a.named_parameters(), bucket, lr=1e-2, weight_decay=0.1)
-    decay = [p for p in b.parameters() if p.dim() > 1]
-    no_decay = [p for p in b.parameters() if p.dim() <= 1]
+    skip = {"scale_not_present"}
+    opt_a = FlatAdamW(a.named_parameters(), bucket, lr=1e-2, weight_decay=0.1, no_decay=skip)
+    decay = [p for n, p in b.named_parameters() if not is_no_decay(n, skip)]
+    no_decay = [p for n, p in b.named_parameters() if is_no_decay(n, skip)]
+    names_decay = {n for n, _ in b.named_parameters() if not is_no_decay(n, skip)}
+    assert "lin.tp.weight" in names_decay and "scale" in names_decay and "fc.weight" in names_decay
+    assert "lin.bias.0" not in names_decay and "fc.bias" not in names_decay and "norm.affine_weight" not in names_decay
     opt_b = torch.optim.AdamW([{"params": decay, "weight_decay": 0.1}, {"params": no_decay, "weight_decay": 0.0}], lr=1e-2)
     g = torch.Generator().manual_seed(1)
     for _ in range(5):
@@ -86,6 +105,12 @@ def test_flat_adamw_matches_torch_adamw():
         opt_b.step()
     for pa, pb in zip(a.parameters(), b.parameters()):
         assert torch.allclose(pa, pb, atol=1e-12), (pa - pb).abs().max()
+    # on the headline model the rule decays every tensor-product weight (3.0 M of 3.5 M parameters)
+    from equiformer_b200.nets import model_entrypoint
+    m = model_entrypoint("graph_attention_transformer_nonlinear_l2")(irreps_in="5x0e", radius=5.0, num_basis=128)
+    skip = m.no_weight_decay()
+    n_exempt = sum(p.numel() for n, p in m.named_parameters() if is_no_decay(n, skip))
+    assert n_exempt < 40000, n_exempt
 
 
 def test_flat_bucket_store_matches_backward_accumulation():

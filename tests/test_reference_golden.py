@@ -293,6 +293,61 @@ def test_cuda_headline_model_matches_reference_model_file(cuda_device):
     assert float((energy.double().cpu() - torch.from_numpy(g["energy"])).abs().max()) < 3e-4
 
 
+@pytest.fixture
+def tensor_core_gemms_everywhere():
+    """Lower the row thresholds of the GEMM policy (``ops._GEMM_MIN_M`` / ``_WGRAD_MIN_K``; env EQF_GEMM_MIN_M /
+    EQF_WGRAD_MIN_K) so that even the 16-atom reference-run fixtures go through the hand-written tcgen05 kernels instead
+    of cuBLAS (at these sizes ``M = E (2l+1) << 16 384`` and every product used to be a cuBLAS call)."""
+    from equiformer_b200 import ops
+    old = ops._GEMM_MIN_M, ops._WGRAD_MIN_K
+    ops._GEMM_MIN_M, ops._WGRAD_MIN_K = 1, 1
+    yield
+    ops._GEMM_MIN_M, ops._WGRAD_MIN_K = old
+
+
+@pytest.mark.gpu
+def test_cuda_headline_model_matches_reference_through_tcgen05_gemms(cuda_device, tensor_core_gemms_everywhere):
+    """As ``test_cuda_headline_model_matches_reference_model_file`` with every aligned product on the tcgen05 3xTF32
+    kernels (forward) - and a backward through the tcgen05 weight / data gradient kernels that must agree with the
+    cuBLAS-policy backward of the same model."""
+    from equiformer_b200 import ops
+    from equiformer_b200.nets import model_entrypoint
+    g, state = _headline_state()
+    model = model_entrypoint("graph_attention_transformer_nonlinear_l2")(irreps_in="5x0e", radius=5.0, num_basis=128)
+    model.load_state_dict(state, strict=False)
+    model = model.eval().to(cuda_device)
+    pos = torch.from_numpy(g["pos"]).to(cuda_device)
+    batch, z = torch.from_numpy(g["batch"]).to(cuda_device), torch.from_numpy(g["z"]).to(cuda_device)
+    prof = ops.KernelProfile(time_events=False)
+    ops.PROFILE = prof
+    try:
+        energy = model(f_in=None, pos=pos, batch=batch, node_atom=z)
+        energy.sum().backward()
+    finally:
+        ops.PROFILE = None
+    assert float((energy.detach().double().cpu() - torch.from_numpy(g["energy"])).abs().max()) < 3e-4
+    grads_tc = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    ops._GEMM_MIN_M, ops._WGRAD_MIN_K = 1 << 30, 1 << 30          # the same model, every product on cuBLAS SGEMM
+    model.zero_grad(set_to_none=True)
+    model(f_in=None, pos=pos, batch=batch, node_atom=z).sum().backward()
+    worst = max(((grads_tc[k] - p.grad).abs().max() / p.grad.abs().max().clamp_min(1e-12)).item()
+                for k, p in model.named_parameters() if p.grad is not None)
+    assert worst < 1e-3, worst
+
+
+@pytest.mark.gpu
+def test_cuda_md17_model_matches_reference_through_tcgen05_gemms(cuda_device, tensor_core_gemms_everywhere):
+    """Energy and forces of the MD17 fixture (a double-backward-capable path) with the tcgen05 kernels forced on."""
+    from equiformer_b200.nets.graph_attention_transformer_md17 import GraphAttentionTransformerMD17
+    g = np.load(os.path.join(os.path.dirname(SMALL), "reference_model_md17_small.npz"))
+    model = _mirror_model(g, GraphAttentionTransformerMD17).to(cuda_device)
+    pos = torch.from_numpy(g["pos"]).to(cuda_device)
+    batch, z = torch.from_numpy(g["batch"]).to(cuda_device), torch.from_numpy(g["z"]).to(cuda_device)
+    energy, forces = model(node_atom=z, pos=pos, batch=batch)
+    assert rel_err(energy.detach(), torch.from_numpy(g["energy"])) < 5e-5
+    assert rel_err(forces.detach(), torch.from_numpy(g["forces"])) < 2e-4
+
+
 # --------------------------------- host logic of the mirrors (kernels emulated in float64 on the CPU) vs the reference
 
 def test_mirror_host_logic_matches_reference_model_files():
