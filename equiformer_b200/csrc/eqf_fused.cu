@@ -1,0 +1,567 @@
+// eqf_fused.cu - K1: the depth-wise tensor product produced ON CHIP as the A operand of the per-degree channel-mixing
+// GEMM that follows it (sm_100a).  Reference path: nets/graph_attention_transformer.py:487-496 -
+//   message = src[edge_src] + dst[edge_dst]; f = dtp(message, edge_attr, dtp_rad(edge_scalars)); lin(f) / sep_alpha(f)
+// (e3nn 'uvu' tensor product -> [E, 3136] in HBM -> 'uvw' einsum = cuBLAS GEMM).  Here, per output degree l3 (group):
+//
+//   C[(e, k), c] = sum_u f[e, k, u] W[u, c],     f[e, k, u(p, u')] = w[e, p, u'] * sum_i M_p[e][i, k] * x[e, i, u']
+//   M_p[e][i, k] = sum_j CG_p[i, j, k] y[e, j]   (the edge's (2 l1 + 1) x (2 l3 + 1) coupling block, channel independent)
+//
+// and f never reaches HBM.  One CTA per SM, persistent over 128-row x n_tile output tiles (rows = (edge, component)
+// pairs of ONE output degree), warp-specialised like eqf_gemm_tf32x3.cu's tensor-memory kernel:
+//   warps 0-3    epilogue      TMEM accumulator -> registers -> swizzled staging -> TMA store of C
+//   warp  4      TMA producer  weight tiles B_hi / B_lo of the k-tile (K-major planes, 128-byte rows)
+//   warp  5      MMA issuer    tcgen05.mma.kind::tf32, A from TENSOR MEMORY, 3xTF32 (stacked [b_hi | b_lo] for N <= 64)
+//   warps 8-11   transform     raw A tile (shared memory) -> a_hi / a_lo in tensor memory (one thread = one row)
+//   warps 12-27  DTP producers two sets of 8 warps alternate k-tiles: gather x = A[src] + B[dst] (float4 per lane, node
+//                tables L2 resident), multiply by the per-edge radial weights, contract with M_p[e] and write the
+//                128 x 32 raw A tile into the stage's shared memory (SWIZZLE_128B row order, conflict-free)
+// Per tile the DTP warps first compute M_p[e] for the tile's <= 128/(2 l3 + 1) + 2 edges into shared memory (dense CG table
+// from the plan; sum_j is at most 7 terms).  Register budget (896 threads x 72 at launch): setmaxnreg moves registers from
+// the TMA / MMA warpgroup (40) to the transform (88) and epilogue (88) warpgroups; the DTP warps keep their 72.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "eqf_common.cuh"
+#include "eqf_tc.cuh"
+
+namespace eqf {
+namespace fused {
+
+using namespace tc;
+
+constexpr int BM = 128;                 // rows per tile (UMMA M)
+constexpr int BKT = 32;                 // channels per k-tile: 128-byte rows
+constexpr int kRowBytes = BKT * 4;
+constexpr int UMMA_K = 8;
+constexpr int kStoreCols = 32;
+constexpr int kEpilogueWarps = 4, kProducerWarp = 4, kMmaWarp = 5;
+constexpr int kTransformWarp0 = 8, kTransformWarps = 4;
+constexpr int kDtpWarp0 = 12, kDtpWarps = 16, kDtpSets = 2, kDtpSetWarps = kDtpWarps / kDtpSets;
+constexpr int kDtpThreads = kDtpWarps * 32, kDtpSetThreads = kDtpSetWarps * 32;
+constexpr int kThreads = (kDtpWarp0 + kDtpWarps) * 32;            // 896
+constexpr int kMaxPaths = 16;
+constexpr int kMaxTileEdges = 136;      // 128 / d3 + 2 <= 130
+constexpr int kMBufFloats = 7168;       // per-tile M rows (28 KB): n_e * m_row floats
+constexpr int kMetaBytes = 2048;        // int32 src / dst rows of the tile's edges
+
+// one CG path feeding the output group of this launch (d3 is common to the group)
+struct FPath {
+  int d1, d2;        // 2 l1 + 1, 2 l2 + 1
+  int xb, mul;       // in1 block and its channel count (row of the block = d1 * mul floats)
+  int y_off, w_off;  // offsets into the edge_attr row / the weight row
+  int cg_off;        // dense CG block [d1][d2][d3] (path weight folded in) inside `cg`
+  int koff;          // first channel of the path inside the group's K
+  int m_off;         // offset of this path's [d1][d3] block inside one edge's M row
+};
+
+struct FArgs {
+  const float* x[EQF_MAX_BLOCKS];
+  const float* x2[EQF_MAX_BLOCKS];
+  const long long* src;
+  const long long* dst;
+  const float* y;
+  const float* w;
+  const float* w_offset;
+  const float* cg;
+  long long E, M;        // edges; GEMM rows = E * d3
+  int d_y, W, w_shared, d3, n_paths, m_row, K, N;
+  int n_tile, n_blocks;
+  long long m_blocks;
+  int dbg_skip;          // measurement aid: bit 0 skips the DTP math, bit 1 the MMAs, bit 2 the transform (garbage results)
+  FPath paths[kMaxPaths];
+};
+
+template <int BN, bool STACK>
+struct FSmem {
+  static constexpr int kAccCols = STACK ? 2 * BN : BN;
+  static constexpr int kABytes = BM * kRowBytes;                    // raw A tile written by the DTP warps
+  static constexpr int kBBytes = BN * kRowBytes;
+  static constexpr int kStageBytes = kABytes + 2 * kBBytes;         // A raw | B hi | B lo
+  static constexpr int kStoreBytes = kEpilogueWarps * 2 * 32 * kStoreCols * 4;
+  static constexpr int kMBytes = kMBufFloats * 4;
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kBudget = 227 * 1024 - 1024;
+  static constexpr int kStagesSmem = (kBudget - kStoreBytes - kMBytes - kMetaBytes - kBarBytes) / kStageBytes;
+  static constexpr int kStagesTmem = (512 - 2 * kAccCols) / (2 * BKT);
+  static constexpr int kStagesMin = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
+  static constexpr int kStages = kStagesMin > 8 ? 8 : kStagesMin;
+  static_assert(kStages >= 2, "tile does not fit");
+  static constexpr int kTotal = kStages * kStageBytes + kStoreBytes + kMBytes + kMetaBytes + kBarBytes + 1024;
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void addv(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+__device__ __forceinline__ void mulv(float4& a, const float4& b) { a.x *= b.x; a.y *= b.y; a.z *= b.z; a.w *= b.w; }
+__device__ __forceinline__ void fs(float4& a, const float4& x, float m) {
+  a.x = fmaf(x.x, m, a.x); a.y = fmaf(x.y, m, a.y); a.z = fmaf(x.z, m, a.z); a.w = fmaf(x.w, m, a.w);
+}
+
+// One k-tile (32 channels `ch0 ..` of path p) of the raw A tile: thread t of the set's 256 handles edge t / 8 (+32 ...)
+// and the four channels 4 (t % 8) of the chunk.
+template <int D1, int D3>
+__device__ __forceinline__ void dtp_ktile(const FArgs& a, const FPath& p, int ch0, int t, long long e0, int n_e, long long row0,
+                                          const int* __restrict__ src_s, const int* __restrict__ dst_s,
+                                          const float* __restrict__ mbuf, uint32_t raw_addr) {
+  const int c8 = t & 7;
+  const int ch = ch0 + c8 * 4;
+  const bool gather = a.src != nullptr;
+  const float* xa = a.x[p.xb];
+  const float* xb = a.x2[p.xb];
+  const long long row_floats = (long long)D1 * p.mul;
+  for (int el = t >> 3; el < n_e; el += kDtpSetThreads / 8) {
+    const long long e = e0 + el;
+    float4 wv = ld4(a.w + (a.w_shared ? 0 : e * a.W) + p.w_off + ch);
+    if (a.w_offset != nullptr) addv(wv, ld4(a.w_offset + p.w_off + ch));
+    const long long rs = gather ? (long long)src_s[el] : e;
+    const float* xp = xa + rs * row_floats + ch;
+    float4 x[D1];
+#pragma unroll
+    for (int i = 0; i < D1; ++i) x[i] = ld4(xp + i * p.mul);
+    if (xb != nullptr) {
+      const float* xq = xb + (long long)dst_s[el] * row_floats + ch;
+#pragma unroll
+      for (int i = 0; i < D1; ++i) addv(x[i], ld4(xq + i * p.mul));
+    }
+#pragma unroll
+    for (int i = 0; i < D1; ++i) mulv(x[i], wv);
+    const float* me = mbuf + el * a.m_row + p.m_off;      // [D1][D3]
+    const int rbase = (int)(e * D3 - row0);
+#pragma unroll
+    for (int k = 0; k < D3; ++k) {
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < D1; ++i) fs(f, x[i], me[i * D3 + k]);
+      const int row = rbase + k;
+      if ((unsigned)row < (unsigned)BM) sts128(raw_addr + (uint32_t)row * 128u + (uint32_t)((c8 ^ (row & 7)) << 4), f);
+    }
+  }
+}
+
+template <int D3>
+__device__ __forceinline__ void dtp_ktile_d1(const FArgs& a, const FPath& p, int ch0, int t, long long e0, int n_e, long long row0,
+                                             const int* src_s, const int* dst_s, const float* mbuf, uint32_t raw_addr) {
+  switch (p.d1) {
+    case 1: dtp_ktile<1, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
+    case 3: dtp_ktile<3, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
+    case 5: dtp_ktile<5, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
+    default: dtp_ktile<7, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
+  }
+}
+
+template <int BN, bool STACK>
+__global__ void __launch_bounds__(kThreads, 1)
+dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+                    const __grid_constant__ CUtensorMap map_c, const __grid_constant__ FArgs a) {
+  using S = FSmem<BN, STACK>;
+  constexpr int kStages = S::kStages;
+  constexpr int kTmemCols = 512;
+  constexpr int kAcc = S::kAccCols;
+  constexpr int kACol0 = 2 * kAcc;                       // first TMEM column of the A staging area
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* store_base = smem + kStages * S::kStageBytes;
+  float* mbuf = reinterpret_cast<float*>(store_base + S::kStoreBytes);
+  int* src_s = reinterpret_cast<int*>(store_base + S::kStoreBytes + S::kMBytes);
+  int* dst_s = src_s + kMaxTileEdges;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(store_base + S::kStoreBytes + S::kMBytes + kMetaBytes);
+  uint64_t* full = bars;                        // [kStages] weight tiles landed (TMA)
+  uint64_t* raw_ready = bars + kStages;         // [kStages] raw A tile written by the DTP set
+  uint64_t* a_ready = bars + 2 * kStages;       // [kStages] a_hi / a_lo in tensor memory
+  uint64_t* empty = bars + 3 * kStages;         // [kStages] MMAs of the stage finished
+  uint64_t* tmem_full = bars + 4 * kStages;     // [2]
+  uint64_t* tmem_empty = bars + 4 * kStages + 2;   // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 4 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k_tiles = a.K / BKT;
+  const long long n_tiles_total = a.m_blocks * a.n_blocks;
+
+  if (warp == kProducerWarp && lane == 0) {
+    prefetch_map(&map_bhi); prefetch_map(&map_blo); prefetch_map(&map_c);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&raw_ready[s], kDtpSetWarps);
+      mbar_init(&a_ready[s], kTransformWarps);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], kEpilogueWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "n"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp < kEpilogueWarps) {
+    // ===================================================================================== epilogue (warpgroup 0)
+    reg_alloc<88>();
+    uint32_t acc_it = 0, chunk_it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
+      const long long mb = tile / a.n_blocks;
+      const int nb = (int)(tile % a.n_blocks);
+      const int ab = acc_it & 1;
+      const uint32_t aph = (acc_it >> 1) & 1;
+      mbar_wait(&tmem_full[ab], aph);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * kAcc);
+      const long long row0 = mb * BM + warp * 32;
+      const int col0 = nb * a.n_tile;
+      uint8_t* wbuf = store_base + warp * (2 * 32 * kStoreCols * 4);
+      const int n_valid = (a.N - col0) < a.n_tile ? (a.N - col0) : a.n_tile;
+      for (int c = 0; c < n_valid; c += kStoreCols, ++chunk_it) {
+        const uint32_t buf = smem_u32(wbuf + (chunk_it & 1) * (32 * kStoreCols * 4));
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)c, v);
+        if constexpr (STACK) {       // add the hi*lo half of the stacked accumulator, 16 columns at a time
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v2[16];
+            tmem_ld16(taddr + (uint32_t)(BN + c + 16 * hh), v2);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[16 * hh + j] = __float_as_uint(__uint_as_float(v[16 * hh + j]) + __uint_as_float(v2[j]));
+          }
+        } else {
+          tmem_wait_ld();
+        }
+        // the buffer about to be overwritten was handed to a TMA store two chunks ago: wait until that store has read it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = buf + (uint32_t)lane * 128u + (uint32_t)((j ^ (lane & 7)) << 4);
+          sts128(dst, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                  __uint_as_float(v[4 * j + 3])));
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0 && row0 < a.M) {
+          tma_store_2d(&map_c, col0 + c, (int)row0, buf);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else if (warp < kTransformWarp0) {
+    // ===================================================================================== warpgroup 1: TMA + MMA
+    reg_dealloc<40>();
+    if (warp == kProducerWarp && lane == 0) {
+      uint32_t it = 0;
+      const uint32_t tx = (uint32_t)(2 * a.n_tile * kRowBytes);
+      for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        const int nb = (int)(tile % a.n_blocks);
+        for (int kt = 0; kt < k_tiles; ++kt, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = stage_base + (size_t)s * S::kStageBytes;
+          mbar_expect_tx(&full[s], tx);
+          tma_load_2d(st + S::kABytes, &map_bhi, kt * BKT, nb * a.n_tile, &full[s]);
+          tma_load_2d(st + S::kABytes + S::kBBytes, &map_blo, kt * BKT, nb * a.n_tile, &full[s]);
+        }
+      }
+    } else if (warp == kMmaWarp && lane == 0) {
+      const uint32_t idesc = instr_desc(a.n_tile);
+      const uint32_t idesc2 = instr_desc(2 * a.n_tile);          // STACK: [b_hi | b_lo] as one operand
+      uint32_t it = 0, acc_it = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
+        const int ab = acc_it & 1;
+        const uint32_t aph = (acc_it >> 1) & 1;
+        mbar_wait(&tmem_empty[ab], aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * kAcc);
+        for (int kt = 0; kt < k_tiles; ++kt, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&full[s], ph);
+          mbar_wait(&a_ready[s], ph);
+          tc_fence_after();
+          const uint32_t st = smem_u32(stage_base + (size_t)s * S::kStageBytes);
+          const uint64_t b_hi = smem_desc_sw128(st + S::kABytes), b_lo = smem_desc_sw128(st + S::kABytes + S::kBBytes);
+          const uint32_t a_hi = tmem_base + (uint32_t)(kACol0 + s * 2 * BKT), a_lo = a_hi + BKT;
+#pragma unroll
+          for (int kb = 0; kb < BKT / UMMA_K; ++kb) {
+            if (a.dbg_skip & 2) break;
+            const uint64_t adv = (uint64_t)((kb * UMMA_K * 4) >> 4);
+            const uint32_t acol = (uint32_t)(kb * UMMA_K);
+            if constexpr (STACK) {
+              umma_tf32_ts(d_tmem, a_hi + acol, b_hi + adv, idesc2, (kt > 0 || kb > 0) ? 1u : 0u);   // hi*hi | hi*lo
+              umma_tf32_ts(d_tmem, a_lo + acol, b_hi + adv, idesc, 1u);                               // + lo*hi
+            } else {
+              umma_tf32_ts(d_tmem, a_lo + acol, b_hi + adv, idesc, (kt > 0 || kb > 0) ? 1u : 0u);
+              umma_tf32_ts(d_tmem, a_hi + acol, b_lo + adv, idesc, 1u);
+              umma_tf32_ts(d_tmem, a_hi + acol, b_hi + adv, idesc, 1u);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[ab]);
+      }
+    }
+  } else if (warp < kDtpWarp0) {
+    // ===================================================================================== transform (warpgroup 2)
+    reg_alloc<88>();
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+      for (int kt = 0; kt < k_tiles; ++kt, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&raw_ready[s], ph);
+        if (!(a.dbg_skip & 4)) {
+          const uint32_t rbase = smem_u32(stage_base + (size_t)s * S::kStageBytes) + (uint32_t)row * (uint32_t)kRowBytes;
+          float hi[BKT], lo[BKT];
+          float4 v[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = lds128(rbase + (uint32_t)((c ^ (row & 7)) << 4));
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float xv[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              hi[4 * c + q] = tf32_rn(xv[q]);
+              lo[4 * c + q] = xv[q] - hi[4 * c + q];
+            }
+          }
+          const uint32_t acol = tmem_base + lane_field + (uint32_t)(kACol0 + s * 2 * BKT);
+          tmem_st32(acol, hi);
+          tmem_st32(acol + BKT, lo);
+          tmem_wait_st();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[s]);
+      }
+    }
+  } else {
+    // ===================================================================================== DTP producers (warpgroups 3-6)
+    const int dt = threadIdx.x - kDtpWarp0 * 32;          // 0 .. 511
+    const int set = (warp - kDtpWarp0) / kDtpSetWarps;    // which half of the k-tiles
+    const int t = dt - set * kDtpSetThreads;              // 0 .. 255 inside the set
+    const int d3 = a.d3;
+    uint32_t it = 0;
+    for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+      const long long mb = tile / a.n_blocks;
+      const long long row0 = mb * BM;
+      const long long e0 = row0 / d3;
+      long long e1 = (row0 + BM - 1) / d3 + 1;
+      if (e1 > a.E) e1 = a.E;
+      const int n_e = (int)(e1 - e0);
+      // ---- per-tile tables: node rows of the tile's edges and the coupling blocks M_p[e] = CG_p . y_e
+      named_barrier(1, kDtpThreads);      // every DTP warp has finished the previous tile (readers of mbuf / src_s / dst_s)
+      if (a.src != nullptr) {
+        for (int i = dt; i < n_e; i += kDtpThreads) {
+          src_s[i] = (int)a.src[e0 + i];
+          dst_s[i] = a.dst != nullptr ? (int)a.dst[e0 + i] : 0;
+        }
+      }
+      {
+        const int m_row = a.m_row;
+        for (int idx = dt; idx < n_e * m_row; idx += kDtpThreads) {
+          const int el = idx / m_row, q = idx - el * m_row;
+          int pi = 0;
+#pragma unroll 1
+          for (int j = 1; j < a.n_paths; ++j) if (q >= a.paths[j].m_off) pi = j;
+          const FPath& p = a.paths[pi];
+          const int r = q - p.m_off;
+          const int i = r / d3, k = r - i * d3;
+          const float* cg = a.cg + p.cg_off + i * p.d2 * d3 + k;
+          const float* yv = a.y + (e0 + el) * a.d_y + p.y_off;
+          float m = 0.f;
+          for (int j = 0; j < p.d2; ++j) m = fmaf(__ldg(cg + j * d3), __ldg(yv + j), m);
+          mbuf[idx] = m;
+        }
+      }
+      named_barrier(1, kDtpThreads);
+      // ---- k-tiles: channel chunks of 32 in group order; set q takes every other one
+      int kt = 0;
+      for (int pi = 0; pi < a.n_paths; ++pi) {
+        const FPath& p = a.paths[pi];
+        for (int ch0 = 0; ch0 < p.mul; ch0 += BKT, ++kt, ++it) {
+          if ((int)(it & 1) != set) continue;
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          const uint32_t raw_addr = smem_u32(stage_base + (size_t)s * S::kStageBytes);
+          if (!(a.dbg_skip & 1)) {
+            switch (d3) {
+              case 1: dtp_ktile_d1<1>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
+              case 3: dtp_ktile_d1<3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
+              case 5: dtp_ktile_d1<5>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
+              default: dtp_ktile_d1<7>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&raw_ready[s]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// hi / lo planes of a weight stored [K, N] (row stride ldw): the planes come out transposed, [N, K] K-major
+__global__ void split_transpose_kernel(const float* __restrict__ w, long long ldw, float* __restrict__ hi,
+                                       float* __restrict__ lo, long long N, long long K) {
+  const long long n_el = N * K;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / K, k = i - n * K;
+    const float v = w[k * ldw + n];
+    const float h = tf32_rn(v);
+    hi[i] = h;
+    lo[i] = v - h;
+  }
+}
+
+template <int BN, bool STACK>
+static int launch_fwd(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mc, const FArgs& a, cudaStream_t s) {
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(dtp_gemm_fwd_kernel<BN, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    FSmem<BN, STACK>::kTotal);
+  });
+  if (attr_err != cudaSuccess) return check_cuda(attr_err, "dtp_gemm_fwd smem attribute");
+  const int sms = device_sms();
+  const long long tiles = a.m_blocks * a.n_blocks;
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  dtp_gemm_fwd_kernel<BN, STACK><<<grid, kThreads, FSmem<BN, STACK>::kTotal, s>>>(mh, ml, mc, a);
+  return check_cuda(cudaGetLastError(), "dtp_gemm_fwd_kernel launch");
+}
+
+// paths of output group `group`, in channel order; returns the number of paths or a negative error
+static int collect_paths(const EqfPlan* plan, int group, FArgs& a) {
+  const PlanHdr& h = plan->hdr;
+  if (group < 0 || group >= h.n_out) { set_error("fused DTP: output group out of range"); return EQF_ERR_INVALID; }
+  const PathDev* pd = reinterpret_cast<const PathDev*>(plan->blob.data() + h.off_paths);
+  std::vector<const PathDev*> ps;
+  for (int p = 0; p < h.n_paths; ++p) if (pd[p].og == group) ps.push_back(&pd[p]);
+  for (size_t i = 0; i < ps.size(); ++i)                     // channel order (a handful of paths: insertion sort)
+    for (size_t j = i; j > 0 && ps[j]->koff < ps[j - 1]->koff; --j) std::swap(ps[j], ps[j - 1]);
+  if (ps.empty() || (int)ps.size() > kMaxPaths) { set_error("fused DTP: unsupported number of paths in the group"); return EQF_ERR_UNSUPPORTED; }
+  int koff = 0, m_off = 0;
+  for (size_t i = 0; i < ps.size(); ++i) {
+    const PathDev& s = *ps[i];
+    if (s.koff != koff || s.mul % BKT != 0) {
+      set_error("fused DTP: group channels must be covered by paths of multiplicity % 32 == 0");
+      return EQF_ERR_UNSUPPORTED;
+    }
+    FPath& f = a.paths[i];
+    f.d1 = s.d1; f.d2 = s.d2; f.xb = s.xb; f.mul = s.mul; f.y_off = s.y_off; f.w_off = s.w_off; f.cg_off = s.cg_off;
+    f.koff = s.koff; f.m_off = m_off;
+    koff += s.mul;
+    m_off += s.d1 * s.d3;
+  }
+  a.n_paths = (int)ps.size();
+  a.d3 = h.out_d[group];
+  a.K = koff;
+  a.m_row = m_off;
+  if (koff != h.out_mul[group]) { set_error("fused DTP: paths do not cover the output group"); return EQF_ERR_INVALID; }
+  if ((BM / a.d3 + 2) * a.m_row > kMBufFloats) { set_error("fused DTP: coupling blocks of a tile exceed shared memory"); return EQF_ERR_UNSUPPORTED; }
+  return a.n_paths;
+}
+
+}  // namespace fused
+}  // namespace eqf
+
+using namespace eqf;
+
+// 1 when eqf_dtp_linear_fwd can run output group `group` of the plan (multiplicities % 32 == 0, tables fit), else 0
+extern "C" int eqf_dtp_linear_supported(const EqfPlan* plan, int32_t group) {
+  if (plan == nullptr) return 0;
+  fused::FArgs a;
+  const PlanHdr& h = plan->hdr;
+  for (int b = 0; b < h.n_in1; ++b) if (h.in1_mul[b] % 4 != 0) return 0;
+  if (h.w_numel % 4 != 0) return 0;
+  return fused::collect_paths(plan, group, a) > 0 ? 1 : 0;
+}
+
+// C[(e, k), :N] = DTP_group(x, y; w)[(e, k), :K] @ Wt[:K, :N]   for output group `group` of the plan: the depth-wise tensor
+// product (nets/graph_attention_transformer.py:491 / :496) feeds the channel-mixing linear (:492, :494, :496) on chip.
+// Operands as for eqf_dtp_forward (gather x = x[src] + x2[dst] when op->src is set; w per edge [E, W] (+ w_offset) or
+// shared [W]); Wt row-major [K, N] with row stride ldw; C [E * (2 l3 + 1), N] with row stride ldc; `split` = device
+// scratch of 2 * N * K floats.  16-byte aligned pointers, N, ldc multiples of 4.
+extern "C" int eqf_dtp_linear_fwd(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_edges, int32_t group,
+                                  const float* Wt, int64_t N, int64_t ldw, float* C, int64_t ldc, float* split,
+                                  void* stream) {
+  using namespace eqf::fused;
+  if (plan == nullptr || op == nullptr) { set_error("eqf_dtp_linear_fwd: null plan / operands"); return EQF_ERR_INVALID; }
+  if (n_edges <= 0 || N <= 0) return EQF_OK;
+  if (!Wt || !C || !split || !op->y || !op->w) { set_error("eqf_dtp_linear_fwd: null pointer"); return EQF_ERR_INVALID; }
+  int rc = ensure_device(plan);
+  if (rc != EQF_OK) return rc;
+  FArgs a;
+  const PlanHdr& h = plan->hdr;
+  rc = collect_paths(plan, group, a);
+  if (rc < 0) return rc;
+  if ((((uintptr_t)C | (uintptr_t)split | (uintptr_t)op->w | (uintptr_t)op->w_offset) & 15) || ((N | ldc) & 3) || ldc < N ||
+      ldw < N || (h.w_numel & 3)) {
+    set_error("eqf_dtp_linear_fwd: operands must be 16-byte aligned, N and ldc multiples of 4");
+    return EQF_ERR_INVALID;
+  }
+  for (int b = 0; b < EQF_MAX_BLOCKS; ++b) { a.x[b] = nullptr; a.x2[b] = nullptr; }
+  for (int b = 0; b < h.n_in1; ++b) {
+    if (op->x[b] == nullptr || ((uintptr_t)op->x[b] & 15) || ((uintptr_t)op->x2[b] & 15) || (h.in1_mul[b] & 3)) {
+      set_error("eqf_dtp_linear_fwd: in1 blocks must be present, 16-byte aligned, multiplicities % 4 == 0");
+      return EQF_ERR_INVALID;
+    }
+    a.x[b] = op->x[b];
+    a.x2[b] = op->x2[b];
+  }
+  a.src = reinterpret_cast<const long long*>(op->src);
+  a.dst = reinterpret_cast<const long long*>(op->dst);
+  if (a.x2[0] != nullptr && (a.src == nullptr || a.dst == nullptr)) { set_error("eqf_dtp_linear_fwd: x2 needs src and dst"); return EQF_ERR_INVALID; }
+  a.y = op->y; a.w = op->w; a.w_offset = op->w_offset; a.w_shared = op->w_shared;
+  if (a.w_shared && a.w_offset != nullptr) { set_error("eqf_dtp_linear_fwd: w_offset needs per-edge weights"); return EQF_ERR_INVALID; }
+  a.cg = reinterpret_cast<const float*>(plan->d_blob + h.off_cg);
+  a.E = n_edges; a.M = n_edges * a.d3; a.d_y = h.d_y; a.W = h.w_numel; a.N = (int)N;
+  if (a.M > 0x7fffffffLL) { set_error("eqf_dtp_linear_fwd: too many rows"); return EQF_ERR_UNSUPPORTED; }
+  { const char* e = std::getenv("EQF_FUSED_DBG_SKIP"); a.dbg_skip = e ? std::atoi(e) : 0; }
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long K = a.K;
+  float* hi = split;
+  float* lo = split + N * K;
+  {
+    const long long n = N * K;
+    const unsigned blocks = (unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    split_transpose_kernel<<<blocks, 256, 0, s>>>(Wt, ldw, hi, lo, N, K);
+  }
+  if ((rc = check_cuda(cudaGetLastError(), "split_transpose_kernel launch")) != EQF_OK) return rc;
+  // column tiles: stacked [b_hi | b_lo] operand for outputs of exactly 32 / 64 columns, else tiles of <= 128 columns
+  const bool stack = (N == 32 || N == 64);
+  const int n_blocks = (int)((N + 127) / 128);
+  const int n_tile = n_blocks == 1 ? (int)((N + 15) & ~15LL) : 128;
+  a.n_tile = n_tile; a.n_blocks = n_blocks; a.m_blocks = (a.M + BM - 1) / BM;
+  CUtensorMap mh, ml, mc;
+  if ((rc = make_map_2d(&mh, hi, N, K, K, n_tile, BKT)) != EQF_OK) return rc;
+  if ((rc = make_map_2d(&ml, lo, N, K, K, n_tile, BKT)) != EQF_OK) return rc;
+  if ((rc = make_map_2d(&mc, C, a.M, N, ldc, 32, kStoreCols)) != EQF_OK) return rc;
+  if (stack && n_tile == 32) return launch_fwd<32, true>(mh, ml, mc, a, s);
+  if (stack && n_tile == 64) return launch_fwd<64, true>(mh, ml, mc, a, s);
+  if (n_tile <= 32) return launch_fwd<32, false>(mh, ml, mc, a, s);
+  if (n_tile <= 64) return launch_fwd<64, false>(mh, ml, mc, a, s);
+  return launch_fwd<128, false>(mh, ml, mc, a, s);
+}

@@ -214,6 +214,26 @@ def _reblock(blocks: Sequence[torch.Tensor], irreps_from: Irreps, irreps_to: Irr
     return ops.to_planar(ops.from_planar(blocks), irreps_to)
 
 
+def _group_weight_matrices(lin, n_groups: int):
+    """``[K_g, N_g]`` weight views of a per-degree linear whose entries map one to one onto the ``n_groups`` output
+    groups of the depth-wise product in front of it (instruction g: group g -> entry g, path constant 1), or None when
+    the linear does not have that canonical structure (then the unfused route is taken)."""
+    try:
+        ins = [(i.i_in1, i.i_in2, i.i_out) for i in lin.tp.instructions]
+        if ins != [(g, 0, g) for g in range(n_groups)] or len(lin.irreps_out) != n_groups:
+            return None
+        blocks = lin.tp.linear_weight_blocks()
+        if any(c != 1.0 for *_i, _W, c in blocks):
+            return None
+        return [W.reshape(W.shape[0], W.shape[2]) for _i1, _i2, _io, W, _c in blocks]
+    except (AttributeError, NotImplementedError):
+        return None
+
+
+def _fused_linear_possible(lin, dtp) -> bool:
+    return _group_weight_matrices(lin, len(dtp.tp.plan.out_groups)) is not None
+
+
 class GraphAttention(torch.nn.Module):
     """Multi-head equivariant graph attention (ref :403-533): message = alpha * value, aggregated at the target."""
 
@@ -305,6 +325,9 @@ class GraphAttention(torch.nn.Module):
             raise NotImplementedError("irreps_head must be sorted (l ascending, even first) with one entry per irrep")
         self._head_layout = ops.HeadLayout([ir.dim for _, ir in irreps_attn_heads],
                                            [mul for mul, _ in irreps_attn_heads], num_heads)
+        # K1 (ops.DtpLinear): both depth-wise products feed their per-degree linears on chip when the linears are canonical
+        self._fuse_act = (self._gate_layout is not None and _fused_linear_possible(self.sep_act.lin, self.sep_act.dtp))
+        self._fuse_value = (self.nonlinear_message and _fused_linear_possible(self.sep_value.lin, self.sep_value.dtp))
 
     # ---------------------------------------------------------------------------------------------
     @property
@@ -338,24 +361,33 @@ class GraphAttention(torch.nn.Module):
             sa = self.sep_act
             # [ref :490] radial weights; the radial offset is added inside the DTP kernel's weight load
             weight = sa.dtp_rad(edge_scalars, add_offset=False)
-            f = sa.dtp.tp.planar_depthwise_gathered(graph, m_src, m_dst, edge_attr, weight,
-                                                    sa.dtp_rad.offset)                    # [ref :487+:491]  DTP #1
+            plan1 = sa.dtp.tp.plan
+            fuse1 = self._fuse_act and ops.dtp_linear_ok(plan1, edge_attr, weight)
+            f = None
+            if not fuse1:
+                f = sa.dtp.tp.planar_depthwise_gathered(graph, m_src, m_dst, edge_attr, weight,
+                                                        sa.dtp_rad.offset)                # [ref :487+:491]  DTP #1
             logits = None
-            if self._gate_layout is not None and ops.fused_ok(f[0]):
+            if self._gate_layout is not None and (fuse1 or ops.fused_ok(f[0])):
                 # one GEMM for alpha and the 0e part of the value linear ([K0, A0 | S + Gates]), then ONE kernel for
                 # the bias adds, the gate and the attention logits                           [ref :492-495, :506-507]
                 lay = self._gate_layout
-                k0 = f[0].shape[2]
                 blocks = {io: (W, c) for _i1, _i2, io, W, c in sa.lin.tp.linear_weight_blocks()}
+                k0 = plan1.out_groups[0][2]
                 w_cat = torch.cat([self.sep_alpha.tp.weight.view(k0, -1), blocks[0][0].reshape(k0, -1)], dim=1)
-                t0 = ops.matmul_f32(f[0].reshape(E, k0), w_cat)
                 bias = torch.cat([self.sep_alpha.bias[0], sa.lin.bias[0]])
-                gated = [ops.matmul_f32(f[g].reshape(E * f[g].shape[1], f[g].shape[2]), blocks[g][0].reshape(f[g].shape[2], -1))
-                         .view(E, f[g].shape[1], -1) for g in range(1, len(f))]
+                if fuse1:
+                    # K1: DTP #1 is the on-chip A operand of the three per-degree GEMMs - [E, 3136] never reaches HBM
+                    Ws = [w_cat] + [blocks[g][0].reshape(blocks[g][0].shape[0], -1) for g in range(1, len(plan1.out_groups))]
+                    outs = ops.dtp_linear(plan1, graph, m_src, m_dst, edge_attr, weight, sa.dtp_rad.offset, Ws)
+                    t0, gated = outs[0].reshape(E, -1), outs[1:]
+                else:
+                    t0 = ops.matmul_f32(f[0].reshape(E, k0), w_cat)
+                    gated = [ops.matmul_f32(f[g].reshape(E * f[g].shape[1], f[g].shape[2]), blocks[g][0].reshape(f[g].shape[2], -1))
+                             .view(E, f[g].shape[1], -1) for g in range(1, len(f))]
                 logits, v0, *vs = ops.GateLogits.apply(lay, t0, bias, self.alpha_dot.view(H, A), *gated)
                 value = _reblock([v0.view(E, 1, -1), *vs], sa.gate.irreps_out, self.sep_value.irreps_node_input)
-                f2 = self.sep_value.dtp.planar(value, edge_attr, None)                    # [ref :496]  DTP #2
-                value = self.sep_value.lin.planar(f2)
+                value = self._value_linear(value, edge_attr)                              # [ref :496]  DTP #2 + lin
                 alpha = None
             elif self._alpha_single_gemm:                                                 # [ref :492]
                 k0 = f[0].shape[2]
@@ -369,8 +401,7 @@ class GraphAttention(torch.nn.Module):
                 value = sa.lin.planar(f)                                                  # [ref :494]
                 value = sa.gate.planar(value) if isinstance(sa.gate, Gate) else [sa.gate(v) for v in value]  # [:495]
                 value = _reblock(value, sa.gate.irreps_out, self.sep_value.irreps_node_input)
-                f2 = self.sep_value.dtp.planar(value, edge_attr, None)                    # [ref :496]  DTP #2
-                value = self.sep_value.lin.planar(f2)
+                value = self._value_linear(value, edge_attr)                              # [ref :496]  DTP #2 + lin
                 alpha = alpha.reshape(E, H, A)                                            # [ref :493]
         else:
             weight = self.sep.dtp_rad(edge_scalars, add_offset=False)
@@ -396,6 +427,17 @@ class GraphAttention(torch.nn.Module):
             degree = (graph.row_ptr[1:] - graph.row_ptr[:-1]).to(node[0].dtype).view(-1, 1, 1)
             node = [t * degree for t in node]
         return self.proj.planar(node)
+
+    def _value_linear(self, value, edge_attr):
+        """``sep_value``: depth-wise product with the shared (internal) weights, then the per-degree linear [ref :496]."""
+        sv = self.sep_value
+        plan2 = sv.dtp.tp.plan
+        w2 = sv.dtp.tp.weight
+        if self._fuse_value and ops.dtp_linear_ok(plan2, edge_attr, w2):
+            Ws = _group_weight_matrices(sv.lin, len(plan2.out_groups))
+            return sv.lin._planar_bias(ops.dtp_linear(plan2, None, [v.contiguous() for v in value], None, edge_attr, w2,
+                                                      None, Ws))
+        return sv.lin.planar(sv.dtp.planar(value, edge_attr, None))
 
     def extra_repr(self) -> str:
         return f"rescale_degree={self.rescale_degree}, "
@@ -576,6 +618,7 @@ class EdgeDegreeEmbeddingNetwork(torch.nn.Module):
         self.scale_scatter = ScaledScatter(avg_aggregate_num)
         self._sum_layout = ops.HeadLayout([ir.dim for _, ir in self.proj.irreps_out],
                                           [mul for mul, _ in self.proj.irreps_out], 1)
+        self._fuse_proj = _fused_linear_possible(self.proj, self.dw)
 
     def forward(self, node_input, edge_attr, edge_scalars, edge_src, edge_dst, batch, **kwargs):
         n_nodes = node_input.shape[0]
@@ -585,8 +628,14 @@ class EdgeDegreeEmbeddingNetwork(torch.nn.Module):
         ones = torch.ones((n_nodes, 1, 1), dtype=node_input.dtype, device=node_input.device)
         node_feats = self.exp.planar([ones])
         weight = self.rad(edge_scalars, add_offset=False)        # the radial offset is added inside the DTP kernel
-        edge_feats = self.dw.tp.planar_depthwise_gathered(graph, node_feats, None, edge_attr, weight, self.rad.offset)
-        edge_feats = self.proj.planar(edge_feats)
+        plan = self.dw.tp.plan
+        if self._fuse_proj and ops.dtp_linear_ok(plan, edge_attr, weight):        # K1: DTP -> proj on chip
+            Ws = _group_weight_matrices(self.proj, len(plan.out_groups))
+            edge_feats = self.proj._planar_bias(ops.dtp_linear(plan, graph, node_feats, None, edge_attr, weight,
+                                                               self.rad.offset, Ws))
+        else:
+            edge_feats = self.dw.tp.planar_depthwise_gathered(graph, node_feats, None, edge_attr, weight, self.rad.offset)
+            edge_feats = self.proj.planar(edge_feats)
         summed = ops.attention_aggregate(self._sum_layout, graph, None, [t.contiguous() for t in edge_feats])
         return ops.from_planar(summed).div(self.scale_scatter.avg_aggregate_num ** 0.5)
 

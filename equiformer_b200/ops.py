@@ -556,6 +556,149 @@ def depthwise_tensor_product_gathered(plan: DtpPlan, graph: "Graph", As, Bs, y, 
     return list(DtpOutGathered.apply(plan, graph, n_b, y, w, *AB))
 
 
+# ----------------------------------------------------------------------------- K1: DTP fused into the per-degree linear
+
+# EQF_FUSED=0 keeps the round-1 pipeline (DTP -> [E, 3136] in HBM -> GEMMs)
+_FUSED = os.environ.get("EQF_FUSED", "1") != "0"
+_FUSED_SPLIT = {}
+
+
+def dtp_linear_supported(plan: DtpPlan) -> bool:
+    """True when every output group of ``plan`` can run through ``eqf_dtp_linear_fwd`` (multiplicities % 32 == 0, the
+    tile's coupling blocks fit shared memory)."""
+    ok = getattr(plan, "_fused_ok", None)
+    if ok is None:
+        lib = _lib.load()
+        ok = all(lib.eqf_dtp_linear_supported(plan.handle, g) == 1 for g in range(len(plan.out_groups)))
+        plan._fused_ok = ok
+    return ok
+
+
+def dtp_linear_ok(plan: DtpPlan, y: torch.Tensor, w: torch.Tensor) -> bool:
+    """Policy: the fused kernel carries first-order training / inference on CUDA; when the edge harmonics need a
+    gradient (MD17 forces, ``create_graph``) the closed differentiable family of the unfused kernels is used."""
+    return (_FUSED and fused_ok(y) and not (torch.is_grad_enabled() and y.requires_grad)
+            and y.shape[0] > 0 and dtp_linear_supported(plan))
+
+
+def dtp_linear_fwd_raw(plan: DtpPlan, group: int, xs, y, w, Wt: torch.Tensor, gather=None, w_offset=None) -> torch.Tensor:
+    """``C[e, k, :] = DTP_group(x, y; w)[e, k, :] @ Wt`` with the tensor product produced on chip as the A operand of the
+    tcgen05 GEMM (``eqf_dtp_linear_fwd``): ``[E, 2 l3 + 1, N]``.  ``Wt`` is ``[K_group, N]``."""
+    y, w, E, shared = _check_yw(plan, y, w)
+    xs, gather = _check_gather(plan, xs, gather, E, "dtp_linear x")
+    l3, _p, K = plan.out_groups[group]
+    Wt = _require_cuda(Wt, "dtp_linear weight")
+    if Wt.dim() != 2 or Wt.shape[0] != K:
+        raise ValueError(f"dtp_linear: weight must be [{K}, N], got {tuple(Wt.shape)}")
+    N = Wt.shape[1]
+    d3 = 2 * l3 + 1
+    C = torch.empty((E, d3, N), device=y.device, dtype=torch.float32)
+    need = 2 * N * K
+    split = _FUSED_SPLIT.get(y.device)
+    if split is None or split.numel() < need:
+        split = torch.empty(max(need, 1 << 20), device=y.device, dtype=torch.float32)
+        _FUSED_SPLIT[y.device] = split
+    op = _operands(plan, xs, y, w, None, shared, gather, w_offset)
+    d_in = sum((2 * l + 1) * m for l, m in plan.in1_blocks)
+    nbytes = 4 * (E * (d_in + plan.d_y + (0 if shared else K) + d3 * N) + K * N)
+    with torch.cuda.device(y.device), _kernel("dtp_linear_fwd", nbytes):
+        rc = _lib.load().eqf_dtp_linear_fwd(plan.handle, ctypes.byref(op), E, group, Wt.data_ptr(), N, Wt.stride(0),
+                                            C.data_ptr(), N, split.data_ptr(), _stream())
+    _lib.check(rc, "eqf_dtp_linear_fwd")
+    return C
+
+
+def _dtp_linear_unfused(plan: DtpPlan, graph, n_b: int, y, w, offset, AB, Ws):
+    """The same map from differentiable primitives (higher-order path, and the statement the fused kernel is tested
+    against): DTP family + one GEMM per output group."""
+    nb = len(plan.in1_blocks)
+    As, Bs = AB[:nb], (AB[nb:] if n_b else None)
+    if graph is not None:
+        f = depthwise_tensor_product_gathered(plan, graph, As, Bs, y, w, offset)
+    else:
+        f = depthwise_tensor_product(plan, As, y, w if offset is None else w + offset)
+    E = y.shape[0]
+    return [matmul_f32(fg.reshape(E * fg.shape[1], fg.shape[2]), W).view(E, fg.shape[1], -1) for fg, W in zip(f, Ws)]
+
+
+class DtpLinear(torch.autograd.Function):
+    """K1 (ref nets/graph_attention_transformer.py:487-496): every output group of a depth-wise tensor product times its
+    channel-mixing matrix, the ``[E, sum K]`` product never leaving the chip.
+
+    apply(plan, graph_or_None, n_b, y, w, offset_or_None, *As, *Bs, *Ws) -> one ``[E, 2 l + 1, N_g]`` tensor per group.
+    ``graph`` given: the in1 operand is ``A[src] (+ B[dst])``; None: ``As`` are per-edge blocks.  Backward (first order)
+    recomputes the tensor product for the weight gradients, then runs the data-gradient GEMMs and the DTP backward;
+    under ``create_graph`` it re-expresses itself with the differentiable primitives."""
+
+    @staticmethod
+    def forward(ctx, plan: DtpPlan, graph, n_b: int, y, w, offset, *rest):
+        nb, ng = len(plan.in1_blocks), len(plan.out_groups)
+        n_ab = nb + (nb if n_b else 0)
+        AB, Ws = rest[:n_ab], rest[n_ab:]
+        if len(Ws) != ng:
+            raise ValueError(f"DtpLinear: expected {ng} weight matrices, got {len(Ws)}")
+        As, Bs = AB[:nb], (AB[nb:] if n_b else None)
+        gather = (graph.src, graph.dst, Bs) if graph is not None else None
+        outs = [dtp_linear_fwd_raw(plan, g, As, y, w, Ws[g], gather=gather, w_offset=offset) for g in range(ng)]
+        ctx.plan, ctx.graph, ctx.n_b, ctx.n_ab, ctx.has_off = plan, graph, n_b, n_ab, offset is not None
+        ctx.save_for_backward(y, w, *([offset] if offset is not None else []), *rest)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *dCs):
+        plan, graph, n_b, n_ab = ctx.plan, ctx.graph, ctx.n_b, ctx.n_ab
+        y, w, *saved = ctx.saved_tensors
+        offset = saved.pop(0) if ctx.has_off else None
+        AB, Ws = saved[:n_ab], saved[n_ab:]
+        nb, ng = len(plan.in1_blocks), len(plan.out_groups)
+        As, Bs = AB[:nb], (AB[nb:] if n_b else None)
+        E = y.shape[0]
+        dCs = [g if g is not None else torch.zeros((E, 2 * l + 1, W.shape[1]), device=y.device)
+               for g, (l, _p, _k), W in zip(dCs, plan.out_groups, Ws)]
+        need = ctx.needs_input_grad
+        need_y, need_w, need_off = need[3], need[4], need[5]
+        need_x = any(need[6:6 + n_ab])
+        need_W = need[6 + n_ab:]
+        if torch.is_grad_enabled() or need_y:
+            fn = lambda yy, ww, oo, *r: tuple(_dtp_linear_unfused(plan, graph, n_b, yy, ww, oo, r[:n_ab], r[n_ab:]))
+            grads = _higher_order_grads(fn, (y, w, offset, *AB, *Ws), dCs)
+            return (None, None, None, *grads)
+        gather = (graph.src, graph.dst, Bs) if graph is not None else None
+        shared = w.dim() == 1
+        f = dtp_forward_raw(plan, As, y, w, gather=gather, w_offset=offset)        # recomputed, not saved
+        gWs, dfs = [], []
+        for g in range(ng):
+            d, K = f[g].shape[1], f[g].shape[2]
+            dC2 = dCs[g].contiguous().reshape(E * d, -1)
+            gWs.append(gemm_raw(2, f[g].reshape(E * d, K), dC2) if need_W[g] else None)
+            dfs.append(gemm_raw(1, dC2, Ws[g]).view(E, d, K) if (need_x or need_w or need_off) else None)
+        del f
+        gw = goff = None
+        gA = [None] * nb
+        gB = [None] * nb
+        if need_x or need_w or need_off:
+            gxs, gw_full = dtp_grad_xw_raw(plan, As, y, w, dfs, gather=gather, w_offset=offset)
+            gw = gw_full if need_w else None
+            if need_off:
+                goff = colsum_raw(gw_full)
+            if need_x:
+                if graph is None:
+                    gA = gxs
+                else:
+                    lay = HeadLayout([2 * l + 1 for l, _ in plan.in1_blocks], [m for _, m in plan.in1_blocks], 1)
+                    gA = attn_aggregate_raw(lay, None, gxs, graph, by_src=True)
+                    if Bs is not None:
+                        gB = attn_aggregate_raw(lay, None, gxs, graph)
+        return (None, None, None, None, gw, goff, *gA, *(gB if Bs is not None else []), *gWs)
+
+
+def dtp_linear(plan: DtpPlan, graph, As, Bs, y, w, w_offset, Ws):
+    """Fused ``[DTP(A[src] (+ B[dst]), y; w (+ w_offset)) @ W_g for every output group g]`` (see :class:`DtpLinear`)."""
+    AB = (*As, *(Bs if Bs is not None else ()))
+    n_b = 0 if Bs is None else len(Bs)
+    return list(DtpLinear.apply(plan, graph, n_b, y, w, w_offset, *AB, *Ws))
+
+
 def depthwise_tensor_product(plan: DtpPlan, xs: Sequence[torch.Tensor], y: torch.Tensor, w: torch.Tensor):
     """Planar DTP: ``xs`` per in1 block ``[E, 2l+1, mul]`` -> list per output group ``[E, 2l+1, K]``."""
     return list(DtpOut.apply(plan, y, w, *xs))

@@ -168,6 +168,19 @@ int eqf_gemm_tf32x3_wgrad_accumulate(const float* A, const float* G, float* W, i
 /* debugging aid: device buffer of 4*1024 int64 receiving CTA 0's clock64 timeline on later launches (NULL = off) */
 void eqf_gemm_tf32x3_set_timeline(long long* device_buffer);
 
+/* K1 - the depth-wise tensor product fused into the per-degree linear that consumes it (the reference's
+ * nets/graph_attention_transformer.py:487-496: dtp(message, edge_attr, weight) -> sep_alpha / lin; :725-733 for the
+ * edge-degree embedding): for output group `group` of the plan
+ *   C[(e, k), :N] = DTP_group(x, y; w)[(e, k), :K] @ Wt[:K, :N]
+ * with the [E * (2 l3 + 1), K] tensor-product block produced ON CHIP as the tensor-memory A operand of a tcgen05 3xTF32
+ * GEMM (csrc/eqf_fused.cu) - it never reaches HBM.  Operands as for eqf_dtp_forward (x gathered as x[src] + x2[dst] when
+ * op->src is set; w per edge [E][W] (+ w_offset) or shared [W]).  Wt row-major [K][N], row stride ldw; C
+ * [E * (2 l3 + 1)][N], row stride ldc; `split` = device scratch of 2 * N * K floats (hi / lo planes of Wt).
+ * eqf_dtp_linear_supported: 1 when the group qualifies (path multiplicities % 32 == 0, tables fit shared memory). */
+int eqf_dtp_linear_supported(const EqfPlan* plan, int32_t group);
+int eqf_dtp_linear_fwd(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_edges, int32_t group,
+                       const float* Wt, int64_t N, int64_t ldw, float* C, int64_t ldc, float* split, void* stream);
+
 /* Neighbour list of the batched molecules: edge (j -> i) iff same graph, j != i (unless loop), |pos_j - pos_i| < r, at
  * most max_neighbors per centre (the first ones in index order); sorted by centre, neighbours ascending - what
  * torch_cluster.radius_graph(pos, r, batch, max_num_neighbors) returns at nets/graph_attention_transformer.py:866-867.

@@ -600,3 +600,75 @@ def test_segment_softmax_backward_fused(cuda_device):
             out = out + torch.zeros(E, H, dtype=torch.float64).masked_scatter(m[:, None].expand(E, H), torch.softmax(z64[m], dim=0))
     (ref,) = torch.autograd.grad(out, z64, ga.double())
     assert rel_err(alpha, out) < TOL and rel_err(gz, ref) < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ K1: fused DTP -> linear
+FUSED_CASES = [("qm9_l2", False, True, 32560), ("qm9_l2", True, False, 32560), ("qm9_l2", False, True, 1000),
+               ("qm9_l2", True, False, 37), ("qm9_l2", False, False, 1), ("md17_l3", False, True, 1700),
+               ("md17_l3", True, False, 345), ("oc20_l1", False, True, 20011), ("oc20_l1", True, False, 4097)]
+
+
+@pytest.mark.parametrize("name,shared,gather,E", FUSED_CASES)
+def test_fused_dtp_linear_forward_vs_fp64(cuda_device, name, shared, gather, E):
+    """``eqf_dtp_linear_fwd`` (tensor product produced on chip as the TMEM A operand of the tcgen05 3xTF32 GEMM) against
+    the fp64 table walk followed by an fp64 matmul, every output group; output widths as the model uses them (wide 0e
+    group in column tiles, 64 / 32 stacked) plus one odd width; gathered per-edge weights with the radial offset folded
+    in, and shared weights on per-edge blocks."""
+    from equiformer_b200 import ops
+    plan = _dtp(name).tp.plan
+    assert ops.dtp_linear_supported(plan)
+    g = torch.Generator().manual_seed(E + 7)
+    n_nodes = max(E // 14, 2)
+    rows = n_nodes if gather else E
+    xs = [torch.randn(rows, 2 * l + 1, mul, generator=g) for l, mul in plan.in1_blocks]
+    x2 = [torch.randn(rows, 2 * l + 1, mul, generator=g) for l, mul in plan.in1_blocks] if gather else None
+    y = torch.randn(E, plan.d_y, generator=g)
+    w = torch.randn((plan.weight_numel,) if shared else (E, plan.weight_numel), generator=g)
+    off = None if shared else torch.randn(plan.weight_numel, generator=g)
+    dst = torch.sort(torch.randint(0, n_nodes, (E,), generator=g)).values
+    src = torch.randint(0, n_nodes, (E,), generator=g)
+    widths = {0: [352, 128], 1: [64, 48], 2: [32], 3: [32]}
+    f = lambda t: t.to(cuda_device)
+    xs_d, y_d, w_d = [f(t) for t in xs], f(y), f(w)
+    gat_d = (f(src), f(dst), [f(t) for t in x2]) if gather else None
+    gat_r = (src, dst, [t.double() for t in x2]) if gather else None
+    ref_f = emu.dtp_forward_raw(plan, [t.double() for t in xs], y.double(), w.double(), gat_r,
+                                off.double() if off is not None else None)
+    for gi, (l, _p, K) in enumerate(plan.out_groups):
+        for N in widths[l]:
+            Wt = torch.randn(K, N, generator=g) / K ** 0.5
+            out = ops.dtp_linear_fwd_raw(plan, gi, xs_d, y_d, w_d, f(Wt), gather=gat_d,
+                                         w_offset=f(off) if off is not None else None)
+            ref = torch.einsum("eku,un->ekn", ref_f[gi], Wt.double())
+            assert out.shape == ref.shape
+            assert rel_err(out, ref) < TOL, (gi, N, rel_err(out, ref))
+
+
+def test_fused_dtp_linear_autograd_matches_unfused(cuda_device):
+    """``ops.DtpLinear`` (forward fused, backward = recompute + GEMMs + DTP backward) against the unfused differentiable
+    composition on the same inputs: outputs and every gradient (node tables, radial weights, offset, linear weights)."""
+    from equiformer_b200 import ops
+    plan = _dtp("qm9_l2").tp.plan
+    E, n_nodes = 20000, 1500
+    g = torch.Generator().manual_seed(3)
+    dev = cuda_device
+    dst = torch.sort(torch.randint(0, n_nodes, (E,), generator=g)).values.to(dev)
+    src = torch.randint(0, n_nodes, (E,), generator=g).to(dev)
+    graph = ops.Graph(src, dst, n_nodes)
+    mk = lambda *s: torch.randn(*s, generator=g).to(dev).requires_grad_(True)
+    As = [mk(n_nodes, 2 * l + 1, m) for l, m in plan.in1_blocks]
+    Bs = [mk(n_nodes, 2 * l + 1, m) for l, m in plan.in1_blocks]
+    y = torch.randn(E, plan.d_y, generator=g).to(dev)
+    w, off = mk(E, plan.weight_numel), mk(plan.weight_numel)
+    Ws = [(torch.randn(K, N, generator=g) / K ** 0.5).to(dev).requires_grad_(True)
+          for (_l, _p, K), N in zip(plan.out_groups, (352, 64, 32))]
+    cots = [torch.randn(E, 2 * l + 1, N, generator=g).to(dev) for (l, _p, _K), N in zip(plan.out_groups, (352, 64, 32))]
+    leaves = [*As, *Bs, w, off, *Ws]
+    outs = ops.dtp_linear(plan, graph, As, Bs, y, w, off, Ws)
+    grads = torch.autograd.grad(outs, leaves, cots)
+    ref_outs = ops._dtp_linear_unfused(plan, graph, len(Bs), y, w, off, (*As, *Bs), Ws)
+    ref_grads = torch.autograd.grad(ref_outs, leaves, cots)
+    for a, b in zip(outs, ref_outs):
+        assert rel_err(a, b) < TOL
+    for a, b in zip(grads, ref_grads):
+        assert rel_err(a, b) < 5e-5
