@@ -124,11 +124,16 @@ SIGNATURES = {
     "eqf_gemm_tf32x3_wgrad_accumulate": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                                                    c_void_p]),
     "eqf_dtp_linear_supported": (c_int32, [c_void_p, c_int32]),
+    "eqf_dtp_group_forward": (c_int32, [c_void_p, POINTER(EqfEdgeOperands), c_int64, c_int32, c_void_p, c_void_p]),
     "eqf_dtp_linear_fwd": (c_int32, [c_void_p, POINTER(EqfEdgeOperands), c_int64, c_int32, c_void_p, c_int64, c_int64, c_void_p,
                                      c_int64, c_void_p, c_void_p]),
     "eqf_radius_graph_count": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_int32, c_int64, c_void_p, c_void_p]),
     "eqf_radius_graph_fill": (c_int32, [c_void_p, c_void_p, c_int64, c_float, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
                                         c_void_p]),
+    "eqf_radius_graph_pbc_count": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int32, c_int32, c_int32,
+                                             c_void_p, c_void_p]),
+    "eqf_radius_graph_pbc_fill": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_int32, c_int32, c_int32,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "eqf_rbf_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int64, c_void_p, c_void_p]),
     "eqf_rbf_bwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_int64, c_void_p, c_void_p,
                               c_void_p]),

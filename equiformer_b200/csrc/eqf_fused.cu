@@ -12,12 +12,17 @@
 //   warp  4      TMA producer  weight tiles B_hi / B_lo of the k-tile (K-major planes, 128-byte rows)
 //   warp  5      MMA issuer    tcgen05.mma.kind::tf32, A from TENSOR MEMORY, 3xTF32 (stacked [b_hi | b_lo] for N <= 64)
 //   warps 8-11   transform     raw A tile (shared memory) -> a_hi / a_lo in tensor memory (one thread = one row)
+//   warps 6-7    table helpers per-tile tables one tile AHEAD of the producers (double-buffered): node rows of the tile's edges
+//                and the coupling blocks M_p[e] of its <= 128/(2 l3 + 1) + 2 edges (dense CG table of the plan)
 //   warps 12-27  DTP producers two sets of 8 warps alternate k-tiles: gather x = A[src] + B[dst] (float4 per lane, node
-//                tables L2 resident), multiply by the per-edge radial weights, contract with M_p[e] and write the
-//                128 x 32 raw A tile into the stage's shared memory (SWIZZLE_128B row order, conflict-free)
-// Per tile the DTP warps first compute M_p[e] for the tile's <= 128/(2 l3 + 1) + 2 edges into shared memory (dense CG table
-// from the plan; sum_j is at most 7 terms).  Register budget (896 threads x 72 at launch): setmaxnreg moves registers from
-// the TMA / MMA warpgroup (40) to the transform (88) and epilogue (88) warpgroups; the DTP warps keep their 72.
+//                tables L2 resident), multiply by the per-edge radial weights (a TMA box of the [E, W] weight matrix that
+//                the producer warp stages with the weight tiles), contract with M_p[e] and write the 128 x 32 raw A tile
+//                into the stage's shared memory (SWIZZLE_128B row order, conflict-free)
+// Register budget (896 threads x 72 at launch): setmaxnreg moves registers from the TMA / MMA / helper warpgroup (40) to
+// the transform (88) and epilogue (88) warpgroups; the DTP warps keep their 72.
+// First version (profiles/r2_fused_fwd_v1_*): correct but 1.6x SLOWER than DTP + GEMM - the DTP warps computed the tile
+// tables themselves between two CTA-wide barriers (pipeline drained at every tile: ~10 us per tile with the math off) and
+// fetched the radial weights with HBM-latency loads.  Hence the helper warps and the TMA weight box.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -40,15 +45,17 @@ constexpr int BKT = 32;                 // channels per k-tile: 128-byte rows
 constexpr int kRowBytes = BKT * 4;
 constexpr int UMMA_K = 8;
 constexpr int kStoreCols = 32;
-constexpr int kEpilogueWarps = 4, kProducerWarp = 4, kMmaWarp = 5;
+constexpr int kEpilogueWarps = 4, kProducerWarp = 4, kMmaWarp = 5, kHelperWarp0 = 6, kHelperWarps = 2;
+constexpr int kHelperThreads = kHelperWarps * 32;
 constexpr int kTransformWarp0 = 8, kTransformWarps = 4;
 constexpr int kDtpWarp0 = 12, kDtpWarps = 16, kDtpSets = 2, kDtpSetWarps = kDtpWarps / kDtpSets;
-constexpr int kDtpThreads = kDtpWarps * 32, kDtpSetThreads = kDtpSetWarps * 32;
+constexpr int kDtpSetThreads = kDtpSetWarps * 32;
 constexpr int kThreads = (kDtpWarp0 + kDtpWarps) * 32;            // 896
 constexpr int kMaxPaths = 16;
 constexpr int kMaxTileEdges = 136;      // 128 / d3 + 2 <= 130
-constexpr int kMBufFloats = 7168;       // per-tile M rows (28 KB): n_e * m_row floats
-constexpr int kMetaBytes = 2048;        // int32 src / dst rows of the tile's edges
+constexpr int kMetaInts = 2 * kMaxTileEdges;   // int32 src / dst rows of the tile's edges
+constexpr int kMaxStages = 8;
+constexpr int kMaxKTiles = 32;          // K <= 1024 channels per output group
 
 // one CG path feeding the output group of this launch (d3 is common to the group)
 struct FPath {
@@ -58,6 +65,7 @@ struct FPath {
   int cg_off;        // dense CG block [d1][d2][d3] (path weight folded in) inside `cg`
   int koff;          // first channel of the path inside the group's K
   int m_off;         // offset of this path's [d1][d3] block inside one edge's M row
+  unsigned long long nz;   // bit (i * d3 + k): CG_p[i, :, k] has a non-zero entry (M_p[e][i, k] can be non-zero)
 };
 
 struct FArgs {
@@ -74,6 +82,9 @@ struct FArgs {
   int n_tile, n_blocks;
   long long m_blocks;
   int dbg_skip;          // measurement aid: bit 0 skips the DTP math, bit 1 the MMAs, bit 2 the transform (garbage results)
+  // shared-memory layout (bytes), fixed by the host: stages | store staging | 2 x (M rows + node rows) | descriptors | barriers
+  int n_stages, stage_bytes, w_tile_off, w_box_rows, tab_bytes, m_buf_floats;
+  unsigned char kt_path[kMaxKTiles];   // path of each 32-channel k-tile, in channel order
   FPath paths[kMaxPaths];
 };
 
@@ -82,17 +93,11 @@ struct FSmem {
   static constexpr int kAccCols = STACK ? 2 * BN : BN;
   static constexpr int kABytes = BM * kRowBytes;                    // raw A tile written by the DTP warps
   static constexpr int kBBytes = BN * kRowBytes;
-  static constexpr int kStageBytes = kABytes + 2 * kBBytes;         // A raw | B hi | B lo
   static constexpr int kStoreBytes = kEpilogueWarps * 2 * 32 * kStoreCols * 4;
-  static constexpr int kMBytes = kMBufFloats * 4;
   static constexpr int kBarBytes = 1024;
   static constexpr int kBudget = 227 * 1024 - 1024;
-  static constexpr int kStagesSmem = (kBudget - kStoreBytes - kMBytes - kMetaBytes - kBarBytes) / kStageBytes;
   static constexpr int kStagesTmem = (512 - 2 * kAccCols) / (2 * BKT);
-  static constexpr int kStagesMin = kStagesSmem < kStagesTmem ? kStagesSmem : kStagesTmem;
-  static constexpr int kStages = kStagesMin > 8 ? 8 : kStagesMin;
-  static_assert(kStages >= 2, "tile does not fit");
-  static constexpr int kTotal = kStages * kStageBytes + kStoreBytes + kMBytes + kMetaBytes + kBarBytes + 1024;
+  static_assert(kStagesTmem >= 2, "accumulators leave no room for the A ring");
 };
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
@@ -103,20 +108,22 @@ __device__ __forceinline__ void fs(float4& a, const float4& x, float m) {
 }
 
 // One k-tile (32 channels `ch0 ..` of path p) of the raw A tile: thread t of the set's 256 handles edge t / 8 (+32 ...)
-// and the four channels 4 (t % 8) of the chunk.
+// and the four channels 4 (t % 8) of the chunk.  `w_tile`: shared-memory address of the [n_e][32] weight box of the
+// k-tile (per-edge weights) or 0 (shared weights, read from global).
 template <int D1, int D3>
 __device__ __forceinline__ void dtp_ktile(const FArgs& a, const FPath& p, int ch0, int t, long long e0, int n_e, long long row0,
                                           const int* __restrict__ src_s, const int* __restrict__ dst_s,
-                                          const float* __restrict__ mbuf, uint32_t raw_addr) {
+                                          const float* __restrict__ mbuf, uint32_t raw_addr, uint32_t w_tile) {
   const int c8 = t & 7;
   const int ch = ch0 + c8 * 4;
   const bool gather = a.src != nullptr;
   const float* xa = a.x[p.xb];
   const float* xb = a.x2[p.xb];
   const long long row_floats = (long long)D1 * p.mul;
+  const unsigned long long nz = p.nz;
   for (int el = t >> 3; el < n_e; el += kDtpSetThreads / 8) {
     const long long e = e0 + el;
-    float4 wv = ld4(a.w + (a.w_shared ? 0 : e * a.W) + p.w_off + ch);
+    float4 wv = w_tile != 0 ? lds128(w_tile + (uint32_t)el * 128u + (uint32_t)c8 * 16u) : ld4(a.w + p.w_off + ch);
     if (a.w_offset != nullptr) addv(wv, ld4(a.w_offset + p.w_off + ch));
     const long long rs = gather ? (long long)src_s[el] : e;
     const float* xp = xa + rs * row_floats + ch;
@@ -136,7 +143,8 @@ __device__ __forceinline__ void dtp_ktile(const FArgs& a, const FPath& p, int ch
     for (int k = 0; k < D3; ++k) {
       float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < D1; ++i) fs(f, x[i], me[i * D3 + k]);
+      for (int i = 0; i < D1; ++i)
+        if ((nz >> (i * D3 + k)) & 1ull) fs(f, x[i], me[i * D3 + k]);
       const int row = rbase + k;
       if ((unsigned)row < (unsigned)BM) sts128(raw_addr + (uint32_t)row * 128u + (uint32_t)((c8 ^ (row & 7)) << 4), f);
     }
@@ -145,46 +153,53 @@ __device__ __forceinline__ void dtp_ktile(const FArgs& a, const FPath& p, int ch
 
 template <int D3>
 __device__ __forceinline__ void dtp_ktile_d1(const FArgs& a, const FPath& p, int ch0, int t, long long e0, int n_e, long long row0,
-                                             const int* src_s, const int* dst_s, const float* mbuf, uint32_t raw_addr) {
+                                             const int* src_s, const int* dst_s, const float* mbuf, uint32_t raw_addr,
+                                             uint32_t w_tile) {
   switch (p.d1) {
-    case 1: dtp_ktile<1, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
-    case 3: dtp_ktile<3, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
-    case 5: dtp_ktile<5, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
-    default: dtp_ktile<7, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
+    case 1: dtp_ktile<1, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
+    case 3: dtp_ktile<3, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
+    case 5: dtp_ktile<5, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
+    default: dtp_ktile<7, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
   }
 }
 
 template <int BN, bool STACK>
 __global__ void __launch_bounds__(kThreads, 1)
 dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
-                    const __grid_constant__ CUtensorMap map_c, const __grid_constant__ FArgs a) {
+                    const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ FArgs a) {
   using S = FSmem<BN, STACK>;
-  constexpr int kStages = S::kStages;
   constexpr int kTmemCols = 512;
   constexpr int kAcc = S::kAccCols;
   constexpr int kACol0 = 2 * kAcc;                       // first TMEM column of the A staging area
+  const int kStages = a.n_stages;
+  const int stage_bytes = a.stage_bytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  uint8_t* store_base = smem + kStages * S::kStageBytes;
-  float* mbuf = reinterpret_cast<float*>(store_base + S::kStoreBytes);
-  int* src_s = reinterpret_cast<int*>(store_base + S::kStoreBytes + S::kMBytes);
-  int* dst_s = src_s + kMaxTileEdges;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(store_base + S::kStoreBytes + S::kMBytes + kMetaBytes);
-  uint64_t* full = bars;                        // [kStages] weight tiles landed (TMA)
-  uint64_t* raw_ready = bars + kStages;         // [kStages] raw A tile written by the DTP set
-  uint64_t* a_ready = bars + 2 * kStages;       // [kStages] a_hi / a_lo in tensor memory
-  uint64_t* empty = bars + 3 * kStages;         // [kStages] MMAs of the stage finished
-  uint64_t* tmem_full = bars + 4 * kStages;     // [2]
-  uint64_t* tmem_empty = bars + 4 * kStages + 2;   // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 4 * kStages + 4);
+  uint8_t* store_base = smem + kStages * stage_bytes;
+  uint8_t* tab_base = store_base + S::kStoreBytes;           // two table buffers: [m_buf_floats] M rows, then src / dst rows
+  int4* mdesc = reinterpret_cast<int4*>(tab_base + 2 * a.tab_bytes);      // per M-row entry: (cg offset, y offset, d2, -)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(mdesc) + ((a.m_row * 16 + 127) & ~127));
+  uint64_t* full = bars;                          // [8] weight tiles (and the radial-weight box) landed (TMA)
+  uint64_t* raw_ready = bars + kMaxStages;        // [8] raw A tile written by the DTP set
+  uint64_t* a_ready = bars + 2 * kMaxStages;      // [8] a_hi / a_lo in tensor memory
+  uint64_t* empty = bars + 3 * kMaxStages;        // [8] MMAs of the stage finished
+  uint64_t* tmem_full = bars + 4 * kMaxStages;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]
+  uint64_t* tab_ready = tmem_full + 4;            // [2] tile tables written by the helper warps
+  uint64_t* tab_free = tmem_full + 6;             // [2] every DTP warp is done with the tile's tables
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_tiles = a.K / BKT;
+  const int d3 = a.d3;
   const long long n_tiles_total = a.m_blocks * a.n_blocks;
+  const bool w_tma = !a.w_shared;
 
   if (warp == kProducerWarp && lane == 0) {
     prefetch_map(&map_bhi); prefetch_map(&map_blo); prefetch_map(&map_c);
+    if (w_tma) prefetch_map(&map_w);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&raw_ready[s], kDtpSetWarps);
@@ -194,6 +209,8 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], kEpilogueWarps);
+      mbar_init(&tab_ready[b], kHelperWarps);
+      mbar_init(&tab_free[b], kDtpWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -260,59 +277,118 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp < kTransformWarp0) {
-    // ===================================================================================== warpgroup 1: TMA + MMA
+    // ===================================================================================== warpgroup 1: TMA, MMA, table helpers
     reg_dealloc<40>();
-    if (warp == kProducerWarp && lane == 0) {
-      uint32_t it = 0;
-      const uint32_t tx = (uint32_t)(2 * a.n_tile * kRowBytes);
-      for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-        const int nb = (int)(tile % a.n_blocks);
-        for (int kt = 0; kt < k_tiles; ++kt, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          uint8_t* st = stage_base + (size_t)s * S::kStageBytes;
-          mbar_expect_tx(&full[s], tx);
-          tma_load_2d(st + S::kABytes, &map_bhi, kt * BKT, nb * a.n_tile, &full[s]);
-          tma_load_2d(st + S::kABytes + S::kBBytes, &map_blo, kt * BKT, nb * a.n_tile, &full[s]);
-        }
-      }
-    } else if (warp == kMmaWarp && lane == 0) {
-      const uint32_t idesc = instr_desc(a.n_tile);
-      const uint32_t idesc2 = instr_desc(2 * a.n_tile);          // STACK: [b_hi | b_lo] as one operand
-      uint32_t it = 0, acc_it = 0;
-      for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
-        const int ab = acc_it & 1;
-        const uint32_t aph = (acc_it >> 1) & 1;
-        mbar_wait(&tmem_empty[ab], aph ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(ab * kAcc);
-        for (int kt = 0; kt < k_tiles; ++kt, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&full[s], ph);
-          mbar_wait(&a_ready[s], ph);
-          tc_fence_after();
-          const uint32_t st = smem_u32(stage_base + (size_t)s * S::kStageBytes);
-          const uint64_t b_hi = smem_desc_sw128(st + S::kABytes), b_lo = smem_desc_sw128(st + S::kABytes + S::kBBytes);
-          const uint32_t a_hi = tmem_base + (uint32_t)(kACol0 + s * 2 * BKT), a_lo = a_hi + BKT;
-#pragma unroll
-          for (int kb = 0; kb < BKT / UMMA_K; ++kb) {
-            if (a.dbg_skip & 2) break;
-            const uint64_t adv = (uint64_t)((kb * UMMA_K * 4) >> 4);
-            const uint32_t acol = (uint32_t)(kb * UMMA_K);
-            if constexpr (STACK) {
-              umma_tf32_ts(d_tmem, a_hi + acol, b_hi + adv, idesc2, (kt > 0 || kb > 0) ? 1u : 0u);   // hi*hi | hi*lo
-              umma_tf32_ts(d_tmem, a_lo + acol, b_hi + adv, idesc, 1u);                               // + lo*hi
-            } else {
-              umma_tf32_ts(d_tmem, a_lo + acol, b_hi + adv, idesc, (kt > 0 || kb > 0) ? 1u : 0u);
-              umma_tf32_ts(d_tmem, a_hi + acol, b_lo + adv, idesc, 1u);
-              umma_tf32_ts(d_tmem, a_hi + acol, b_hi + adv, idesc, 1u);
+    if (warp == kProducerWarp) {
+      if (lane == 0) {
+        uint32_t it = 0;
+        const uint32_t tx = (uint32_t)(2 * a.n_tile * kRowBytes) + (w_tma ? (uint32_t)(a.w_box_rows * kRowBytes) : 0u);
+        for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+          const long long mb = tile / a.n_blocks;
+          const int nb = (int)(tile % a.n_blocks);
+          const int e0 = (int)((mb * BM) / d3);
+          for (int kt = 0; kt < k_tiles; ++kt, ++it) {
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            uint8_t* st = stage_base + (size_t)s * stage_bytes;
+            mbar_expect_tx(&full[s], tx);
+            tma_load_2d(st + S::kABytes, &map_bhi, kt * BKT, nb * a.n_tile, &full[s]);
+            tma_load_2d(st + S::kABytes + S::kBBytes, &map_blo, kt * BKT, nb * a.n_tile, &full[s]);
+            if (w_tma) {
+              const FPath& p = a.paths[a.kt_path[kt]];
+              tma_load_2d(st + a.w_tile_off, &map_w, p.w_off + (kt * BKT - p.koff), e0, &full[s]);
             }
           }
-          umma_commit(&empty[s]);
         }
-        umma_commit(&tmem_full[ab]);
+      }
+    } else if (warp == kMmaWarp) {
+      if (lane == 0) {
+        const uint32_t idesc = instr_desc(a.n_tile);
+        const uint32_t idesc2 = instr_desc(2 * a.n_tile);          // STACK: [b_hi | b_lo] as one operand
+        uint32_t it = 0, acc_it = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
+          const int ab = acc_it & 1;
+          const uint32_t aph = (acc_it >> 1) & 1;
+          mbar_wait(&tmem_empty[ab], aph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(ab * kAcc);
+          for (int kt = 0; kt < k_tiles; ++kt, ++it) {
+            const int s = it % kStages;
+            const uint32_t ph = (it / kStages) & 1;
+            mbar_wait(&full[s], ph);
+            mbar_wait(&a_ready[s], ph);
+            tc_fence_after();
+            const uint32_t st = smem_u32(stage_base + (size_t)s * stage_bytes);
+            const uint64_t b_hi = smem_desc_sw128(st + S::kABytes), b_lo = smem_desc_sw128(st + S::kABytes + S::kBBytes);
+            const uint32_t a_hi = tmem_base + (uint32_t)(kACol0 + s * 2 * BKT), a_lo = a_hi + BKT;
+#pragma unroll
+            for (int kb = 0; kb < BKT / UMMA_K; ++kb) {
+              if (a.dbg_skip & 2) break;
+              const uint64_t adv = (uint64_t)((kb * UMMA_K * 4) >> 4);
+              const uint32_t acol = (uint32_t)(kb * UMMA_K);
+              if constexpr (STACK) {
+                umma_tf32_ts(d_tmem, a_hi + acol, b_hi + adv, idesc2, (kt > 0 || kb > 0) ? 1u : 0u);   // hi*hi | hi*lo
+                umma_tf32_ts(d_tmem, a_lo + acol, b_hi + adv, idesc, 1u);                               // + lo*hi
+              } else {
+                umma_tf32_ts(d_tmem, a_lo + acol, b_hi + adv, idesc, (kt > 0 || kb > 0) ? 1u : 0u);
+                umma_tf32_ts(d_tmem, a_hi + acol, b_lo + adv, idesc, 1u);
+                umma_tf32_ts(d_tmem, a_hi + acol, b_hi + adv, idesc, 1u);
+              }
+            }
+            umma_commit(&empty[s]);
+          }
+          umma_commit(&tmem_full[ab]);
+        }
+      }
+    } else {
+      // ------------------------------------------------------------------- table helpers (warps 6, 7): one tile ahead
+      const int ht = (warp - kHelperWarp0) * 32 + lane;       // 0 .. 63
+      const int m_row = a.m_row;
+      for (int q = ht; q < m_row; q += kHelperThreads) {      // descriptors of the M-row entries this thread owns
+        int pi = 0;
+        for (int j = 1; j < a.n_paths; ++j) if (q >= a.paths[j].m_off) pi = j;
+        const FPath& p = a.paths[pi];
+        const int r = q - p.m_off;
+        const int i = r / d3, k = r - i * d3;
+        mdesc[q] = make_int4(p.cg_off + i * p.d2 * d3 + k, p.y_off, p.d2, 0);
+      }
+      uint32_t tile_it = 0;
+      long long mb_prev = -1;
+      for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        const long long mb = tile / a.n_blocks;
+        if (mb == mb_prev) continue;                          // column tiles of one row block share the tables
+        mb_prev = mb;
+        const int b = tile_it & 1;
+        mbar_wait(&tab_free[b], ((tile_it >> 1) & 1) ^ 1);
+        ++tile_it;
+        const long long row0 = mb * BM;
+        const long long e0 = row0 / d3;
+        long long e1 = (row0 + BM - 1) / d3 + 1;
+        if (e1 > a.E) e1 = a.E;
+        const int n_e = (int)(e1 - e0);
+        float* mbuf = reinterpret_cast<float*>(tab_base + b * a.tab_bytes);
+        int* src_s = reinterpret_cast<int*>(mbuf + a.m_buf_floats);
+        int* dst_s = src_s + kMaxTileEdges;
+        if (a.src != nullptr) {
+          for (int i = ht; i < n_e; i += kHelperThreads) {
+            src_s[i] = (int)a.src[e0 + i];
+            dst_s[i] = a.dst != nullptr ? (int)a.dst[e0 + i] : 0;
+          }
+        }
+        for (int q = ht; q < m_row; q += kHelperThreads) {
+          const int4 dsc = mdesc[q];
+          const float* cg = a.cg + dsc.x;
+          const float* yv = a.y + e0 * a.d_y + dsc.y;
+#pragma unroll 2
+          for (int el = 0; el < n_e; ++el) {
+            float m = 0.f;
+            for (int j = 0; j < dsc.z; ++j) m = fmaf(__ldg(cg + j * d3), __ldg(yv + el * a.d_y + j), m);
+            mbuf[el * m_row + q] = m;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tab_ready[b]);
       }
     }
   } else if (warp < kDtpWarp0) {
@@ -327,7 +403,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(&raw_ready[s], ph);
         if (!(a.dbg_skip & 4)) {
-          const uint32_t rbase = smem_u32(stage_base + (size_t)s * S::kStageBytes) + (uint32_t)row * (uint32_t)kRowBytes;
+          const uint32_t rbase = smem_u32(stage_base + (size_t)s * stage_bytes) + (uint32_t)row * (uint32_t)kRowBytes;
           float hi[BKT], lo[BKT];
           float4 v[8];
 #pragma unroll
@@ -356,8 +432,9 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
     const int dt = threadIdx.x - kDtpWarp0 * 32;          // 0 .. 511
     const int set = (warp - kDtpWarp0) / kDtpSetWarps;    // which half of the k-tiles
     const int t = dt - set * kDtpSetThreads;              // 0 .. 255 inside the set
-    const int d3 = a.d3;
-    uint32_t it = 0;
+    uint32_t it = 0, tile_it = 0;
+    long long mb_prev = -1;
+    int b = 0;
     for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
       const long long mb = tile / a.n_blocks;
       const long long row0 = mb * BM;
@@ -365,61 +442,122 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
       long long e1 = (row0 + BM - 1) / d3 + 1;
       if (e1 > a.E) e1 = a.E;
       const int n_e = (int)(e1 - e0);
-      // ---- per-tile tables: node rows of the tile's edges and the coupling blocks M_p[e] = CG_p . y_e
-      named_barrier(1, kDtpThreads);      // every DTP warp has finished the previous tile (readers of mbuf / src_s / dst_s)
-      if (a.src != nullptr) {
-        for (int i = dt; i < n_e; i += kDtpThreads) {
-          src_s[i] = (int)a.src[e0 + i];
-          dst_s[i] = a.dst != nullptr ? (int)a.dst[e0 + i] : 0;
-        }
+      if (mb != mb_prev) {                                 // tables of this row block (written one tile ahead)
+        if (mb_prev >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&tab_free[b]); }
+        mb_prev = mb;
+        b = tile_it & 1;
+        mbar_wait(&tab_ready[b], (tile_it >> 1) & 1);
+        ++tile_it;
       }
-      {
-        const int m_row = a.m_row;
-        for (int idx = dt; idx < n_e * m_row; idx += kDtpThreads) {
-          const int el = idx / m_row, q = idx - el * m_row;
-          int pi = 0;
-#pragma unroll 1
-          for (int j = 1; j < a.n_paths; ++j) if (q >= a.paths[j].m_off) pi = j;
-          const FPath& p = a.paths[pi];
-          const int r = q - p.m_off;
-          const int i = r / d3, k = r - i * d3;
-          const float* cg = a.cg + p.cg_off + i * p.d2 * d3 + k;
-          const float* yv = a.y + (e0 + el) * a.d_y + p.y_off;
-          float m = 0.f;
-          for (int j = 0; j < p.d2; ++j) m = fmaf(__ldg(cg + j * d3), __ldg(yv + j), m);
-          mbuf[idx] = m;
+      const float* mbuf = reinterpret_cast<const float*>(tab_base + b * a.tab_bytes);
+      const int* src_s = reinterpret_cast<const int*>(mbuf + a.m_buf_floats);
+      const int* dst_s = src_s + kMaxTileEdges;
+      for (int kt = 0; kt < k_tiles; ++kt, ++it) {
+        if ((int)(it & 1) != set) continue;               // the two sets alternate k-tiles
+        const FPath& p = a.paths[a.kt_path[kt]];
+        const int ch0 = kt * BKT - p.koff;
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const uint32_t raw_addr = smem_u32(stage_base + (size_t)s * stage_bytes);
+        uint32_t w_tile = 0;
+        if (w_tma) {
+          mbar_wait(&full[s], ph);                        // the k-tile's radial-weight box has landed
+          w_tile = raw_addr + (uint32_t)a.w_tile_off;
         }
-      }
-      named_barrier(1, kDtpThreads);
-      // ---- k-tiles: channel chunks of 32 in group order; set q takes every other one
-      int kt = 0;
-      for (int pi = 0; pi < a.n_paths; ++pi) {
-        const FPath& p = a.paths[pi];
-        for (int ch0 = 0; ch0 < p.mul; ch0 += BKT, ++kt, ++it) {
-          if ((int)(it & 1) != set) continue;
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          const uint32_t raw_addr = smem_u32(stage_base + (size_t)s * S::kStageBytes);
-          if (!(a.dbg_skip & 1)) {
-            switch (d3) {
-              case 1: dtp_ktile_d1<1>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
-              case 3: dtp_ktile_d1<3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
-              case 5: dtp_ktile_d1<5>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
-              default: dtp_ktile_d1<7>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr); break;
-            }
+        if (!(a.dbg_skip & 1)) {
+          switch (d3) {
+            case 1: dtp_ktile_d1<1>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
+            case 3: dtp_ktile_d1<3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
+            case 5: dtp_ktile_d1<5>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
+            default: dtp_ktile_d1<7>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
           }
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&raw_ready[s]);
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_ready[s]);
       }
     }
+    if (mb_prev >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&tab_free[b]); }
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- one group to HBM
+// The same producer for an output group whose linear is too WIDE to fuse (N > 128 columns: every column tile would
+// recompute the product): write f_g[e, k, :K] to HBM (the 0e group of the QM9 model is 224 of the 3136 floats per edge) and
+// let the wide tcgen05 GEMM read it.  One CTA = 32 edges: coupling blocks of its edges in shared memory, then the
+// group's k-tiles with the thread layout of dtp_ktile (8 lanes x float4 per edge).
+template <int D1, int D3>
+__device__ __forceinline__ void group_ktile(const FArgs& a, const FPath& p, int ch0, int el, int c8, long long e,
+                                            const float* __restrict__ me, float* __restrict__ out) {
+  const int ch = ch0 + c8 * 4;
+  float4 wv = ld4(a.w + (a.w_shared ? 0 : e * a.W) + p.w_off + ch);
+  if (a.w_offset != nullptr) addv(wv, ld4(a.w_offset + p.w_off + ch));
+  const long long row_floats = (long long)D1 * p.mul;
+  const long long rs = a.src != nullptr ? a.src[e] : e;
+  const float* xp = a.x[p.xb] + rs * row_floats + ch;
+  float4 x[D1];
+#pragma unroll
+  for (int i = 0; i < D1; ++i) x[i] = ld4(xp + i * p.mul);
+  if (a.x2[p.xb] != nullptr) {
+    const float* xq = a.x2[p.xb] + a.dst[e] * row_floats + ch;
+#pragma unroll
+    for (int i = 0; i < D1; ++i) addv(x[i], ld4(xq + i * p.mul));
+  }
+#pragma unroll
+  for (int i = 0; i < D1; ++i) mulv(x[i], wv);
+#pragma unroll
+  for (int k = 0; k < D3; ++k) {
+    float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < D1; ++i)
+      if ((p.nz >> (i * D3 + k)) & 1ull) fs(f, x[i], me[i * D3 + k]);
+    *reinterpret_cast<float4*>(out + (e * D3 + k) * a.K + p.koff + ch) = f;
+  }
+}
+
+template <int D3>
+__global__ void __launch_bounds__(256) dtp_group_forward_kernel(const __grid_constant__ FArgs a, float* __restrict__ out) {
+  extern __shared__ float msm[];                       // [32][m_row]
+  const int t = threadIdx.x, el = t >> 3, c8 = t & 7;
+  const int m_row = a.m_row;
+  for (long long eb = (long long)blockIdx.x * 32; eb < a.E; eb += (long long)gridDim.x * 32) {
+    const int n_e = (int)((a.E - eb) < 32 ? (a.E - eb) : 32);
+    __syncthreads();
+    for (int idx = t; idx < n_e * m_row; idx += 256) {
+      const int ee = idx / m_row, q = idx - ee * m_row;
+      int pi = 0;
+      for (int j = 1; j < a.n_paths; ++j) if (q >= a.paths[j].m_off) pi = j;
+      const FPath& p = a.paths[pi];
+      const int r = q - p.m_off;
+      const int i = r / D3, k = r - i * D3;
+      const float* cg = a.cg + p.cg_off + i * p.d2 * D3 + k;
+      const float* yv = a.y + (eb + ee) * a.d_y + p.y_off;
+      float m = 0.f;
+      for (int j = 0; j < p.d2; ++j) m = fmaf(__ldg(cg + j * D3), __ldg(yv + j), m);
+      msm[idx] = m;
+    }
+    __syncthreads();
+    if (el < n_e) {
+      const long long e = eb + el;
+      for (int pi = 0; pi < a.n_paths; ++pi) {
+        const FPath& p = a.paths[pi];
+        const float* me = msm + el * m_row + p.m_off;
+        for (int ch0 = 0; ch0 < p.mul; ch0 += BKT) {
+          switch (p.d1) {
+            case 1: group_ktile<1, D3>(a, p, ch0, el, c8, e, me, out); break;
+            case 3: group_ktile<3, D3>(a, p, ch0, el, c8, e, me, out); break;
+            case 5: group_ktile<5, D3>(a, p, ch0, el, c8, e, me, out); break;
+            default: group_ktile<7, D3>(a, p, ch0, el, c8, e, me, out); break;
+          }
+        }
+      }
+    }
   }
 }
 
@@ -437,18 +575,37 @@ __global__ void split_transpose_kernel(const float* __restrict__ w, long long ld
 }
 
 template <int BN, bool STACK>
-static int launch_fwd(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mc, const FArgs& a, cudaStream_t s) {
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(dtp_gemm_fwd_kernel<BN, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    FSmem<BN, STACK>::kTotal);
-  });
-  if (attr_err != cudaSuccess) return check_cuda(attr_err, "dtp_gemm_fwd smem attribute");
+static int launch_fwd(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mc, const CUtensorMap& mw, FArgs& a,
+                      cudaStream_t s) {
+  using S = FSmem<BN, STACK>;
+  // shared-memory layout: stages (raw A | B hi | B lo | radial-weight box) | store staging | 2 table buffers | descriptors | barriers
+  const int n_e_max = BM / a.d3 + 2;
+  a.w_box_rows = a.w_shared ? 0 : n_e_max;
+  a.w_tile_off = S::kABytes + 2 * S::kBBytes;
+  a.stage_bytes = (a.w_tile_off + a.w_box_rows * kRowBytes + 1023) & ~1023;
+  a.m_buf_floats = (n_e_max * a.m_row + 31) & ~31;
+  a.tab_bytes = (a.m_buf_floats * 4 + kMetaInts * 4 + 127) & ~127;
+  const int fixed = S::kStoreBytes + 2 * a.tab_bytes + ((a.m_row * 16 + 127) & ~127) + S::kBarBytes;
+  int stages = (S::kBudget - fixed) / a.stage_bytes;
+  if (stages > S::kStagesTmem) stages = S::kStagesTmem;
+  if (stages > kMaxStages) stages = kMaxStages;
+  if (stages < 2) { set_error("fused DTP: the tile does not fit shared memory"); return EQF_ERR_UNSUPPORTED; }
+  a.n_stages = stages;
+  const int total = stages * a.stage_bytes + fixed + 1024;
+  static std::mutex mtx;
+  static int attr_bytes = 0;
+  {
+    std::lock_guard<std::mutex> lock(mtx);
+    if (total > attr_bytes) {
+      cudaError_t e = cudaFuncSetAttribute(dtp_gemm_fwd_kernel<BN, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
+      if (e != cudaSuccess) return check_cuda(e, "dtp_gemm_fwd smem attribute");
+      attr_bytes = total;
+    }
+  }
   const int sms = device_sms();
   const long long tiles = a.m_blocks * a.n_blocks;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  dtp_gemm_fwd_kernel<BN, STACK><<<grid, kThreads, FSmem<BN, STACK>::kTotal, s>>>(mh, ml, mc, a);
+  dtp_gemm_fwd_kernel<BN, STACK><<<grid, kThreads, total, s>>>(mh, ml, mc, mw, a);
   return check_cuda(cudaGetLastError(), "dtp_gemm_fwd_kernel launch");
 }
 
@@ -472,6 +629,18 @@ static int collect_paths(const EqfPlan* plan, int group, FArgs& a) {
     FPath& f = a.paths[i];
     f.d1 = s.d1; f.d2 = s.d2; f.xb = s.xb; f.mul = s.mul; f.y_off = s.y_off; f.w_off = s.w_off; f.cg_off = s.cg_off;
     f.koff = s.koff; f.m_off = m_off;
+    f.nz = 0;
+    const float* cgp = reinterpret_cast<const float*>(plan->blob.data() + h.off_cg) + s.cg_off;
+    for (int ii = 0; ii < s.d1; ++ii)
+      for (int kk = 0; kk < s.d3; ++kk) {
+        bool any = false;
+        for (int jj = 0; jj < s.d2; ++jj) any = any || cgp[(ii * s.d2 + jj) * s.d3 + kk] != 0.0f;
+        if (any) f.nz |= 1ull << (ii * s.d3 + kk);
+      }
+    for (int c = 0; c < s.mul / BKT; ++c) {
+      if (koff / BKT + c >= kMaxKTiles) { set_error("fused DTP: output group wider than 1024 channels"); return EQF_ERR_UNSUPPORTED; }
+      a.kt_path[koff / BKT + c] = (unsigned char)i;
+    }
     koff += s.mul;
     m_off += s.d1 * s.d3;
   }
@@ -480,7 +649,7 @@ static int collect_paths(const EqfPlan* plan, int group, FArgs& a) {
   a.K = koff;
   a.m_row = m_off;
   if (koff != h.out_mul[group]) { set_error("fused DTP: paths do not cover the output group"); return EQF_ERR_INVALID; }
-  if ((BM / a.d3 + 2) * a.m_row > kMBufFloats) { set_error("fused DTP: coupling blocks of a tile exceed shared memory"); return EQF_ERR_UNSUPPORTED; }
+  if ((BM / a.d3 + 2) * a.m_row * 4 > 40 * 1024) { set_error("fused DTP: coupling blocks of a tile exceed shared memory"); return EQF_ERR_UNSUPPORTED; }
   return a.n_paths;
 }
 
@@ -499,6 +668,68 @@ extern "C" int eqf_dtp_linear_supported(const EqfPlan* plan, int32_t group) {
   return fused::collect_paths(plan, group, a) > 0 ? 1 : 0;
 }
 
+// operands of one output group -> FArgs (shared by the fused and the group-forward entry points)
+static int fill_fargs(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_edges, int32_t group, eqf::fused::FArgs& a,
+                      const char* who) {
+  using namespace eqf::fused;
+  if (plan == nullptr || op == nullptr) { set_error(std::string(who) + ": null plan / operands"); return EQF_ERR_INVALID; }
+  if (!op->y || !op->w) { set_error(std::string(who) + ": null pointer"); return EQF_ERR_INVALID; }
+  int rc = ensure_device(plan);
+  if (rc != EQF_OK) return rc;
+  const PlanHdr& h = plan->hdr;
+  rc = collect_paths(plan, group, a);
+  if (rc < 0) return rc;
+  if ((((uintptr_t)op->w | (uintptr_t)op->w_offset) & 15) || (h.w_numel & 3)) {
+    set_error(std::string(who) + ": weights must be 16-byte aligned, weight_numel % 4 == 0");
+    return EQF_ERR_INVALID;
+  }
+  for (int b = 0; b < EQF_MAX_BLOCKS; ++b) { a.x[b] = nullptr; a.x2[b] = nullptr; }
+  for (int b = 0; b < h.n_in1; ++b) {
+    if (op->x[b] == nullptr || ((uintptr_t)op->x[b] & 15) || ((uintptr_t)op->x2[b] & 15) || (h.in1_mul[b] & 3)) {
+      set_error(std::string(who) + ": in1 blocks must be present, 16-byte aligned, multiplicities % 4 == 0");
+      return EQF_ERR_INVALID;
+    }
+    a.x[b] = op->x[b];
+    a.x2[b] = op->x2[b];
+  }
+  a.src = reinterpret_cast<const long long*>(op->src);
+  a.dst = reinterpret_cast<const long long*>(op->dst);
+  if (a.x2[0] != nullptr && (a.src == nullptr || a.dst == nullptr)) { set_error(std::string(who) + ": x2 needs src and dst"); return EQF_ERR_INVALID; }
+  a.y = op->y; a.w = op->w; a.w_offset = op->w_offset; a.w_shared = op->w_shared;
+  if (a.w_shared && a.w_offset != nullptr) { set_error(std::string(who) + ": w_offset needs per-edge weights"); return EQF_ERR_INVALID; }
+  a.cg = reinterpret_cast<const float*>(plan->d_blob + h.off_cg);
+  a.E = n_edges; a.M = n_edges * a.d3; a.d_y = h.d_y; a.W = h.w_numel; a.N = 0;
+  if (a.M > 0x7fffffffLL) { set_error(std::string(who) + ": too many rows"); return EQF_ERR_UNSUPPORTED; }
+  a.n_tile = a.n_blocks = 0; a.m_blocks = 0;
+  a.n_stages = a.stage_bytes = a.w_tile_off = a.w_box_rows = a.tab_bytes = a.m_buf_floats = 0;
+  { const char* e = std::getenv("EQF_FUSED_DBG_SKIP"); a.dbg_skip = e ? std::atoi(e) : 0; }
+  return EQF_OK;
+}
+
+// out[e, k, :K] = DTP_group(x, y; w) for ONE output group of the plan, planar [E][2 l3 + 1][K] (the operand of a wide
+// linear that is not worth fusing).  Operands as for eqf_dtp_forward.
+extern "C" int eqf_dtp_group_forward(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_edges, int32_t group,
+                                     float* out, void* stream) {
+  using namespace eqf::fused;
+  if (n_edges <= 0) return EQF_OK;
+  if (out == nullptr || ((uintptr_t)out & 15)) { set_error("eqf_dtp_group_forward: bad output pointer"); return EQF_ERR_INVALID; }
+  FArgs a;
+  int rc = fill_fargs(plan, op, n_edges, group, a, "eqf_dtp_group_forward");
+  if (rc != EQF_OK) return rc;
+  const size_t smem = (size_t)32 * a.m_row * sizeof(float);
+  const long long blocks = (n_edges + 31) / 32;
+  const int cap = device_sms() * 8;
+  const int grid = (int)(blocks < cap ? blocks : cap);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (a.d3) {
+    case 1: dtp_group_forward_kernel<1><<<grid, 256, smem, s>>>(a, out); break;
+    case 3: dtp_group_forward_kernel<3><<<grid, 256, smem, s>>>(a, out); break;
+    case 5: dtp_group_forward_kernel<5><<<grid, 256, smem, s>>>(a, out); break;
+    default: dtp_group_forward_kernel<7><<<grid, 256, smem, s>>>(a, out); break;
+  }
+  return check_cuda(cudaGetLastError(), "dtp_group_forward_kernel launch");
+}
+
 // C[(e, k), :N] = DTP_group(x, y; w)[(e, k), :K] @ Wt[:K, :N]   for output group `group` of the plan: the depth-wise tensor
 // product (nets/graph_attention_transformer.py:491 / :496) feeds the channel-mixing linear (:492, :494, :496) on chip.
 // Operands as for eqf_dtp_forward (gather x = x[src] + x2[dst] when op->src is set; w per edge [E, W] (+ w_offset) or
@@ -508,38 +739,17 @@ extern "C" int eqf_dtp_linear_fwd(const EqfPlan* plan, const EqfEdgeOperands* op
                                   const float* Wt, int64_t N, int64_t ldw, float* C, int64_t ldc, float* split,
                                   void* stream) {
   using namespace eqf::fused;
-  if (plan == nullptr || op == nullptr) { set_error("eqf_dtp_linear_fwd: null plan / operands"); return EQF_ERR_INVALID; }
   if (n_edges <= 0 || N <= 0) return EQF_OK;
-  if (!Wt || !C || !split || !op->y || !op->w) { set_error("eqf_dtp_linear_fwd: null pointer"); return EQF_ERR_INVALID; }
-  int rc = ensure_device(plan);
-  if (rc != EQF_OK) return rc;
+  if (!Wt || !C || !split) { set_error("eqf_dtp_linear_fwd: null pointer"); return EQF_ERR_INVALID; }
   FArgs a;
+  int rc = fill_fargs(plan, op, n_edges, group, a, "eqf_dtp_linear_fwd");
+  if (rc != EQF_OK) return rc;
   const PlanHdr& h = plan->hdr;
-  rc = collect_paths(plan, group, a);
-  if (rc < 0) return rc;
-  if ((((uintptr_t)C | (uintptr_t)split | (uintptr_t)op->w | (uintptr_t)op->w_offset) & 15) || ((N | ldc) & 3) || ldc < N ||
-      ldw < N || (h.w_numel & 3)) {
+  if ((((uintptr_t)C | (uintptr_t)split) & 15) || ((N | ldc) & 3) || ldc < N || ldw < N) {
     set_error("eqf_dtp_linear_fwd: operands must be 16-byte aligned, N and ldc multiples of 4");
     return EQF_ERR_INVALID;
   }
-  for (int b = 0; b < EQF_MAX_BLOCKS; ++b) { a.x[b] = nullptr; a.x2[b] = nullptr; }
-  for (int b = 0; b < h.n_in1; ++b) {
-    if (op->x[b] == nullptr || ((uintptr_t)op->x[b] & 15) || ((uintptr_t)op->x2[b] & 15) || (h.in1_mul[b] & 3)) {
-      set_error("eqf_dtp_linear_fwd: in1 blocks must be present, 16-byte aligned, multiplicities % 4 == 0");
-      return EQF_ERR_INVALID;
-    }
-    a.x[b] = op->x[b];
-    a.x2[b] = op->x2[b];
-  }
-  a.src = reinterpret_cast<const long long*>(op->src);
-  a.dst = reinterpret_cast<const long long*>(op->dst);
-  if (a.x2[0] != nullptr && (a.src == nullptr || a.dst == nullptr)) { set_error("eqf_dtp_linear_fwd: x2 needs src and dst"); return EQF_ERR_INVALID; }
-  a.y = op->y; a.w = op->w; a.w_offset = op->w_offset; a.w_shared = op->w_shared;
-  if (a.w_shared && a.w_offset != nullptr) { set_error("eqf_dtp_linear_fwd: w_offset needs per-edge weights"); return EQF_ERR_INVALID; }
-  a.cg = reinterpret_cast<const float*>(plan->d_blob + h.off_cg);
-  a.E = n_edges; a.M = n_edges * a.d3; a.d_y = h.d_y; a.W = h.w_numel; a.N = (int)N;
-  if (a.M > 0x7fffffffLL) { set_error("eqf_dtp_linear_fwd: too many rows"); return EQF_ERR_UNSUPPORTED; }
-  { const char* e = std::getenv("EQF_FUSED_DBG_SKIP"); a.dbg_skip = e ? std::atoi(e) : 0; }
+  a.N = (int)N;
   cudaStream_t s = (cudaStream_t)stream;
   const long long K = a.K;
   float* hi = split;
@@ -555,13 +765,17 @@ extern "C" int eqf_dtp_linear_fwd(const EqfPlan* plan, const EqfEdgeOperands* op
   const int n_blocks = (int)((N + 127) / 128);
   const int n_tile = n_blocks == 1 ? (int)((N + 15) & ~15LL) : 128;
   a.n_tile = n_tile; a.n_blocks = n_blocks; a.m_blocks = (a.M + BM - 1) / BM;
-  CUtensorMap mh, ml, mc;
+  CUtensorMap mh, ml, mc, mw;
   if ((rc = make_map_2d(&mh, hi, N, K, K, n_tile, BKT)) != EQF_OK) return rc;
   if ((rc = make_map_2d(&ml, lo, N, K, K, n_tile, BKT)) != EQF_OK) return rc;
   if ((rc = make_map_2d(&mc, C, a.M, N, ldc, 32, kStoreCols)) != EQF_OK) return rc;
-  if (stack && n_tile == 32) return launch_fwd<32, true>(mh, ml, mc, a, s);
-  if (stack && n_tile == 64) return launch_fwd<64, true>(mh, ml, mc, a, s);
-  if (n_tile <= 32) return launch_fwd<32, false>(mh, ml, mc, a, s);
-  if (n_tile <= 64) return launch_fwd<64, false>(mh, ml, mc, a, s);
-  return launch_fwd<128, false>(mh, ml, mc, a, s);
+  mw = mc;    // placeholder when the weights are shared (never dereferenced)
+  // per-edge radial weights: [E, W] row-major, a box of (128 / d3 + 2) edges x 32 channels per k-tile, rows back to back
+  if (!a.w_shared && (rc = make_map_2d(&mw, a.w, n_edges, h.w_numel, h.w_numel, BM / a.d3 + 2, BKT, MapKind::kLinear)) != EQF_OK)
+    return rc;
+  if (stack && n_tile == 32) return launch_fwd<32, true>(mh, ml, mc, mw, a, s);
+  if (stack && n_tile == 64) return launch_fwd<64, true>(mh, ml, mc, mw, a, s);
+  if (n_tile <= 32) return launch_fwd<32, false>(mh, ml, mc, mw, a, s);
+  if (n_tile <= 64) return launch_fwd<64, false>(mh, ml, mc, mw, a, s);
+  return launch_fwd<128, false>(mh, ml, mc, mw, a, s);
 }

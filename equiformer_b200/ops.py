@@ -608,6 +608,26 @@ def dtp_linear_fwd_raw(plan: DtpPlan, group: int, xs, y, w, Wt: torch.Tensor, ga
     return C
 
 
+# widest linear that is fused: beyond it every 128-column tile would recompute the product, so the group is written to HBM
+# once (eqf_dtp_group_forward) and read by the wide tcgen05 GEMM
+_FUSED_MAX_N = int(os.environ.get("EQF_FUSED_MAX_N", "128"))
+
+
+def dtp_group_forward_raw(plan: DtpPlan, group: int, xs, y, w, gather=None, w_offset=None) -> torch.Tensor:
+    """One output group of the depth-wise product, ``[E, 2 l3 + 1, K]`` (``eqf_dtp_group_forward``)."""
+    y, w, E, shared = _check_yw(plan, y, w)
+    xs, gather = _check_gather(plan, xs, gather, E, "dtp_group_forward x")
+    l3, _p, K = plan.out_groups[group]
+    out = torch.empty((E, 2 * l3 + 1, K), device=y.device, dtype=torch.float32)
+    op = _operands(plan, xs, y, w, None, shared, gather, w_offset)
+    d_in = sum((2 * l + 1) * m for l, m in plan.in1_blocks)
+    nbytes = 4 * E * (d_in + plan.d_y + (0 if shared else K) + (2 * l3 + 1) * K)
+    with torch.cuda.device(y.device), _kernel("dtp_group_forward", nbytes):
+        rc = _lib.load().eqf_dtp_group_forward(plan.handle, ctypes.byref(op), E, group, out.data_ptr(), _stream())
+    _lib.check(rc, "eqf_dtp_group_forward")
+    return out
+
+
 def _dtp_linear_unfused(plan: DtpPlan, graph, n_b: int, y, w, offset, AB, Ws):
     """The same map from differentiable primitives (higher-order path, and the statement the fused kernel is tested
     against): DTP family + one GEMM per output group."""
@@ -639,7 +659,14 @@ class DtpLinear(torch.autograd.Function):
             raise ValueError(f"DtpLinear: expected {ng} weight matrices, got {len(Ws)}")
         As, Bs = AB[:nb], (AB[nb:] if n_b else None)
         gather = (graph.src, graph.dst, Bs) if graph is not None else None
-        outs = [dtp_linear_fwd_raw(plan, g, As, y, w, Ws[g], gather=gather, w_offset=offset) for g in range(ng)]
+        outs = []
+        for g in range(ng):
+            if Ws[g].shape[1] <= _FUSED_MAX_N:
+                outs.append(dtp_linear_fwd_raw(plan, g, As, y, w, Ws[g], gather=gather, w_offset=offset))
+            else:
+                fg = dtp_group_forward_raw(plan, g, As, y, w, gather=gather, w_offset=offset)
+                E, d = fg.shape[0], fg.shape[1]
+                outs.append(gemm_raw(0, fg.reshape(E * d, fg.shape[2]), Ws[g].contiguous()).view(E, d, -1))
         ctx.plan, ctx.graph, ctx.n_b, ctx.n_ab, ctx.has_off = plan, graph, n_b, n_ab, offset is not None
         ctx.save_for_backward(y, w, *([offset] if offset is not None else []), *rest)
         return tuple(outs)

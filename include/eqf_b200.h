@@ -178,6 +178,10 @@ void eqf_gemm_tf32x3_set_timeline(long long* device_buffer);
  * [E * (2 l3 + 1)][N], row stride ldc; `split` = device scratch of 2 * N * K floats (hi / lo planes of Wt).
  * eqf_dtp_linear_supported: 1 when the group qualifies (path multiplicities % 32 == 0, tables fit shared memory). */
 int eqf_dtp_linear_supported(const EqfPlan* plan, int32_t group);
+/* out[e][k][:K] = DTP_group(x, y; w): ONE output group of the product written to HBM, planar [E][2 l3 + 1][K] - the
+ * operand of a linear too wide to fuse (N > 128 columns; e.g. the 224-channel 0e group in front of sep_alpha | lin). */
+int eqf_dtp_group_forward(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_edges, int32_t group, float* out,
+                          void* stream);
 int eqf_dtp_linear_fwd(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_edges, int32_t group,
                        const float* Wt, int64_t N, int64_t ldw, float* C, int64_t ldc, float* split, void* stream);
 
@@ -189,6 +193,20 @@ int eqf_radius_graph_count(const float* pos, const int64_t* batch, int64_t n, fl
                            int64_t max_neighbors, int64_t* deg, void* stream);
 int eqf_radius_graph_fill(const float* pos, const int64_t* batch, int64_t n, float r_squared, int32_t loop,
                           int64_t max_neighbors, const int64_t* row_ptr, int64_t* src, int64_t* dst, void* stream);
+
+/* Neighbour list under periodic boundary conditions - ocpmodels' radius_graph_pbc + the cell offsets get_pbc_distances
+ * turns into edge vectors, as the OC20 model uses them (nets/graph_attention_transformer_oc20.py:267-302): edge
+ * (j, image c) -> i iff same frame and 1e-4 < |pos_j + c . cell[frame] - pos_i| < r, images c in [-rep, rep] per lattice
+ * vector; sorted by centre i, then atom j, then image.  cell [n_frames][3][3] (rows = lattice vectors), frame_ptr
+ * [n_frames + 1] = first atom of each frame (batch ascending).  count -> scan -> fill (also returns the squared
+ * distances, for the nearest-`max_neighbors` cut the caller applies when a centre exceeds it). */
+int eqf_radius_graph_pbc_count(const float* pos, const int64_t* batch, const int64_t* frame_ptr, const float* cell,
+                               int64_t n, float r_squared, int32_t rep_a, int32_t rep_b, int32_t rep_c, int64_t* deg,
+                               void* stream);
+int eqf_radius_graph_pbc_fill(const float* pos, const int64_t* batch, const int64_t* frame_ptr, const float* cell,
+                              int64_t n, float r_squared, int32_t rep_a, int32_t rep_b, int32_t rep_c,
+                              const int64_t* row_ptr, int64_t* src, int64_t* dst, int32_t* cell_offsets, float* dist2,
+                              void* stream);
 
 /* GaussianRadialBasisLayer with 128 basis functions (nets/gaussian_rbf.py:5-40): out[e, k] = exp(-z^2/2) / (a s_k),
  * z = (weight * dist_e / cutoff + bias - mean_k) / s_k, s_k = |std_k| + 1e-5, a = sqrt(2 * 3.14159); weight and bias

@@ -53,6 +53,10 @@ def dtp_linear_fwd_raw(plan, group, xs, y, w, Wt, gather=None, w_offset=None):
     return torch.einsum("eku,un->ekn", f, Wt)
 
 
+def dtp_group_forward_raw(plan, group, xs, y, w, gather=None, w_offset=None):
+    return dtp_forward_raw(plan, xs, y, w, gather, w_offset)[group]
+
+
 def dtp_grad_x_raw(plan, gs, y, w):
     E = y.shape[0]
     gxs = [y.new_zeros((E, 2 * l + 1, mul)) for l, mul in plan.in1_blocks]
@@ -225,7 +229,7 @@ def gate_logits_bwd_raw(lay, t0, bias, alpha_dot, gated, gz, gv0, gvout):
     return grads[0], list(grads[2:]), (grads[1].reshape(-1) if lay.n_alpha > 0 else None)
 
 
-_PATCHED = ["rbf_fwd_raw", "rbf_bwd_raw", "colsum_raw", "eln_fwd_raw", "eln_bwd_raw", "eln_planar_fwd_raw", "eln_planar_bwd_raw", "ln_silu_fwd_raw", "ln_silu_bwd_raw", "gate_logits_fwd_raw", "gate_logits_bwd_raw", "gemm_raw", "dtp_forward_raw", "dtp_linear_fwd_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
+_PATCHED = ["rbf_fwd_raw", "rbf_bwd_raw", "colsum_raw", "eln_fwd_raw", "eln_bwd_raw", "eln_planar_fwd_raw", "eln_planar_bwd_raw", "ln_silu_fwd_raw", "ln_silu_bwd_raw", "gate_logits_fwd_raw", "gate_logits_bwd_raw", "gemm_raw", "dtp_forward_raw", "dtp_linear_fwd_raw", "dtp_group_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
             "seg_softmax_raw", "seg_softmax_bwd_raw", "attn_aggregate_raw", "attn_edge_dot_raw", "attn_edge_scale_raw"]
 
 

@@ -635,6 +635,8 @@ def test_fused_dtp_linear_forward_vs_fp64(cuda_device, name, shared, gather, E):
     ref_f = emu.dtp_forward_raw(plan, [t.double() for t in xs], y.double(), w.double(), gat_r,
                                 off.double() if off is not None else None)
     for gi, (l, _p, K) in enumerate(plan.out_groups):
+        fg = ops.dtp_group_forward_raw(plan, gi, xs_d, y_d, w_d, gather=gat_d, w_offset=f(off) if off is not None else None)
+        assert rel_err(fg, ref_f[gi]) < TOL, gi                 # the same producer writing one group to HBM
         for N in widths[l]:
             Wt = torch.randn(K, N, generator=g) / K ** 0.5
             out = ops.dtp_linear_fwd_raw(plan, gi, xs_d, y_d, w_d, f(Wt), gather=gat_d,

@@ -68,8 +68,14 @@ def main():
             err = ((ops.dtp_linear_fwd_raw(plan, gi, xs, y, ww, Ws[gi], gather=gat, w_offset=oo).reshape(E * d, N)
                     - ops.gemm_tf32x3_raw(a2, Ws[gi], b_is_kn=True)).abs().max() / (a2 @ Ws[gi]).abs().max()).item()
             flops = 2.0 * E * d * K * N
-            row["groups"].append({"l": l, "rows": E * d, "K": K, "N": N, "gemm_us": round(us_gemm, 1), "fused_us": round(us_fused, 1),
-                                  "fused_tflops_useful": round(flops / us_fused / 1e6, 1), "rel_diff": err})
+            rec = {"l": l, "rows": E * d, "K": K, "N": N, "gemm_us": round(us_gemm, 1), "fused_us": round(us_fused, 1),
+                   "fused_tflops_useful": round(flops / us_fused / 1e6, 1), "rel_diff": err}
+            if N > ops._FUSED_MAX_N:       # the route DtpLinear takes for wide linears: one group to HBM + wide GEMM
+                us_grp = timeit(lambda: ops.dtp_group_forward_raw(plan, gi, xs, y, ww, gather=gat, w_offset=oo))
+                rec["group_forward_us"] = round(us_grp, 1)
+                us_fused = us_grp + us_gemm
+                rec["route_us"] = round(us_fused, 1)
+            row["groups"].append(rec)
             tot_f += us_fused
             tot_u += us_gemm
         row["fused_total_us"] = round(tot_f, 1)
