@@ -345,7 +345,8 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
       // ------------------------------------------------------------------- table helpers (warps 6, 7): one tile ahead
       const int ht = (warp - kHelperWarp0) * 32 + lane;       // 0 .. 63
       const int m_row = a.m_row;
-      for (int q = ht; q < m_row; q += kHelperThreads) {      // descriptors of the M-row entries this thread owns
+      int4* mdesc_all = mdesc;
+      for (int q = ht; q < m_row; q += kHelperThreads) {      // descriptors of the M-row entries (shared by both helper warps)
         int pi = 0;
         for (int j = 1; j < a.n_paths; ++j) if (q >= a.paths[j].m_off) pi = j;
         const FPath& p = a.paths[pi];
@@ -353,6 +354,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
         const int i = r / d3, k = r - i * d3;
         mdesc[q] = make_int4(p.cg_off + i * p.d2 * d3 + k, p.y_off, p.d2, 0);
       }
+      named_barrier(2, kHelperThreads);
       uint32_t tile_it = 0;
       long long mb_prev = -1;
       for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
@@ -376,15 +378,29 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
             dst_s[i] = a.dst != nullptr ? (int)a.dst[e0 + i] : 0;
           }
         }
-        for (int q = ht; q < m_row; q += kHelperThreads) {
-          const int4 dsc = mdesc[q];
-          const float* cg = a.cg + dsc.x;
-          const float* yv = a.y + e0 * a.d_y + dsc.y;
-#pragma unroll 2
-          for (int el = 0; el < n_e; ++el) {
-            float m = 0.f;
-            for (int j = 0; j < dsc.z; ++j) m = fmaf(__ldg(cg + j * d3), __ldg(yv + el * a.d_y + j), m);
-            mbuf[el * m_row + q] = m;
+        // items (edge, M-row entry) dealt round-robin to the 64 helper threads, four independent items in flight per thread
+        {
+          const int n_items = n_e * m_row;
+          const float* ybase = a.y + e0 * a.d_y;
+          for (int idx0 = ht; idx0 < n_items; idx0 += 4 * kHelperThreads) {
+            float acc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int idx = idx0 + u * kHelperThreads;
+              acc[u] = 0.f;
+              if (idx < n_items) {
+                const int el = idx / m_row, q = idx - el * m_row;
+                const int4 dsc = mdesc_all[q];
+                const float* cg = a.cg + dsc.x;
+                const float* yv = ybase + el * a.d_y + dsc.y;
+                for (int j = 0; j < dsc.z; ++j) acc[u] = fmaf(__ldg(cg + j * d3), __ldg(yv + j), acc[u]);
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int idx = idx0 + u * kHelperThreads;
+              if (idx < n_items) mbuf[idx] = acc[u];
+            }
           }
         }
         __syncwarp();

@@ -78,9 +78,10 @@ extern "C" int eqf_radius_graph_fill(const float* pos, const int64_t* batch, int
 // Neighbour list under periodic boundary conditions (what ocpmodels' radius_graph_pbc + get_pbc_distances give the OC20
 // model at nets/graph_attention_transformer_oc20.py:267-302): edge (j, image c) -> i iff atoms i and j belong to the
 // same frame and |pos_j + c . cell - pos_i| < r with (j, c) != (i, 0); images c in [-rep_a, rep_a] x [-rep_b, rep_b] x
-// [-rep_c, rep_c] (the caller derives the repetitions from the cell heights and r, as ocpmodels does).  One warp per
+// [-rep_c, rep_c] (the caller derives the repetitions from the cell heights and r, as ocpmodels does); the pair is kept
+// when 1e-4 < distance^2 <= r^2 (ocpmodels' two masks).  One warp per
 // centre walks the frame's atoms x images in a fixed order (atom ascending, image index ascending); ballot / popc ranks
-// give each hit its slot: sorted by centre, deterministic.  Pair distances below 1e-4 are skipped like ocpmodels' mask.
+// give each hit its slot: sorted by centre, deterministic.
 namespace eqf {
 
 template <bool FILL>
@@ -122,7 +123,7 @@ __global__ void __launch_bounds__(256) radius_graph_pbc_kernel(const float* __re
       const float oz = ia * cm[2] + ib * cm[5] + ic * cm[8];
       const float dx = __ldg(pos + 3 * j) + ox - xi, dy = __ldg(pos + 3 * j + 1) + oy - yi, dz = __ldg(pos + 3 * j + 2) + oz - zi;
       d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      hit = d2 < r2 && d2 > 1e-8f;           // ocpmodels: distance > 0.0001 removes the atom itself (zero offset)
+      hit = d2 <= r2 && d2 > 1e-4f;          // ocpmodels' masks: distance_sqr <= r^2 and distance_sqr > 0.0001 (the atom itself)
     }
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     if (FILL && hit) {

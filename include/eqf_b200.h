@@ -196,7 +196,7 @@ int eqf_radius_graph_fill(const float* pos, const int64_t* batch, int64_t n, flo
 
 /* Neighbour list under periodic boundary conditions - ocpmodels' radius_graph_pbc + the cell offsets get_pbc_distances
  * turns into edge vectors, as the OC20 model uses them (nets/graph_attention_transformer_oc20.py:267-302): edge
- * (j, image c) -> i iff same frame and 1e-4 < |pos_j + c . cell[frame] - pos_i| < r, images c in [-rep, rep] per lattice
+ * (j, image c) -> i iff same frame and 1e-4 < |pos_j + c . cell[frame] - pos_i|^2 <= r^2, images c in [-rep, rep] per lattice
  * vector; sorted by centre i, then atom j, then image.  cell [n_frames][3][3] (rows = lattice vectors), frame_ptr
  * [n_frames + 1] = first atom of each frame (batch ascending).  count -> scan -> fill (also returns the squared
  * distances, for the nearest-`max_neighbors` cut the caller applies when a centre exceeds it). */

@@ -395,6 +395,45 @@ def model_forward(params: Params, cfg: Config, pos, batch, node_atom, n_graphs: 
     return scatter_sum(h, batch, n_graphs) / math.sqrt(cfg.avg_num_nodes)                      # :894
 
 
+def pbc_edge_vectors(pos, cell, batch, edge_src, edge_dst, cell_offsets):
+    """ocpmodels ``get_pbc_distances`` as consumed at nets/graph_attention_transformer_oc20.py:283-296:
+    ``pos[src] - pos[dst] + cell_offsets @ cell[frame]`` (rows of ``cell`` = lattice vectors)."""
+    cells = cell.to(pos.dtype).index_select(0, batch.index_select(0, edge_dst))
+    offsets = torch.bmm(cell_offsets.to(pos.dtype).view(-1, 1, 3), cells).view(-1, 3)
+    return pos.index_select(0, edge_src) - pos.index_select(0, edge_dst) + offsets
+
+
+def model_forward_oc20(params: Params, cfg: Config, pos, cell, batch, atomic_numbers, tags, n_graphs: int, edge_src,
+                       edge_dst, cell_offsets):
+    """GraphAttentionTransformerOC20.forward - nets/graph_attention_transformer_oc20.py:305-380 (feed-forward energy head,
+    no auxiliary task); the periodic neighbour list (ocpmodels ``radius_graph_pbc``) is an input.  ``cfg`` carries the OC20
+    statistics (``avg_degree`` 23.395..., ``avg_num_nodes`` 77.81317, :60-66) and ``max_atom_type`` 84."""
+    dtype = pos.dtype
+    emb = e3.parse_irreps(cfg.irreps_node_embedding)
+    feat = e3.parse_irreps(cfg.irreps_feature)
+    irreps_edge = e3.parse_irreps(cfg.irreps_sh)
+    edge_vec = pbc_edge_vectors(pos, cell, batch, edge_src, edge_dst, cell_offsets)                  # :283-296
+    edge_sh = e3.spherical_harmonics([l for _, l, _ in irreps_edge], edge_vec, True, "component")   # :311-312
+    onehot = F.one_hot(atomic_numbers, cfg.max_atom_type).to(dtype)
+    atom_embedding = linear_rs(params, "atom_embed.atom_type_lin", [(cfg.max_atom_type, 0, 1)], emb, onehot)   # :316
+    tag_embedding = linear_rs(params, "tag_embed.atom_type_lin", [(3, 0, 1)], emb, F.one_hot(tags, 3).to(dtype))  # :318
+    edge_scalars = gaussian_rbf(params, "rbf", edge_vec.norm(dim=1), cfg.max_radius)                # :320-321
+    deg = edge_degree_embedding(params, "edge_deg_embed", cfg, pos.shape[0], edge_sh, edge_scalars, edge_src, edge_dst,
+                                dtype)
+    x = atom_embedding + tag_embedding + deg                                                        # :329
+    node_attr = torch.ones_like(x[:, 0:1])
+    for i in range(cfg.num_layers):
+        out_irreps = emb if i != cfg.num_layers - 1 else feat
+        x = trans_block(params, f"blocks.{i}", cfg, emb, out_irreps, x, node_attr, edge_src, edge_dst, edge_sh,
+                        edge_scalars)
+    x = layer_norm_v2(params, "norm", feat, x)
+    scalars = [(m, l, p) for m, l, p in feat if l == 0 and p == 1]
+    h = linear_rs(params, "head.0", feat, scalars, x)                                               # :176-179
+    h = F.silu(h) * e3.NORMALIZE2MOM["silu"]
+    h = linear_rs(params, "head.2", scalars, [(1, 0, 1)], h)
+    return scatter_sum(h, batch, n_graphs) / math.sqrt(cfg.avg_num_nodes)                          # :365-366
+
+
 def energy_and_forces(params: Params, cfg: Config, pos, batch, node_atom, n_graphs: int, create_graph: bool = False):
     """GraphAttentionTransformerMD17.forward - nets/graph_attention_transformer_md17.py:276-327"""
     with torch.enable_grad():

@@ -637,3 +637,93 @@ def test_dot_product_md17_variant_matches_reference_model_file():
     assert rel_err(e.detach(), torch.from_numpy(g["energy"])) < 1e-10
     assert rel_err(f.detach(), torch.from_numpy(g["forces"])) < 1e-9
     assert _worst_grad({k: p.grad for k, p in model.named_parameters()}, g, 70) < 1e-6
+
+
+# --------------------------------------------------------------- the OC20 model file (periodic boundary conditions, tags)
+OC20_SMALL = os.path.join(os.path.dirname(SMALL), "reference_model_oc20_small.npz")
+OC20_STATS = dict(max_atom_type=84, qm9_atom_remap=False, avg_degree=23.395238876342773, avg_num_nodes=77.81317)
+
+
+def _oc20_fixture():
+    g = np.load(OC20_SMALL)
+    cfg = {k[4:]: g[k].tolist() for k in g.files if k.startswith("cfg/")}
+    state = {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state/")}
+    return g, cfg, state
+
+
+def test_oracle_oc20_model_matches_reference_model_file():
+    """``nets/graph_attention_transformer_oc20.py`` run end to end (tests/golden/make_reference_golden_oc20.py: two
+    triclinic periodic frames, tags, 84 atom types) vs ``oracle.model_forward_oc20``: energy and parameter gradients."""
+    g, cfg, state = _oc20_fixture()
+    ocfg = R.Config(irreps_node_embedding=cfg["irreps_node_embedding"], irreps_sh=cfg["irreps_sh"], irreps_head=cfg["irreps_head"],
+                    irreps_mlp_mid=cfg["irreps_mlp_mid"], irreps_feature=cfg["irreps_feature"], num_heads=cfg["num_heads"],
+                    num_layers=cfg["num_layers"], max_radius=cfg["max_radius"], number_of_basis=cfg["number_of_basis"],
+                    nonlinear_message=True, **OC20_STATS)
+    params = {k: v.requires_grad_(v.is_floating_point() and v.numel() > 0) for k, v in R.cast_params(state, torch.float64).items()}
+    t = lambda k: torch.from_numpy(g[k])
+    edge = t("edge_index")
+    energy = R.model_forward_oc20(params, ocfg, t("pos").double(), t("cell").double(), t("batch"), t("z"), t("tags"), 2,
+                                  edge[0], edge[1], t("cell_offsets"))
+    assert rel_err(energy, t("energy")) < 1e-10
+    (energy * torch.tensor([[1.0], [-0.7]])).sum().backward()
+    for k in g.files:
+        if k.startswith("grad/"):
+            assert rel_err(params[k[5:]].grad, t(k)) < 1e-6, k
+
+
+def _oc20_mirror(cfg, state):
+    from equiformer_b200.nets.graph_attention_transformer_oc20 import GraphAttentionTransformerOC20
+    cfg = dict(cfg)
+    cfg["fc_neurons"] = list(cfg["fc_neurons"])
+    model = GraphAttentionTransformerOC20(None, None, 1, **cfg)
+    res = model.load_state_dict(state, strict=False)
+    assert not res.unexpected_keys and all(k.endswith("tp.output_mask") for k in res.missing_keys), res
+    return model.eval()
+
+
+def _oc20_data(g, dev=None, dtype=torch.float64):
+    import types
+    t = lambda k: torch.from_numpy(g[k])
+    d = types.SimpleNamespace(pos=t("pos").to(dtype), cell=t("cell").to(dtype), batch=t("batch"), atomic_numbers=t("z"),
+                              tags=t("tags"), n_graphs=2)
+    if dev is not None:
+        for k, v in vars(d).items():
+            if isinstance(v, torch.Tensor):
+                setattr(d, k, v.to(dev))
+    return d
+
+
+def test_mirror_oc20_model_matches_reference_model_file():
+    """The OC20 mirror (own periodic neighbour list, kernels emulated in float64) loaded with the reference's
+    ``state_dict``: same edge list as the fixture's, energy 1e-10, parameter gradients 1e-6."""
+    from equiformer_b200.graph import radius_graph_pbc
+    from tests._emulation import emulated_kernels
+    g, cfg, state = _oc20_fixture()
+    model = _oc20_mirror(cfg, state).double()
+    data = _oc20_data(g)
+    edge, offs, _d2 = radius_graph_pbc(data.pos.float(), data.batch, data.cell.float(), cfg["max_radius"], cfg["max_neighbors"])
+    assert torch.equal(edge, torch.from_numpy(g["edge_index"])) and torch.equal(offs.long(), torch.from_numpy(g["cell_offsets"]).long())
+    with emulated_kernels():
+        energy = model(data)
+        (energy * torch.tensor([[1.0], [-0.7]], dtype=torch.float64)).sum().backward()
+    assert rel_err(energy, torch.from_numpy(g["energy"])) < 1e-10
+    for k in g.files:
+        if k.startswith("grad/"):
+            assert rel_err(model.get_parameter(k[5:]).grad, torch.from_numpy(g[k])) < 1e-6, k
+
+
+@pytest.mark.gpu
+def test_cuda_oc20_model_matches_reference_model_file(cuda_device):
+    """The OC20 mirror on CUDA (periodic neighbour-list kernels + the edge kernels) against the reference's own output."""
+    from equiformer_b200.graph import radius_graph_pbc
+    g, cfg, state = _oc20_fixture()
+    model = _oc20_mirror(cfg, state).to(cuda_device)
+    data = _oc20_data(g, cuda_device, torch.float32)
+    edge, offs, _d2 = radius_graph_pbc(data.pos, data.batch, data.cell, cfg["max_radius"], cfg["max_neighbors"])
+    assert torch.equal(edge.cpu(), torch.from_numpy(g["edge_index"]))
+    assert torch.equal(offs.cpu().long(), torch.from_numpy(g["cell_offsets"]).long())
+    energy = model(data)
+    (energy * torch.tensor([[1.0], [-0.7]], device=cuda_device)).sum().backward()
+    assert rel_err(energy, torch.from_numpy(g["energy"])) < 1e-4
+    worst = max(rel_err(model.get_parameter(k[5:]).grad, torch.from_numpy(g[k])) for k in g.files if k.startswith("grad/"))
+    assert worst < 1e-3, worst
