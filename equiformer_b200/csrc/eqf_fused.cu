@@ -12,17 +12,17 @@
 //   warp  4      TMA producer  weight tiles B_hi / B_lo of the k-tile (K-major planes, 128-byte rows)
 //   warp  5      MMA issuer    tcgen05.mma.kind::tf32, A from TENSOR MEMORY, 3xTF32 (stacked [b_hi | b_lo] for N <= 64)
 //   warps 8-11   transform     raw A tile (shared memory) -> a_hi / a_lo in tensor memory (one thread = one row)
-//   warps 6-7    table helpers per-tile tables one tile AHEAD of the producers (double-buffered): node rows of the tile's edges
-//                and the coupling blocks M_p[e] of its <= 128/(2 l3 + 1) + 2 edges (dense CG table of the plan)
 //   warps 12-27  DTP producers two sets of 8 warps alternate k-tiles: gather x = A[src] + B[dst] (float4 per lane, node
 //                tables L2 resident), multiply by the per-edge radial weights (a TMA box of the [E, W] weight matrix that
 //                the producer warp stages with the weight tiles), contract with M_p[e] and write the 128 x 32 raw A tile
 //                into the stage's shared memory (SWIZZLE_128B row order, conflict-free)
 // Register budget (896 threads x 72 at launch): setmaxnreg moves registers from the TMA / MMA / helper warpgroup (40) to
 // the transform (88) and epilogue (88) warpgroups; the DTP warps keep their 72.
-// First version (profiles/r2_fused_fwd_v1_*): correct but 1.6x SLOWER than DTP + GEMM - the DTP warps computed the tile
-// tables themselves between two CTA-wide barriers (pipeline drained at every tile: ~10 us per tile with the math off) and
-// fetched the radial weights with HBM-latency loads.  Hence the helper warps and the TMA weight box.
+// Per row block the 16 DTP warps first build the block's tables in shared memory (double-buffered, two named barriers): node
+// rows and harmonics of its <= 128/(2 l3 + 1) + 2 edges, then the coupling blocks M_p[e] from the group's CG blocks (packed
+// into shared memory once per CTA).  History (profiles/r2_fused_fwd_v*): v1 computed M_p[e] with dependent GLOBAL loads of CG
+// and y inside that window (~12 k cycles per tile: the fused kernel was 1.6x slower than DTP + GEMM); v2 moved the tables to
+// two helper warps one tile ahead - 64 threads could not keep up (28 us per tile) and it got slower still.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -45,11 +45,10 @@ constexpr int BKT = 32;                 // channels per k-tile: 128-byte rows
 constexpr int kRowBytes = BKT * 4;
 constexpr int UMMA_K = 8;
 constexpr int kStoreCols = 32;
-constexpr int kEpilogueWarps = 4, kProducerWarp = 4, kMmaWarp = 5, kHelperWarp0 = 6, kHelperWarps = 2;
-constexpr int kHelperThreads = kHelperWarps * 32;
+constexpr int kEpilogueWarps = 4, kProducerWarp = 4, kMmaWarp = 5;   // warps 6, 7 idle (fill the warpgroup)
 constexpr int kTransformWarp0 = 8, kTransformWarps = 4;
 constexpr int kDtpWarp0 = 12, kDtpWarps = 16, kDtpSets = 2, kDtpSetWarps = kDtpWarps / kDtpSets;
-constexpr int kDtpSetThreads = kDtpSetWarps * 32;
+constexpr int kDtpThreads = kDtpWarps * 32, kDtpSetThreads = kDtpSetWarps * 32;
 constexpr int kThreads = (kDtpWarp0 + kDtpWarps) * 32;            // 896
 constexpr int kMaxPaths = 16;
 constexpr int kMaxTileEdges = 136;      // 128 / d3 + 2 <= 130
@@ -83,7 +82,7 @@ struct FArgs {
   long long m_blocks;
   int dbg_skip;          // measurement aid: bit 0 skips the DTP math, bit 1 the MMAs, bit 2 the transform (garbage results)
   // shared-memory layout (bytes), fixed by the host: stages | store staging | 2 x (M rows + node rows) | descriptors | barriers
-  int n_stages, stage_bytes, w_tile_off, w_box_rows, tab_bytes, m_buf_floats;
+  int n_stages, stage_bytes, w_tile_off, w_box_rows, tab_bytes, m_buf_floats, y_buf_floats, cg_floats;
   unsigned char kt_path[kMaxKTiles];   // path of each 32-channel k-tile, in channel order
   FPath paths[kMaxPaths];
 };
@@ -180,16 +179,15 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
   uint8_t* store_base = smem + kStages * stage_bytes;
   uint8_t* tab_base = store_base + S::kStoreBytes;           // two table buffers: [m_buf_floats] M rows, then src / dst rows
   int4* mdesc = reinterpret_cast<int4*>(tab_base + 2 * a.tab_bytes);      // per M-row entry: (cg offset, y offset, d2, -)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(mdesc) + ((a.m_row * 16 + 127) & ~127));
+  float* cg_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(mdesc) + ((a.m_row * 16 + 127) & ~127));   // the group's CG blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(cg_s) + ((a.cg_floats * 4 + 127) & ~127));
   uint64_t* full = bars;                          // [8] weight tiles (and the radial-weight box) landed (TMA)
   uint64_t* raw_ready = bars + kMaxStages;        // [8] raw A tile written by the DTP set
   uint64_t* a_ready = bars + 2 * kMaxStages;      // [8] a_hi / a_lo in tensor memory
   uint64_t* empty = bars + 3 * kMaxStages;        // [8] MMAs of the stage finished
   uint64_t* tmem_full = bars + 4 * kMaxStages;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;           // [2]
-  uint64_t* tab_ready = tmem_full + 4;            // [2] tile tables written by the helper warps
-  uint64_t* tab_free = tmem_full + 6;             // [2] every DTP warp is done with the tile's tables
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full + 8);
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_tiles = a.K / BKT;
@@ -209,8 +207,6 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], kEpilogueWarps);
-      mbar_init(&tab_ready[b], kHelperWarps);
-      mbar_init(&tab_free[b], kDtpWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -341,71 +337,6 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
           umma_commit(&tmem_full[ab]);
         }
       }
-    } else {
-      // ------------------------------------------------------------------- table helpers (warps 6, 7): one tile ahead
-      const int ht = (warp - kHelperWarp0) * 32 + lane;       // 0 .. 63
-      const int m_row = a.m_row;
-      int4* mdesc_all = mdesc;
-      for (int q = ht; q < m_row; q += kHelperThreads) {      // descriptors of the M-row entries (shared by both helper warps)
-        int pi = 0;
-        for (int j = 1; j < a.n_paths; ++j) if (q >= a.paths[j].m_off) pi = j;
-        const FPath& p = a.paths[pi];
-        const int r = q - p.m_off;
-        const int i = r / d3, k = r - i * d3;
-        mdesc[q] = make_int4(p.cg_off + i * p.d2 * d3 + k, p.y_off, p.d2, 0);
-      }
-      named_barrier(2, kHelperThreads);
-      uint32_t tile_it = 0;
-      long long mb_prev = -1;
-      for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-        const long long mb = tile / a.n_blocks;
-        if (mb == mb_prev) continue;                          // column tiles of one row block share the tables
-        mb_prev = mb;
-        const int b = tile_it & 1;
-        mbar_wait(&tab_free[b], ((tile_it >> 1) & 1) ^ 1);
-        ++tile_it;
-        const long long row0 = mb * BM;
-        const long long e0 = row0 / d3;
-        long long e1 = (row0 + BM - 1) / d3 + 1;
-        if (e1 > a.E) e1 = a.E;
-        const int n_e = (int)(e1 - e0);
-        float* mbuf = reinterpret_cast<float*>(tab_base + b * a.tab_bytes);
-        int* src_s = reinterpret_cast<int*>(mbuf + a.m_buf_floats);
-        int* dst_s = src_s + kMaxTileEdges;
-        if (a.src != nullptr) {
-          for (int i = ht; i < n_e; i += kHelperThreads) {
-            src_s[i] = (int)a.src[e0 + i];
-            dst_s[i] = a.dst != nullptr ? (int)a.dst[e0 + i] : 0;
-          }
-        }
-        // items (edge, M-row entry) dealt round-robin to the 64 helper threads, four independent items in flight per thread
-        {
-          const int n_items = n_e * m_row;
-          const float* ybase = a.y + e0 * a.d_y;
-          for (int idx0 = ht; idx0 < n_items; idx0 += 4 * kHelperThreads) {
-            float acc[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int idx = idx0 + u * kHelperThreads;
-              acc[u] = 0.f;
-              if (idx < n_items) {
-                const int el = idx / m_row, q = idx - el * m_row;
-                const int4 dsc = mdesc_all[q];
-                const float* cg = a.cg + dsc.x;
-                const float* yv = ybase + el * a.d_y + dsc.y;
-                for (int j = 0; j < dsc.z; ++j) acc[u] = fmaf(__ldg(cg + j * d3), __ldg(yv + j), acc[u]);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int idx = idx0 + u * kHelperThreads;
-              if (idx < n_items) mbuf[idx] = acc[u];
-            }
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tab_ready[b]);
-      }
     }
   } else if (warp < kDtpWarp0) {
     // ===================================================================================== transform (warpgroup 2)
@@ -448,9 +379,32 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
     const int dt = threadIdx.x - kDtpWarp0 * 32;          // 0 .. 511
     const int set = (warp - kDtpWarp0) / kDtpSetWarps;    // which half of the k-tiles
     const int t = dt - set * kDtpSetThreads;              // 0 .. 255 inside the set
+    const int m_row = a.m_row, d_y = a.d_y;
+    // once per CTA: the group's CG blocks packed into shared memory and one descriptor per M-row entry
+    {
+      int off = 0;
+      for (int pi = 0; pi < a.n_paths; ++pi) {
+        const FPath& p = a.paths[pi];
+        const int n = p.d1 * p.d2 * d3;
+        for (int i = dt; i < n; i += kDtpThreads) cg_s[off + i] = __ldg(a.cg + p.cg_off + i);
+        off += n;
+      }
+      for (int q = dt; q < m_row; q += kDtpThreads) {
+        int pi = 0, cg0 = 0;
+        for (int j = 1; j < a.n_paths; ++j) if (q >= a.paths[j].m_off) pi = j;
+        for (int j = 0; j < pi; ++j) cg0 += a.paths[j].d1 * a.paths[j].d2 * d3;
+        const FPath& p = a.paths[pi];
+        const int r = q - p.m_off;
+        const int i = r / d3, k = r - i * d3;
+        mdesc[q] = make_int4(cg0 + i * p.d2 * d3 + k, p.y_off, p.d2, 0);
+      }
+    }
+    const float inv_m_row = 1.0f / (float)m_row;
     uint32_t it = 0, tile_it = 0;
     long long mb_prev = -1;
-    int b = 0;
+    const float* mbuf = nullptr;
+    const int* src_s = nullptr;
+    const int* dst_s = nullptr;
     for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
       const long long mb = tile / a.n_blocks;
       const long long row0 = mb * BM;
@@ -458,16 +412,39 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
       long long e1 = (row0 + BM - 1) / d3 + 1;
       if (e1 > a.E) e1 = a.E;
       const int n_e = (int)(e1 - e0);
-      if (mb != mb_prev) {                                 // tables of this row block (written one tile ahead)
-        if (mb_prev >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&tab_free[b]); }
+      if (mb != mb_prev) {
+        // ---- tables of this row block, double-buffered (a warp may start them while slower warps still read the previous
+        // block's): the edges' node rows and harmonics, then the coupling blocks M_p[e] = CG_p . y_e - operands in shared memory
         mb_prev = mb;
-        b = tile_it & 1;
-        mbar_wait(&tab_ready[b], (tile_it >> 1) & 1);
+        float* mw = reinterpret_cast<float*>(tab_base + (tile_it & 1) * a.tab_bytes);
+        float* ybuf = mw + a.m_buf_floats;
+        int* ss = reinterpret_cast<int*>(ybuf + a.y_buf_floats);
+        int* ds = ss + kMaxTileEdges;
         ++tile_it;
+        if (a.src != nullptr) {
+          for (int i = dt; i < n_e; i += kDtpThreads) {
+            ss[i] = (int)a.src[e0 + i];
+            ds[i] = a.dst != nullptr ? (int)a.dst[e0 + i] : 0;
+          }
+        }
+        for (int i = dt; i < n_e * d_y; i += kDtpThreads) ybuf[i] = __ldg(a.y + e0 * d_y + i);
+        named_barrier(1, kDtpThreads);
+        const int n_items = n_e * m_row;
+        for (int idx = dt; idx < n_items; idx += kDtpThreads) {
+          const int el = (int)(((float)idx + 0.5f) * inv_m_row);
+          const int q = idx - el * m_row;
+          const int4 dsc = mdesc[q];
+          const float* cgp = cg_s + dsc.x;
+          const float* yv = ybuf + el * d_y + dsc.y;
+          float m = 0.f;
+#pragma unroll
+          for (int j = 0; j < kMaxD; ++j)
+            if (j < dsc.z) m = fmaf(cgp[j * d3], yv[j], m);
+          mw[idx] = m;
+        }
+        named_barrier(1, kDtpThreads);
+        mbuf = mw; src_s = ss; dst_s = ds;
       }
-      const float* mbuf = reinterpret_cast<const float*>(tab_base + b * a.tab_bytes);
-      const int* src_s = reinterpret_cast<const int*>(mbuf + a.m_buf_floats);
-      const int* dst_s = src_s + kMaxTileEdges;
       for (int kt = 0; kt < k_tiles; ++kt, ++it) {
         if ((int)(it & 1) != set) continue;               // the two sets alternate k-tiles
         const FPath& p = a.paths[a.kt_path[kt]];
@@ -493,7 +470,6 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
         if (lane == 0) mbar_arrive(&raw_ready[s]);
       }
     }
-    if (mb_prev >= 0) { __syncwarp(); if (lane == 0) mbar_arrive(&tab_free[b]); }
   }
 
   tc_fence_before();
@@ -600,8 +576,11 @@ static int launch_fwd(const CUtensorMap& mh, const CUtensorMap& ml, const CUtens
   a.w_tile_off = S::kABytes + 2 * S::kBBytes;
   a.stage_bytes = (a.w_tile_off + a.w_box_rows * kRowBytes + 1023) & ~1023;
   a.m_buf_floats = (n_e_max * a.m_row + 31) & ~31;
-  a.tab_bytes = (a.m_buf_floats * 4 + kMetaInts * 4 + 127) & ~127;
-  const int fixed = S::kStoreBytes + 2 * a.tab_bytes + ((a.m_row * 16 + 127) & ~127) + S::kBarBytes;
+  a.y_buf_floats = (n_e_max * a.d_y + 31) & ~31;
+  a.cg_floats = 0;
+  for (int i = 0; i < a.n_paths; ++i) a.cg_floats += a.paths[i].d1 * a.paths[i].d2 * a.d3;
+  a.tab_bytes = ((a.m_buf_floats + a.y_buf_floats) * 4 + kMetaInts * 4 + 127) & ~127;
+  const int fixed = S::kStoreBytes + 2 * a.tab_bytes + ((a.m_row * 16 + 127) & ~127) + ((a.cg_floats * 4 + 127) & ~127) + S::kBarBytes;
   int stages = (S::kBudget - fixed) / a.stage_bytes;
   if (stages > S::kStagesTmem) stages = S::kStagesTmem;
   if (stages > kMaxStages) stages = kMaxStages;
@@ -717,7 +696,7 @@ static int fill_fargs(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_
   a.E = n_edges; a.M = n_edges * a.d3; a.d_y = h.d_y; a.W = h.w_numel; a.N = 0;
   if (a.M > 0x7fffffffLL) { set_error(std::string(who) + ": too many rows"); return EQF_ERR_UNSUPPORTED; }
   a.n_tile = a.n_blocks = 0; a.m_blocks = 0;
-  a.n_stages = a.stage_bytes = a.w_tile_off = a.w_box_rows = a.tab_bytes = a.m_buf_floats = 0;
+  a.n_stages = a.stage_bytes = a.w_tile_off = a.w_box_rows = a.tab_bytes = a.m_buf_floats = a.y_buf_floats = a.cg_floats = 0;
   { const char* e = std::getenv("EQF_FUSED_DBG_SKIP"); a.dbg_skip = e ? std::atoi(e) : 0; }
   return EQF_OK;
 }
