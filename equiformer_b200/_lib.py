@@ -124,6 +124,7 @@ SIGNATURES = {
     "eqf_gemm_tf32x3_wgrad_accumulate": (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int64,
                                                    c_void_p]),
     "eqf_dtp_linear_supported": (c_int32, [c_void_p, c_int32]),
+    "eqf_fused_set_timeline": (None, [c_void_p]),
     "eqf_dtp_group_forward": (c_int32, [c_void_p, POINTER(EqfEdgeOperands), c_int64, c_int32, c_void_p, c_void_p]),
     "eqf_dtp_linear_fwd": (c_int32, [c_void_p, POINTER(EqfEdgeOperands), c_int64, c_int32, c_void_p, c_int64, c_int64, c_void_p,
                                      c_int64, c_void_p, c_void_p]),

@@ -81,11 +81,18 @@ struct FArgs {
   int n_tile, n_blocks;
   long long m_blocks;
   int dbg_skip;          // measurement aid: bit 0 skips the DTP math, bit 1 the MMAs, bit 2 the transform (garbage results)
+  long long* dbg;        // optional clock64 timeline of CTA 0: dbg[role * 2048 + n] (eqf_fused_set_timeline)
   // shared-memory layout (bytes), fixed by the host: stages | store staging | 2 x (M rows + node rows) | descriptors | barriers
   int n_stages, stage_bytes, w_tile_off, w_box_rows, tab_bytes, m_buf_floats, y_buf_floats, cg_floats;
   unsigned char kt_path[kMaxKTiles];   // path of each 32-channel k-tile, in channel order
   FPath paths[kMaxPaths];
 };
+
+// timeline of CTA 0: role 0 TMA producer, 1 MMA issuer, 2 transform (warp 8), 3 epilogue (warp 0), 4 / 5 DTP set 0 / 1 (first warp)
+__device__ __forceinline__ void stamp(const FArgs& a, int role, int& n) {
+  if (a.dbg != nullptr && blockIdx.x == 0 && n < 2048) a.dbg[role * 2048 + n] = clock64();
+  ++n;
+}
 
 template <int BN, bool STACK>
 struct FSmem {
@@ -223,12 +230,14 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
     // ===================================================================================== epilogue (warpgroup 0)
     reg_alloc<88>();
     uint32_t acc_it = 0, chunk_it = 0;
+    int n_stamp = 0;
     for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
       const long long mb = tile / a.n_blocks;
       const int nb = (int)(tile % a.n_blocks);
       const int ab = acc_it & 1;
       const uint32_t aph = (acc_it >> 1) & 1;
       mbar_wait(&tmem_full[ab], aph);
+      if (threadIdx.x == 0) stamp(a, 3, n_stamp);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * kAcc);
       const long long row0 = mb * BM + warp * 32;
@@ -270,6 +279,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[ab]);
+      if (threadIdx.x == 0) stamp(a, 3, n_stamp);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp < kTransformWarp0) {
@@ -278,6 +288,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
     if (warp == kProducerWarp) {
       if (lane == 0) {
         uint32_t it = 0;
+        int n_stamp = 0;
         const uint32_t tx = (uint32_t)(2 * a.n_tile * kRowBytes) + (w_tma ? (uint32_t)(a.w_box_rows * kRowBytes) : 0u);
         for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
           const long long mb = tile / a.n_blocks;
@@ -287,6 +298,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
             const int s = it % kStages;
             const uint32_t ph = (it / kStages) & 1;
             mbar_wait(&empty[s], ph ^ 1);
+            stamp(a, 0, n_stamp);
             uint8_t* st = stage_base + (size_t)s * stage_bytes;
             mbar_expect_tx(&full[s], tx);
             tma_load_2d(st + S::kABytes, &map_bhi, kt * BKT, nb * a.n_tile, &full[s]);
@@ -303,6 +315,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
         const uint32_t idesc = instr_desc(a.n_tile);
         const uint32_t idesc2 = instr_desc(2 * a.n_tile);          // STACK: [b_hi | b_lo] as one operand
         uint32_t it = 0, acc_it = 0;
+        int n_stamp = 0;
         for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
           const int ab = acc_it & 1;
           const uint32_t aph = (acc_it >> 1) & 1;
@@ -313,7 +326,9 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
             const int s = it % kStages;
             const uint32_t ph = (it / kStages) & 1;
             mbar_wait(&full[s], ph);
+            stamp(a, 1, n_stamp);
             mbar_wait(&a_ready[s], ph);
+            stamp(a, 1, n_stamp);
             tc_fence_after();
             const uint32_t st = smem_u32(stage_base + (size_t)s * stage_bytes);
             const uint64_t b_hi = smem_desc_sw128(st + S::kABytes), b_lo = smem_desc_sw128(st + S::kABytes + S::kBBytes);
@@ -333,6 +348,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
               }
             }
             umma_commit(&empty[s]);
+            stamp(a, 1, n_stamp);
           }
           umma_commit(&tmem_full[ab]);
         }
@@ -344,11 +360,14 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t it = 0;
+    int n_stamp = 0;
+    const bool stamper = warp == kTransformWarp0 && lane == 0;
     for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
       for (int kt = 0; kt < k_tiles; ++kt, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(&raw_ready[s], ph);
+        if (stamper) stamp(a, 2, n_stamp);
         if (!(a.dbg_skip & 4)) {
           const uint32_t rbase = smem_u32(stage_base + (size_t)s * stage_bytes) + (uint32_t)row * (uint32_t)kRowBytes;
           float hi[BKT], lo[BKT];
@@ -372,6 +391,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready[s]);
+        if (stamper) stamp(a, 2, n_stamp);
       }
     }
   } else {
@@ -401,6 +421,8 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
     }
     const float inv_m_row = 1.0f / (float)m_row;
     uint32_t it = 0, tile_it = 0;
+    int n_stamp = 0;
+    const bool stamper = (t == 0);                       // first thread of each set: roles 4 and 5
     long long mb_prev = -1;
     const float* mbuf = nullptr;
     const int* src_s = nullptr;
@@ -416,6 +438,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
         // ---- tables of this row block, double-buffered (a warp may start them while slower warps still read the previous
         // block's): the edges' node rows and harmonics, then the coupling blocks M_p[e] = CG_p . y_e - operands in shared memory
         mb_prev = mb;
+        if (stamper) stamp(a, 4 + set, n_stamp);
         float* mw = reinterpret_cast<float*>(tab_base + (tile_it & 1) * a.tab_bytes);
         float* ybuf = mw + a.m_buf_floats;
         int* ss = reinterpret_cast<int*>(ybuf + a.y_buf_floats);
@@ -429,6 +452,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
         }
         for (int i = dt; i < n_e * d_y; i += kDtpThreads) ybuf[i] = __ldg(a.y + e0 * d_y + i);
         named_barrier(1, kDtpThreads);
+        if (stamper) stamp(a, 4 + set, n_stamp);
         const int n_items = n_e * m_row;
         for (int idx = dt; idx < n_items; idx += kDtpThreads) {
           const int el = (int)(((float)idx + 0.5f) * inv_m_row);
@@ -443,6 +467,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
           mw[idx] = m;
         }
         named_barrier(1, kDtpThreads);
+        if (stamper) stamp(a, 4 + set, n_stamp);
         mbuf = mw; src_s = ss; dst_s = ds;
       }
       for (int kt = 0; kt < k_tiles; ++kt, ++it) {
@@ -452,12 +477,14 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(&empty[s], ph ^ 1);
+        if (stamper) stamp(a, 4 + set, n_stamp);
         const uint32_t raw_addr = smem_u32(stage_base + (size_t)s * stage_bytes);
         uint32_t w_tile = 0;
         if (w_tma) {
           mbar_wait(&full[s], ph);                        // the k-tile's radial-weight box has landed
           w_tile = raw_addr + (uint32_t)a.w_tile_off;
         }
+        if (stamper) stamp(a, 4 + set, n_stamp);
         if (!(a.dbg_skip & 1)) {
           switch (d3) {
             case 1: dtp_ktile_d1<1>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
@@ -468,6 +495,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_ready[s]);
+        if (stamper) stamp(a, 4 + set, n_stamp);
       }
     }
   }
@@ -663,6 +691,10 @@ extern "C" int eqf_dtp_linear_supported(const EqfPlan* plan, int32_t group) {
   return fused::collect_paths(plan, group, a) > 0 ? 1 : 0;
 }
 
+static long long* g_fused_dbg = nullptr;
+// debugging aid: device buffer of 6 * 2048 int64 that receives CTA 0's clock64 timeline on the next fused launches (NULL = off)
+extern "C" void eqf_fused_set_timeline(long long* device_buffer) { g_fused_dbg = device_buffer; }
+
 // operands of one output group -> FArgs (shared by the fused and the group-forward entry points)
 static int fill_fargs(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_edges, int32_t group, eqf::fused::FArgs& a,
                       const char* who) {
@@ -698,6 +730,7 @@ static int fill_fargs(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_
   a.n_tile = a.n_blocks = 0; a.m_blocks = 0;
   a.n_stages = a.stage_bytes = a.w_tile_off = a.w_box_rows = a.tab_bytes = a.m_buf_floats = a.y_buf_floats = a.cg_floats = 0;
   { const char* e = std::getenv("EQF_FUSED_DBG_SKIP"); a.dbg_skip = e ? std::atoi(e) : 0; }
+  a.dbg = g_fused_dbg;
   return EQF_OK;
 }
 

@@ -738,13 +738,17 @@ class GraphAttentionTransformer(torch.nn.Module):
                                   edges_sorted=True)
 
     def forward_edges(self, pos, batch, node_atom, edge_src, edge_dst, graph=None, n_graphs=None,
-                      edges_sorted: bool = False) -> torch.Tensor:
+                      edges_sorted: bool = False, edge_vec=None) -> torch.Tensor:
         """Everything after neighbour search (ref :868-899); free of host synchronisation when ``graph`` (the CSR of
         the destination-sorted edge list) and ``n_graphs`` are supplied, so it can be captured in a CUDA graph.
         Contract: the kernels need the edge list sorted by destination.  A caller-supplied ``graph`` carries its own
         order; otherwise the list is checked (one host synchronisation) and, when unsorted, everything per-edge is
-        permuted - unless the caller vouches for the order with ``edges_sorted=True``."""
-        edge_vec = pos.index_select(0, edge_src) - pos.index_select(0, edge_dst)
+        permuted - unless the caller vouches for the order with ``edges_sorted=True``.  ``edge_vec`` overrides
+        ``pos[src] - pos[dst]`` (periodic cells: the caller adds the image offsets; needs a sorted edge list)."""
+        if edge_vec is None:
+            edge_vec = pos.index_select(0, edge_src) - pos.index_select(0, edge_dst)
+        elif not (edges_sorted or graph is not None):
+            raise ValueError("edge_vec needs a destination-sorted edge list (edges_sorted=True or a graph)")
         edge_sh = o3.spherical_harmonics(l=self.irreps_edge_attr, x=edge_vec, normalize=True, normalization="component")
         edge_length = edge_vec.norm(dim=1)
         atom_embedding, _attr, _onehot = self.atom_embed(self._atom_remap[node_atom])

@@ -133,8 +133,9 @@ def _check_yw(plan: DtpPlan, y, w, E: Optional[int] = None):
 class KernelProfile:
     """Optional per-launch accounting used by ``bench.py``: launch count and CUDA-event timing per kernel name.
 
-    ``records`` holds ``(name, algorithmic_bytes, start_event, end_event)`` for every launch of one of *our* kernels
-    while the profile is installed (events are recorded on the launching stream, around the launch only).
+    ``records`` holds ``(name, algorithmic_bytes, start_event, end_event, flops)`` for every launch of one of *our*
+    kernels while the profile is installed (events are recorded on the launching stream, around the launch only);
+    ``flops`` = useful multiply-adds x 2 of a contraction kernel (0 for streaming kernels).
     """
 
     def __init__(self, time_events: bool = True, presleep_cycles: int = 0):
@@ -147,12 +148,13 @@ class KernelProfile:
 
     def summary(self):
         out = {}
-        for name, nbytes, s, e in self.records:
+        for name, nbytes, s, e, flops in self.records:
             ms = s.elapsed_time(e)
-            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0})
+            d = out.setdefault(name, {"launches": 0, "ms": 0.0, "bytes": 0, "flops": 0})
             d["launches"] += 1
             d["ms"] += ms
             d["bytes"] += nbytes
+            d["flops"] += flops
         return out
 
 
@@ -160,7 +162,7 @@ PROFILE: Optional[KernelProfile] = None
 
 
 @contextlib.contextmanager
-def _kernel(name: str, nbytes: int):
+def _kernel(name: str, nbytes: int, flops: int = 0):
     prof = PROFILE
     if prof is None:
         yield
@@ -176,7 +178,7 @@ def _kernel(name: str, nbytes: int):
     s.record()
     yield
     e.record()
-    prof.records.append((name, nbytes, s, e))
+    prof.records.append((name, nbytes, s, e, flops))
 
 
 def _dtp_bytes(plan: DtpPlan, E: int, shared: bool, kind: str) -> int:
@@ -601,7 +603,7 @@ def dtp_linear_fwd_raw(plan: DtpPlan, group: int, xs, y, w, Wt: torch.Tensor, ga
     op = _operands(plan, xs, y, w, None, shared, gather, w_offset)
     d_in = sum((2 * l + 1) * m for l, m in plan.in1_blocks)
     nbytes = 4 * (E * (d_in + plan.d_y + (0 if shared else K) + d3 * N) + K * N)
-    with torch.cuda.device(y.device), _kernel("dtp_linear_fwd", nbytes):
+    with torch.cuda.device(y.device), _kernel("dtp_linear_fwd", nbytes, 2 * E * d3 * K * N):
         rc = _lib.load().eqf_dtp_linear_fwd(plan.handle, ctypes.byref(op), E, group, Wt.data_ptr(), N, Wt.stride(0),
                                             C.data_ptr(), N, split.data_ptr(), _stream())
     _lib.check(rc, "eqf_dtp_linear_fwd")
@@ -1127,7 +1129,8 @@ def gemm_tf32x3_raw(A: torch.Tensor, Bt: torch.Tensor, b_is_kn: bool = False) ->
     if split is None or split.numel() < need:
         split = torch.empty(max(need, 1 << 20), device=A.device, dtype=torch.float32)
         _TF32X3_SPLIT[A.device] = split
-    with torch.cuda.device(A.device), _kernel(_gemm_name("gemm_tf32x3", 1, M, N, K), 4 * (A.numel() + Bt.numel() + C.numel())):
+    with torch.cuda.device(A.device), _kernel(_gemm_name("gemm_tf32x3", 1, M, N, K), 4 * (A.numel() + Bt.numel() + C.numel()),
+                                              2 * M * N * K):
         rc = _lib.load().eqf_gemm_tf32x3(A.data_ptr(), Bt.data_ptr(), C.data_ptr(), M, N, K, lda, Bt.stride(0), N,
                                          1 if b_is_kn else 0, split.data_ptr(), _stream())
     _lib.check(rc, "eqf_gemm_tf32x3")
@@ -1147,13 +1150,14 @@ def gemm_tf32x3_wgrad_raw(A: torch.Tensor, G: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     if not _DETERMINISTIC:      # slices add into W through TMA reduce-adds: one launch, no partial buffer / column sum
         W = torch.empty((K1, N), device=A.device, dtype=torch.float32)
-        with torch.cuda.device(A.device), _kernel(_gemm_name("gemm_tf32x3_wgrad", 2, K1, N, R), 4 * (A.numel() + G.numel() + W.numel())):
+        with torch.cuda.device(A.device), _kernel(_gemm_name("gemm_tf32x3_wgrad", 2, K1, N, R), 4 * (A.numel() + G.numel() + W.numel()),
+                                                  2 * R * K1 * N):
             rc = lib.eqf_gemm_tf32x3_wgrad_accumulate(A.data_ptr(), G.data_ptr(), W.data_ptr(), R, K1, N, lda, ldg, _stream())
         _lib.check(rc, "eqf_gemm_tf32x3_wgrad_accumulate")
         return W
     slices = int(lib.eqf_gemm_tf32x3_wgrad_slices(R, K1, N))
     part = torch.empty((max(slices, 1), K1, N), device=A.device, dtype=torch.float32)
-    with torch.cuda.device(A.device), _kernel("gemm_tf32x3_wgrad", 4 * (A.numel() + G.numel() + 2 * part.numel())):
+    with torch.cuda.device(A.device), _kernel("gemm_tf32x3_wgrad", 4 * (A.numel() + G.numel() + 2 * part.numel()), 2 * R * K1 * N):
         rc = lib.eqf_gemm_tf32x3_wgrad(A.data_ptr(), G.data_ptr(), part.data_ptr(), R, K1, N, lda, ldg, _stream())
     _lib.check(rc, "eqf_gemm_tf32x3_wgrad")
     if slices == 1:

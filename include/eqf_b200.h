@@ -178,6 +178,8 @@ void eqf_gemm_tf32x3_set_timeline(long long* device_buffer);
  * [E * (2 l3 + 1)][N], row stride ldc; `split` = device scratch of 2 * N * K floats (hi / lo planes of Wt).
  * eqf_dtp_linear_supported: 1 when the group qualifies (path multiplicities % 32 == 0, tables fit shared memory). */
 int eqf_dtp_linear_supported(const EqfPlan* plan, int32_t group);
+/* debugging aid: device buffer of 6 * 2048 int64 receiving CTA 0's clock64 timeline of later fused launches (NULL = off) */
+void eqf_fused_set_timeline(long long* device_buffer);
 /* out[e][k][:K] = DTP_group(x, y; w): ONE output group of the product written to HBM, planar [E][2 l3 + 1][K] - the
  * operand of a linear too wide to fuse (N > 128 columns; e.g. the 224-channel 0e group in front of sep_alpha | lin). */
 int eqf_dtp_group_forward(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_edges, int32_t group, float* out,

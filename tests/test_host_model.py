@@ -188,3 +188,26 @@ def test_dot_product_attention_rescale_degree_divides_by_the_average_degree():
     ref = R.dot_product_attention(params, "dpa", ir, e3.parse_irreps(sh), e3.parse_irreps(head), 4, ir, x, src, dst, sh_e,
                                   rbf, rescale_degree=True)
     assert rel_err(out, ref) < 1e-10
+
+
+def test_bucketed_step_padding_leaves_loss_and_gradients_unchanged():
+    """``graphs.BucketedForwardBackward`` pads atoms / edges to bucket sizes with a dummy molecule whose energy never
+    enters the loss: loss and every parameter gradient equal the unpadded step (kernels emulated, no capture)."""
+    from equiformer_b200.graphs import BucketedForwardBackward
+    from equiformer_b200.parallel import FlatGradAllReduce
+    model = _build("graph_attention_transformer_nonlinear_l2")
+    pos, batch, z = molecules([5, 7, 4], seed=3, dtype=torch.float64)
+    tgt = torch.tensor([[0.3], [-1.0], [2.0]], dtype=torch.float64)
+    loss_fn = lambda o, t: (o - t).abs().mean()
+    with emulated_kernels():
+        out = model(f_in=None, pos=pos, batch=batch, node_atom=z, n_graphs=3)
+        l0 = loss_fn(out, tgt)
+        g0 = torch.autograd.grad(l0, list(model.parameters()), allow_unused=True)
+        bucket = FlatGradAllReduce(model.parameters())
+        bfb = BucketedForwardBackward(model, loss_fn, bucket, 5.0, atom_quantum=8, edge_quantum=64, capture=False)
+        l1 = bfb(pos, batch, z, tgt)
+    assert list(bfb._cache) == [(24, 128, 3)]          # 16 atoms + >= 2 dummies -> 24; 106 edges -> 128
+    assert rel_err(l1, l0) < 1e-12
+    for p, g in zip(model.parameters(), g0):
+        if g is not None:
+            assert rel_err(p.grad, g) < 1e-10
