@@ -127,6 +127,8 @@ __device__ __forceinline__ void dtp_ktile(const FArgs& a, const FPath& p, int ch
   const float* xb = a.x2[p.xb];
   const long long row_floats = (long long)D1 * p.mul;
   const unsigned long long nz = p.nz;
+  // node tables (gathered, re-read by every path and every neighbour) stay in L2; per-edge blocks are a read-once stream
+  const uint64_t pol = gather ? l2_policy_evict_last() : l2_policy_evict_first();
   for (int el = t >> 3; el < n_e; el += kDtpSetThreads / 8) {
     const long long e = e0 + el;
     float4 wv = w_tile != 0 ? lds128(w_tile + (uint32_t)el * 128u + (uint32_t)c8 * 16u) : ld4(a.w + p.w_off + ch);
@@ -135,11 +137,11 @@ __device__ __forceinline__ void dtp_ktile(const FArgs& a, const FPath& p, int ch
     const float* xp = xa + rs * row_floats + ch;
     float4 x[D1];
 #pragma unroll
-    for (int i = 0; i < D1; ++i) x[i] = ld4(xp + i * p.mul);
+    for (int i = 0; i < D1; ++i) x[i] = ldg128_hint(xp + i * p.mul, pol);
     if (xb != nullptr) {
       const float* xq = xb + (long long)dst_s[el] * row_floats + ch;
 #pragma unroll
-      for (int i = 0; i < D1; ++i) addv(x[i], ld4(xq + i * p.mul));
+      for (int i = 0; i < D1; ++i) addv(x[i], ldg128_hint(xq + i * p.mul, pol));
     }
 #pragma unroll
     for (int i = 0; i < D1; ++i) mulv(x[i], wv);
@@ -236,7 +238,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
       const int nb = (int)(tile % a.n_blocks);
       const int ab = acc_it & 1;
       const uint32_t aph = (acc_it >> 1) & 1;
-      mbar_wait(&tmem_full[ab], aph);
+      mbar_wait_warp(&tmem_full[ab], aph);
       if (threadIdx.x == 0) stamp(a, 3, n_stamp);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * kAcc);
@@ -290,6 +292,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
         uint32_t it = 0;
         int n_stamp = 0;
         const uint32_t tx = (uint32_t)(2 * a.n_tile * kRowBytes) + (w_tma ? (uint32_t)(a.w_box_rows * kRowBytes) : 0u);
+        const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
         for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
           const long long mb = tile / a.n_blocks;
           const int nb = (int)(tile % a.n_blocks);
@@ -301,11 +304,11 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
             stamp(a, 0, n_stamp);
             uint8_t* st = stage_base + (size_t)s * stage_bytes;
             mbar_expect_tx(&full[s], tx);
-            tma_load_2d(st + S::kABytes, &map_bhi, kt * BKT, nb * a.n_tile, &full[s]);
-            tma_load_2d(st + S::kABytes + S::kBBytes, &map_blo, kt * BKT, nb * a.n_tile, &full[s]);
-            if (w_tma) {
+            tma_load_2d_hint(st + S::kABytes, &map_bhi, kt * BKT, nb * a.n_tile, &full[s], pol_keep);
+            tma_load_2d_hint(st + S::kABytes + S::kBBytes, &map_blo, kt * BKT, nb * a.n_tile, &full[s], pol_keep);
+            if (w_tma) {          // read once: must not evict the node tables
               const FPath& p = a.paths[a.kt_path[kt]];
-              tma_load_2d(st + a.w_tile_off, &map_w, p.w_off + (kt * BKT - p.koff), e0, &full[s]);
+              tma_load_2d_hint(st + a.w_tile_off, &map_w, p.w_off + (kt * BKT - p.koff), e0, &full[s], pol_stream);
             }
           }
         }
@@ -366,7 +369,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
       for (int kt = 0; kt < k_tiles; ++kt, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&raw_ready[s], ph);
+        mbar_wait_warp(&raw_ready[s], ph);
         if (stamper) stamp(a, 2, n_stamp);
         if (!(a.dbg_skip & 4)) {
           const uint32_t rbase = smem_u32(stage_base + (size_t)s * stage_bytes) + (uint32_t)row * (uint32_t)kRowBytes;
@@ -476,12 +479,12 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
         const int ch0 = kt * BKT - p.koff;
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+        mbar_wait_warp(&empty[s], ph ^ 1);
         if (stamper) stamp(a, 4 + set, n_stamp);
         const uint32_t raw_addr = smem_u32(stage_base + (size_t)s * stage_bytes);
         uint32_t w_tile = 0;
         if (w_tma) {
-          mbar_wait(&full[s], ph);                        // the k-tile's radial-weight box has landed
+          mbar_wait_warp(&full[s], ph);                   // the k-tile's radial-weight box has landed
           w_tile = raw_addr + (uint32_t)a.w_tile_off;
         }
         if (stamper) stamp(a, 4 + set, n_stamp);
