@@ -397,11 +397,22 @@ def run_ours(args):
         return loss
 
     graphed = None
-    use_graph = args.graph and wl != "md17_l3"      # the MD17 step differentiates through a backward: eager (launch bound)
+    use_graph = args.graph
     if use_graph:
         if wl == "qm9":
             cls = BucketedForwardBackward if args.stream > 1 else GraphedForwardBackward
             graphed = cls(model, l1, bucket, max_radius=5.0)
+        elif wl == "md17_l3":
+            # the whole energy + force step - a backward inside the forward and the backward of that - in one CUDA graph
+            def captured_md17(pos, target, ftarget, batch, z, src, dst, row_ptr):
+                csr = ops.Graph.__new__(ops.Graph)
+                csr.n_nodes, csr.n_edges, csr.perm = int(batch.shape[0]), int(src.numel()), None
+                csr.src, csr.dst, csr.row_ptr = src, dst, row_ptr
+                csr._src_perm = csr._src_row_ptr = None
+                p = pos.detach().requires_grad_(True)
+                energy, forces = model.forward_edges(z, p, batch, src, dst, graph=csr, n_graphs=target.shape[0])
+                return 1.0 * l2mae(energy, target) + 100.0 * l2mae(forces, ftarget)
+            graphed = GraphedStep(captured_md17, bucket)
         else:
             def captured(edge_vec, pos, target, batch, z, tags, src, dst, row_ptr):
                 csr = ops.Graph.__new__(ops.Graph)
@@ -418,6 +429,11 @@ def run_ours(args):
     def step_graph(d):
         if wl == "qm9":
             loss = graphed(d["pos"], d["batch"], d["z"], d["target"])     # neighbour search (eager) + replay
+        elif wl == "md17_l3":
+            from equiformer_b200.graph import radius_graph_csr
+            edge, row_ptr = radius_graph_csr(d["pos"], 5.0, d["batch"], max_num_neighbors=1000)
+            loss = graphed((int(d["pos"].shape[0]), int(edge.shape[1]), int(d["target"].shape[0])),
+                           [d["pos"], d["target"], d["ftarget"], d["batch"], d["z"], edge[0], edge[1], row_ptr])
         else:
             src, dst, edge_vec = pbc_graph(d)                             # periodic neighbour list (eager) + replay
             n = d["batch"].shape[0]

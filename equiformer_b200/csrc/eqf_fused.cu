@@ -127,8 +127,7 @@ __device__ __forceinline__ void dtp_ktile(const FArgs& a, const FPath& p, int ch
   const float* xb = a.x2[p.xb];
   const long long row_floats = (long long)D1 * p.mul;
   const unsigned long long nz = p.nz;
-  // node tables (gathered, re-read by every path and every neighbour) stay in L2; per-edge blocks are a read-once stream
-  const uint64_t pol = gather ? l2_policy_evict_last() : l2_policy_evict_first();
+#pragma unroll 1
   for (int el = t >> 3; el < n_e; el += kDtpSetThreads / 8) {
     const long long e = e0 + el;
     float4 wv = w_tile != 0 ? lds128(w_tile + (uint32_t)el * 128u + (uint32_t)c8 * 16u) : ld4(a.w + p.w_off + ch);
@@ -137,11 +136,11 @@ __device__ __forceinline__ void dtp_ktile(const FArgs& a, const FPath& p, int ch
     const float* xp = xa + rs * row_floats + ch;
     float4 x[D1];
 #pragma unroll
-    for (int i = 0; i < D1; ++i) x[i] = ldg128_hint(xp + i * p.mul, pol);
+    for (int i = 0; i < D1; ++i) x[i] = ld4(xp + i * p.mul);
     if (xb != nullptr) {
       const float* xq = xb + (long long)dst_s[el] * row_floats + ch;
 #pragma unroll
-      for (int i = 0; i < D1; ++i) addv(x[i], ldg128_hint(xq + i * p.mul, pol));
+      for (int i = 0; i < D1; ++i) addv(x[i], ld4(xq + i * p.mul));
     }
 #pragma unroll
     for (int i = 0; i < D1; ++i) mulv(x[i], wv);
@@ -171,7 +170,7 @@ __device__ __forceinline__ void dtp_ktile_d1(const FArgs& a, const FPath& p, int
   }
 }
 
-template <int BN, bool STACK>
+template <int BN, bool STACK, int D3>
 __global__ void __launch_bounds__(kThreads, 1)
 dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_w,
@@ -200,7 +199,8 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_tiles = a.K / BKT;
-  const int d3 = a.d3;
+  constexpr int d3 = D3;        // compile-time output degree: the kernel carries the D1 variants of one degree only (the
+                                // all-degrees build was 142 KB of code per kernel - instruction-cache misses everywhere)
   const long long n_tiles_total = a.m_blocks * a.n_blocks;
   const bool w_tma = !a.w_shared;
 
@@ -238,7 +238,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
       const int nb = (int)(tile % a.n_blocks);
       const int ab = acc_it & 1;
       const uint32_t aph = (acc_it >> 1) & 1;
-      mbar_wait_warp(&tmem_full[ab], aph);
+      mbar_wait(&tmem_full[ab], aph);
       if (threadIdx.x == 0) stamp(a, 3, n_stamp);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * kAcc);
@@ -292,7 +292,6 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
         uint32_t it = 0;
         int n_stamp = 0;
         const uint32_t tx = (uint32_t)(2 * a.n_tile * kRowBytes) + (w_tma ? (uint32_t)(a.w_box_rows * kRowBytes) : 0u);
-        const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
         for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
           const long long mb = tile / a.n_blocks;
           const int nb = (int)(tile % a.n_blocks);
@@ -304,11 +303,11 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
             stamp(a, 0, n_stamp);
             uint8_t* st = stage_base + (size_t)s * stage_bytes;
             mbar_expect_tx(&full[s], tx);
-            tma_load_2d_hint(st + S::kABytes, &map_bhi, kt * BKT, nb * a.n_tile, &full[s], pol_keep);
-            tma_load_2d_hint(st + S::kABytes + S::kBBytes, &map_blo, kt * BKT, nb * a.n_tile, &full[s], pol_keep);
-            if (w_tma) {          // read once: must not evict the node tables
+            tma_load_2d(st + S::kABytes, &map_bhi, kt * BKT, nb * a.n_tile, &full[s]);
+            tma_load_2d(st + S::kABytes + S::kBBytes, &map_blo, kt * BKT, nb * a.n_tile, &full[s]);
+            if (w_tma) {
               const FPath& p = a.paths[a.kt_path[kt]];
-              tma_load_2d_hint(st + a.w_tile_off, &map_w, p.w_off + (kt * BKT - p.koff), e0, &full[s], pol_stream);
+              tma_load_2d(st + a.w_tile_off, &map_w, p.w_off + (kt * BKT - p.koff), e0, &full[s]);
             }
           }
         }
@@ -369,7 +368,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
       for (int kt = 0; kt < k_tiles; ++kt, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
-        mbar_wait_warp(&raw_ready[s], ph);
+        mbar_wait(&raw_ready[s], ph);
         if (stamper) stamp(a, 2, n_stamp);
         if (!(a.dbg_skip & 4)) {
           const uint32_t rbase = smem_u32(stage_base + (size_t)s * stage_bytes) + (uint32_t)row * (uint32_t)kRowBytes;
@@ -479,23 +478,16 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
         const int ch0 = kt * BKT - p.koff;
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
-        mbar_wait_warp(&empty[s], ph ^ 1);
+        mbar_wait(&empty[s], ph ^ 1);
         if (stamper) stamp(a, 4 + set, n_stamp);
         const uint32_t raw_addr = smem_u32(stage_base + (size_t)s * stage_bytes);
         uint32_t w_tile = 0;
         if (w_tma) {
-          mbar_wait_warp(&full[s], ph);                   // the k-tile's radial-weight box has landed
+          mbar_wait(&full[s], ph);                        // the k-tile's radial-weight box has landed
           w_tile = raw_addr + (uint32_t)a.w_tile_off;
         }
         if (stamper) stamp(a, 4 + set, n_stamp);
-        if (!(a.dbg_skip & 1)) {
-          switch (d3) {
-            case 1: dtp_ktile_d1<1>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
-            case 3: dtp_ktile_d1<3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
-            case 5: dtp_ktile_d1<5>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
-            default: dtp_ktile_d1<7>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
-          }
-        }
+        if (!(a.dbg_skip & 1)) dtp_ktile_d1<D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile);
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_ready[s]);
         if (stamper) stamp(a, 4 + set, n_stamp);
@@ -597,8 +589,8 @@ __global__ void split_transpose_kernel(const float* __restrict__ w, long long ld
   }
 }
 
-template <int BN, bool STACK>
-static int launch_fwd(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mc, const CUtensorMap& mw, FArgs& a,
+template <int BN, bool STACK, int D3>
+static int launch_fwd_d3(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mc, const CUtensorMap& mw, FArgs& a,
                       cudaStream_t s) {
   using S = FSmem<BN, STACK>;
   // shared-memory layout: stages (raw A | B hi | B lo | radial-weight box) | store staging | 2 table buffers | descriptors | barriers
@@ -623,7 +615,7 @@ static int launch_fwd(const CUtensorMap& mh, const CUtensorMap& ml, const CUtens
   {
     std::lock_guard<std::mutex> lock(mtx);
     if (total > attr_bytes) {
-      cudaError_t e = cudaFuncSetAttribute(dtp_gemm_fwd_kernel<BN, STACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
+      cudaError_t e = cudaFuncSetAttribute(dtp_gemm_fwd_kernel<BN, STACK, D3>, cudaFuncAttributeMaxDynamicSharedMemorySize, total);
       if (e != cudaSuccess) return check_cuda(e, "dtp_gemm_fwd smem attribute");
       attr_bytes = total;
     }
@@ -631,8 +623,19 @@ static int launch_fwd(const CUtensorMap& mh, const CUtensorMap& ml, const CUtens
   const int sms = device_sms();
   const long long tiles = a.m_blocks * a.n_blocks;
   const int grid = (int)(tiles < sms ? tiles : sms);
-  dtp_gemm_fwd_kernel<BN, STACK><<<grid, kThreads, total, s>>>(mh, ml, mc, mw, a);
+  dtp_gemm_fwd_kernel<BN, STACK, D3><<<grid, kThreads, total, s>>>(mh, ml, mc, mw, a);
   return check_cuda(cudaGetLastError(), "dtp_gemm_fwd_kernel launch");
+}
+
+template <int BN, bool STACK>
+static int launch_fwd(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mc, const CUtensorMap& mw, FArgs& a,
+                      cudaStream_t s) {
+  switch (a.d3) {
+    case 1: return launch_fwd_d3<BN, STACK, 1>(mh, ml, mc, mw, a, s);
+    case 3: return launch_fwd_d3<BN, STACK, 3>(mh, ml, mc, mw, a, s);
+    case 5: return launch_fwd_d3<BN, STACK, 5>(mh, ml, mc, mw, a, s);
+    default: return launch_fwd_d3<BN, STACK, 7>(mh, ml, mc, mw, a, s);
+  }
 }
 
 // paths of output group `group`, in channel order; returns the number of paths or a negative error

@@ -65,12 +65,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                  : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   } while (!done);
 }
-// whole-warp wait: one lane polls, __syncwarp releases the others (round 2: 128 - 256 threads polling one barrier word cost
-// 450-900 cycles per satisfied wait in the fused kernel's timeline, profiles/r2_fused_fwd_v3_timeline_l2_dtp1.txt)
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
-  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
-  __syncwarp();
-}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
@@ -273,7 +267,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
-        mbar_wait_warp(&full[s], ph);
+        mbar_wait(&full[s], ph);
         if (t == 0) stamp(p, 2, n_stamp);
         // loads are batched ahead of the stores (explicit ld/st.shared: with generic pointers the compiler serialised
         // load -> use -> store and the transform, not the tensor pipe, set the pace)
@@ -302,7 +296,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const int nb = (int)(tile % p.n_blocks);
       const int a = acc_it & 1;
       const uint32_t aph = (acc_it >> 1) & 1;
-      mbar_wait_warp(&tmem_full[a], aph);
+      mbar_wait(&tmem_full[a], aph);
       if (threadIdx.x == 0) stamp(p, 3, n_stamp);
       tc_fence_after();
       // TMEM -> registers -> swizzled staging rows (this warp's 32 rows x 32 columns) -> TMA store; two staging buffers
@@ -536,7 +530,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
-        mbar_wait_warp(&full[s], ph);
+        mbar_wait(&full[s], ph);
         if (stamper) stamp(p, 2, n_stamp);
         if (p.dbg_skip & 1) {
           tc_fence_before();
@@ -576,7 +570,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       const int nb = (int)(tile % p.n_blocks);
       const int a = acc_it & 1;
       const uint32_t aph = (acc_it >> 1) & 1;
-      mbar_wait_warp(&tmem_full[a], aph);
+      mbar_wait(&tmem_full[a], aph);
       if (threadIdx.x == 0) stamp(p, 3, n_stamp);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kAcc);
@@ -851,7 +845,7 @@ gemm_tf32x3_ts2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
-        mbar_wait_warp(&full[s], ph);
+        mbar_wait(&full[s], ph);
         if (stamper) stamp(p, 2, n_stamp);
         if (!(p.dbg_skip & 1)) {
           const uint32_t rbase = smem_u32(stage_base + (size_t)s * S::kStageBytes) + (uint32_t)row * (uint32_t)kRowBytesT;
@@ -887,7 +881,7 @@ gemm_tf32x3_ts2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       const int nb = (int)(tile % p.n_blocks);
       const int a = acc_it & 1;
       const uint32_t aph = (acc_it >> 1) & 1;
-      mbar_wait_warp(&tmem_full[a], aph);
+      mbar_wait(&tmem_full[a], aph);
       if (threadIdx.x == 0) stamp(p, 3, n_stamp);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kAcc);
@@ -1168,7 +1162,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     for (int kt = 0; kt < k_tiles; ++kt) {
       const int s = kt % kStages;
       const uint32_t ph = (kt / kStages) & 1;
-      mbar_wait_warp(&full[s], ph);
+      mbar_wait(&full[s], ph);
       const uint32_t st = smem_u32(stage_base_of(smem, s, S::kStageBytes));
       for (int base = (p.dbg_skip & 1) ? n_piece : 0; base < n_piece; base += 4 * kTransformThreads) {
         float4 v[4];
@@ -1189,7 +1183,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else {
     // epilogue: partial[slice][mt * 128 + row][nt * n_tile + col]
-    mbar_wait_warp(tmem_full, 0);
+    mbar_wait(tmem_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint8_t* wbuf = store_base + warp * (2 * 32 * kStoreCols * 4);
@@ -1413,7 +1407,7 @@ wgrad_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     for (int kt = 0; kt < k_tiles; ++kt) {
       const int s = kt % kStages;
       const uint32_t ph = (kt / kStages) & 1;
-      mbar_wait_warp(&full[s], ph);
+      mbar_wait(&full[s], ph);
       const uint32_t st = smem_u32(stage_base_of(smem, s, S::kStageBytes));
       if (!(p.dbg_skip & 1)) {
         const uint32_t gbase = st + S::kABytes;
@@ -1442,7 +1436,7 @@ wgrad_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       if (lane == 0) mbar_arrive(&a_ready[s]);
     }
   } else {
-    mbar_wait_warp(tmem_full, 0);
+    mbar_wait(tmem_full, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint8_t* wbuf = store_base + warp * (2 * 32 * kStoreCols * 4);

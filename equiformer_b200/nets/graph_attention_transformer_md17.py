@@ -121,11 +121,19 @@ class GraphAttentionTransformerMD17(torch.nn.Module):
     def forward(self, node_atom, pos, batch):
         pos = pos.requires_grad_(True)
         edge_src, edge_dst = radius_graph(pos, r=self.max_radius, batch=batch, max_num_neighbors=1000)
+        return self.forward_edges(node_atom, pos, batch, edge_src, edge_dst)
+
+    @torch.enable_grad()
+    def forward_edges(self, node_atom, pos, batch, edge_src, edge_dst, graph=None, n_graphs=None):
+        """Everything after the neighbour search (ref :283-327): energies and ``-dE/dpos`` with ``create_graph=True``.
+        ``pos`` must require grad; with ``graph`` (CSR of the destination-sorted edge list) and ``n_graphs`` supplied nothing
+        here synchronises with the host, so the whole energy + force step can be captured in a CUDA graph."""
         edge_vec = pos.index_select(0, edge_src) - pos.index_select(0, edge_dst)
         edge_sh = o3.spherical_harmonics(l=self.irreps_edge_attr, x=edge_vec, normalize=True, normalization="component")
         atom_embedding, _attr, _onehot = self.atom_embed(node_atom)
         edge_length_embedding = self.rbf(edge_vec.norm(dim=1))
-        graph = ops.Graph(edge_src, edge_dst, pos.shape[0], check_sorted=False)
+        if graph is None:
+            graph = ops.Graph(edge_src, edge_dst, pos.shape[0], check_sorted=False)
         edge_degree_embedding = self.edge_deg_embed(atom_embedding, edge_sh, edge_length_embedding, edge_src, edge_dst,
                                                     batch, graph=graph)
         node_features = atom_embedding + edge_degree_embedding
@@ -141,7 +149,7 @@ class GraphAttentionTransformerMD17(torch.nn.Module):
                                 edge_attr=edge_sh, edge_scalars=edge_length_embedding, batch=batch, graph=graph)
         else:
             outputs = self.head(node_features)
-        outputs = self.scale_scatter(outputs, batch, dim=0)
+        outputs = self.scale_scatter(outputs, batch, dim=0, dim_size=n_graphs)
         if self.scale is not None:
             outputs = self.scale * outputs
         energy = outputs
