@@ -576,8 +576,10 @@ def run_ours(args):
                        "parallelism": f"dp{world}", "l2": f"inputs larger than L2: {mem_gb:.2f} GB of activations per step",
                        "dropout": (f"attention-weight dropout p = {args.alpha_drop} (reference default 0.2; the only stochastic op "
                                    "of the step; p = 0 keeps the run comparable with the parity tests)"),
-                       "fused": "K1 on: depth-wise tensor product produced on chip as the A operand of the tcgen05 GEMMs "
-                                "(EQF_FUSED=1)" if ops._FUSED else "K1 off (EQF_FUSED=0): DTP -> HBM -> GEMM",
+                       "fused": (f"EQF_FUSED={ops._FUSED_MODE}: the depth-wise tensor product is produced on chip as the A operand of "
+                                 f"the tcgen05 GEMMs (K1) from {ops._FUSED_MIN_EDGES} edges per call in 'auto' mode - "
+                                 + ("ON" if ops._FUSED and (ops._FUSED_MODE == "1" or edges_of[0] >= ops._FUSED_MIN_EDGES) else "OFF")
+                                 + " for this workload"),
                        "gemm": "tcgen05 3xTF32, hand-written (edge-level forward / dgrad / wgrad, node-level wgrad); cuBLAS SGEMM "
                                f"below {ops._GEMM_MIN_M} rows" if ops.gemm_backend() == "tf32x3" else ops.gemm_backend(),
                        "launch": ("CUDA-graph replay of forward+loss+backward; neighbour search, all-reduce and AdamW eager"

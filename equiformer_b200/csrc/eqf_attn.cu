@@ -225,6 +225,53 @@ __global__ void __launch_bounds__(256) aggregate_vec_kernel(HeadArgs a, const fl
       make_float4(acc0.x + acc1.x, acc0.y + acc1.y, acc0.z + acc1.z, acc0.w + acc1.w);
 }
 
+// K2: segment softmax AND attention-weighted aggregation in one pass (ref :508 + :512-513): one warp per (node, 128-column
+// chunk) first reduces its head's logits over the destination segment (max, then sum of exponentials - the segment is a
+// few dozen edges of one L1-resident row range, every lane of a head reads the same addresses), then accumulates
+// alpha_e V_e with alpha_e = exp(z_e - max) / (sum + 1e-16) computed on the fly; alpha[E, H] is written once (by the lanes
+// that own the first channel of each head in the 0e group) because the backward needs it.
+__global__ void __launch_bounds__(256) softmax_aggregate_vec_kernel(HeadArgs a, const float* __restrict__ z,
+                                                                    const long long* __restrict__ row_ptr, long long n_nodes,
+                                                                    float* __restrict__ alpha_out) {
+  const int n_chunks = a.chunk_start[a.n_groups];
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= n_nodes * n_chunks) return;
+  const long long t = wid / n_chunks;
+  const int chunk = (int)(wid - t * n_chunks);
+  const int g = find_group(a, chunk);
+  const int j = (chunk - a.chunk_start[g]) * 128 + (threadIdx.x & 31) * 4;
+  const int rowlen = a.rowlen[g];
+  if (j >= rowlen) return;
+  const int H = a.n_heads;
+  const int per_head = a.C[g] / H;
+  const int h = (j % a.C[g]) / per_head;
+  const long long r0 = row_ptr[t], r1 = row_ptr[t + 1];
+  float m = -CUDART_INF_F;
+  for (long long e = r0; e < r1; ++e) m = fmaxf(m, __ldg(z + e * H + h));
+  float sum = 0.f;
+  for (long long e = r0; e < r1; ++e) sum += expf(__ldg(z + e * H + h) - m);
+  const float inv = 1.f / (sum + 1e-16f);
+  const bool writer = alpha_out != nullptr && g == 0 && j < a.C[0] && (j % per_head) == 0;
+  const float* __restrict__ v = a.V[g] + j;
+  float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
+  long long e = r0;
+  for (; e + 1 < r1; e += 2) {
+    const float a0 = expf(__ldg(z + e * H + h) - m) * inv, a1 = expf(__ldg(z + (e + 1) * H + h) - m) * inv;
+    const float4 v0 = ldv(v + e * rowlen), v1 = ldv(v + (e + 1) * rowlen);
+    if (writer) { alpha_out[e * H + h] = a0; alpha_out[(e + 1) * H + h] = a1; }
+    acc0.x = fmaf(a0, v0.x, acc0.x); acc0.y = fmaf(a0, v0.y, acc0.y); acc0.z = fmaf(a0, v0.z, acc0.z); acc0.w = fmaf(a0, v0.w, acc0.w);
+    acc1.x = fmaf(a1, v1.x, acc1.x); acc1.y = fmaf(a1, v1.y, acc1.y); acc1.z = fmaf(a1, v1.z, acc1.z); acc1.w = fmaf(a1, v1.w, acc1.w);
+  }
+  if (e < r1) {
+    const float a0 = expf(__ldg(z + e * H + h) - m) * inv;
+    const float4 v0 = ldv(v + e * rowlen);
+    if (writer) alpha_out[e * H + h] = a0;
+    acc0.x = fmaf(a0, v0.x, acc0.x); acc0.y = fmaf(a0, v0.y, acc0.y); acc0.z = fmaf(a0, v0.z, acc0.z); acc0.w = fmaf(a0, v0.w, acc0.w);
+  }
+  *reinterpret_cast<float4*>(a.out[g] + t * rowlen + j) =
+      make_float4(acc0.x + acc1.x, acc0.y + acc1.y, acc0.z + acc1.z, acc0.w + acc1.w);
+}
+
 // one warp per edge, H accumulators per lane
 template <int H>
 __global__ void __launch_bounds__(256) edge_dot_vec_kernel(HeadArgs a, const long long* __restrict__ dst, long long n_edges,
@@ -353,6 +400,33 @@ extern "C" int eqf_attn_aggregate(const EqfHeadLayout* lay, const float* alpha, 
   aggregate_kernel<<<(unsigned)blocks, wpb * 32, 0, (cudaStream_t)stream>>>(
       a, alpha, reinterpret_cast<const long long*>(row_ptr), reinterpret_cast<const long long*>(perm), n_nodes);
   return check_cuda(cudaGetLastError(), "aggregate_kernel launch");
+}
+
+// out[g][t] = sum_{e -> t} softmax_t(z)[e, head] V[g][e]  and  alpha[E, H] = the softmax (PyG semantics) in ONE launch.
+// Needs the float4 layout (every group's channels % 4 == 0), a leading group with one component (0e) whose channels per
+// head are a multiple of 4 (it is the one whose lanes write alpha); EQF_ERR_UNSUPPORTED otherwise.
+extern "C" int eqf_attn_softmax_aggregate(const EqfHeadLayout* lay, const float* z, const float* const* V,
+                                          const int64_t* row_ptr, int64_t n_nodes, float* const* out, float* alpha,
+                                          void* stream) {
+  HeadArgs a;
+  int rc = fill_head_args(lay, a);
+  if (rc != EQF_OK || n_nodes == 0) return rc;
+  if (z == nullptr || V == nullptr || out == nullptr || row_ptr == nullptr || alpha == nullptr) {
+    set_error("eqf_attn_softmax_aggregate: null pointer"); return EQF_ERR_INVALID;
+  }
+  for (int g = 0; g < a.n_groups; ++g) {
+    if (V[g] == nullptr || out[g] == nullptr) { set_error("eqf_attn_softmax_aggregate: null group"); return EQF_ERR_INVALID; }
+    a.V[g] = V[g]; a.out[g] = out[g];
+  }
+  if (!vec_ok(a) || a.d[0] != 1 || (a.C[0] / a.n_heads) % 4 != 0) {
+    set_error("eqf_attn_softmax_aggregate: layout not supported by the fused kernel"); return EQF_ERR_UNSUPPORTED;
+  }
+  for (int g = 0; g < a.n_groups; ++g) a.chunk_start[g + 1] = a.chunk_start[g] + (a.rowlen[g] + 127) / 128;
+  const int wpb = 8;
+  const long long warps = n_nodes * a.chunk_start[a.n_groups];
+  softmax_aggregate_vec_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      a, z, reinterpret_cast<const long long*>(row_ptr), n_nodes, alpha);
+  return check_cuda(cudaGetLastError(), "softmax_aggregate_vec_kernel launch");
 }
 
 extern "C" int eqf_attn_edge_dot(const EqfHeadLayout* lay, const float* const* V, const float* const* G,

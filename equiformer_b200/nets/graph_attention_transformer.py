@@ -418,10 +418,15 @@ class GraphAttention(torch.nn.Module):
 
         # logits -> segment softmax -> weighted aggregation                               [ref :506-513]
         z = logits if logits is not None else (self.alpha_act(alpha) * self.alpha_dot).sum(dim=-1)
-        attn = ops.segment_softmax(z.contiguous(), graph)
-        if self.alpha_dropout is not None:
-            attn = self.alpha_dropout(attn)
-        node = ops.attention_aggregate(self._head_layout, graph, attn.contiguous(), [v.contiguous() for v in value])
+        no_drop = self.alpha_dropout is None or not self.training or self.alpha_dropout.p == 0.0
+        if no_drop and ops.softmax_aggregate_ok(self._head_layout, z):
+            # K2: softmax over the destination segment and the weighted aggregation in one kernel
+            node = list(ops.SoftmaxAggregate.apply(self._head_layout, graph, z.contiguous(), *[v.contiguous() for v in value]))
+        else:
+            attn = ops.segment_softmax(z.contiguous(), graph)
+            if self.alpha_dropout is not None:
+                attn = self.alpha_dropout(attn)
+            node = ops.attention_aggregate(self._head_layout, graph, attn.contiguous(), [v.contiguous() for v in value])
 
         if self.rescale_degree:                                                           # [ref :516-520]
             degree = (graph.row_ptr[1:] - graph.row_ptr[:-1]).to(node[0].dtype).view(-1, 1, 1)

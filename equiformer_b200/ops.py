@@ -560,8 +560,14 @@ def depthwise_tensor_product_gathered(plan: DtpPlan, graph: "Graph", As, Bs, y, 
 
 # ----------------------------------------------------------------------------- K1: DTP fused into the per-degree linear
 
-# EQF_FUSED=0 keeps the round-1 pipeline (DTP -> [E, 3136] in HBM -> GEMMs)
-_FUSED = os.environ.get("EQF_FUSED", "1") != "0"
+# EQF_FUSED: "1" fused forward everywhere, "0" the round-1 pipeline (DTP -> [E, 3136] in HBM -> GEMMs), "auto" (default) by
+# size.  MEASURED (profiles/r2_fused_fwd_*): the fused forward keeps the [E, 3136] products out of HBM and out of the saved
+# activations - the 10 k-atom periodic cell (E = 5e5) trains under CUDA-graph capture in 224 ms / step with it and runs out
+# of the 180 GB without - but its producer warps are latency bound (gathers + per-k-tile handshakes: 157 vs 124 us on the
+# Lmax = 2 group of the QM9 batch), so below _FUSED_MIN_EDGES the faster unfused pipeline is kept.
+_FUSED_MODE = os.environ.get("EQF_FUSED", "auto")
+_FUSED = _FUSED_MODE != "0"
+_FUSED_MIN_EDGES = int(os.environ.get("EQF_FUSED_MIN_EDGES", "200000"))
 _FUSED_SPLIT = {}
 
 
@@ -579,7 +585,9 @@ def dtp_linear_supported(plan: DtpPlan) -> bool:
 def dtp_linear_ok(plan: DtpPlan, y: torch.Tensor, w: torch.Tensor) -> bool:
     """Policy: the fused kernel carries first-order training / inference on CUDA; when the edge harmonics need a
     gradient (MD17 forces, ``create_graph``) the closed differentiable family of the unfused kernels is used."""
-    return (_FUSED and fused_ok(y) and not (torch.is_grad_enabled() and y.requires_grad)
+    if not _FUSED or (_FUSED_MODE == "auto" and y.shape[0] < _FUSED_MIN_EDGES and not FUSED_ON_ANY_DEVICE):
+        return False
+    return (fused_ok(y) and not (torch.is_grad_enabled() and y.requires_grad)
             and y.shape[0] > 0 and dtp_linear_supported(plan))
 
 
@@ -987,6 +995,60 @@ class EdgeScale(torch.autograd.Function):
         if any(ctx.needs_input_grad[3:]):
             gGs = list(AttnAggregate.apply(lay, graph, alpha, *cVs))
         return (None, None, ga, *gGs)
+
+
+def softmax_aggregate_raw(lay: HeadLayout, z: torch.Tensor, Vs, graph: Graph):
+    """(outs, alpha): segment softmax of ``z`` and the alpha-weighted segment sums of ``Vs`` in one kernel."""
+    Vs = lay.check(Vs, graph.n_edges, "softmax_aggregate V")
+    z = _require_cuda(z, "attention logits")
+    if tuple(z.shape) != (graph.n_edges, lay.n_heads):
+        raise ValueError("logits must be [E, H]")
+    dev = z.device
+    outs = [torch.empty((graph.n_nodes, d, C), device=dev, dtype=torch.float32) for d, C in zip(lay.ds, lay.Cs)]
+    alpha = torch.empty_like(z)
+    nbytes = _attn_bytes(lay, graph.n_edges, graph.n_nodes, "aggregate") + 4 * z.numel()
+    with torch.cuda.device(dev), _kernel("softmax_aggregate", nbytes):
+        rc = _lib.load().eqf_attn_softmax_aggregate(ctypes.byref(lay.c), z.data_ptr(), _ptr_array(Vs), graph.row_ptr.data_ptr(),
+                                                    graph.n_nodes, _ptr_array(outs), alpha.data_ptr(), _stream())
+    _lib.check(rc, "eqf_attn_softmax_aggregate")
+    return outs, alpha
+
+
+def softmax_aggregate_ok(lay: HeadLayout, z: torch.Tensor) -> bool:
+    return (fused_ok(z) and lay.ds[0] == 1 and all(c % 4 == 0 for c in lay.Cs) and (lay.Cs[0] // lay.n_heads) % 4 == 0
+            and z.shape[0] > 0)
+
+
+class SoftmaxAggregate(torch.autograd.Function):
+    """K2 (ref :508-513): ``outs[g][t] = sum_{e->t} softmax_t(z)[e, head] V[g][e]`` - softmax and aggregation in one launch.
+    apply(lay, graph, z, *Vs).  Backward: EdgeDot / EdgeScale / segment-softmax backward on the saved alpha; under
+    ``create_graph`` the softmax is rebuilt differentiably and the closed families take over."""
+
+    @staticmethod
+    def forward(ctx, lay: HeadLayout, graph: Graph, z, *Vs):
+        outs, alpha = softmax_aggregate_raw(lay, z, Vs, graph)
+        ctx.lay, ctx.graph = lay, graph
+        ctx.save_for_backward(z, alpha, *Vs)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *Gs):
+        lay, graph = ctx.lay, ctx.graph
+        z, alpha, *Vs = ctx.saved_tensors
+        Gs = [G.contiguous() if G is not None else torch.zeros((graph.n_nodes, d, C), device=z.device)
+              for G, d, C in zip(Gs, lay.ds, lay.Cs)]
+        need_z, need_V = ctx.needs_input_grad[2], any(ctx.needs_input_grad[3:])
+        if torch.is_grad_enabled():
+            fn = lambda zz, *vv: tuple(AttnAggregate.apply(lay, graph, SegSoftmax.apply(zz, graph), *vv))
+            grads = _higher_order_grads(fn, (z, *Vs), Gs)
+            return (None, None, *grads)
+        gz = None
+        gVs = [None] * len(Vs)
+        if need_z:
+            gz = seg_softmax_bwd_raw(alpha, attn_edge_dot_raw(lay, Vs, Gs, graph), graph)
+        if need_V:
+            gVs = attn_edge_scale_raw(lay, alpha, Gs, graph)
+        return (None, None, gz, *gVs)
 
 
 def attention_aggregate(lay: HeadLayout, graph: Graph, alpha: Optional[torch.Tensor], Vs: Sequence[torch.Tensor]):

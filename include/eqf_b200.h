@@ -129,6 +129,12 @@ int eqf_seg_softmax_bwd(const float* alpha, const float* ga, const int64_t* row_
  * sorted by (the transpose of `message_src[edge_src]`, :487, in the backward pass).                */
 int eqf_attn_aggregate(const EqfHeadLayout* lay, const float* alpha, const float* const* V,
                        const int64_t* row_ptr, const int64_t* perm, int64_t n_nodes, float* const* out, void* stream);
+/* K2 - the PyG segment softmax (nets/graph_attention_transformer.py:508) and the attention-weighted scatter (:512-513)
+ * in ONE kernel over the destination-sorted edge list: out[g][t] = sum_{e->t} softmax_t(z)[e, head] V[g][e], one warp per
+ * (node, 128 columns), no atomics; alpha [E][H] (the softmax itself) is written once for the backward.  Needs the float4
+ * layout and a leading 0e group (EQF_ERR_UNSUPPORTED otherwise - callers fall back to eqf_seg_softmax + eqf_attn_aggregate). */
+int eqf_attn_softmax_aggregate(const EqfHeadLayout* lay, const float* z, const float* const* V,
+                               const int64_t* row_ptr, int64_t n_nodes, float* const* out, float* alpha, void* stream);
 
 /* galpha[e,h] = sum_{j in head h} V[g][e,j] * G[g][dst[e],j]       (transpose of aggregate w.r.t. alpha) */
 int eqf_attn_edge_dot(const EqfHeadLayout* lay, const float* const* V, const float* const* G,

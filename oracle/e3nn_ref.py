@@ -215,7 +215,7 @@ def tensor_product(x: torch.Tensor, y: torch.Tensor, weight: torch.Tensor, irrep
         mulo, lo, _ = irreps_out[io]
         x1 = x[:, sl1[i1]].reshape(z, mul1, 2 * l1 + 1)
         x2 = y[:, sl2[i2]].reshape(z, mul2, 2 * l2 + 1)
-        w3j = wigner_3j(l1, l2, lo).to(x.dtype)
+        w3j = wigner_3j(l1, l2, lo).to(device=x.device, dtype=x.dtype)    # device-following: bench.py's reference-gpu arm
         pw = math.sqrt(2 * lo + 1)
         xx = torch.einsum("zui,zvj->zuvij", x1, x2)
         if mode == "uvu":

@@ -48,7 +48,7 @@ def scatter_sum(x, index, dim_size):
 def pyg_softmax(src, index, num_nodes):
     """torch_geometric.utils.softmax (2.0.3): (src - max).exp() / (scatter_sum + 1e-16) - :508"""
     expanded = index.view(-1, *([1] * (src.dim() - 1))).expand_as(src)
-    src_max = torch.full((num_nodes,) + tuple(src.shape[1:]), float("-inf"), dtype=src.dtype)
+    src_max = torch.full((num_nodes,) + tuple(src.shape[1:]), float("-inf"), dtype=src.dtype, device=src.device)
     src_max = src_max.scatter_reduce(0, expanded, src, reduce="amax", include_self=True)
     out = (src - src_max.index_select(0, index)).exp()
     out_sum = scatter_sum(out, index, num_nodes).index_select(0, index)
@@ -283,7 +283,8 @@ def dot_product_attention(params: Params, prefix: str, irreps_in, irreps_edge, i
     attn = scatter_sum(v * alpha, edge_dst, n)                                                  # :150-151
     attn = heads2vec(attn, irreps_head)                                                         # :146
     if rescale_degree:                                                                          # :148-152
-        degree = torch.zeros(n, dtype=x.dtype).index_add_(0, edge_dst, torch.ones(edge_dst.numel(), dtype=x.dtype))
+        degree = torch.zeros(n, dtype=x.dtype, device=x.device).index_add_(
+            0, edge_dst, torch.ones(edge_dst.numel(), dtype=x.dtype, device=x.device))
         attn = attn * degree.view(-1, 1) / 15.57930850982666
     return linear_rs(params, f"{prefix}.proj", heads_q, irreps_node_output, attn)               # :154
 
@@ -323,7 +324,7 @@ def edge_degree_embedding(params: Params, prefix: str, cfg: Config, n_nodes, edg
     """EdgeDegreeEmbeddingNetwork.forward - :725-733"""
     emb = e3.parse_irreps(cfg.irreps_node_embedding)
     irreps_edge = e3.parse_irreps(cfg.irreps_sh)
-    ones = torch.ones((n_nodes, 1), dtype=dtype)
+    ones = torch.ones((n_nodes, 1), dtype=dtype, device=edge_sh.device)
     feats = linear_rs(params, f"{prefix}.exp", [(1, 0, 1)], emb, ones)
     weight = radial_profile(params, f"{prefix}.rad", edge_scalars)
     dw_out, dw_ins = dtp_instructions(emb, irreps_edge, emb)

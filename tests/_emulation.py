@@ -129,6 +129,11 @@ def attn_aggregate_raw(lay, alpha, Vs, graph, by_src=False):
     return outs
 
 
+def softmax_aggregate_raw(lay, z, Vs, graph):
+    alpha = seg_softmax_raw(z, graph)
+    return attn_aggregate_raw(lay, alpha, Vs, graph), alpha
+
+
 def attn_edge_dot_raw(lay, Vs, Gs, graph):
     E = graph.n_edges
     out = Vs[0].new_zeros((E, lay.n_heads))
@@ -230,7 +235,7 @@ def gate_logits_bwd_raw(lay, t0, bias, alpha_dot, gated, gz, gv0, gvout):
 
 
 _PATCHED = ["rbf_fwd_raw", "rbf_bwd_raw", "colsum_raw", "eln_fwd_raw", "eln_bwd_raw", "eln_planar_fwd_raw", "eln_planar_bwd_raw", "ln_silu_fwd_raw", "ln_silu_bwd_raw", "gate_logits_fwd_raw", "gate_logits_bwd_raw", "gemm_raw", "dtp_forward_raw", "dtp_linear_fwd_raw", "dtp_group_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
-            "seg_softmax_raw", "seg_softmax_bwd_raw", "attn_aggregate_raw", "attn_edge_dot_raw", "attn_edge_scale_raw"]
+            "seg_softmax_raw", "seg_softmax_bwd_raw", "softmax_aggregate_raw", "attn_aggregate_raw", "attn_edge_dot_raw", "attn_edge_scale_raw"]
 
 
 @contextlib.contextmanager

@@ -148,6 +148,19 @@ def test_attention_family(cuda_device, H, dims, chans):
     sc = ops.attn_edge_scale_raw(lay, dev(a64.float()), [dev(t) for t in Gs], graph)
     for a, b in zip(sc, emu.attn_edge_scale_raw(lay, a64.float().double(), [t.double() for t in Gs], cpu_graph)):
         assert rel_err(a, b) < TOL
+    # K2: softmax + aggregation in one kernel == the two-kernel result, and its autograd == the unfused composition
+    if ops.softmax_aggregate_ok(lay, dev(z)):
+        outs, alpha2 = ops.softmax_aggregate_raw(lay, dev(z), [dev(v) for v in Vs], graph)
+        assert rel_err(alpha2, alpha_ref) < TOL
+        for a, b in zip(outs, emu.attn_aggregate_raw(lay, a64, [v.double() for v in Vs], cpu_graph)):
+            assert rel_err(a, b) < TOL
+        zz = dev(z).requires_grad_(True)
+        vv = [dev(v).requires_grad_(True) for v in Vs]
+        cots = [dev(t) for t in Gs]
+        g1 = torch.autograd.grad(ops.SoftmaxAggregate.apply(lay, graph, zz, *vv), [zz, *vv], cots)
+        g2 = torch.autograd.grad(ops.AttnAggregate.apply(lay, graph, ops.SegSoftmax.apply(zz, graph), *vv), [zz, *vv], cots)
+        for a, b in zip(g1, g2):
+            assert rel_err(a, b) < 1e-5
 
 
 def test_unsorted_edges_are_sorted_once(cuda_device):

@@ -240,3 +240,31 @@ def test_bucketed_stream_of_batches_matches_eager(cuda_device):
         loss_e.backward()
         assert rel_err(loss_g, loss_e) < 1e-5
         assert rel_err(grads_g, bucket.flat) < 2e-5
+
+
+def test_fused_forward_model_matches_unfused_model(cuda_device, monkeypatch):
+    """K1 on (EQF_FUSED=1: every depth-wise product feeds its linears on chip, backward recomputes) against K1 off on the
+    same model and batch: energies and every parameter gradient."""
+    from equiformer_b200 import ops
+    model = _build("graph_attention_transformer_nonlinear_l2", cuda_device)
+    _perturb(model)
+    pos, batch, z = qm9_like_batch(24, seed=5)
+    d = lambda t: t.to(cuda_device)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setattr(ops, "_FUSED_MODE", mode)
+        monkeypatch.setattr(ops, "_FUSED", mode != "0")
+        prof = ops.KernelProfile(time_events=False)
+        ops.PROFILE = prof
+        try:
+            model.zero_grad(set_to_none=True)
+            out = model(f_in=None, pos=d(pos), batch=d(batch), node_atom=d(z), n_graphs=24)
+            (out * torch.linspace(-1, 1, 24, device=cuda_device).view(24, 1)).sum().backward()
+        finally:
+            ops.PROFILE = None
+        res[mode] = (out.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None},
+                     prof.launches)
+    assert rel_err(res["1"][0], res["0"][0]) < 2e-5
+    worst = max(rel_err(res["1"][1][k], g) for k, g in res["0"][1].items())
+    assert worst < 2e-4, worst
+    assert res["1"][2] != res["0"][2]          # the two modes really launched different kernel sets
