@@ -49,6 +49,9 @@ class ExpNormalSmearing(nn.Module):
         self.betas.data.copy_(betas)
 
     def forward(self, dist):
+        if self.cutoff_lower == 0 and dist.is_cuda and dist.dtype == torch.float32 and dist.dim() == 1:
+            from .. import ops          # one kernel each way (ops.ExpNormalRbf); second order via the torch statement
+            return ops.expnorm_rbf(dist, self.means, self.betas, self.alpha, self.cutoff_upper)
         dist = dist.unsqueeze(-1)
         return self.cutoff_fn(dist) * torch.exp(
             -self.betas * (torch.exp(self.alpha * (-dist + self.cutoff_lower)) - self.means) ** 2)

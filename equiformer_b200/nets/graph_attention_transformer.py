@@ -750,23 +750,16 @@ class GraphAttentionTransformer(torch.nn.Module):
         order; otherwise the list is checked (one host synchronisation) and, when unsorted, everything per-edge is
         permuted - unless the caller vouches for the order with ``edges_sorted=True``.  ``edge_vec`` overrides
         ``pos[src] - pos[dst]`` (periodic cells: the caller adds the image offsets; needs a sorted edge list)."""
-        if edge_vec is None:
-            edge_vec = pos.index_select(0, edge_src) - pos.index_select(0, edge_dst)
-        elif not (edges_sorted or graph is not None):
+        if edge_vec is not None and not (edges_sorted or graph is not None):
             raise ValueError("edge_vec needs a destination-sorted edge list (edges_sorted=True or a graph)")
-        edge_sh = o3.spherical_harmonics(l=self.irreps_edge_attr, x=edge_vec, normalize=True, normalization="component")
-        edge_length = edge_vec.norm(dim=1)
-        atom_embedding, _attr, _onehot = self.atom_embed(self._atom_remap[node_atom])
-        edge_length_embedding = self.rbf(edge_length)
         if graph is None:
             graph = ops.Graph(edge_src, edge_dst, pos.shape[0], check_sorted=not edges_sorted)
-            if graph.perm is not None:      # unsorted input: work on the sorted copy (per-edge tensors are derived below)
+            if graph.perm is not None:      # unsorted input: work on the sorted copy
                 edge_src, edge_dst = graph.src, graph.dst
-                edge_vec = pos.index_select(0, edge_src) - pos.index_select(0, edge_dst)
-                edge_sh = o3.spherical_harmonics(l=self.irreps_edge_attr, x=edge_vec, normalize=True,
-                                                 normalization="component")
-                edge_length_embedding = self.rbf(edge_vec.norm(dim=1))
                 graph.perm = None
+        edge_vec, edge_length, edge_sh = edge_features(self.irreps_edge_attr, pos, graph, edge_vec)
+        atom_embedding, _attr, _onehot = self.atom_embed(self._atom_remap[node_atom])
+        edge_length_embedding = self.rbf(edge_length)
         edge_degree_embedding = self.edge_deg_embed(atom_embedding, edge_sh, edge_length_embedding, edge_src, edge_dst,
                                                     batch, graph=graph)
         node_features = atom_embedding + edge_degree_embedding
@@ -782,6 +775,20 @@ class GraphAttentionTransformer(torch.nn.Module):
         if self.scale is not None:
             outputs = self.scale * outputs
         return outputs
+
+
+def edge_features(irreps_edge_attr, pos, graph, edge_vec=None):
+    """``(edge_vec, edge_length, edge_sh)`` of a destination-sorted graph (ref :866-870).  When the edge irreps are the plain
+    harmonics ``0 .. lmax <= 3`` and the vector is ``pos[src] - pos[dst]`` this is ONE kernel (``ops.EdgeGeometry``; its
+    backward scatters to ``pos``); a caller-supplied ``edge_vec`` (periodic images) or other irreps take the torch chain."""
+    ls = [ir.l for mul, ir in irreps_edge_attr for _ in range(mul)]
+    if (edge_vec is None and ls == list(range(len(ls))) and 1 <= len(ls) <= 4 and pos.is_cuda and pos.dtype == torch.float32
+            and graph.perm is None and graph.n_edges > 0):
+        return ops.edge_geometry(pos, graph, len(ls) - 1)
+    if edge_vec is None:
+        edge_vec = pos.index_select(0, graph.src) - pos.index_select(0, graph.dst)
+    edge_sh = o3.spherical_harmonics(l=irreps_edge_attr, x=edge_vec, normalize=True, normalization="component")
+    return edge_vec, edge_vec.norm(dim=1), edge_sh
 
 
 def _run_blocks(blocks, node_features, irreps, node_attr, edge_src, edge_dst, edge_sh, edge_scalars, batch, graph):

@@ -14,7 +14,7 @@ from .drop import EquivariantDropout
 from .expnorm_rbf import ExpNormalSmearing
 from .fast_activation import Activation
 from .gaussian_rbf import GaussianRadialBasisLayer
-from .graph_attention_transformer import (_run_blocks, EdgeDegreeEmbeddingNetwork, GraphAttention, NodeEmbeddingNetwork,
+from .graph_attention_transformer import (_run_blocks, edge_features, EdgeDegreeEmbeddingNetwork, GraphAttention, NodeEmbeddingNetwork,
                                           ScaledScatter, TransBlock, get_norm_layer)
 from .layer_norm import EquivariantLayerNormV2
 from .registry import register_model
@@ -128,12 +128,11 @@ class GraphAttentionTransformerMD17(torch.nn.Module):
         """Everything after the neighbour search (ref :283-327): energies and ``-dE/dpos`` with ``create_graph=True``.
         ``pos`` must require grad; with ``graph`` (CSR of the destination-sorted edge list) and ``n_graphs`` supplied nothing
         here synchronises with the host, so the whole energy + force step can be captured in a CUDA graph."""
-        edge_vec = pos.index_select(0, edge_src) - pos.index_select(0, edge_dst)
-        edge_sh = o3.spherical_harmonics(l=self.irreps_edge_attr, x=edge_vec, normalize=True, normalization="component")
-        atom_embedding, _attr, _onehot = self.atom_embed(node_atom)
-        edge_length_embedding = self.rbf(edge_vec.norm(dim=1))
         if graph is None:
             graph = ops.Graph(edge_src, edge_dst, pos.shape[0], check_sorted=False)
+        _edge_vec, edge_length, edge_sh = edge_features(self.irreps_edge_attr, pos, graph)
+        atom_embedding, _attr, _onehot = self.atom_embed(node_atom)
+        edge_length_embedding = self.rbf(edge_length)
         edge_degree_embedding = self.edge_deg_embed(atom_embedding, edge_sh, edge_length_embedding, edge_src, edge_dst,
                                                     batch, graph=graph)
         node_features = atom_embedding + edge_degree_embedding

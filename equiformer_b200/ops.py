@@ -1015,8 +1015,8 @@ def softmax_aggregate_raw(lay: HeadLayout, z: torch.Tensor, Vs, graph: Graph):
 
 
 def softmax_aggregate_ok(lay: HeadLayout, z: torch.Tensor) -> bool:
-    return (fused_ok(z) and lay.ds[0] == 1 and all(c % 4 == 0 for c in lay.Cs) and (lay.Cs[0] // lay.n_heads) % 4 == 0
-            and z.shape[0] > 0)
+    # float4 lanes: every group's channels PER HEAD must be a multiple of 4 (a lane's four channels belong to one head)
+    return (fused_ok(z) and lay.ds[0] == 1 and all((c // lay.n_heads) % 4 == 0 for c in lay.Cs) and z.shape[0] > 0)
 
 
 class SoftmaxAggregate(torch.autograd.Function):
@@ -1683,6 +1683,124 @@ def gaussian_rbf(dist, mean, std, weight, bias, cutoff: float):
     if fused_ok(dist) and dist.dim() == 1 and mean.numel() == 128 and dist.shape[0] > 0:
         return GaussianRbf.apply(dist.contiguous(), mean, std, weight, bias, float(cutoff))
     return gaussian_rbf_torch(dist, mean, std, weight, bias, cutoff)
+
+
+# ----------------------------------------------------------------------------- edge geometry / exp-normal basis
+
+
+def edge_geometry_torch(pos, src, dst, lmax: int, offsets=None):
+    """Torch statement of the fused edge-geometry kernel (ref :866-870): (edge_vec, length, harmonics 0..lmax)."""
+    from .o3.sh import spherical_harmonics
+    vec = pos.index_select(0, src) - pos.index_select(0, dst)
+    if offsets is not None:
+        vec = vec + offsets
+    return vec, vec.norm(dim=1), spherical_harmonics(list(range(lmax + 1)), vec, True, "component")
+
+
+def _sh_couplings(device):
+    from .o3.sh import _coupling_tensor
+    return _coupling_tensor(1, torch.float32, device).contiguous(), _coupling_tensor(2, torch.float32, device).contiguous()
+
+
+class EdgeGeometry(torch.autograd.Function):
+    """(edge_vec, length, sh) of ``pos[src] - pos[dst] (+ offsets)`` in one kernel; backward = one kernel + two segment sums
+    to the positions (destination-sorted CSR and its CSC).  apply(pos, graph, lmax, offsets_or_None)."""
+
+    @staticmethod
+    def forward(ctx, pos, graph: "Graph", lmax: int, offsets):
+        pos = _require_cuda(pos, "pos")
+        E = graph.n_edges
+        a1, a2 = _sh_couplings(pos.device)
+        vec = torch.empty((E, 3), device=pos.device, dtype=torch.float32)
+        length = torch.empty(E, device=pos.device, dtype=torch.float32)
+        sh = torch.empty((E, (lmax + 1) ** 2), device=pos.device, dtype=torch.float32)
+        with torch.cuda.device(pos.device), _kernel("edge_geom_fwd", 4 * E * (6 + 4 + (lmax + 1) ** 2)):
+            rc = _lib.load().eqf_edge_geom_fwd(pos.data_ptr(), graph.src.data_ptr(), graph.dst.data_ptr(),
+                                               offsets.data_ptr() if offsets is not None else None, a1.data_ptr(), a2.data_ptr(),
+                                               E, lmax, vec.data_ptr(), length.data_ptr(), sh.data_ptr(), _stream())
+        _lib.check(rc, "eqf_edge_geom_fwd")
+        ctx.graph, ctx.lmax, ctx.has_off = graph, lmax, offsets is not None
+        ctx.save_for_backward(pos, vec, *([offsets] if offsets is not None else []))
+        return vec, length, sh
+
+    @staticmethod
+    def backward(ctx, g_vec_out, g_len, g_sh):
+        graph, lmax = ctx.graph, ctx.lmax
+        pos, vec, *rest = ctx.saved_tensors
+        offsets = rest[0] if ctx.has_off else None
+        if torch.is_grad_enabled():        # second order (MD17 force training): differentiate the torch statement
+            fn = lambda p, o: edge_geometry_torch(p, graph.src, graph.dst, lmax, o)
+            gp, go = _higher_order_grads(fn, (pos, offsets), (g_vec_out, g_len, g_sh))
+            return gp, None, None, go
+        E = graph.n_edges
+        a1, a2 = _sh_couplings(pos.device)
+        gv = torch.empty((E, 3), device=pos.device, dtype=torch.float32)
+        gs = g_sh.contiguous() if g_sh is not None else None
+        gl = g_len.contiguous() if g_len is not None else None
+        with torch.cuda.device(pos.device), _kernel("edge_geom_bwd", 4 * E * (6 + (lmax + 1) ** 2)):
+            rc = _lib.load().eqf_edge_geom_bwd(vec.data_ptr(), a1.data_ptr(), a2.data_ptr(), E, lmax,
+                                               gs.data_ptr() if gs is not None else None,
+                                               gl.data_ptr() if gl is not None else None, gv.data_ptr(), _stream())
+        _lib.check(rc, "eqf_edge_geom_bwd")
+        if g_vec_out is not None:
+            gv = gv + g_vec_out
+        lay = HeadLayout([1], [3], 1)
+        gsrc = attn_aggregate_raw(lay, None, [gv.view(E, 1, 3)], graph, by_src=True)[0].view(-1, 3)
+        gdst = attn_aggregate_raw(lay, None, [gv.view(E, 1, 3)], graph)[0].view(-1, 3)
+        return gsrc - gdst, None, None, (gv if offsets is not None and ctx.needs_input_grad[3] else None)
+
+
+def edge_geometry(pos, graph: "Graph", lmax: int, offsets=None):
+    """(edge_vec [E, 3], length [E], sh [E, (lmax + 1)^2]) - fused kernel on CUDA fp32, torch statement otherwise."""
+    if pos.is_cuda and pos.dtype == torch.float32 and lmax <= 3 and graph.n_edges > 0:
+        return EdgeGeometry.apply(pos, graph, lmax, offsets)
+    return edge_geometry_torch(pos, graph.src, graph.dst, lmax, offsets)
+
+
+def expnorm_torch(dist, means, betas, alpha: float, cutoff_upper: float):
+    """Torch statement of ExpNormalSmearing.forward with CosineCutoff(0, cutoff_upper) (ref nets/expnorm_rbf.py:11-33, 73-78)."""
+    d = dist.unsqueeze(-1)
+    cut = 0.5 * (torch.cos(d * (3.141592653589793 / cutoff_upper)) + 1.0) * (d < cutoff_upper).to(d.dtype)
+    return cut * torch.exp(-betas * (torch.exp(-alpha * d) - means) ** 2)
+
+
+class ExpNormalRbf(torch.autograd.Function):
+    """Exp-normal radial basis on ``[E]`` distances -> ``[E, B]`` (fixed means / betas); one kernel each way."""
+
+    @staticmethod
+    def forward(ctx, dist, means, betas, alpha: float, hi: float):
+        dist = _require_cuda(dist, "expnorm dist")
+        E, B = dist.shape[0], means.numel()
+        out = torch.empty((E, B), device=dist.device, dtype=torch.float32)
+        with torch.cuda.device(dist.device), _kernel("expnorm_fwd", 4 * (E + E * B)):
+            rc = _lib.load().eqf_expnorm_fwd(dist.data_ptr(), means.data_ptr(), betas.data_ptr(), alpha, hi, E, B,
+                                             out.data_ptr(), _stream())
+        _lib.check(rc, "eqf_expnorm_fwd")
+        ctx.alpha, ctx.hi = alpha, hi
+        ctx.save_for_backward(dist, means, betas)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        dist, means, betas = ctx.saved_tensors
+        if torch.is_grad_enabled() or ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            fn = lambda d, m, b: expnorm_torch(d, m, b, ctx.alpha, ctx.hi)
+            gd, gm, gb = _higher_order_grads(fn, (dist, means, betas), (g,))
+            return gd, gm, gb, None, None
+        E, B = g.shape
+        gd = torch.empty(E, device=g.device, dtype=torch.float32)
+        g = g.contiguous()
+        with torch.cuda.device(g.device), _kernel("expnorm_bwd", 4 * (2 * E + E * B)):
+            rc = _lib.load().eqf_expnorm_bwd(dist.data_ptr(), means.data_ptr(), betas.data_ptr(), ctx.alpha, ctx.hi, E, B,
+                                             g.data_ptr(), gd.data_ptr(), _stream())
+        _lib.check(rc, "eqf_expnorm_bwd")
+        return gd, None, None, None, None
+
+
+def expnorm_rbf(dist, means, betas, alpha: float, cutoff_upper: float):
+    if dist.is_cuda and dist.dtype == torch.float32 and dist.dim() == 1 and dist.shape[0] > 0:
+        return ExpNormalRbf.apply(dist.contiguous(), means.contiguous(), betas.contiguous(), float(alpha), float(cutoff_upper))
+    return expnorm_torch(dist, means, betas, alpha, cutoff_upper)
 
 
 class GateLayout:

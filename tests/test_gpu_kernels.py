@@ -687,3 +687,49 @@ def test_fused_dtp_linear_autograd_matches_unfused(cuda_device):
         assert rel_err(a, b) < TOL
     for a, b in zip(grads, ref_grads):
         assert rel_err(a, b) < 5e-5
+
+
+# ------------------------------------------------------------------------------------------------ edge-feature producers
+@pytest.mark.parametrize("lmax", [1, 2, 3])
+@pytest.mark.parametrize("with_offsets", [False, True])
+def test_edge_geometry_kernel_vs_torch_statement(cuda_device, lmax, with_offsets):
+    """``ops.EdgeGeometry`` (edge vector, length, harmonics up to l = 3 in one kernel; backward kernel + two segment sums to
+    the positions) against the fp64 torch chain it replaces (ref :866-870), values and the gradient w.r.t. ``pos``."""
+    from equiformer_b200 import ops
+    g = torch.Generator().manual_seed(11 + lmax)
+    n, E = 300, 4000
+    pos = torch.randn(n, 3, generator=g) * 2.0
+    dst = torch.sort(torch.randint(0, n, (E,), generator=g)).values
+    src = torch.randint(0, n, (E,), generator=g)
+    src = torch.where(src == dst, (src + 1) % n, src)
+    off = torch.randn(E, 3, generator=g) * 0.3 if with_offsets else None
+    graph = ops.Graph(src.to(cuda_device), dst.to(cuda_device), n)
+    p = pos.to(cuda_device).requires_grad_(True)
+    vec, length, sh = ops.edge_geometry(p, graph, lmax, off.to(cuda_device) if off is not None else None)
+    p64 = pos.double().requires_grad_(True)
+    rvec, rlen, rsh = ops.edge_geometry_torch(p64, src, dst, lmax, off.double() if off is not None else None)
+    assert rel_err(vec, rvec) < 1e-6 and rel_err(length, rlen) < 1e-6 and rel_err(sh, rsh) < 5e-6
+    cs, cl = torch.randn(E, (lmax + 1) ** 2, generator=g), torch.randn(E, generator=g)
+    (gp,) = torch.autograd.grad([sh, length], [p], [cs.to(cuda_device), cl.to(cuda_device)])
+    (rp,) = torch.autograd.grad([rsh, rlen], [p64], [cs.double(), cl.double()])
+    assert rel_err(gp, rp) < 2e-5
+
+
+def test_expnorm_rbf_kernel_vs_torch_statement(cuda_device):
+    """``ops.ExpNormalRbf`` (ref nets/expnorm_rbf.py:73-78 with the cosine cutoff) values and d/d dist vs fp64 torch, and the
+    module against the reference-run fixture's parameters."""
+    from equiformer_b200 import ops
+    from equiformer_b200.nets.expnorm_rbf import ExpNormalSmearing
+    mod = ExpNormalSmearing(0.0, 5.0, 32, trainable=False)
+    g = torch.Generator().manual_seed(3)
+    d = torch.rand(5000, generator=g) * 6.0              # some beyond the cutoff
+    dd = d.to(cuda_device).requires_grad_(True)
+    out = ops.expnorm_rbf(dd, mod.means.to(cuda_device), mod.betas.to(cuda_device), mod.alpha, 5.0)
+    d64 = d.double().requires_grad_(True)
+    ref = ops.expnorm_torch(d64, mod.means.double(), mod.betas.double(), mod.alpha, 5.0)
+    assert rel_err(out, ref) < 2e-6
+    cot = torch.randn(5000, 32, generator=g)
+    (gd,) = torch.autograd.grad(out, dd, cot.to(cuda_device))
+    (rd,) = torch.autograd.grad(ref, d64, cot.double())
+    assert rel_err(gd, rd) < 1e-5
+    assert rel_err(mod.to(cuda_device)(d.to(cuda_device)), ref) < 2e-6
