@@ -727,3 +727,54 @@ def test_cuda_oc20_model_matches_reference_model_file(cuda_device):
     assert rel_err(energy, torch.from_numpy(g["energy"])) < 1e-4
     worst = max(rel_err(model.get_parameter(k[5:]).grad, torch.from_numpy(g[k])) for k in g.files if k.startswith("grad/"))
     assert worst < 1e-3, worst
+
+
+# --------------------------------------------------------------- the DeNS variant (nets/equiformer_md17_dens.py)
+DENS_SMALL = os.path.join(os.path.dirname(SMALL), "reference_model_dens_small.npz")
+
+
+def _dens_setup(dev=None, dtype=torch.float64):
+    import types
+    from equiformer_b200.nets.equiformer_md17_dens import Equiformer_MD17_DeNS
+    g = np.load(DENS_SMALL)
+    cfg = {k[4:]: g[k].tolist() for k in g.files if k.startswith("cfg/")}
+    cfg["fc_neurons"] = list(cfg["fc_neurons"])
+    state = {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("state/")}
+    model = Equiformer_MD17_DeNS(**cfg)
+    res = model.load_state_dict(state, strict=False)
+    assert not res.unexpected_keys and all(k.endswith("tp.output_mask") for k in res.missing_keys), res
+    model = model.eval().to(dtype)
+    t = lambda k: torch.from_numpy(g[k])
+    data = types.SimpleNamespace(z=t("z"), pos=t("pos").to(dtype), batch=t("batch"), force=t("force").to(dtype),
+                                 noise_mask=t("noise_mask"))
+    if dev is not None:
+        model = model.to(dev)
+        for k, v in vars(data).items():
+            setattr(data, k, v.to(dev))
+    return g, model, data
+
+
+def test_mirror_dens_model_matches_reference_model_file():
+    """``Equiformer_MD17_DeNS`` (force encoding + denoising head on) loaded with the reference's ``state_dict``, kernels
+    emulated in float64: energies, the forces / predicted-noise output and the gradients of an energy + output loss."""
+    from tests._emulation import emulated_kernels
+    g, model, data = _dens_setup()
+    with emulated_kernels():
+        energy, dy = model(data)
+        (energy.sum() + (dy ** 2).sum()).backward()
+    assert rel_err(energy, torch.from_numpy(g["energy"])) < 1e-10
+    assert rel_err(dy, torch.from_numpy(g["dy"])) < 1e-9
+    for k in g.files:
+        if k.startswith("grad/"):
+            assert rel_err(model.get_parameter(k[5:]).grad, torch.from_numpy(g[k])) < 1e-6, k
+
+
+@pytest.mark.gpu
+def test_cuda_dens_model_matches_reference_model_file(cuda_device):
+    g, model, data = _dens_setup(cuda_device, torch.float32)
+    energy, dy = model(data)
+    (energy.sum() + (dy ** 2).sum()).backward()
+    assert rel_err(energy, torch.from_numpy(g["energy"])) < 1e-4
+    assert rel_err(dy, torch.from_numpy(g["dy"])) < 3e-4
+    worst = max(rel_err(model.get_parameter(k[5:]).grad, torch.from_numpy(g[k])) for k in g.files if k.startswith("grad/"))
+    assert worst < 2e-3, worst
