@@ -45,7 +45,8 @@ constexpr int BKT = 32;                 // channels per k-tile: 128-byte rows
 constexpr int kRowBytes = BKT * 4;
 constexpr int UMMA_K = 8;
 constexpr int kStoreCols = 32;
-constexpr int kEpilogueWarps = 4, kProducerWarp = 4, kMmaWarp = 5;   // warps 6, 7 idle (fill the warpgroup)
+constexpr int kEpilogueWarps = 4, kProducerWarp = 4, kMmaWarp = 5;
+constexpr int kHelperWarp0 = 6, kHelperWarps = 2, kHelperThreads = kHelperWarps * 32;   // table helpers
 constexpr int kTransformWarp0 = 8, kTransformWarps = 4;
 constexpr int kDtpWarp0 = 12, kDtpWarps = 16, kDtpSets = 2, kDtpSetWarps = kDtpWarps / kDtpSets;
 constexpr int kDtpThreads = kDtpWarps * 32, kDtpSetThreads = kDtpSetWarps * 32;
@@ -80,15 +81,19 @@ struct FArgs {
   int d_y, W, w_shared, d3, n_paths, m_row, K, N;
   int n_tile, n_blocks;
   long long m_blocks;
-  int dbg_skip;          // measurement aid: bit 0 skips the DTP math, bit 1 the MMAs, bit 2 the transform (garbage results)
+  int dbg_skip;          // measurement aid: bit 0 skips the DTP math, bit 1 the MMAs, bit 2 the transform (garbage results);
+                         // v4 switches (results unchanged): 8 try_wait with a suspend-time hint, 16 two-instruction tf32 rounding,
+                         // 32 dense vector-load k-tile producer, 64 entry-per-thread table build, 128 gathers before the handshake
   long long* dbg;        // optional clock64 timeline of CTA 0: dbg[role * 2048 + n] (eqf_fused_set_timeline)
-  // shared-memory layout (bytes), fixed by the host: stages | store staging | 2 x (M rows + node rows) | descriptors | barriers
-  int n_stages, stage_bytes, w_tile_off, w_box_rows, tab_bytes, m_buf_floats, y_buf_floats, cg_floats;
+  // shared-memory layout (bytes), fixed by the host: n_op operand slots (B hi | B lo | weight box) | n_raw raw A tiles |
+  // store staging | 2 x (M rows + harmonics + node rows) | descriptors | barriers
+  int n_op, n_raw, op_bytes, w_tile_off, w_box_rows, tab_bytes, m_buf_floats, y_buf_floats, cg_floats;
   unsigned char kt_path[kMaxKTiles];   // path of each 32-channel k-tile, in channel order
   FPath paths[kMaxPaths];
 };
 
-// timeline of CTA 0: role 0 TMA producer, 1 MMA issuer, 2 transform (warp 8), 3 epilogue (warp 0), 4 / 5 DTP set 0 / 1 (first warp)
+// timeline of CTA 0: role 0 TMA producer, 1 MMA issuer, 2 transform (warp 8), 3 epilogue (warp 0), 4 DTP set 0 (first
+// thread: tables ready, then k-tile start / end), 5 table helper (row block start / end)
 __device__ __forceinline__ void stamp(const FArgs& a, int role, int& n) {
   if (a.dbg != nullptr && blockIdx.x == 0 && n < 2048) a.dbg[role * 2048 + n] = clock64();
   ++n;
@@ -113,60 +118,112 @@ __device__ __forceinline__ void fs(float4& a, const float4& x, float m) {
   a.x = fmaf(x.x, m, a.x); a.y = fmaf(x.y, m, a.y); a.z = fmaf(x.z, m, a.z); a.w = fmaf(x.w, m, a.w);
 }
 
+// ring position + phase parity of a circular buffer of barriers (advanced once per k-tile by every role that uses it)
+struct Ring {
+  int n, idx;
+  uint32_t ph;
+  __device__ __forceinline__ Ring(int n_) : n(n_), idx(0), ph(0) {}
+  __device__ __forceinline__ void next() { if (++idx == n) { idx = 0; ph ^= 1u; } }
+};
+
 // One k-tile (32 channels `ch0 ..` of path p) of the raw A tile: thread t of the set's 256 handles edge t / 8 (+32 ...)
-// and the four channels 4 (t % 8) of the chunk.  `w_tile`: shared-memory address of the [n_e][32] weight box of the
-// k-tile (per-edge weights) or 0 (shared weights, read from global).
-template <int D1, int D3>
+// and the four channels 4 (t % 8) of the chunk.  The coupling block of (edge, path) is read with ceil(D1 D3 / 4) 128-bit
+// shared loads from its 16-byte aligned slot and contracted densely, i outermost (v3 used D1 D3 generic scalar loads, each
+// behind a structural-zero test: 2/3 of the producer's instructions were not arithmetic); DIAG = the l2 = 0 paths, whose
+// block is m_i delta_ik.  The first pass's gathers are issued BEFORE the warp waits for its raw slot and the weight box, so
+// the L2 round trip overlaps the handshake.  `w_tile`: shared-memory address of the [n_e][32] weight box or 0 (shared w).
+struct KtWaits { uint64_t* raw_free; uint32_t raw_ph; uint64_t* op_full; uint32_t op_ph; bool hint; };
+
+template <int D1, int D3, bool DIAG>
 __device__ __forceinline__ void dtp_ktile(const FArgs& a, const FPath& p, int ch0, int t, long long e0, int n_e, long long row0,
-                                          const int* __restrict__ src_s, const int* __restrict__ dst_s,
-                                          const float* __restrict__ mbuf, uint32_t raw_addr, uint32_t w_tile) {
+                                          const int* __restrict__ src_s, const int* __restrict__ dst_s, uint32_t m_addr,
+                                          uint32_t raw_addr, uint32_t w_tile, const KtWaits& wt) {
+  constexpr int NM = (D1 * D3 + 3) / 4;
   const int c8 = t & 7;
   const int ch = ch0 + c8 * 4;
   const bool gather = a.src != nullptr;
   const float* xa = a.x[p.xb];
   const float* xb = a.x2[p.xb];
   const long long row_floats = (long long)D1 * p.mul;
-  const unsigned long long nz = p.nz;
+  float4 woff = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.w_offset != nullptr) woff = ld4(a.w_offset + p.w_off + ch);
+  bool waited = false;
+  int el = t >> 3;
 #pragma unroll 1
-  for (int el = t >> 3; el < n_e; el += kDtpSetThreads / 8) {
-    const long long e = e0 + el;
-    float4 wv = w_tile != 0 ? lds128(w_tile + (uint32_t)el * 128u + (uint32_t)c8 * 16u) : ld4(a.w + p.w_off + ch);
-    if (a.w_offset != nullptr) addv(wv, ld4(a.w_offset + p.w_off + ch));
-    const long long rs = gather ? (long long)src_s[el] : e;
+  do {                                   // at least one trip: every warp has to pass the waits
+    const bool active = el < n_e;
+    const int els = active ? el : 0;
+    const long long e = e0 + els;
+    const long long rs = gather ? (long long)src_s[els] : e;
     const float* xp = xa + rs * row_floats + ch;
     float4 x[D1];
 #pragma unroll
     for (int i = 0; i < D1; ++i) x[i] = ld4(xp + i * p.mul);
     if (xb != nullptr) {
-      const float* xq = xb + (long long)dst_s[el] * row_floats + ch;
+      const float* xq = xb + (long long)dst_s[els] * row_floats + ch;
+      float4 x2[D1];
 #pragma unroll
-      for (int i = 0; i < D1; ++i) addv(x[i], ld4(xq + i * p.mul));
+      for (int i = 0; i < D1; ++i) x2[i] = ld4(xq + i * p.mul);
+#pragma unroll
+      for (int i = 0; i < D1; ++i) addv(x[i], x2[i]);
     }
+    if (!waited) {
+      waited = true;
+      if (wt.hint) { mbar_wait_hint(wt.raw_free, wt.raw_ph); if (wt.op_full) mbar_wait_hint(wt.op_full, wt.op_ph); }
+      else { mbar_wait(wt.raw_free, wt.raw_ph); if (wt.op_full) mbar_wait(wt.op_full, wt.op_ph); }
+    }
+    if (!active || (a.dbg_skip & 1)) break;
+    float4 wv = w_tile != 0 ? lds128(w_tile + (uint32_t)el * 128u + (uint32_t)c8 * 16u) : ld4(a.w + p.w_off + ch);
+    addv(wv, woff);
+    float m[NM * 4];
+    const uint32_t ma = m_addr + (uint32_t)(el * a.m_row + p.m_off) * 4u;
 #pragma unroll
-    for (int i = 0; i < D1; ++i) mulv(x[i], wv);
-    const float* me = mbuf + el * a.m_row + p.m_off;      // [D1][D3]
+    for (int q = 0; q < NM; ++q) {
+      const float4 v = lds128(ma + (uint32_t)q * 16u);
+      m[4 * q] = v.x; m[4 * q + 1] = v.y; m[4 * q + 2] = v.z; m[4 * q + 3] = v.w;
+    }
+    float4 f[D3];
+    if constexpr (DIAG) {
+#pragma unroll
+      for (int k = 0; k < D3; ++k) {
+        f[k] = x[k];
+        mulv(f[k], wv);
+        f[k].x *= m[k * D3 + k]; f[k].y *= m[k * D3 + k]; f[k].z *= m[k * D3 + k]; f[k].w *= m[k * D3 + k];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < D3; ++k) f[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < D1; ++i) {
+#pragma unroll
+        for (int k = 0; k < D3; ++k) fs(f[k], x[i], m[i * D3 + k]);
+      }
+#pragma unroll
+      for (int k = 0; k < D3; ++k) mulv(f[k], wv);
+    }
     const int rbase = (int)(e * D3 - row0);
 #pragma unroll
     for (int k = 0; k < D3; ++k) {
-      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int i = 0; i < D1; ++i)
-        if ((nz >> (i * D3 + k)) & 1ull) fs(f, x[i], me[i * D3 + k]);
       const int row = rbase + k;
-      if ((unsigned)row < (unsigned)BM) sts128(raw_addr + (uint32_t)row * 128u + (uint32_t)((c8 ^ (row & 7)) << 4), f);
+      if ((unsigned)row < (unsigned)BM) sts128(raw_addr + (uint32_t)row * 128u + (uint32_t)((c8 ^ (row & 7)) << 4), f[k]);
     }
-  }
+    el += kDtpSetThreads / 8;
+  } while (el < n_e);
 }
 
 template <int D3>
 __device__ __forceinline__ void dtp_ktile_d1(const FArgs& a, const FPath& p, int ch0, int t, long long e0, int n_e, long long row0,
-                                             const int* src_s, const int* dst_s, const float* mbuf, uint32_t raw_addr,
-                                             uint32_t w_tile) {
+                                             const int* src_s, const int* dst_s, uint32_t m_addr, uint32_t raw_addr,
+                                             uint32_t w_tile, const KtWaits& wt) {
+  if (p.d2 == 1 && p.d1 == D3) {     // l2 = 0: identity coupling (a multiple of it)
+    dtp_ktile<D3, D3, true>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, m_addr, raw_addr, w_tile, wt);
+    return;
+  }
   switch (p.d1) {
-    case 1: dtp_ktile<1, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
-    case 3: dtp_ktile<3, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
-    case 5: dtp_ktile<5, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
-    default: dtp_ktile<7, D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile); break;
+    case 1: dtp_ktile<1, D3, false>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, m_addr, raw_addr, w_tile, wt); break;
+    case 3: dtp_ktile<3, D3, false>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, m_addr, raw_addr, w_tile, wt); break;
+    case 5: dtp_ktile<5, D3, false>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, m_addr, raw_addr, w_tile, wt); break;
+    default: dtp_ktile<7, D3, false>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, m_addr, raw_addr, w_tile, wt); break;
   }
 }
 
@@ -179,43 +236,53 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
   constexpr int kTmemCols = 512;
   constexpr int kAcc = S::kAccCols;
   constexpr int kACol0 = 2 * kAcc;                       // first TMEM column of the A staging area
-  const int kStages = a.n_stages;
-  const int stage_bytes = a.stage_bytes;
+  constexpr int kTS = S::kStagesTmem > kMaxStages ? kMaxStages : S::kStagesTmem;    // a_hi / a_lo slots in tensor memory
+  const int n_op = a.n_op, n_raw = a.n_raw;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_base = smem;
-  uint8_t* store_base = smem + kStages * stage_bytes;
-  uint8_t* tab_base = store_base + S::kStoreBytes;           // two table buffers: [m_buf_floats] M rows, then src / dst rows
+  uint8_t* op_base = smem;                                            // [n_op] x (B hi | B lo | radial-weight box)
+  uint8_t* raw_base = smem + (size_t)n_op * a.op_bytes;               // [n_raw] x raw A tile
+  uint8_t* store_base = raw_base + (size_t)n_raw * S::kABytes;
+  uint8_t* tab_base = store_base + S::kStoreBytes;           // two table buffers: [m_buf_floats] M rows, harmonics, src / dst rows
   int4* mdesc = reinterpret_cast<int4*>(tab_base + 2 * a.tab_bytes);      // per M-row entry: (cg offset, y offset, d2, -)
   float* cg_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(mdesc) + ((a.m_row * 16 + 127) & ~127));   // the group's CG blocks
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(cg_s) + ((a.cg_floats * 4 + 127) & ~127));
-  uint64_t* full = bars;                          // [8] weight tiles (and the radial-weight box) landed (TMA)
-  uint64_t* raw_ready = bars + kMaxStages;        // [8] raw A tile written by the DTP set
-  uint64_t* a_ready = bars + 2 * kMaxStages;      // [8] a_hi / a_lo in tensor memory
-  uint64_t* empty = bars + 3 * kMaxStages;        // [8] MMAs of the stage finished
-  uint64_t* tmem_full = bars + 4 * kMaxStages;    // [2]
-  uint64_t* tmem_empty = tmem_full + 2;           // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full + 4);
+  uint64_t* op_full = bars;                        // [8] weight tiles and the radial-weight box landed (TMA)
+  uint64_t* op_empty = bars + kMaxStages;          // [8] the MMAs that read the slot's weight tiles finished
+  uint64_t* raw_ready = bars + 2 * kMaxStages;     // [8] raw A tile written by the DTP set
+  uint64_t* raw_free = bars + 3 * kMaxStages;      // [8] the transform warps hold the raw tile in registers
+  uint64_t* a_ready = bars + 4 * kMaxStages;       // [8] a_hi / a_lo in tensor memory
+  uint64_t* a_free = bars + 5 * kMaxStages;        // [8] the MMAs that read the tensor-memory slot finished
+  uint64_t* tmem_full = bars + 6 * kMaxStages;     // [2]
+  uint64_t* tmem_empty = tmem_full + 2;            // [2]
+  uint64_t* tab_ready = tmem_full + 4;             // [2] tables of a row block built (helper warps)
+  uint64_t* tab_free = tmem_full + 6;              // [2] the DTP warps finished the row block
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int k_tiles = a.K / BKT;
-  constexpr int d3 = D3;        // compile-time output degree: the kernel carries the D1 variants of one degree only (the
-                                // all-degrees build was 142 KB of code per kernel - instruction-cache misses everywhere)
+  constexpr int d3 = D3;        // compile-time output degree: one kernel per degree (the all-degrees build was 142 KB of code)
   const long long n_tiles_total = a.m_blocks * a.n_blocks;
   const bool w_tma = !a.w_shared;
+  const bool hint = (a.dbg_skip & 8) == 0;         // try_wait with the long suspend-time hint (bit 3 turns it off: A/B)
+  auto wait = [hint](uint64_t* bar, uint32_t parity) { if (hint) mbar_wait_hint(bar, parity); else mbar_wait(bar, parity); };
 
   if (warp == kProducerWarp && lane == 0) {
     prefetch_map(&map_bhi); prefetch_map(&map_blo); prefetch_map(&map_c);
     if (w_tma) prefetch_map(&map_w);
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], 1);
+    for (int s = 0; s < kMaxStages; ++s) {
+      mbar_init(&op_full[s], 1);
+      mbar_init(&op_empty[s], 1);
       mbar_init(&raw_ready[s], kDtpSetWarps);
+      mbar_init(&raw_free[s], kTransformWarps);
       mbar_init(&a_ready[s], kTransformWarps);
-      mbar_init(&empty[s], 1);
+      mbar_init(&a_free[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], kEpilogueWarps);
+      mbar_init(&tab_ready[b], kHelperWarps);
+      mbar_init(&tab_free[b], kDtpWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -230,7 +297,6 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
 
   if (warp < kEpilogueWarps) {
     // ===================================================================================== epilogue (warpgroup 0)
-    reg_alloc<88>();
     uint32_t acc_it = 0, chunk_it = 0;
     int n_stamp = 0;
     for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
@@ -238,7 +304,7 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
       const int nb = (int)(tile % a.n_blocks);
       const int ab = acc_it & 1;
       const uint32_t aph = (acc_it >> 1) & 1;
-      mbar_wait(&tmem_full[ab], aph);
+      wait(&tmem_full[ab], aph);
       if (threadIdx.x == 0) stamp(a, 3, n_stamp);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(ab * kAcc);
@@ -286,28 +352,26 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
     if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp < kTransformWarp0) {
     // ===================================================================================== warpgroup 1: TMA, MMA, table helpers
-    reg_dealloc<40>();
+    reg_dealloc<56>();
     if (warp == kProducerWarp) {
       if (lane == 0) {
-        uint32_t it = 0;
+        Ring op(n_op);
         int n_stamp = 0;
         const uint32_t tx = (uint32_t)(2 * a.n_tile * kRowBytes) + (w_tma ? (uint32_t)(a.w_box_rows * kRowBytes) : 0u);
         for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
           const long long mb = tile / a.n_blocks;
           const int nb = (int)(tile % a.n_blocks);
           const int e0 = (int)((mb * BM) / d3);
-          for (int kt = 0; kt < k_tiles; ++kt, ++it) {
-            const int s = it % kStages;
-            const uint32_t ph = (it / kStages) & 1;
-            mbar_wait(&empty[s], ph ^ 1);
+          for (int kt = 0; kt < k_tiles; ++kt, op.next()) {
+            wait(&op_empty[op.idx], op.ph ^ 1);
             stamp(a, 0, n_stamp);
-            uint8_t* st = stage_base + (size_t)s * stage_bytes;
-            mbar_expect_tx(&full[s], tx);
-            tma_load_2d(st + S::kABytes, &map_bhi, kt * BKT, nb * a.n_tile, &full[s]);
-            tma_load_2d(st + S::kABytes + S::kBBytes, &map_blo, kt * BKT, nb * a.n_tile, &full[s]);
+            uint8_t* st = op_base + (size_t)op.idx * a.op_bytes;
+            mbar_expect_tx(&op_full[op.idx], tx);
+            tma_load_2d(st, &map_bhi, kt * BKT, nb * a.n_tile, &op_full[op.idx]);
+            tma_load_2d(st + S::kBBytes, &map_blo, kt * BKT, nb * a.n_tile, &op_full[op.idx]);
             if (w_tma) {
               const FPath& p = a.paths[a.kt_path[kt]];
-              tma_load_2d(st + a.w_tile_off, &map_w, p.w_off + (kt * BKT - p.koff), e0, &full[s]);
+              tma_load_2d(st + a.w_tile_off, &map_w, p.w_off + (kt * BKT - p.koff), e0, &op_full[op.idx]);
             }
           }
         }
@@ -316,25 +380,24 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
       if (lane == 0) {
         const uint32_t idesc = instr_desc(a.n_tile);
         const uint32_t idesc2 = instr_desc(2 * a.n_tile);          // STACK: [b_hi | b_lo] as one operand
-        uint32_t it = 0, acc_it = 0;
+        Ring op(n_op), ts(kTS);
+        uint32_t acc_it = 0;
         int n_stamp = 0;
         for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
           const int ab = acc_it & 1;
           const uint32_t aph = (acc_it >> 1) & 1;
-          mbar_wait(&tmem_empty[ab], aph ^ 1);
+          wait(&tmem_empty[ab], aph ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(ab * kAcc);
-          for (int kt = 0; kt < k_tiles; ++kt, ++it) {
-            const int s = it % kStages;
-            const uint32_t ph = (it / kStages) & 1;
-            mbar_wait(&full[s], ph);
+          for (int kt = 0; kt < k_tiles; ++kt, op.next(), ts.next()) {
+            wait(&op_full[op.idx], op.ph);
             stamp(a, 1, n_stamp);
-            mbar_wait(&a_ready[s], ph);
+            wait(&a_ready[ts.idx], ts.ph);
             stamp(a, 1, n_stamp);
             tc_fence_after();
-            const uint32_t st = smem_u32(stage_base + (size_t)s * stage_bytes);
-            const uint64_t b_hi = smem_desc_sw128(st + S::kABytes), b_lo = smem_desc_sw128(st + S::kABytes + S::kBBytes);
-            const uint32_t a_hi = tmem_base + (uint32_t)(kACol0 + s * 2 * BKT), a_lo = a_hi + BKT;
+            const uint32_t st = smem_u32(op_base + (size_t)op.idx * a.op_bytes);
+            const uint64_t b_hi = smem_desc_sw128(st), b_lo = smem_desc_sw128(st + S::kBBytes);
+            const uint32_t a_hi = tmem_base + (uint32_t)(kACol0 + ts.idx * 2 * BKT), a_lo = a_hi + BKT;
 #pragma unroll
             for (int kb = 0; kb < BKT / UMMA_K; ++kb) {
               if (a.dbg_skip & 2) break;
@@ -349,11 +412,85 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
                 umma_tf32_ts(d_tmem, a_hi + acol, b_hi + adv, idesc, 1u);
               }
             }
-            umma_commit(&empty[s]);
+            umma_commit(&op_empty[op.idx]);
+            umma_commit(&a_free[ts.idx]);
             stamp(a, 1, n_stamp);
           }
           umma_commit(&tmem_full[ab]);
         }
+      }
+    } else {
+      // ------------------------------------------------------------------------------------- table helpers (warps 6, 7)
+      // One row block AHEAD of the DTP warps: the block's edges (src / dst rows, harmonics) into shared memory, then the
+      // coupling blocks M_p[e] = CG_p . y_e, one thread per entry q of the edge's M row (its CG column in registers)
+      // walking the block's edges.  (v3 did this inside the DTP warps between two 512-thread barriers: ~7 k cycles per row
+      // block during which the whole pipeline drained - 23 % of the kernel.)
+      const int ht = threadIdx.x - kHelperWarp0 * 32;          // 0 .. 63
+      const int m_row = a.m_row, d_y = a.d_y;
+      {
+        int off = 0;
+        for (int pi = 0; pi < a.n_paths; ++pi) {
+          const FPath& p = a.paths[pi];
+          const int n = p.d1 * p.d2 * d3;
+          for (int i = ht; i < n; i += kHelperThreads) cg_s[off + i] = __ldg(a.cg + p.cg_off + i);
+          off += n;
+        }
+        for (int q = ht; q < m_row; q += kHelperThreads) {
+          int pi = 0, cg0 = 0;
+          for (int j = 1; j < a.n_paths; ++j) if (q >= a.paths[j].m_off) pi = j;
+          for (int j = 0; j < pi; ++j) cg0 += a.paths[j].d1 * a.paths[j].d2 * d3;
+          const FPath& p = a.paths[pi];
+          const int r = q - p.m_off;
+          const int i = r / d3, k = r - i * d3;
+          if (i < p.d1) mdesc[q] = make_int4(cg0 + i * p.d2 * d3 + k, p.y_off, p.d2, 0);
+          else mdesc[q] = make_int4(0, 0, 0, 0);           // padding of the path's block to a multiple of 4 floats
+        }
+        named_barrier(2, kHelperThreads);
+      }
+      const uint32_t cg_addr = smem_u32(cg_s);
+      uint32_t tile_it = 0;
+      int n_stamp = 0;
+      for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tile_it) {
+        const long long mb = tile / a.n_blocks;
+        const long long row0 = mb * BM;
+        const long long e0 = row0 / d3;
+        long long e1 = (row0 + BM - 1) / d3 + 1;
+        if (e1 > a.E) e1 = a.E;
+        const int n_e = (int)(e1 - e0);
+        const int b = tile_it & 1;
+        wait(&tab_free[b], ((tile_it >> 1) & 1) ^ 1);
+        if (ht == 0) stamp(a, 5, n_stamp);
+        float* mw = reinterpret_cast<float*>(tab_base + b * a.tab_bytes);
+        float* ybuf = mw + a.m_buf_floats;
+        int* ss = reinterpret_cast<int*>(ybuf + a.y_buf_floats);
+        int* ds = ss + kMaxTileEdges;
+        if (a.src != nullptr) {
+          for (int i = ht; i < n_e; i += kHelperThreads) {
+            ss[i] = (int)a.src[e0 + i];
+            ds[i] = a.dst != nullptr ? (int)a.dst[e0 + i] : 0;
+          }
+        }
+        for (int i = ht; i < n_e * d_y; i += kHelperThreads) ybuf[i] = __ldg(a.y + e0 * d_y + i);
+        named_barrier(2, kHelperThreads);
+        const uint32_t y_addr = smem_u32(ybuf);
+        for (int q = ht; q < m_row; q += kHelperThreads) {
+          const int4 dsc = mdesc[q];
+          float cgr[kMaxD];
+#pragma unroll
+          for (int j = 0; j < kMaxD; ++j) cgr[j] = j < dsc.z ? lds32(cg_addr + (uint32_t)(dsc.x + j * d3) * 4u) : 0.f;
+#pragma unroll 4
+          for (int el = 0; el < n_e; ++el) {
+            const uint32_t ya = y_addr + (uint32_t)(el * d_y + dsc.y) * 4u;
+            float m = 0.f;
+#pragma unroll
+            for (int j = 0; j < kMaxD; ++j)
+              if (j < dsc.z) m = fmaf(cgr[j], lds32(ya + (uint32_t)j * 4u), m);
+            mw[el * m_row + q] = m;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tab_ready[b]);
+        if (ht == 0) stamp(a, 5, n_stamp);
       }
     }
   } else if (warp < kDtpWarp0) {
@@ -361,38 +498,44 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
     reg_alloc<88>();
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_field = (uint32_t)((warp & 3) * 32) << 16;
-    uint32_t it = 0;
+    Ring raw(n_raw), ts(kTS);
     int n_stamp = 0;
     const bool stamper = warp == kTransformWarp0 && lane == 0;
     for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-      for (int kt = 0; kt < k_tiles; ++kt, ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&raw_ready[s], ph);
+      for (int kt = 0; kt < k_tiles; ++kt, raw.next(), ts.next()) {
+        wait(&raw_ready[raw.idx], raw.ph);
         if (stamper) stamp(a, 2, n_stamp);
-        if (!(a.dbg_skip & 4)) {
-          const uint32_t rbase = smem_u32(stage_base + (size_t)s * stage_bytes) + (uint32_t)row * (uint32_t)kRowBytes;
-          float hi[BKT], lo[BKT];
+        float hi[BKT], lo[BKT];
+        {
+          const uint32_t rbase = smem_u32(raw_base + (size_t)raw.idx * S::kABytes) + (uint32_t)row * (uint32_t)kRowBytes;
           float4 v[8];
 #pragma unroll
           for (int c = 0; c < 8; ++c) v[c] = lds128(rbase + (uint32_t)((c ^ (row & 7)) << 4));
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float xv[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
+          for (int c = 0; c < 8; ++c) { hi[4 * c] = v[c].x; hi[4 * c + 1] = v[c].y; hi[4 * c + 2] = v[c].z; hi[4 * c + 3] = v[c].w; }
+        }
+        // the raw tile is in registers: hand the slot back to the DTP warps before the conversion (the arrive's release
+        // orders the loads above before it; __syncwarp extends that to the other lanes)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_free[raw.idx]);
+        wait(&a_free[ts.idx], ts.ph ^ 1);
+        tc_fence_after();
+        if (!(a.dbg_skip & 4)) {
+          if (!(a.dbg_skip & 16)) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              hi[4 * c + q] = tf32_rn(xv[q]);
-              lo[4 * c + q] = xv[q] - hi[4 * c + q];
-            }
+            for (int j = 0; j < BKT; ++j) { const float xv = hi[j]; hi[j] = tf32_rn_fast(xv); lo[j] = xv - hi[j]; }
+          } else {
+#pragma unroll
+            for (int j = 0; j < BKT; ++j) { const float xv = hi[j]; hi[j] = tf32_rn(xv); lo[j] = xv - hi[j]; }
           }
-          const uint32_t acol = tmem_base + lane_field + (uint32_t)(kACol0 + s * 2 * BKT);
+          const uint32_t acol = tmem_base + lane_field + (uint32_t)(kACol0 + ts.idx * 2 * BKT);
           tmem_st32(acol, hi);
           tmem_st32(acol + BKT, lo);
           tmem_wait_st();
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&a_ready[s]);
+        if (lane == 0) mbar_arrive(&a_ready[ts.idx]);
         if (stamper) stamp(a, 2, n_stamp);
       }
     }
@@ -401,97 +544,42 @@ dtp_gemm_fwd_kernel(const __grid_constant__ CUtensorMap map_bhi, const __grid_co
     const int dt = threadIdx.x - kDtpWarp0 * 32;          // 0 .. 511
     const int set = (warp - kDtpWarp0) / kDtpSetWarps;    // which half of the k-tiles
     const int t = dt - set * kDtpSetThreads;              // 0 .. 255 inside the set
-    const int m_row = a.m_row, d_y = a.d_y;
-    // once per CTA: the group's CG blocks packed into shared memory and one descriptor per M-row entry
-    {
-      int off = 0;
-      for (int pi = 0; pi < a.n_paths; ++pi) {
-        const FPath& p = a.paths[pi];
-        const int n = p.d1 * p.d2 * d3;
-        for (int i = dt; i < n; i += kDtpThreads) cg_s[off + i] = __ldg(a.cg + p.cg_off + i);
-        off += n;
-      }
-      for (int q = dt; q < m_row; q += kDtpThreads) {
-        int pi = 0, cg0 = 0;
-        for (int j = 1; j < a.n_paths; ++j) if (q >= a.paths[j].m_off) pi = j;
-        for (int j = 0; j < pi; ++j) cg0 += a.paths[j].d1 * a.paths[j].d2 * d3;
-        const FPath& p = a.paths[pi];
-        const int r = q - p.m_off;
-        const int i = r / d3, k = r - i * d3;
-        mdesc[q] = make_int4(cg0 + i * p.d2 * d3 + k, p.y_off, p.d2, 0);
-      }
-    }
-    const float inv_m_row = 1.0f / (float)m_row;
+    Ring op(n_op), raw(n_raw);
     uint32_t it = 0, tile_it = 0;
     int n_stamp = 0;
-    const bool stamper = (t == 0);                       // first thread of each set: roles 4 and 5
-    long long mb_prev = -1;
-    const float* mbuf = nullptr;
-    const int* src_s = nullptr;
-    const int* dst_s = nullptr;
-    for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+    const bool stamper = (t == 0 && set == 0);            // role 4: first thread of set 0
+    for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tile_it) {
       const long long mb = tile / a.n_blocks;
       const long long row0 = mb * BM;
       const long long e0 = row0 / d3;
       long long e1 = (row0 + BM - 1) / d3 + 1;
       if (e1 > a.E) e1 = a.E;
       const int n_e = (int)(e1 - e0);
-      if (mb != mb_prev) {
-        // ---- tables of this row block, double-buffered (a warp may start them while slower warps still read the previous
-        // block's): the edges' node rows and harmonics, then the coupling blocks M_p[e] = CG_p . y_e - operands in shared memory
-        mb_prev = mb;
-        if (stamper) stamp(a, 4 + set, n_stamp);
-        float* mw = reinterpret_cast<float*>(tab_base + (tile_it & 1) * a.tab_bytes);
-        float* ybuf = mw + a.m_buf_floats;
-        int* ss = reinterpret_cast<int*>(ybuf + a.y_buf_floats);
-        int* ds = ss + kMaxTileEdges;
-        ++tile_it;
-        if (a.src != nullptr) {
-          for (int i = dt; i < n_e; i += kDtpThreads) {
-            ss[i] = (int)a.src[e0 + i];
-            ds[i] = a.dst != nullptr ? (int)a.dst[e0 + i] : 0;
-          }
-        }
-        for (int i = dt; i < n_e * d_y; i += kDtpThreads) ybuf[i] = __ldg(a.y + e0 * d_y + i);
-        named_barrier(1, kDtpThreads);
-        if (stamper) stamp(a, 4 + set, n_stamp);
-        const int n_items = n_e * m_row;
-        for (int idx = dt; idx < n_items; idx += kDtpThreads) {
-          const int el = (int)(((float)idx + 0.5f) * inv_m_row);
-          const int q = idx - el * m_row;
-          const int4 dsc = mdesc[q];
-          const float* cgp = cg_s + dsc.x;
-          const float* yv = ybuf + el * d_y + dsc.y;
-          float m = 0.f;
-#pragma unroll
-          for (int j = 0; j < kMaxD; ++j)
-            if (j < dsc.z) m = fmaf(cgp[j * d3], yv[j], m);
-          mw[idx] = m;
-        }
-        named_barrier(1, kDtpThreads);
-        if (stamper) stamp(a, 4 + set, n_stamp);
-        mbuf = mw; src_s = ss; dst_s = ds;
-      }
-      for (int kt = 0; kt < k_tiles; ++kt, ++it) {
+      const int b = tile_it & 1;
+      wait(&tab_ready[b], (tile_it >> 1) & 1);            // the helper warps built this row block's tables
+      if (stamper) stamp(a, 4, n_stamp);
+      const float* mw = reinterpret_cast<const float*>(tab_base + b * a.tab_bytes);
+      const float* ybuf = mw + a.m_buf_floats;
+      const int* src_s = reinterpret_cast<const int*>(ybuf + a.y_buf_floats);
+      const int* dst_s = src_s + kMaxTileEdges;
+      const uint32_t m_addr = smem_u32(mw);
+      for (int kt = 0; kt < k_tiles; ++kt, ++it, op.next(), raw.next()) {
         if ((int)(it & 1) != set) continue;               // the two sets alternate k-tiles
         const FPath& p = a.paths[a.kt_path[kt]];
         const int ch0 = kt * BKT - p.koff;
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        if (stamper) stamp(a, 4 + set, n_stamp);
-        const uint32_t raw_addr = smem_u32(stage_base + (size_t)s * stage_bytes);
-        uint32_t w_tile = 0;
-        if (w_tma) {
-          mbar_wait(&full[s], ph);                        // the k-tile's radial-weight box has landed
-          w_tile = raw_addr + (uint32_t)a.w_tile_off;
-        }
-        if (stamper) stamp(a, 4 + set, n_stamp);
-        if (!(a.dbg_skip & 1)) dtp_ktile_d1<D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, mbuf, raw_addr, w_tile);
+        const uint32_t raw_addr = smem_u32(raw_base + (size_t)raw.idx * S::kABytes);
+        const uint32_t w_tile = w_tma ? smem_u32(op_base + (size_t)op.idx * a.op_bytes) + (uint32_t)a.w_tile_off : 0u;
+        KtWaits wt;
+        wt.raw_free = &raw_free[raw.idx]; wt.raw_ph = raw.ph ^ 1;
+        wt.op_full = w_tma ? &op_full[op.idx] : nullptr; wt.op_ph = op.ph; wt.hint = hint;
+        if (stamper) stamp(a, 4, n_stamp);
+        dtp_ktile_d1<D3>(a, p, ch0, t, e0, n_e, row0, src_s, dst_s, m_addr, raw_addr, w_tile, wt);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_ready[s]);
-        if (stamper) stamp(a, 4 + set, n_stamp);
+        if (lane == 0) mbar_arrive(&raw_ready[raw.idx]);
+        if (stamper) stamp(a, 4, n_stamp);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tab_free[b]);           // this warp no longer reads the row block's tables
     }
   }
 
@@ -554,7 +642,7 @@ __global__ void __launch_bounds__(256) dtp_group_forward_kernel(const __grid_con
       const float* cg = a.cg + p.cg_off + i * p.d2 * D3 + k;
       const float* yv = a.y + (eb + ee) * a.d_y + p.y_off;
       float m = 0.f;
-      for (int j = 0; j < p.d2; ++j) m = fmaf(__ldg(cg + j * D3), __ldg(yv + j), m);
+      for (int j = 0; j < (i < p.d1 ? p.d2 : 0); ++j) m = fmaf(__ldg(cg + j * D3), __ldg(yv + j), m);   // i >= d1: block padding
       msm[idx] = m;
     }
     __syncthreads();
@@ -593,23 +681,30 @@ template <int BN, bool STACK, int D3>
 static int launch_fwd_d3(const CUtensorMap& mh, const CUtensorMap& ml, const CUtensorMap& mc, const CUtensorMap& mw, FArgs& a,
                       cudaStream_t s) {
   using S = FSmem<BN, STACK>;
-  // shared-memory layout: stages (raw A | B hi | B lo | radial-weight box) | store staging | 2 table buffers | descriptors | barriers
+  // shared-memory layout: operand slots (B hi | B lo | radial-weight box) | raw A tiles | store staging | 2 table buffers |
+  // descriptors | barriers.  The rings are independent: an operand slot is held from its TMA to the MMAs that read the
+  // weight tiles, a raw tile only from the DTP warps' stores to the transform warps' loads, a tensor-memory A slot from
+  // the transform's stores to the MMAs (v3 tied all three to ONE 5-deep ring whose round trip - TMA from HBM, producer,
+  // transform, MMA - was ~7 k cycles: 1.4 k cycles per k-tile before any arithmetic).
   const int n_e_max = BM / a.d3 + 2;
   a.w_box_rows = a.w_shared ? 0 : n_e_max;
-  a.w_tile_off = S::kABytes + 2 * S::kBBytes;
-  a.stage_bytes = (a.w_tile_off + a.w_box_rows * kRowBytes + 1023) & ~1023;
+  a.w_tile_off = 2 * S::kBBytes;
+  a.op_bytes = (a.w_tile_off + a.w_box_rows * kRowBytes + 1023) & ~1023;
   a.m_buf_floats = (n_e_max * a.m_row + 31) & ~31;
   a.y_buf_floats = (n_e_max * a.d_y + 31) & ~31;
   a.cg_floats = 0;
   for (int i = 0; i < a.n_paths; ++i) a.cg_floats += a.paths[i].d1 * a.paths[i].d2 * a.d3;
   a.tab_bytes = ((a.m_buf_floats + a.y_buf_floats) * 4 + kMetaInts * 4 + 127) & ~127;
   const int fixed = S::kStoreBytes + 2 * a.tab_bytes + ((a.m_row * 16 + 127) & ~127) + ((a.cg_floats * 4 + 127) & ~127) + S::kBarBytes;
-  int stages = (S::kBudget - fixed) / a.stage_bytes;
-  if (stages > S::kStagesTmem) stages = S::kStagesTmem;
-  if (stages > kMaxStages) stages = kMaxStages;
-  if (stages < 2) { set_error("fused DTP: the tile does not fit shared memory"); return EQF_ERR_UNSUPPORTED; }
-  a.n_stages = stages;
-  const int total = stages * a.stage_bytes + fixed + 1024;
+  int n_raw = 0, n_op = 0;
+  for (int r = 4; r >= 2 && n_raw == 0; --r) {             // prefer 4 raw tiles (two per DTP set) if >= r operand slots remain
+    const int o = (S::kBudget - fixed - r * S::kABytes) / a.op_bytes;
+    if (o >= r || (r == 2 && o >= 2)) { n_raw = r; n_op = o; }
+  }
+  if (n_raw == 0) { set_error("fused DTP: the tile does not fit shared memory"); return EQF_ERR_UNSUPPORTED; }
+  if (n_op > kMaxStages) n_op = kMaxStages;
+  a.n_raw = n_raw; a.n_op = n_op;
+  const int total = n_op * a.op_bytes + n_raw * S::kABytes + fixed + 1024;
   static std::mutex mtx;
   static int attr_bytes = 0;
   {
@@ -671,7 +766,7 @@ static int collect_paths(const EqfPlan* plan, int group, FArgs& a) {
       a.kt_path[koff / BKT + c] = (unsigned char)i;
     }
     koff += s.mul;
-    m_off += s.d1 * s.d3;
+    m_off += (s.d1 * s.d3 + 3) & ~3;           // every path's [d1][d3] block starts 16-byte aligned (128-bit shared loads)
   }
   a.n_paths = (int)ps.size();
   a.d3 = h.out_d[group];
@@ -734,7 +829,7 @@ static int fill_fargs(const EqfPlan* plan, const EqfEdgeOperands* op, int64_t n_
   a.E = n_edges; a.M = n_edges * a.d3; a.d_y = h.d_y; a.W = h.w_numel; a.N = 0;
   if (a.M > 0x7fffffffLL) { set_error(std::string(who) + ": too many rows"); return EQF_ERR_UNSUPPORTED; }
   a.n_tile = a.n_blocks = 0; a.m_blocks = 0;
-  a.n_stages = a.stage_bytes = a.w_tile_off = a.w_box_rows = a.tab_bytes = a.m_buf_floats = a.y_buf_floats = a.cg_floats = 0;
+  a.n_op = a.n_raw = a.op_bytes = a.w_tile_off = a.w_box_rows = a.tab_bytes = a.m_buf_floats = a.y_buf_floats = a.cg_floats = 0;
   { const char* e = std::getenv("EQF_FUSED_DBG_SKIP"); a.dbg_skip = e ? std::atoi(e) : 0; }
   a.dbg = g_fused_dbg;
   return EQF_OK;

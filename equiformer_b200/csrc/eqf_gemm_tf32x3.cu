@@ -65,6 +65,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                  : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   } while (!done);
 }
+// the same wait with the suspend-time hint CUTLASS passes: the warp sleeps in hardware until the phase completes instead
+// of returning after the short default limit and being re-issued (one polling lane per warp + __syncwarp was measured
+// SLOWER than all lanes waiting: profiles/r2_v4_ab_*.jsonl)
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_x(uint64_t* bar, uint32_t parity, bool hinted) {
+  if (hinted) mbar_wait_hint(bar, parity); else mbar_wait(bar, parity);
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
@@ -100,6 +116,12 @@ __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float(r);
 }
 
+// the same rounding (nearest, ties away from zero) in two integer instructions: cvt.rna.tf32.f32 compiles to five on
+// sm_100a (it also keeps NaN payloads; here a NaN still reaches the product through lo = x - hi = NaN)
+__device__ __forceinline__ float tf32_rn_fast(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
@@ -111,9 +133,10 @@ __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
 
 // x -> (hi, lo): hi = x rounded to tf32 written back in place (the MMA truncates its fp32 operand, so it must be
 // handed the rounded value explicitly), lo = x - hi written `lo_offset` bytes further
-__device__ __forceinline__ void split_store(uint32_t addr, uint32_t lo_offset, const float4& v) {
+__device__ __forceinline__ void split_store(uint32_t addr, uint32_t lo_offset, const float4& v, bool fast = false) {
   float4 h, r;
-  h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w);
+  if (fast) { h.x = tf32_rn_fast(v.x); h.y = tf32_rn_fast(v.y); h.z = tf32_rn_fast(v.z); h.w = tf32_rn_fast(v.w); }
+  else { h.x = tf32_rn(v.x); h.y = tf32_rn(v.y); h.z = tf32_rn(v.z); h.w = tf32_rn(v.w); }
   r.x = v.x - h.x; r.y = v.y - h.y; r.z = v.z - h.z; r.w = v.w - h.w;
   sts128(addr, h);
   sts128(addr + lo_offset, r);
@@ -129,7 +152,9 @@ struct Params {
   long long m_blocks;
   long long* dbg;    // optional timeline of CTA 0 (clock64 stamps), see tools/tf32x3_timeline.py
   int dbg_skip;      // measurement aid (EQF_TF32X3_DBG_SKIP): bit 0 skips the transform math, bit 1 the MMAs - results are
-                     // garbage then; what remains is the load / synchronisation skeleton
+                     // garbage then; what remains is the load / synchronisation skeleton.  Bit 3 (8) turns OFF the
+                     // suspend-time hint of the barrier waits, bit 4 (16) the two-instruction tf32 rounding (A/B switches of
+                     // tools/v4_ab.py; the results do not change)
 };
 
 // dbg layout: role r in {0 producer, 1 mma, 2 transform, 3 epilogue}: dbg[r * 1024 + n] = n-th stamp of that role
@@ -212,7 +237,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait_x(&empty[s], ph ^ 1, (p.dbg_skip & 8) == 0);
           stamp(p, 0, n_stamp);
           uint8_t* st = stage_base + (size_t)s * S::kStageBytes;
           mbar_expect_tx(&full[s], tx);
@@ -231,15 +256,15 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
         const int a = acc_it & 1;
         const uint32_t aph = (acc_it >> 1) & 1;
-        mbar_wait(&tmem_empty[a], aph ^ 1);
+        mbar_wait_x(&tmem_empty[a], aph ^ 1, (p.dbg_skip & 8) == 0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
         for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&full[s], ph);
+          mbar_wait_x(&full[s], ph, (p.dbg_skip & 8) == 0);
           stamp(p, 1, n_stamp);
-          mbar_wait(&lo_ready[s], ph);
+          mbar_wait_x(&lo_ready[s], ph, (p.dbg_skip & 8) == 0);
           stamp(p, 1, n_stamp);
           tc_fence_after();
           const uint32_t st = smem_u32(stage_base + (size_t)s * S::kStageBytes);
@@ -267,7 +292,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&full[s], ph);
+        mbar_wait_x(&full[s], ph, (p.dbg_skip & 8) == 0);
         if (t == 0) stamp(p, 2, n_stamp);
         // loads are batched ahead of the stores (explicit ld/st.shared: with generic pointers the compiler serialised
         // load -> use -> store and the transform, not the tensor pipe, set the pace)
@@ -279,7 +304,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
           for (int i = 0; i < kPer; ++i) v[i] = lds128(raw_addr + (uint32_t)i * (kTransformThreads * 16));
 #pragma unroll
-          for (int i = 0; i < kPer; ++i) split_store(raw_addr + (uint32_t)i * (kTransformThreads * 16), S::kABytes, v[i]);
+          for (int i = 0; i < kPer; ++i) split_store(raw_addr + (uint32_t)i * (kTransformThreads * 16), S::kABytes, v[i], (p.dbg_skip & 16) == 0);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA's async proxy
         __syncwarp();
@@ -296,7 +321,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const int nb = (int)(tile % p.n_blocks);
       const int a = acc_it & 1;
       const uint32_t aph = (acc_it >> 1) & 1;
-      mbar_wait(&tmem_full[a], aph);
+      mbar_wait_x(&tmem_full[a], aph, (p.dbg_skip & 8) == 0);
       if (threadIdx.x == 0) stamp(p, 3, n_stamp);
       tc_fence_after();
       // TMEM -> registers -> swizzled staging rows (this warp's 32 rows x 32 columns) -> TMA store; two staging buffers
@@ -465,7 +490,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait_x(&empty[s], ph ^ 1, (p.dbg_skip & 8) == 0);
           stamp(p, 0, n_stamp);
           uint8_t* st = stage_base + (size_t)s * S::kStageBytes;
           mbar_expect_tx(&full[s], tx);
@@ -484,15 +509,15 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       for (long long tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++acc_it) {
         const int a = acc_it & 1;
         const uint32_t aph = (acc_it >> 1) & 1;
-        mbar_wait(&tmem_empty[a], aph ^ 1);
+        mbar_wait_x(&tmem_empty[a], aph ^ 1, (p.dbg_skip & 8) == 0);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * kAcc);
         for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&full[s], ph);          // the weight tiles (and the raw A tile) have landed
+          mbar_wait_x(&full[s], ph, (p.dbg_skip & 8) == 0);          // the weight tiles (and the raw A tile) have landed
           stamp(p, 1, n_stamp);
-          mbar_wait(&a_ready[s], ph);       // A hi / lo are in TMEM
+          mbar_wait_x(&a_ready[s], ph, (p.dbg_skip & 8) == 0);       // A hi / lo are in TMEM
           stamp(p, 1, n_stamp);
           tc_fence_after();
           const uint32_t st = smem_u32(stage_base + (size_t)s * S::kStageBytes);
@@ -530,7 +555,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&full[s], ph);
+        mbar_wait_x(&full[s], ph, (p.dbg_skip & 8) == 0);
         if (stamper) stamp(p, 2, n_stamp);
         if (p.dbg_skip & 1) {
           tc_fence_before();
@@ -547,10 +572,14 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         for (int c = 0; c < 8; ++c) {
           const float x[4] = {v[c].x, v[c].y, v[c].z, v[c].w};
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            hi[4 * c + q] = tf32_rn(x[q]);
-            lo[4 * c + q] = x[q] - hi[4 * c + q];
-          }
+          for (int q = 0; q < 4; ++q) hi[4 * c + q] = x[q];
+        }
+        if (!(p.dbg_skip & 16)) {
+#pragma unroll
+          for (int j = 0; j < BKT; ++j) { const float x = hi[j]; hi[j] = tf32_rn_fast(x); lo[j] = x - hi[j]; }
+        } else {
+#pragma unroll
+          for (int j = 0; j < BKT; ++j) { const float x = hi[j]; hi[j] = tf32_rn(x); lo[j] = x - hi[j]; }
         }
         const uint32_t acol = tmem_base + lane_field + (uint32_t)(kACol0 + s * 2 * BKT);
         tmem_st32(acol, hi);
@@ -570,7 +599,7 @@ gemm_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
       const int nb = (int)(tile % p.n_blocks);
       const int a = acc_it & 1;
       const uint32_t aph = (acc_it >> 1) & 1;
-      mbar_wait(&tmem_full[a], aph);
+      mbar_wait_x(&tmem_full[a], aph, (p.dbg_skip & 8) == 0);
       if (threadIdx.x == 0) stamp(p, 3, n_stamp);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kAcc);
@@ -788,7 +817,7 @@ gemm_tf32x3_ts2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait_x(&empty[s], ph ^ 1, (p.dbg_skip & 8) == 0);
           stamp(p, 0, n_stamp);
           uint8_t* st = stage_base + (size_t)s * S::kStageBytes;
           mbar_expect_tx(&full[s], tx);
@@ -813,7 +842,7 @@ gemm_tf32x3_ts2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&full[s], ph);
+          mbar_wait_x(&full[s], ph, (p.dbg_skip & 8) == 0);
           stamp(p, 1, n_stamp);
           mbar_wait_cluster(&a_ready[s], ph);      // both CTAs: operand tiles landed, A hi / lo in tensor memory
           stamp(p, 1, n_stamp);
@@ -845,7 +874,7 @@ gemm_tf32x3_ts2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       for (long long kt = 0; kt < k_tiles; ++kt, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(&full[s], ph);
+        mbar_wait_x(&full[s], ph, (p.dbg_skip & 8) == 0);
         if (stamper) stamp(p, 2, n_stamp);
         if (!(p.dbg_skip & 1)) {
           const uint32_t rbase = smem_u32(stage_base + (size_t)s * S::kStageBytes) + (uint32_t)row * (uint32_t)kRowBytesT;
@@ -881,7 +910,7 @@ gemm_tf32x3_ts2_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       const int nb = (int)(tile % p.n_blocks);
       const int a = acc_it & 1;
       const uint32_t aph = (acc_it >> 1) & 1;
-      mbar_wait(&tmem_full[a], aph);
+      mbar_wait_x(&tmem_full[a], aph, (p.dbg_skip & 8) == 0);
       if (threadIdx.x == 0) stamp(p, 3, n_stamp);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * kAcc);
@@ -1123,7 +1152,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (int kt = 0; kt < k_tiles; ++kt) {
         const int s = kt % kStages;
         const uint32_t ph = (kt / kStages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+        mbar_wait_x(&empty[s], ph ^ 1, (p.dbg_skip & 8) == 0);
         uint8_t* st = stage_base_of(smem, s, S::kStageBytes);
         mbar_expect_tx(&full[s], tx);
         const int row = (int)(r0 + (long long)kt * BKR);
@@ -1138,8 +1167,8 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       for (int kt = 0; kt < k_tiles; ++kt) {
         const int s = kt % kStages;
         const uint32_t ph = (kt / kStages) & 1;
-        mbar_wait(&full[s], ph);
-        mbar_wait(&lo_ready[s], ph);
+        mbar_wait_x(&full[s], ph, (p.dbg_skip & 8) == 0);
+        mbar_wait_x(&lo_ready[s], ph, (p.dbg_skip & 8) == 0);
         tc_fence_after();
         const uint32_t st = smem_u32(stage_base_of(smem, s, S::kStageBytes));
 #pragma unroll
@@ -1162,7 +1191,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     for (int kt = 0; kt < k_tiles; ++kt) {
       const int s = kt % kStages;
       const uint32_t ph = (kt / kStages) & 1;
-      mbar_wait(&full[s], ph);
+      mbar_wait_x(&full[s], ph, (p.dbg_skip & 8) == 0);
       const uint32_t st = smem_u32(stage_base_of(smem, s, S::kStageBytes));
       for (int base = (p.dbg_skip & 1) ? n_piece : 0; base < n_piece; base += 4 * kTransformThreads) {
         float4 v[4];
@@ -1174,7 +1203,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int idx = base + i * kTransformThreads + t;
-          if (idx < n_piece) split_store(st + (uint32_t)idx * 16u, S::kRaw, v[i]);
+          if (idx < n_piece) split_store(st + (uint32_t)idx * 16u, S::kRaw, v[i], (p.dbg_skip & 16) == 0);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -1183,7 +1212,7 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else {
     // epilogue: partial[slice][mt * 128 + row][nt * n_tile + col]
-    mbar_wait(tmem_full, 0);
+    mbar_wait_x(tmem_full, 0, (p.dbg_skip & 8) == 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint8_t* wbuf = store_base + warp * (2 * 32 * kStoreCols * 4);
@@ -1369,7 +1398,7 @@ wgrad_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       for (int kt = 0; kt < k_tiles; ++kt) {
         const int s = kt % kStages;
         const uint32_t ph = (kt / kStages) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
+        mbar_wait_x(&empty[s], ph ^ 1, (p.dbg_skip & 8) == 0);
         uint8_t* st = stage_base_of(smem, s, S::kStageBytes);
         mbar_expect_tx(&full[s], tx);
         const int row = (int)(r0 + (long long)kt * BKR);
@@ -1383,7 +1412,7 @@ wgrad_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       for (int kt = 0; kt < k_tiles; ++kt) {
         const int s = kt % kStages;
         const uint32_t ph = (kt / kStages) & 1;
-        mbar_wait(&a_ready[s], ph);
+        mbar_wait_x(&a_ready[s], ph, (p.dbg_skip & 8) == 0);
         tc_fence_after();
         const uint32_t st = smem_u32(stage_base_of(smem, s, S::kStageBytes));
         const uint32_t a_hi = tmem_base + (uint32_t)(kACol0 + s * 2 * BKR), a_lo = a_hi + BKR;
@@ -1407,7 +1436,7 @@ wgrad_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     for (int kt = 0; kt < k_tiles; ++kt) {
       const int s = kt % kStages;
       const uint32_t ph = (kt / kStages) & 1;
-      mbar_wait(&full[s], ph);
+      mbar_wait_x(&full[s], ph, (p.dbg_skip & 8) == 0);
       const uint32_t st = smem_u32(stage_base_of(smem, s, S::kStageBytes));
       if (!(p.dbg_skip & 1)) {
         const uint32_t gbase = st + S::kABytes;
@@ -1416,13 +1445,13 @@ wgrad_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         for (int i = 0; i < n_piece / kTransformThreads; ++i) v[i] = lds128(gbase + (uint32_t)(i * kTransformThreads + t) * 16u);
 #pragma unroll
         for (int i = 0; i < n_piece / kTransformThreads; ++i)
-          split_store(gbase + (uint32_t)(i * kTransformThreads + t) * 16u, S::kGBytes, v[i]);
+          split_store(gbase + (uint32_t)(i * kTransformThreads + t) * 16u, S::kGBytes, v[i], (p.dbg_skip & 16) == 0);
         float hi[BKR], lo[BKR];
 #pragma unroll
         for (int r = 0; r < BKR; ++r) {
           float x;
           asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(st + (uint32_t)(r * BM * 4 + col * 4)));
-          hi[r] = tf32_rn(x);
+          hi[r] = (p.dbg_skip & 16) ? tf32_rn(x) : tf32_rn_fast(x);
           lo[r] = x - hi[r];
         }
         const uint32_t acol = tmem_base + lane_field + (uint32_t)(kACol0 + s * 2 * BKR);
@@ -1436,7 +1465,7 @@ wgrad_tf32x3_ts_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       if (lane == 0) mbar_arrive(&a_ready[s]);
     }
   } else {
-    mbar_wait(tmem_full, 0);
+    mbar_wait_x(tmem_full, 0, (p.dbg_skip & 8) == 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint8_t* wbuf = store_base + warp * (2 * 32 * kStoreCols * 4);

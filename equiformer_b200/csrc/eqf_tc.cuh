@@ -33,6 +33,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                  : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   } while (!done);
 }
+// the same wait with the suspend-time hint CUTLASS passes (ticks): the hardware keeps the warp asleep until the phase
+// completes or the (long) limit expires, instead of returning after the short default limit and being re-issued
+__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
+}
 // whole-warp wait: ONE lane polls the barrier, the others are released by __syncwarp (which also orders their later reads
 // after the poller's acquire).  256 threads polling one barrier word serialise on it: measured ~450-900 cycles per SATISFIED
 // wait in the first fused kernel (profiles/r2_fused_fwd_v3_timeline_*.txt).
@@ -116,6 +128,17 @@ __device__ __forceinline__ float tf32_rn(float x) {
   return __uint_as_float(r);
 }
 
+// the same rounding (nearest, ties away from zero) in two integer instructions; cvt.rna.tf32.f32 compiles to five on
+// sm_100a (it also keeps NaN payloads - here a NaN still reaches the product through lo = x - hi = NaN)
+__device__ __forceinline__ float tf32_rn_fast(float x) {
+  return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+}
+
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
   float4 v;
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));

@@ -2,8 +2,8 @@
 
 usage: python tools/fused_timeline.py [config] [E] [group] [N] [dtp 1|2] > timeline.txt
 Roles: 0 TMA producer (stamp = stage free, about to issue), 1 MMA issuer (B landed / A ready / committed), 2 transform
-(raw tile ready / a_ready arrived), 3 epilogue (tile start / end), 4, 5 DTP set 0 / 1 (row block: start, harmonics staged,
-tables built; k-tile: stage free, weight box landed, tile written)."""
+(raw tile ready / a_ready arrived), 3 epilogue (tile start / end), 4 DTP set 0 (row block: tables ready; own k-tile: start,
+tile written), 5 table helper warps (row block: buffer free, tables built)."""
 import os
 import sys
 
@@ -56,20 +56,27 @@ def main():
     t0 = int(t[t > 0].min())
     k_tiles = K // 32
     print(f"# {name} E={E} group={group} (l={l}, K={K}, {k_tiles} k-tiles) N={N} dtp{which}; cycles relative to the first stamp of CTA 0")
-    names = ["tma", "mma", "transform", "epilogue", "dtp set0", "dtp set1"]
+    names = ["tma", "mma", "transform", "epilogue", "dtp set0", "table helper"]
     for r in range(6):
         v = [int(x) - t0 for x in t[r].tolist() if x > 0]
         print(f"## role {r} {names[r]}: {len(v)} stamps, last {v[-1] if v else 0}")
         print("   first 60:", v[:60])
-    # per-tile summary from the DTP set 0 stamps: 3 per row block + 3 per own k-tile
+    # DTP set 0 (role 4): per row block one stamp (tables ready) then (start, end) per own k-tile; set 0 owns the even
+    # k-tiles of the CTA's running count, so blocks alternate between ceil and floor of k_tiles / 2
     v = [int(x) - t0 for x in t[4].tolist() if x > 0]
-    own = (k_tiles + 1) // 2
-    per_tile = 3 + 3 * own
-    print("## dtp set0 per row block (first 6): [tables: stage y, build M] then per own k-tile (wait stage, wait weights, math)")
-    for b in range(min(6, len(v) // max(per_tile, 1))):
-        seg = v[b * per_tile:(b + 1) * per_tile]
-        kt = [(seg[3 + 3 * i + 0], seg[3 + 3 * i + 1] - seg[3 + 3 * i + 0], seg[3 + 3 * i + 2] - seg[3 + 3 * i + 1]) for i in range((len(seg) - 3) // 3)]
-        print(f"   block {b}: start {seg[0]} stage_y {seg[1] - seg[0]} build_M {seg[2] - seg[1]} | k-tiles (t_stage_free, wait_w, math): {kt}")
+    print("## dtp set0 per row block (first 6): t_tables_ready | own k-tiles (t_start, wait + math)")
+    pos, it = 0, 0
+    for b in range(6):
+        own = sum(1 for kt in range(k_tiles) if (it + kt) % 2 == 0)
+        it += k_tiles
+        if pos + 1 + 2 * own > len(v):
+            break
+        seg = v[pos:pos + 1 + 2 * own]
+        pos += 1 + 2 * own
+        print(f"   block {b}: tables ready {seg[0]} | {[(seg[1 + 2 * i], seg[2 + 2 * i] - seg[1 + 2 * i]) for i in range(own)]}")
+    h = [int(x) - t0 for x in t[5].tolist() if x > 0]
+    print("## table helper per row block (first 8): (t_buffer_free, build)")
+    print("   ", [(h[2 * i], h[2 * i + 1] - h[2 * i]) for i in range(min(8, len(h) // 2))])
     m = [int(x) - t0 for x in t[1].tolist() if x > 0]
     print("## mma per k-tile (first 24): (t_B_landed, wait_A, issue)")
     print("   ", [(m[3 * i], m[3 * i + 1] - m[3 * i], m[3 * i + 2] - m[3 * i + 1]) for i in range(min(24, len(m) // 3))])
