@@ -20,7 +20,7 @@ CSRC_DIR = PKG_DIR / "csrc"
 INCLUDE_DIR = PKG_DIR.parent / "include"
 LIB_PATH = PKG_DIR / "libeqf_b200.so"
 SOURCES = ("eqf_abi.cu", "eqf_dtp.cu", "eqf_dtp_vec.cu", "eqf_dtp_v3.cu", "eqf_attn.cu", "eqf_pointwise.cu", "eqf_gemm_tf32x3.cu", "eqf_graph.cu",
-           "eqf_fused.cu", "eqf_edge.cu")
+           "eqf_fused.cu", "eqf_edge.cu", "eqf_gemm_small.cu")
 GEMM_LIB_PATH = PKG_DIR / "libeqf_gemm.so"
 GEMM_SOURCES = ("eqf_gemm.cu",)
 
@@ -82,6 +82,17 @@ class EqfHeadLayout(ctypes.Structure):
         ("d", c_int32 * EQF_MAX_BLOCKS),
         ("C", c_int32 * EQF_MAX_BLOCKS),
         ("n_heads", c_int32),
+    ]
+
+
+EQF_GROUP_MAX = 8
+
+
+class EqfGemmProblem(ctypes.Structure):
+    _fields_ = [
+        ("A", c_void_p), ("B", c_void_p), ("C", c_void_p),
+        ("M", c_int64), ("N", c_int64), ("K", c_int64), ("lda", c_int64), ("ldb", c_int64), ("ldc", c_int64),
+        ("mode", c_int32), ("accumulate", c_int32), ("alpha", c_float), ("pad", c_int32),
     ]
 
 
@@ -147,6 +158,7 @@ SIGNATURES = {
                               c_void_p]),
     "eqf_colsum_scratch_floats": (c_int64, [c_int64, c_int64]),
     "eqf_colsum": (c_int32, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "eqf_gemm_grouped": (c_int32, [ctypes.POINTER(EqfGemmProblem), c_int32, c_void_p]),
     "eqf_eln_rows": (c_int32, [POINTER(EqfNormLayout), c_int64]),
     "eqf_eln_fwd": (c_int32, [POINTER(EqfNormLayout), c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "eqf_eln_bwd": (c_int32, [POINTER(EqfNormLayout), c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,

@@ -192,6 +192,22 @@ class TensorProduct(torch.nn.Module):
             out.append((ins.i_in1, ins.i_in2, ins.i_out, view, c))
         return out
 
+    def _linear_spec(self):
+        """``ops.LinearSpec`` of the scalar-in2 'uvw' paths (None when a path has a non-scalar second operand)."""
+        if getattr(self, "_lin_spec", False) is False:
+            from .. import ops
+            paths, off = [], 0
+            ok = self._kind == "linear"
+            for ins in (i for i in self.instructions if i.has_weight):
+                mul_in, m2, mul_out = ins.path_shape
+                ir1 = self.irreps_in1[ins.i_in1].ir
+                c = ins.path_weight * float(wigner_3j_np(ir1.l, 0, ir1.l)[0, 0, 0])
+                ok = ok and m2 == 1
+                paths.append((ins.i_in1, ins.i_out, off, mul_in, mul_out, 1.0 if abs(c - 1.0) < 1e-12 else c))
+                off += mul_in * m2 * mul_out
+            self._lin_spec = ops.LinearSpec(paths, off) if ok and off == self.weight_numel else None
+        return self._lin_spec
+
     def planar_linear(self, xs, y=None, weight=None):
         """Per-degree channel mix on planar blocks: one ``[R*(2l+1), mul_in] @ [mul_in, mul_out]`` GEMM per path.
 
@@ -205,6 +221,17 @@ class TensorProduct(torch.nn.Module):
         in2_off = [s.start for s in self.irreps_in2.slices()]
         outs: List[Optional[torch.Tensor]] = [None] * len(self.irreps_out)
         R = xs[0].shape[0]
+        if y is None:
+            # small products (node-level linears, every linear of the small-graph models): all degrees in one launch
+            spec = self._linear_spec()
+            if spec is not None and ops.planar_linear_grouped_ok(spec, w, [xs[p[0]] for p in spec.paths]):
+                ts = ops.planar_linear_grouped(spec, w, [xs[p[0]] for p in spec.paths])
+                for p, t in zip(spec.paths, ts):
+                    outs[p[1]] = t
+                for io, (mul, ir) in enumerate(self.irreps_out):
+                    if outs[io] is None:
+                        outs[io] = xs[0].new_zeros((R, ir.dim, mul))
+                return outs
         for i1, i2, io, W, c in self.linear_weight_blocks(w):
             x = xs[i1]
             d = x.shape[1]

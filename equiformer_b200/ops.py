@@ -1308,6 +1308,181 @@ def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
     return torch.nn.functional.linear(x, weight, bias)
 
 
+# ----------------------------------------------------------------------------- grouped small products
+# All degrees of a node-level linear in one launch of the exact-fp32 CUDA-core kernel (csrc/eqf_gemm_small.cu): forward,
+# data gradients and weight gradients (the two gradient sets share a launch in a first-order backward).  Round 1 sent each
+# of these 30-80 MFLOP products to cuBLAS separately (~180 SIMT SGEMM launches per QM9 step).
+_GROUPED = os.environ.get("EQF_GROUPED_GEMM", "1") != "0"
+
+
+class LinearSpec:
+    """Paths of a scalar-in2 'uvw' product on planar blocks: ``(i_in, i_out, w_off, mul_in, mul_out, c)`` per path,
+    ``W_p = w[w_off : w_off + mul_in * mul_out].view(mul_in, mul_out)``, ``out[i_out] = c * x[i_in] @ W_p``."""
+
+    def __init__(self, paths, w_numel: int):
+        self.paths = tuple(paths)
+        self.w_numel = int(w_numel)
+
+    def aligned(self) -> bool:
+        outs = [p[1] for p in self.paths]
+        return (0 < len(self.paths) <= _lib.EQF_GROUP_MAX and len(set(outs)) == len(outs)
+                and all(p[3] % 4 == 0 and p[4] % 4 == 0 and p[2] % 4 == 0 for p in self.paths))
+
+
+def grouped_gemm_raw(problems) -> None:
+    """``problems``: ``(mode, A, B, C, alpha, accumulate)`` with 2-D fp32 CUDA tensors (C written / added in place)."""
+    lib = _lib.load()
+    table = (_lib.EqfGemmProblem * len(problems))()
+    nbytes = flops = 0
+    keep = []
+    for q, (mode, A, B, C, alpha, acc) in zip(table, problems):
+        A, lda = _gemm_operand(A)
+        B, ldb = _gemm_operand(B)
+        keep += [A, B]
+        if mode == 0:
+            (M, K), N = A.shape, B.shape[1]
+        elif mode == 1:
+            (M, K), N = A.shape, B.shape[0]
+        else:
+            (K, M), N = A.shape, B.shape[1]
+        if tuple(C.shape) != (M, N) or C.stride(1) != 1:
+            raise ValueError(f"grouped gemm: output {tuple(C.shape)} does not match {(M, N)}")
+        q.A, q.B, q.C = A.data_ptr(), B.data_ptr(), C.data_ptr()
+        q.M, q.N, q.K, q.lda, q.ldb, q.ldc = M, N, K, lda, ldb, C.stride(0)
+        q.mode, q.accumulate, q.alpha = mode, 1 if acc else 0, float(alpha)
+        nbytes += 4 * (A.numel() + B.numel() + C.numel())
+        flops += 2 * M * N * K
+    dev = problems[0][1].device
+    with torch.cuda.device(dev), _kernel("gemm_grouped", nbytes, flops):
+        rc = lib.eqf_gemm_grouped(table, len(problems), _stream())
+    _lib.check(rc, "eqf_gemm_grouped")
+
+
+def _lin_w(spec: LinearSpec, w: torch.Tensor, p):
+    return w.narrow(0, p[2], p[3] * p[4]).view(p[3], p[4])
+
+
+def _lin_rows(t: torch.Tensor) -> torch.Tensor:
+    return t.reshape(t.shape[0] * t.shape[1], t.shape[2])
+
+
+def _lin_fwd_problems(spec, w, xs, outs):
+    return [(0, _lin_rows(x), _lin_w(spec, w, p), _lin_rows(o), p[5], False) for p, x, o in zip(spec.paths, xs, outs)]
+
+
+def _lin_dgrad_problems(spec, w, gs, dxs):
+    return [(1, _lin_rows(g), _lin_w(spec, w, p), _lin_rows(dx), p[5], False) for p, g, dx in zip(spec.paths, gs, dxs)]
+
+
+def _lin_wgrad_problems(spec, xs, gs, gw):
+    return [(2, _lin_rows(x), _lin_rows(g), _lin_w(spec, gw, p), p[5], True) for p, x, g in zip(spec.paths, xs, gs)]
+
+
+def _launch_grouped(problems):
+    for i in range(0, len(problems), _lib.EQF_GROUP_MAX):
+        grouped_gemm_raw(problems[i:i + _lib.EQF_GROUP_MAX])
+
+
+class PlanarLinearFwd(torch.autograd.Function):
+    """``outs[p] = c_p * xs[p] @ W_p`` for every path of the spec (``xs`` in path order); one launch."""
+
+    @staticmethod
+    def forward(ctx, spec: LinearSpec, w, *xs):
+        ctx.spec = spec
+        ctx.save_for_backward(w, *xs)
+        w = w.detach()
+        outs = [x.new_empty((x.shape[0], x.shape[1], p[4])) for p, x in zip(spec.paths, xs)]
+        _launch_grouped(_lin_fwd_problems(spec, w, [x.detach() for x in xs], outs))
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        spec = ctx.spec
+        w, *xs = ctx.saved_tensors
+        gs = [g if g is not None else torch.zeros((x.shape[0], x.shape[1], p[4]), device=x.device, dtype=x.dtype)
+              for g, p, x in zip(gs, spec.paths, xs)]
+        need_w = ctx.needs_input_grad[1]
+        need_x = any(ctx.needs_input_grad[2:])
+        if torch.is_grad_enabled():          # create_graph: stay inside the closed family
+            gw = PlanarLinearWgrad.apply(spec, *xs, *gs) if need_w else None
+            dxs = PlanarLinearDgrad.apply(spec, w, *gs) if need_x else [None] * len(xs)
+            return (None, gw, *dxs)
+        gs = [g.contiguous() for g in gs]
+        problems, gw, dxs = [], None, [None] * len(xs)
+        if need_x:
+            dxs = [torch.empty_like(x) for x in xs]
+            problems += _lin_dgrad_problems(spec, w, gs, dxs)
+        if need_w:
+            gw = torch.zeros_like(w)
+            problems += _lin_wgrad_problems(spec, xs, gs, gw)
+        if problems:
+            _launch_grouped(problems)
+        return (None, gw, *dxs)
+
+
+class PlanarLinearDgrad(torch.autograd.Function):
+    """``dxs[p] = c_p * gs[p] @ W_p^T``."""
+
+    @staticmethod
+    def forward(ctx, spec: LinearSpec, w, *gs):
+        ctx.spec = spec
+        ctx.save_for_backward(w, *gs)
+        gs = [g.detach().contiguous() for g in gs]
+        dxs = [g.new_empty((g.shape[0], g.shape[1], p[3])) for p, g in zip(spec.paths, gs)]
+        _launch_grouped(_lin_dgrad_problems(spec, w.detach(), gs, dxs))
+        return tuple(dxs)
+
+    @staticmethod
+    def backward(ctx, *ddx):
+        spec = ctx.spec
+        w, *gs = ctx.saved_tensors
+        ddx = [d if d is not None else torch.zeros((g.shape[0], g.shape[1], p[3]), device=g.device, dtype=g.dtype)
+               for d, p, g in zip(ddx, spec.paths, gs)]
+        gw = PlanarLinearWgrad.apply(spec, *ddx, *gs) if ctx.needs_input_grad[1] else None
+        ggs = PlanarLinearFwd.apply(spec, w, *ddx) if any(ctx.needs_input_grad[2:]) else [None] * len(gs)
+        return (None, gw, *ggs)
+
+
+class PlanarLinearWgrad(torch.autograd.Function):
+    """flat ``gw`` with ``gw_p = c_p * xs[p]^T @ gs[p]`` (reduction over rows split across CTAs, fp32 atomic adds)."""
+
+    @staticmethod
+    def forward(ctx, spec: LinearSpec, *ts):
+        n = len(spec.paths)
+        xs, gs = ts[:n], ts[n:]
+        ctx.spec = spec
+        ctx.save_for_backward(*ts)
+        gw = torch.zeros(spec.w_numel, device=xs[0].device, dtype=torch.float32)
+        _launch_grouped(_lin_wgrad_problems(spec, [x.detach().contiguous() for x in xs], [g.detach().contiguous() for g in gs], gw))
+        return gw
+
+    @staticmethod
+    def backward(ctx, ggw):
+        spec = ctx.spec
+        n = len(spec.paths)
+        ts = ctx.saved_tensors
+        xs, gs = ts[:n], ts[n:]
+        ggw = ggw.contiguous()
+        dxs = PlanarLinearDgrad.apply(spec, ggw, *gs) if any(ctx.needs_input_grad[1:1 + n]) else [None] * n
+        dgs = PlanarLinearFwd.apply(spec, ggw, *xs) if any(ctx.needs_input_grad[1 + n:]) else [None] * n
+        return (None, *dxs, *dgs)
+
+
+def planar_linear_grouped_ok(spec: LinearSpec, w: torch.Tensor, xs) -> bool:
+    """All paths in one launch of the small-product kernel: CUDA fp32, aligned channels, every product below the row count
+    from which the tcgen05 kernels take over."""
+    if not (_GROUPED and w.is_cuda and w.dtype == torch.float32 and w.dim() == 1 and w.is_contiguous()
+            and w.data_ptr() % 16 == 0 and spec.aligned() and gemm_backend() != "torch"):
+        return False
+    return all(x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[2] == p[3]
+               and x.shape[0] * x.shape[1] < _GEMM_MIN_M for p, x in zip(spec.paths, xs))
+
+
+def planar_linear_grouped(spec: LinearSpec, w: torch.Tensor, xs):
+    """``[c_p * xs[p] @ W_p]`` in path order (autograd: the closed family above)."""
+    return list(PlanarLinearFwd.apply(spec, w, *[x.contiguous() for x in xs]))
+
+
 # ----------------------------------------------------------------------------- column sums / bias adds
 _COLSUM_COUNTERS = {}
 

@@ -249,6 +249,26 @@ int64_t eqf_colsum_scratch_floats(int64_t rows, int64_t cols);
 int eqf_colsum(const float* x, int64_t rows, int64_t cols, int64_t ld, float* out, float* part, uint32_t* counters,
                void* stream);
 
+/* Grouped fp32 GEMM for the SMALL products of the path: all degrees of a node-level linear (reference
+ * nets/tensor_product_rescale.py:LinearRS -> e3nn 'uvw' with a scalar second operand = one [rows * (2l+1), mul_in] x
+ * [mul_in, mul_out] product per degree; nets/graph_attention_transformer.py:430-431, :515, FeedForwardNetwork) - forward,
+ * data gradients and weight gradients - in ONE launch of exact-fp32 CUDA-core tiles (replaces the per-degree cuBLAS calls).
+ * Problem i: C[M, N] = alpha * op(A) op(B); mode 0: A[M, K] B[K, N], 1: A[M, K] B[N, K]^T, 2: A[K, M]^T B[K, N];
+ * accumulate != 0: the reduction is split across CTAs and ADDED into C with fp32 atomics (C holds the initial value).
+ * 16-byte aligned pointers; leading dimensions and every contiguous extent multiples of 4. */
+#define EQF_GROUP_MAX 8
+typedef struct {
+  const float* A;
+  const float* B;
+  float* C;
+  int64_t M, N, K, lda, ldb, ldc;
+  int32_t mode;
+  int32_t accumulate;
+  float alpha;
+  int32_t pad;
+} EqfGemmProblem;
+int eqf_gemm_grouped(const EqfGemmProblem* problems, int32_t n, void* stream);
+
 /* EquivariantLayerNormV2 ('component' normalisation, affine; nets/layer_norm.py:89-152) on e3nn-layout rows:
  * one fused kernel forward, one backward (per-CTA partial sums of the affine gradients:
  * part[eqf_eln_rows(N)][n_weight + n_bias] = d weight | d bias). */

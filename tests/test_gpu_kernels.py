@@ -733,3 +733,60 @@ def test_expnorm_rbf_kernel_vs_torch_statement(cuda_device):
     (rd,) = torch.autograd.grad(ref, d64, cot.double())
     assert rel_err(gd, rd) < 1e-5
     assert rel_err(mod.to(cuda_device)(d.to(cuda_device)), ref) < 2e-6
+
+
+# ------------------------------------------------------------------------------------------------ grouped small products
+def test_grouped_gemm_three_modes_vs_fp64(cuda_device):
+    """``eqf_gemm_grouped``: the three operand layouts (forward, data gradient, split-reduction weight gradient) in one
+    launch, ragged row counts, outputs narrower than a tile, reductions that are not multiples of the k-chunk."""
+    from equiformer_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    dev = cuda_device
+    r = lambda *s: torch.randn(*s, generator=g)
+    cases = [(0, r(2324 * 3, 64), r(64, 64), 0.5, False), (0, r(1001, 100), r(100, 32), 1.0, False),
+             (1, r(2324 * 5, 32), r(36, 32), 0.25, False), (1, r(130, 128), r(128, 128), 1.0, False),
+             (2, r(6972, 64), r(6972, 64), 2.0, True), (2, r(300, 128), r(300, 36), 1.0, True),
+             (2, r(11620, 32), r(11620, 32), 1.0, True), (0, r(7, 4), r(4, 4), 1.0, False)]
+    probs, refs = [], []
+    for mode, A, B, alpha, acc in cases:
+        Ad, Bd = A.double(), B.double()
+        ref = alpha * (Ad @ Bd if mode == 0 else Ad @ Bd.t() if mode == 1 else Ad.t() @ Bd)
+        C = torch.zeros(ref.shape, device=dev) if acc else torch.full(ref.shape, float("nan"), device=dev)
+        probs.append((mode, A.to(dev), B.to(dev), C, alpha, acc))
+        refs.append(ref)
+    ops.grouped_gemm_raw(probs)
+    for (mode, _A, _B, C, _a, _acc), ref in zip(probs, refs):
+        assert rel_err(C, ref) < TOL, (mode, tuple(C.shape), rel_err(C, ref))
+
+
+def test_planar_linear_grouped_matches_per_path_products(cuda_device, monkeypatch):
+    """``LinearRS.planar`` through the grouped launch (forward, first-order gradients in one launch, the ``create_graph``
+    family for the MD17 forces) against the per-degree products it replaces: outputs, gradients, second-order gradients."""
+    from equiformer_b200 import ops
+    from equiformer_b200.nets.tensor_product_rescale import LinearRS
+    torch.manual_seed(0)
+    lin = LinearRS("128x0e+64x1e+32x2e", "64x0e+64x1e+16x2e", bias=True).to(cuda_device)
+    R = 777
+    g = torch.Generator().manual_seed(1)
+    xs0 = [torch.randn(R, 2 * l + 1, m, generator=g).to(cuda_device) for l, m in ((0, 128), (1, 64), (2, 32))]
+    cots = [torch.randn(R, 2 * l + 1, m, generator=g).to(cuda_device) for l, m in ((0, 64), (1, 64), (2, 16))]
+
+    def run(grouped):
+        monkeypatch.setattr(ops, "_GROUPED", grouped)
+        prof = ops.KernelProfile(time_events=False)
+        xs = [x.clone().requires_grad_(True) for x in xs0]
+        monkeypatch.setattr(ops, "PROFILE", prof)
+        outs = lin.planar(xs)
+        grads = torch.autograd.grad(outs, [*xs, lin.tp.weight], cots, create_graph=True)
+        # a scalar of the first-order gradients, differentiated again (the shape of the MD17 force loss)
+        s = sum((gr * gr).sum() for gr in grads)
+        second = torch.autograd.grad(s, [*xs, lin.tp.weight])
+        plain = torch.autograd.grad(lin.planar(xs), [*xs, lin.tp.weight], cots)      # first-order backward: one launch
+        monkeypatch.setattr(ops, "PROFILE", None)
+        return outs, [*grads, *plain], second, prof.launches
+
+    o1, g1, s1, n1 = run(True)
+    o0, g0, s0, _n0 = run(False)
+    for a, b in zip([*o1, *g1, *s1], [*o0, *g0, *s0]):
+        assert rel_err(a, b) < 5e-5, rel_err(a, b)
+    assert n1 >= 3            # grouped launches were counted (forward, data gradients, weight gradients, second order)
