@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <string>
 
 #include "eqf_common.cuh"
@@ -151,6 +152,165 @@ __global__ void __launch_bounds__(kThreadsG) grouped_gemm_kernel(const __grid_co
   }
 }
 
+// ---------------------------------------------------------------------------------------------- warp-MMA variant
+// The same tiles on the tensor cores' warp-level path (mma.sync m16n8k8, tf32 inputs, fp32 accumulate) with the 3xTF32
+// split done in registers: a = a_hi + a_lo, b = b_hi + b_lo, acc += a_lo b_hi + a_hi b_lo + a_hi b_hi (the error of the
+// dropped a_lo b_lo term is ~2^-22 relative, like the tcgen05 kernels of eqf_gemm_tf32x3.cu).  The CUDA-core kernel
+// above is bound by FMA issue (a 64 x 64 x 128 tile is 16 k warp-FMAs: 2.2 us alone on an SM); here a k-step of 8 costs a
+// warp 24 MMAs + 16 shared loads + 48 split instructions for its 32 x 32 sub-tile instead of 256 FMAs + 32 loads.
+// tcgen05 is not worth its prologue at this size (measured: 8.7 us vs 5.5 us for cuBLAS on 2 324 x 128 x 128).
+// 128 threads = 4 warps (2 x 2) per 64 x 64 tile; operands in shared memory in whichever orientation makes the global
+// load a 128-bit access AND the fragment loads conflict-free: k-contiguous operands as [row][16 + 4], the others as
+// [k][64 + 8].
+constexpr int kThreadsM = 128, kLdK = BK + 4, kLdN = 64 + 8, kMmaStages = 4;
+constexpr int kTileFloats = (64 * kLdK) > (BK * kLdN) ? (64 * kLdK) : (BK * kLdN);
+
+__device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// 64 x 16 (or 16 x 64) operand tile: two 16-byte cp.async per thread along the contiguous dimension, straight into the
+// shared-memory orientation the fragments are read from (out-of-range pieces are zero-filled: src-size 0)
+template <bool KC>
+__device__ __forceinline__ void mma_load_async(float* sm, const float* base, int ld, int rows, int r0, int k0, int k_end) {
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = t + h * kThreadsM;
+    const float* src;
+    float* dst;
+    bool ok;
+    if constexpr (KC) {          // base[r * ld + k]
+      const int r = r0 + (i >> 2), k = k0 + (i & 3) * 4;
+      ok = r < rows && k < k_end;
+      src = base + (size_t)(ok ? r : 0) * ld + (ok ? k : 0);
+      dst = sm + (i >> 2) * kLdK + (i & 3) * 4;
+    } else {                     // base[k * ld + r]
+      const int k = k0 + (i >> 4), r = r0 + (i & 15) * 4;
+      ok = k < k_end && r < rows;
+      src = base + (size_t)(ok ? k : 0) * ld + (ok ? r : 0);
+      dst = sm + (i >> 4) * kLdN + (i & 15) * 4;
+    }
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src), "r"(ok ? 16 : 0) : "memory");
+  }
+}
+template <bool KC>
+__device__ __forceinline__ float mma_at(const float* sm, int r, int k) { return KC ? sm[r * kLdK + k] : sm[k * kLdN + r]; }
+
+template <bool AKC, bool BKC>
+__device__ __forceinline__ void mma_tile(const Prob& p, int tm, int tn, int split, float (*As)[kTileFloats], float (*Bs)[kTileFloats]) {
+  const int m0 = tm * BM, n0 = tn * BN;
+  const int k_begin = split * p.k_per_split;
+  const int k_end = (k_begin + p.k_per_split) < p.K ? (k_begin + p.k_per_split) : p.K;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+  // kMmaStages-deep cp.async ring: with one chunk of register prefetch every 16-deep chunk cost a full L2 round trip (8.8 us
+  // for the 157 MFLOP forward of a node-level linear, of which ~6 us were eight exposed load latencies)
+  const int n_chunks = (k_end - k_begin + BK - 1) / BK;
+#pragma unroll
+  for (int s = 0; s < kMmaStages - 1; ++s) {
+    if (s < n_chunks) {
+      mma_load_async<AKC>(As[s], p.A, p.lda, p.M, m0, k_begin + s * BK, k_end);
+      mma_load_async<BKC>(Bs[s], p.B, p.ldb, p.N, n0, k_begin + s * BK, k_end);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kMmaStages - 2) : "memory");
+    __syncthreads();                       // chunk c landed for every thread; everyone is done with chunk c - 1's buffer
+    {
+      const int nc = c + kMmaStages - 1;
+      if (nc < n_chunks) {
+        mma_load_async<AKC>(As[nc % kMmaStages], p.A, p.lda, p.M, m0, k_begin + nc * BK, k_end);
+        mma_load_async<BKC>(Bs[nc % kMmaStages], p.B, p.ldb, p.N, n0, k_begin + nc * BK, k_end);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const int buf = c % kMmaStages;
+#pragma unroll
+    for (int ks = 0; ks < BK; ks += 8) {
+      uint32_t ahi[2][4], alo[2][4], bhi[4][2], blo[4][2];
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi) {
+        const int r = wm + mi * 16 + g;
+        const float v[4] = {mma_at<AKC>(As[buf], r, ks + t), mma_at<AKC>(As[buf], r + 8, ks + t),
+                            mma_at<AKC>(As[buf], r, ks + t + 4), mma_at<AKC>(As[buf], r + 8, ks + t + 4)};
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const float h = rn_tf32(v[cc]);
+          ahi[mi][cc] = __float_as_uint(h);
+          alo[mi][cc] = __float_as_uint(v[cc] - h);
+        }
+      }
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni) {
+        const int n = wn + ni * 8 + g;
+        const float v[2] = {mma_at<BKC>(Bs[buf], n, ks + t), mma_at<BKC>(Bs[buf], n, ks + t + 4)};
+#pragma unroll
+        for (int cc = 0; cc < 2; ++cc) {
+          const float h = rn_tf32(v[cc]);
+          bhi[ni][cc] = __float_as_uint(h);
+          blo[ni][cc] = __float_as_uint(v[cc] - h);
+        }
+      }
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni) {
+          mma_tf32(acc[mi][ni], alo[mi], bhi[ni]);
+          mma_tf32(acc[mi][ni], ahi[mi], blo[ni]);
+          mma_tf32(acc[mi][ni], ahi[mi], bhi[ni]);
+        }
+    }
+  }
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) {
+      const int n = n0 + wn + ni * 8 + 2 * t;
+      if (n >= p.N) continue;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int m = m0 + wm + mi * 16 + g + hh * 8;
+        if (m >= p.M) continue;
+        float* c = p.C + (size_t)m * p.ldc + n;
+        const float v0 = p.alpha * acc[mi][ni][2 * hh], v1 = p.alpha * acc[mi][ni][2 * hh + 1];
+        if (!p.atomic) *reinterpret_cast<float2*>(c) = make_float2(v0, v1);
+        else { atomicAdd(c, v0); atomicAdd(c + 1, v1); }
+      }
+    }
+}
+
+__global__ void __launch_bounds__(kThreadsM) grouped_gemm_mma_kernel(const __grid_constant__ Args g) {
+  __shared__ __align__(16) float As[kMmaStages][kTileFloats];
+  __shared__ __align__(16) float Bs[kMmaStages][kTileFloats];
+  int pi = 0;
+  for (int i = 1; i < g.n; ++i) if ((int)blockIdx.x >= g.p[i].tile0) pi = i;
+  const Prob& p = g.p[pi];
+  int local = (int)blockIdx.x - p.tile0;
+  const int tn = local % p.tiles_n; local /= p.tiles_n;
+  const int tm = local % p.tiles_m;
+  const int split = local / p.tiles_m;
+  if (p.a_kc) {
+    if (p.b_kc) mma_tile<true, true>(p, tm, tn, split, As, Bs);
+    else mma_tile<true, false>(p, tm, tn, split, As, Bs);
+  } else {
+    if (p.b_kc) mma_tile<false, true>(p, tm, tn, split, As, Bs);
+    else mma_tile<false, false>(p, tm, tn, split, As, Bs);
+  }
+}
+
 }  // namespace small
 }  // namespace eqf
 
@@ -210,6 +370,9 @@ extern "C" int eqf_gemm_grouped(const EqfGemmProblem* problems, int32_t n, void*
     ++g.n;
   }
   if (g.n == 0) return EQF_OK;
-  small::grouped_gemm_kernel<<<tiles, kThreadsG, 0, (cudaStream_t)stream>>>(g);
+  // EQF_SMALL_MMA=0: the CUDA-core (exact fp32 FMA) kernel instead of the warp-MMA 3xTF32 one
+  static const bool use_mma = [] { const char* e = std::getenv("EQF_SMALL_MMA"); return e == nullptr || e[0] != '0'; }();
+  if (use_mma) small::grouped_gemm_mma_kernel<<<tiles, kThreadsM, 0, (cudaStream_t)stream>>>(g);
+  else small::grouped_gemm_kernel<<<tiles, kThreadsG, 0, (cudaStream_t)stream>>>(g);
   return check_cuda(cudaGetLastError(), "grouped_gemm_kernel launch");
 }

@@ -1136,6 +1136,12 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
             return gemm_tf32x3_wgrad_raw(A, B)
     use_cutlass = fast and (forced or (backend == "cutlass" and ((mode != 2 and M >= _GEMM_MIN_M)
                                                                   or (mode == 2 and K >= _WGRAD_MIN_K))))
+    if not use_cutlass and fast and backend != "torch" and _SMALL_OWN:
+        # small products (the whole MD17 regime, node-level leftovers): the exact-fp32 CUDA-core kernel, not cuBLAS
+        split = mode == 2 and K >= 1024            # long reduction, small output: split across CTAs, atomic adds
+        C = (torch.zeros if split else torch.empty)((M, N), device=A.device, dtype=torch.float32)
+        grouped_gemm_raw([(mode, A, B, C, 1.0, split)])
+        return C
     if not use_cutlass:
         if mode == 0:
             return A @ B
@@ -1313,6 +1319,8 @@ def linear_f32(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tenso
 # data gradients and weight gradients (the two gradient sets share a launch in a first-order backward).  Round 1 sent each
 # of these 30-80 MFLOP products to cuBLAS separately (~180 SIMT SGEMM launches per QM9 step).
 _GROUPED = os.environ.get("EQF_GROUPED_GEMM", "1") != "0"
+# EQF_SMALL_GEMM=cublas hands single small products (below the tcgen05 thresholds) back to torch / cuBLAS (A/B switch)
+_SMALL_OWN = os.environ.get("EQF_SMALL_GEMM", "own") != "cublas"
 
 
 class LinearSpec:
