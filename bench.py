@@ -580,8 +580,10 @@ def run_ours(args):
                                  f"the tcgen05 GEMMs (K1) from {ops._FUSED_MIN_EDGES} edges per call in 'auto' mode - "
                                  + ("ON" if ops._FUSED and (ops._FUSED_MODE == "1" or edges_of[0] >= ops._FUSED_MIN_EDGES) else "OFF")
                                  + " for this workload"),
-                       "gemm": "tcgen05 3xTF32, hand-written (edge-level forward / dgrad / wgrad, node-level wgrad); cuBLAS SGEMM "
-                               f"below {ops._GEMM_MIN_M} rows" if ops.gemm_backend() == "tf32x3" else ops.gemm_backend(),
+                       "gemm": ("tcgen05 3xTF32, hand-written (forward / dgrad from "
+                                f"{ops._GEMM_MIN_M} rows, wgrad from {ops._WGRAD_MIN_K} reduction rows); below "
+                                "that the grouped warp-MMA 3xTF32 kernel (all degrees of a linear per launch); no cuBLAS on the path")
+                               if ops.gemm_backend() == "tf32x3" else ops.gemm_backend(),
                        "launch": ("CUDA-graph replay of forward+loss+backward; neighbour search, all-reduce and AdamW eager"
                                   + (f"; stream of {len(hosts)} different batches over {graphed.captures} captured size buckets"
                                      if args.stream > 1 and graphed is not None else "")) if use_graph else "eager",

@@ -1104,6 +1104,17 @@ _WGRAD_MIN_K = int(os.environ.get("EQF_WGRAD_MIN_K", "2048"))
 # rows from which forward / data-gradient products leave cuBLAS for the tcgen05 kernels; EQF_GEMM_MIN_M=1 sends the small
 # reference-run fixtures (tests/golden/reference_model_*.npz) through the hand-written kernels as well
 _GEMM_MIN_M = int(os.environ.get("EQF_GEMM_MIN_M", "16384"))
+# ... or this many flops (EQF_GEMM_MIN_FLOP; off by default).  Alone, the MD17 edge-level products (6 300-14 700 rows x
+# 576-672 x 64: 0.45-0.9 GFLOP) take 15-18 us on the tcgen05 kernels against 21-36 us on the warp-MMA kernel
+# (profiles/r2_small_gemm_backends.jsonl), but inside the step a threshold of 4e8 LOSES (43.7 vs 41.1 ms per MD17 step,
+# profiles/r2_bench_md17_*_c21.json): the tcgen05 route costs a weight-split + GEMM launch pair per degree where the
+# grouped kernel takes all degrees - and, in the backward, data and weight gradients - in one launch.
+_GEMM_MIN_FLOP = float(os.environ.get("EQF_GEMM_MIN_FLOP", "inf"))
+
+
+def _use_tcgen05(M: int, N: int, K: int) -> bool:
+    """Forward / data-gradient product [M, K] x [K, N]: the tcgen05 3xTF32 kernels (True) or the small-product kernel."""
+    return M >= _GEMM_MIN_M or (M >= 1024 and 2.0 * M * N * K >= _GEMM_MIN_FLOP)
 
 
 def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
@@ -1130,11 +1141,11 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
     # (profiles/r1_tf32x3_microbench.jsonl); the weight gradient (one TMEM accumulator per row slice, 32-row TMA boxes)
     # is ahead of the sliced CUTLASS launch on every layer shape (profiles/r1_tf32x3_wgrad_microbench.jsonl)
     if backend == "tf32x3" and not forced:
-        if mode != 2 and M >= _GEMM_MIN_M:
+        if mode != 2 and _use_tcgen05(M, N, K):
             return gemm_tf32x3_raw(A, B, b_is_kn=(mode == 0))
         if mode == 2 and K >= _WGRAD_MIN_K:
             return gemm_tf32x3_wgrad_raw(A, B)
-    use_cutlass = fast and (forced or (backend == "cutlass" and ((mode != 2 and M >= _GEMM_MIN_M)
+    use_cutlass = fast and (forced or (backend == "cutlass" and ((mode != 2 and _use_tcgen05(M, N, K))
                                                                   or (mode == 2 and K >= _WGRAD_MIN_K))))
     if not use_cutlass and fast and backend != "torch" and _SMALL_OWN:
         # small products (the whole MD17 regime, node-level leftovers): the exact-fp32 CUDA-core kernel, not cuBLAS
@@ -1483,7 +1494,7 @@ def planar_linear_grouped_ok(spec: LinearSpec, w: torch.Tensor, xs) -> bool:
             and w.data_ptr() % 16 == 0 and spec.aligned() and gemm_backend() != "torch"):
         return False
     return all(x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[2] == p[3]
-               and x.shape[0] * x.shape[1] < _GEMM_MIN_M for p, x in zip(spec.paths, xs))
+               and not _use_tcgen05(x.shape[0] * x.shape[1], max(p[3], p[4]), min(p[3], p[4])) for p, x in zip(spec.paths, xs))
 
 
 def planar_linear_grouped(spec: LinearSpec, w: torch.Tensor, xs):
