@@ -9,20 +9,23 @@
 // and f never reaches HBM.  One CTA per SM, persistent over 128-row x n_tile output tiles (rows = (edge, component)
 // pairs of ONE output degree), warp-specialised like eqf_gemm_tf32x3.cu's tensor-memory kernel:
 //   warps 0-3    epilogue      TMEM accumulator -> registers -> swizzled staging -> TMA store of C
-//   warp  4      TMA producer  weight tiles B_hi / B_lo of the k-tile (K-major planes, 128-byte rows)
+//   warp  4      TMA producer  weight tiles B_hi / B_lo of the k-tile (K-major planes, 128-byte rows) and, for per-edge
+//                              weights, a box of the [E, W] radial-weight matrix - one "operand slot" per k-tile
 //   warp  5      MMA issuer    tcgen05.mma.kind::tf32, A from TENSOR MEMORY, 3xTF32 (stacked [b_hi | b_lo] for N <= 64)
+//   warps 6-7    table helpers ONE ROW BLOCK AHEAD: the block's src / dst rows and harmonics into shared memory, then the
+//                              coupling blocks M_p[e] from the group's CG blocks (double-buffered, tab_ready / tab_free)
 //   warps 8-11   transform     raw A tile (shared memory) -> a_hi / a_lo in tensor memory (one thread = one row)
 //   warps 12-27  DTP producers two sets of 8 warps alternate k-tiles: gather x = A[src] + B[dst] (float4 per lane, node
-//                tables L2 resident), multiply by the per-edge radial weights (a TMA box of the [E, W] weight matrix that
-//                the producer warp stages with the weight tiles), contract with M_p[e] and write the 128 x 32 raw A tile
-//                into the stage's shared memory (SWIZZLE_128B row order, conflict-free)
-// Register budget (896 threads x 72 at launch): setmaxnreg moves registers from the TMA / MMA / helper warpgroup (40) to
-// the transform (88) and epilogue (88) warpgroups; the DTP warps keep their 72.
-// Per row block the 16 DTP warps first build the block's tables in shared memory (double-buffered, two named barriers): node
-// rows and harmonics of its <= 128/(2 l3 + 1) + 2 edges, then the coupling blocks M_p[e] from the group's CG blocks (packed
-// into shared memory once per CTA).  History (profiles/r2_fused_fwd_v*): v1 computed M_p[e] with dependent GLOBAL loads of CG
-// and y inside that window (~12 k cycles per tile: the fused kernel was 1.6x slower than DTP + GEMM); v2 moved the tables to
-// two helper warps one tile ahead - 64 threads could not keep up (28 us per tile) and it got slower still.
+//                tables L2 resident; issued before the handshake), multiply by the radial weights, contract with M_p[e]
+//                (128-bit shared loads, dense) and write the 128 x 32 raw A tile (SWIZZLE_128B row order, conflict-free)
+// Three independent rings (v5): operand slots (TMA -> MMA commit), raw A tiles (producers -> transform loads), tensor-memory
+// A slots (transform -> MMA commit).  Register budget (896 threads x 72 at launch): setmaxnreg gives the TMA / MMA / helper
+// warpgroup 56 and the transform warpgroup 88.
+// History (profiles/r2_fused_fwd_v*): v1 computed M_p[e] with dependent GLOBAL loads of CG and y inside
+// the tile loop (~12 k cycles per tile); v2 moved the tables to two helper warps that walked the entries serially (28 us per
+// tile); v3 built them with all 16 DTP warps between two 512-thread barriers (7 k cycles per row block with the pipeline
+// drained) and tied weight tiles, raw tile and TMEM slot to ONE 5-deep ring; v4 = dense producer, cheaper table build,
+// wait hints (A/B: the producer's instruction count is not the limiter); v5 = this file.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
