@@ -1471,7 +1471,7 @@ class PlanarLinearWgrad(torch.autograd.Function):
         xs, gs = ts[:n], ts[n:]
         ctx.spec = spec
         ctx.save_for_backward(*ts)
-        gw = torch.zeros(spec.w_numel, device=xs[0].device, dtype=torch.float32)
+        gw = torch.zeros(spec.w_numel, device=xs[0].device, dtype=xs[0].dtype)
         _launch_grouped(_lin_wgrad_problems(spec, [x.detach().contiguous() for x in xs], [g.detach().contiguous() for g in gs], gw))
         return gw
 

@@ -159,6 +159,16 @@ def gemm_raw(mode, A, B):
     return A @ B.t() if mode == 1 else A.t() @ B
 
 
+def grouped_gemm_raw(problems):
+    """``(mode, A, B, C, alpha, accumulate)``: C is written (or added to) in place, like the kernel."""
+    for mode, A, B, C, alpha, acc in problems:
+        val = alpha * (A @ B if mode == 0 else A @ B.t() if mode == 1 else A.t() @ B)
+        if acc:
+            C.add_(val)
+        else:
+            C.copy_(val)
+
+
 def ln_silu_fwd_raw(x, gamma, beta, eps, bias=None):
     xb = x if bias is None else x + bias
     mean = xb.mean(-1)
@@ -234,7 +244,7 @@ def gate_logits_bwd_raw(lay, t0, bias, alpha_dot, gated, gz, gv0, gvout):
     return grads[0], list(grads[2:]), (grads[1].reshape(-1) if lay.n_alpha > 0 else None)
 
 
-_PATCHED = ["rbf_fwd_raw", "rbf_bwd_raw", "colsum_raw", "eln_fwd_raw", "eln_bwd_raw", "eln_planar_fwd_raw", "eln_planar_bwd_raw", "ln_silu_fwd_raw", "ln_silu_bwd_raw", "gate_logits_fwd_raw", "gate_logits_bwd_raw", "gemm_raw", "dtp_forward_raw", "dtp_linear_fwd_raw", "dtp_group_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
+_PATCHED = ["rbf_fwd_raw", "rbf_bwd_raw", "colsum_raw", "eln_fwd_raw", "eln_bwd_raw", "eln_planar_fwd_raw", "eln_planar_bwd_raw", "ln_silu_fwd_raw", "ln_silu_bwd_raw", "gate_logits_fwd_raw", "gate_logits_bwd_raw", "gemm_raw", "grouped_gemm_raw", "dtp_forward_raw", "dtp_linear_fwd_raw", "dtp_group_forward_raw", "dtp_grad_x_raw", "dtp_grad_w_raw", "dtp_grad_y_raw", "dtp_grad_xw_raw",
             "seg_softmax_raw", "seg_softmax_bwd_raw", "softmax_aggregate_raw", "attn_aggregate_raw", "attn_edge_dot_raw", "attn_edge_scale_raw"]
 
 

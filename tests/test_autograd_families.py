@@ -106,3 +106,46 @@ def test_dtp_gathered_offset_gradcheck_with_dependent_inputs():
 
         assert torch.autograd.gradcheck(f, (y, w, off, *A0, *B0), atol=1e-7)
         assert torch.autograd.gradgradcheck(f, (y, w, off, *A0, *B0), atol=1e-6)
+
+
+def test_planar_linear_family_gradcheck_and_gradgradcheck():
+    """``PlanarLinearFwd / Dgrad / Wgrad`` (all degrees of a linear in one grouped launch): first and second order in fp64,
+    with a path constant != 1 and a weight offset != 0 for every path."""
+    spec = ops.LinearSpec([(0, 0, 0, 4, 8, 0.5), (1, 1, 32, 4, 4, 1.0), (2, 2, 48, 8, 4, 1.7)], 80)
+    assert spec.aligned()
+    R = 3
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(80, generator=g, dtype=torch.float64, requires_grad=True)
+    xs = [torch.randn(R, d, m, generator=g, dtype=torch.float64, requires_grad=True) for d, m in ((1, 4), (3, 4), (5, 8))]
+
+    def f(w, *xs):
+        return ops.PlanarLinearFwd.apply(spec, w, *xs)
+
+    with emulated_kernels():
+        outs = f(w, *xs)
+        for p, x, o in zip(spec.paths, xs, outs):
+            W = w[p[2]:p[2] + p[3] * p[4]].view(p[3], p[4])
+            assert torch.allclose(o, p[5] * torch.einsum("rdu,uw->rdw", x, W), atol=1e-12)
+        assert torch.autograd.gradcheck(f, (w, *xs), atol=1e-7)
+        assert torch.autograd.gradgradcheck(f, (w, *xs), atol=1e-6)
+        # the first-order backward takes the single-launch route when no graph is being built: same numbers
+        cots = [torch.randn_like(o) for o in outs]
+        a = torch.autograd.grad(f(w, *xs), (w, *xs), cots)
+        b = torch.autograd.grad(f(w, *xs), (w, *xs), cots, create_graph=True)
+        for u, v in zip(a, b):
+            assert torch.allclose(u, v, atol=1e-12)
+
+
+def test_linear_spec_matches_weight_views():
+    """``TensorProduct._linear_spec`` (offsets, shapes, path constants of the grouped launch) against the per-path views and
+    constants of ``linear_weight_blocks`` that the per-degree route uses."""
+    from equiformer_b200.nets.tensor_product_rescale import LinearRS
+    lin = LinearRS("8x0e+4x1e+4x2e", "4x0e+8x1e+4x2e", bias=True)
+    spec = lin.tp._linear_spec()
+    assert spec is not None and spec.w_numel == lin.tp.weight_numel
+    w = lin.tp.weight.detach()
+    blocks = lin.tp.linear_weight_blocks(w)
+    assert len(blocks) == len(spec.paths)
+    for (i1, _i2, io, W, c), p in zip(blocks, spec.paths):
+        assert (i1, io) == (p[0], p[1]) and abs(c - p[5]) < 1e-12
+        assert torch.equal(W.reshape(p[3], p[4]), w[p[2]:p[2] + p[3] * p[4]].view(p[3], p[4]))
