@@ -28,7 +28,7 @@ from .drop import EquivariantDropout, GraphDropPath
 from .fast_activation import Activation, Gate
 from .gaussian_rbf import GaussianRadialBasisLayer
 from .layer_norm import EquivariantLayerNormV2
-from .radial_func import RadialProfile
+from .radial_func import RadialProfile, clear_hoisted, hoist_first_layers
 from .registry import register_model
 from .tensor_product_rescale import (FullyConnectedTensorProductRescale,
                                      FullyConnectedTensorProductRescaleSwishGate, LinearRS, TensorProductRescale,
@@ -760,13 +760,17 @@ class GraphAttentionTransformer(torch.nn.Module):
         edge_vec, edge_length, edge_sh = edge_features(self.irreps_edge_attr, pos, graph, edge_vec)
         atom_embedding, _attr, _onehot = self.atom_embed(self._atom_remap[node_atom])
         edge_length_embedding = self.rbf(edge_length)
-        edge_degree_embedding = self.edge_deg_embed(atom_embedding, edge_sh, edge_length_embedding, edge_src, edge_dst,
-                                                    batch, graph=graph)
-        node_features = atom_embedding + edge_degree_embedding
-        node_attr = torch.ones_like(node_features.narrow(1, 0, 1))
-        node_attr._eqf_all_ones = True          # lets the node-level FCTPs skip the multiply by the constant 1
-        node_features = _run_blocks(self.blocks, node_features, self.irreps_node_embedding, node_attr, edge_src, edge_dst,
-                                    edge_sh, edge_length_embedding, batch, graph)
+        served = hoist_radial(self, edge_length_embedding)     # first Linear of all radial MLPs: one GEMM
+        try:
+            edge_degree_embedding = self.edge_deg_embed(atom_embedding, edge_sh, edge_length_embedding, edge_src, edge_dst,
+                                                        batch, graph=graph)
+            node_features = atom_embedding + edge_degree_embedding
+            node_attr = torch.ones_like(node_features.narrow(1, 0, 1))
+            node_attr._eqf_all_ones = True          # lets the node-level FCTPs skip the multiply by the constant 1
+            node_features = _run_blocks(self.blocks, node_features, self.irreps_node_embedding, node_attr, edge_src, edge_dst,
+                                        edge_sh, edge_length_embedding, batch, graph)
+        finally:
+            clear_hoisted(served)
         node_features = self.norm(node_features, batch=batch)
         if self.out_dropout is not None:
             node_features = self.out_dropout(node_features)
@@ -789,6 +793,15 @@ def edge_features(irreps_edge_attr, pos, graph, edge_vec=None):
         edge_vec = pos.index_select(0, graph.src) - pos.index_select(0, graph.dst)
     edge_sh = o3.spherical_harmonics(l=irreps_edge_attr, x=edge_vec, normalize=True, normalization="component")
     return edge_vec, edge_vec.norm(dim=1), edge_sh
+
+
+def hoist_radial(model, edge_scalars):
+    """``radial_func.hoist_first_layers`` over every ``RadialProfile`` of ``model`` (list cached on the instance)."""
+    mods = model.__dict__.get("_rad_modules")
+    if mods is None:
+        mods = [m for m in model.modules() if isinstance(m, RadialProfile)]
+        model.__dict__["_rad_modules"] = mods
+    return hoist_first_layers(mods, edge_scalars)
 
 
 def _run_blocks(blocks, node_features, irreps, node_attr, edge_src, edge_dst, edge_sh, edge_scalars, batch, graph):

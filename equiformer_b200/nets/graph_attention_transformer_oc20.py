@@ -19,7 +19,7 @@ from ..o3 import Irreps
 from .drop import EquivariantDropout
 from .fast_activation import Activation
 from .gaussian_rbf import GaussianRadialBasisLayer
-from .graph_attention_transformer import (_run_blocks, EdgeDegreeEmbeddingNetwork, NodeEmbeddingNetwork, ScaledScatter,
+from .graph_attention_transformer import (_run_blocks, clear_hoisted, hoist_radial, EdgeDegreeEmbeddingNetwork, NodeEmbeddingNetwork, ScaledScatter,
                                           TransBlock, get_norm_layer)
 from .layer_norm import EquivariantLayerNormV2
 from .registry import register_model
@@ -153,13 +153,17 @@ class GraphAttentionTransformerOC20(torch.nn.Module):
             graph = ops.Graph(edge_src, edge_dst, n_nodes, check_sorted=not edges_sorted)
             if graph.perm is not None:
                 raise ValueError("forward_edges needs the edge list sorted by destination")
-        edge_degree_embedding = self.edge_deg_embed(atom_embedding, edge_sh, edge_length_embedding, edge_src, edge_dst,
-                                                    batch, graph=graph)
-        node_features = atom_embedding + tag_embedding + edge_degree_embedding
-        node_attr = torch.ones_like(node_features.narrow(1, 0, 1))
-        node_attr._eqf_all_ones = True
-        node_features = _run_blocks(self.blocks, node_features, self.irreps_node_embedding, node_attr, edge_src, edge_dst,
-                                    edge_sh, edge_length_embedding, batch, graph)
+        served = hoist_radial(self, edge_length_embedding)     # first Linear of every radial MLP: one GEMM
+        try:
+            edge_degree_embedding = self.edge_deg_embed(atom_embedding, edge_sh, edge_length_embedding, edge_src, edge_dst,
+                                                        batch, graph=graph)
+            node_features = atom_embedding + tag_embedding + edge_degree_embedding
+            node_attr = torch.ones_like(node_features.narrow(1, 0, 1))
+            node_attr._eqf_all_ones = True
+            node_features = _run_blocks(self.blocks, node_features, self.irreps_node_embedding, node_attr, edge_src, edge_dst,
+                                        edge_sh, edge_length_embedding, batch, graph)
+        finally:
+            clear_hoisted(served)
         node_features = self.norm(node_features, batch=batch)
         outputs = self.out_dropout(node_features) if self.out_dropout is not None else node_features
         outputs = self.head(outputs)

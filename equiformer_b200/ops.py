@@ -2220,6 +2220,27 @@ class _SplitFlat(torch.autograd.Function):
         return torch.cat(parts), None
 
 
+class _SplitColumns(torch.autograd.Function):
+    """Contiguous column blocks of ``[R, sum(sizes)]``; the backward is ONE concatenation (autograd's per-slice backward
+    would zero-fill and copy a full-width buffer per block)."""
+
+    @staticmethod
+    def forward(ctx, x, sizes):
+        ctx.sizes = sizes
+        ctx.rows = x.shape[0]
+        return tuple(c.contiguous() for c in x.split(list(sizes), dim=1))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        ref = next(g for g in gs if g is not None)
+        gs = [g if g is not None else ref.new_zeros((ctx.rows, n)) for g, n in zip(gs, ctx.sizes)]
+        return torch.cat(gs, dim=1), None
+
+
+def split_columns(x: torch.Tensor, sizes: Sequence[int]) -> List[torch.Tensor]:
+    return list(_SplitColumns.apply(x, tuple(int(n) for n in sizes)))
+
+
 def split_flat(w: torch.Tensor, sizes: Sequence[int]) -> List[torch.Tensor]:
     if not w.requires_grad or w.dim() != 1:
         out, off = [], 0

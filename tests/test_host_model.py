@@ -211,3 +211,29 @@ def test_bucketed_step_padding_leaves_loss_and_gradients_unchanged():
     for p, g in zip(model.parameters(), g0):
         if g is not None:
             assert rel_err(p.grad, g) < 1e-10
+
+
+def test_radial_first_layers_run_as_one_product(monkeypatch):
+    """The first Linear of the 7 radial MLPs of the QM9 model is ONE stacked product (``radial_func.hoist_first_layers``);
+    outputs and gradients equal the per-module evaluation (``EQF_RAD_HOIST=0``)."""
+    from equiformer_b200 import ops
+    from equiformer_b200.nets import radial_func
+    model = _build("graph_attention_transformer_nonlinear_l2")
+    pos, batch, z = molecules([5, 7], seed=3, dtype=torch.float64)
+    real = ops.linear_f32
+    results = {}
+    for hoist in (True, False):
+        monkeypatch.setattr(radial_func, "_HOIST", hoist)
+        calls = []
+        monkeypatch.setattr(ops, "linear_f32", lambda x, w, b=None: (calls.append(tuple(w.shape)), real(x, w, b))[1])
+        model.zero_grad(set_to_none=True)
+        with emulated_kernels():
+            out = model(f_in=None, pos=pos, batch=batch, node_atom=z)
+            out.sum().backward()
+        first = [s for s in calls if s[1] == 128]
+        results[hoist] = (out.detach().clone(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}, first)
+    assert results[True][2] == [(7 * 64, 128)] and len(results[False][2]) == 7      # 6 blocks + the degree embedding
+    assert rel_err(results[True][0], results[False][0]) < 1e-12
+    for k, g in results[False][1].items():
+        assert rel_err(results[True][1][k], g) < 1e-10, k
+    assert all(getattr(m, "_hoisted", None) is None for m in model.modules())
