@@ -45,38 +45,10 @@ __device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity) {
       "DONE_%=:\n\t}"
       ::"r"(smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
-// whole-warp wait: ONE lane polls the barrier, the others are released by __syncwarp (which also orders their later reads
-// after the poller's acquire).  256 threads polling one barrier word serialise on it: measured ~450-900 cycles per SATISFIED
-// wait in the first fused kernel (profiles/r2_fused_fwd_v3_timeline_*.txt).
-__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
-  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
-  __syncwarp();
-}
+// (one polling lane per warp + __syncwarp was measured 5-35 % SLOWER than all lanes waiting: profiles/r2_v4_ab_*_elected_waits.jsonl)
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-// L2 eviction policies: streams that are read once (per-edge radial weights) must not push the node tables - gathered
-// again and again - out of the 126 MB L2
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ void tma_load_2d_hint(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint64_t policy) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
-               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy) : "memory");
-}
-__device__ __forceinline__ float4 ldg128_hint(const float* p, uint64_t policy) {
-  float4 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(policy));
-  return v;
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, uint32_t src_smem) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
