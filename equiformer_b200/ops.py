@@ -1149,7 +1149,7 @@ def gemm_raw(mode: int, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
                                                                   or (mode == 2 and K >= _WGRAD_MIN_K))))
     if not use_cutlass and fast and backend != "torch" and _SMALL_OWN:
         # small products (the whole MD17 regime, node-level leftovers): the exact-fp32 CUDA-core kernel, not cuBLAS
-        split = mode == 2 and K >= 1024            # long reduction, small output: split across CTAs, atomic adds
+        split = mode == 2 and K >= 1024 and not _DETERMINISTIC   # long reduction, small output: split across CTAs, atomic adds
         C = (torch.zeros if split else torch.empty)((M, N), device=A.device, dtype=torch.float32)
         grouped_gemm_raw([(mode, A, B, C, 1.0, split)])
         return C
@@ -1489,8 +1489,9 @@ class PlanarLinearWgrad(torch.autograd.Function):
 
 def planar_linear_grouped_ok(spec: LinearSpec, w: torch.Tensor, xs) -> bool:
     """All paths in one launch of the small-product kernel: CUDA fp32, aligned channels, every product below the row count
-    from which the tcgen05 kernels take over."""
-    if not (_GROUPED and w.is_cuda and w.dtype == torch.float32 and w.dim() == 1 and w.is_contiguous()
+    from which the tcgen05 kernels take over.  ``EQF_DETERMINISTIC=1`` keeps the per-degree route (the grouped weight
+    gradients meet in ``gw`` through fp32 atomics, whose order is not fixed)."""
+    if not (_GROUPED and not _DETERMINISTIC and w.is_cuda and w.dtype == torch.float32 and w.dim() == 1 and w.is_contiguous()
             and w.data_ptr() % 16 == 0 and spec.aligned() and gemm_backend() != "torch"):
         return False
     return all(x.is_cuda and x.dtype == torch.float32 and x.dim() == 3 and x.shape[2] == p[3]
