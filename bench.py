@@ -37,7 +37,6 @@ import subprocess
 import sys
 import threading
 import time
-import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:

@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import torch
 
-from .. import o3, ops
+from .. import ops
 from ..o3 import Irreps
 from .drop import EquivariantDropout
 from .expnorm_rbf import ExpNormalSmearing

@@ -2,7 +2,6 @@
 ``grouped_gemm_raw`` would hand to ``eqf_gemm_grouped`` (layout flags and leading dimensions), without launching anything."""
 import ctypes
 
-import pytest
 import torch
 
 from equiformer_b200 import _lib, ops
